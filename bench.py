@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the CGG decoder-head hot path (BASELINE.json metric: decoder-head images/s at
+1024x1024).  One "step" = one pass of the path (Mask2FormerHeadOpen.forward after the pixel
+decoder, open_set/models/mask2former_head.py:787-849) over one batch of synthetic pixel-decoder
+outputs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--batch B_per_gpu] [--precision bf16|fp32] [--queries Q]
+
+N>1 is launched by torch.distributed.run, one rank per GPU; images shard by batch, no data-path
+collective, so "scaling" is weak.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'decoder_head_images_per_sec_1024'
+UNIT = 'images/s'
+H = W = 1024
+C = 256
+FFN = 2048
+D_L = 768
+NCLS1 = 49
+LAYERS = 9
+
+
+def flops_per_image(Q, height=H, width=W):
+    """Dense algorithmic FLOPs of the path per image."""
+    HW4 = (height // 4) * (width // 4)
+    Ks = [(height // s) * (width // s) for s in (32, 16, 8)]
+    f = (LAYERS + 1) * (2 * Q * C * HW4 + 2 * Q * C * (3 * C + D_L + NCLS1))
+    for i in range(LAYERS):
+        K = Ks[i % 3]
+        f += 4 * Q * C * C + 4 * K * C * C + 4 * Q * K * C
+    f += LAYERS * (8 * Q * C * C + 4 * Q * Q * C)
+    f += LAYERS * (4 * Q * C * FFN)
+    return float(f)
+
+
+def einsum_flops_per_launch(Q, batch):
+    return 2.0 * Q * C * (H // 4) * (W // 4) * batch
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], tflops=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    tflops_burst=d['bf16_tflops'], source='MEASURED_PEAKS.json')
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+# ------------------------------------------------------------------------------ CPU legs
+def cpu_reference_step(sd, mf, mems):
+    from oracle import cgg_oracle as O
+    with torch.no_grad():
+        return O.decoder_forward(sd, mf, mems)
+
+
+def cpu_baseline(Q, threads, repeats=3):
+    """The oracle (a port of the reference's fp32 PyTorch path) timed on the host cores on a
+    bounded sample: one 1024x1024 image per pass."""
+    from cgg_b200 import synth
+    torch.set_num_threads(threads)
+    sd = synth.make_params(seed=0, num_queries=Q)
+    mf, mems = synth.make_inputs(0, 1, H, W)
+    cpu_reference_step(sd, mf, mems)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_reference_step(sd, mf, mems)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return dict(value=1.0 / ts[len(ts) // 2], unit=UNIT, cores=threads, kind='port',
+                sample='1 image 1024x1024 per pass, Q=%d, fp32, median of %d passes after 1 warm-up' % (Q, repeats))
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot
+    travel to the GPU box) with all host threads, each step a bounded sample of the same workload."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from cgg_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Q = args.queries
+    sample_b = 1
+    sd = synth.make_params(seed=0, num_queries=Q)
+    mf, mems = synth.make_inputs(0, sample_b, H, W)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(sd, mf, mems)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sd, mf, mems)
+    dt = time.perf_counter() - t0
+    val = sample_b * args.steps / dt
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload='configs[1]: COCO-OVIS instance decoder head, Q=%d, 9 layers, 256-d, 1024x1024' % Q,
+                            batch_per_step=sample_b, note='CPU path, bounded sample of 1 image per step'),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind='port',
+                                  sample='%d image(s) 1024x1024 per step, fp32 oracle port of the reference path' % sample_b),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_b200_arm(args):
+    import torch.distributed as dist
+    from cgg_b200 import synth, lib as clib
+    from cgg_b200.head import build_head_from_state_dict
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    Q, B = args.queries, args.batch
+    dt_in = torch.bfloat16 if args.precision == 'bf16' else torch.float32
+    sd = synth.make_params(seed=0, num_queries=Q)
+    head = build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev)
+    # synthetic pixel-decoder outputs, per-rank seed; kept in PINNED host memory for the e2e leg
+    mf_h, mems_h = synth.make_inputs(rank, B, H, W, dtype=dt_in)
+    mf_h = mf_h.pin_memory()
+    mems_h = [m.pin_memory() for m in mems_h]
+    mf_d = mf_h.to(dev, non_blocking=True)
+    mems_d = [m.to(dev, non_blocking=True) for m in mems_h]
+    lib = clib.load()
+
+    def step_resident():
+        return head.decoder_forward(mf_d, mems_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cgg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.cgg_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API with HOST buffers; H2D of the step's inputs and D2H of the step's
+    # result (last layer's cls / cls_emb / mask logits, what simple_test consumes, head.py:943-945)
+    res_h = None
+    h2d = mf_h.numel() * mf_h.element_size() + sum(m.numel() * m.element_size() for m in mems_h)
+
+    def step_e2e():
+        nonlocal res_h
+        a = mf_h.to(dev, non_blocking=True)
+        ms_ = [m.to(dev, non_blocking=True) for m in mems_h]
+        cls, emb, mask = head.decoder_forward(a, ms_)
+        if res_h is None:
+            res_h = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (cls[-1], emb[-1], mask[-1])]
+        for dst, src in zip(res_h, (cls[-1], emb[-1], mask[-1])):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(2, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(t_e2e.item())
+    d2h = sum(x.numel() * x.element_size() for x in res_h)
+
+    # ---- roofline of the dominant kernel (the mask einsum, 55% of the path's FLOPs): CUDA events
+    # on the launching stream around that stage alone, same inputs, averaged over launches
+    rt = head._runtime(dev)
+    x0 = torch.randn((B, Q, C), device=dev)
+    for _ in range(3):
+        rt.head_call(x0, mf_d, 0, want_bits=False)
+    torch.cuda.synchronize()
+    reps = 10
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the small head GEMMs run inside the same stage; time them separately and subtract
+    k0.record()
+    for _ in range(reps):
+        rt.head_call(x0, mf_d, 0, want_bits=False)
+    k1.record()
+    torch.cuda.synchronize()
+    stage_ms = k0.elapsed_time(k1) / reps
+    peaks = measured_peaks()
+    ach = einsum_flops_per_launch(Q, B) / (stage_ms * 1e-3) / 1e12
+    roofline = dict(bound='tensor', achieved=ach, peak=peaks['tflops'], unit='TFLOP/s', frac=ach / peaks['tflops'],
+                    traffic=None, kernel='mask einsum stage (cgg_head_call: K1 heads + K2 einsum)',
+                    peak_source=peaks['source'] + ' (sustained bf16)',
+                    whole_path=dict(achieved=flops_per_image(Q) * value / 1e12, unit='TFLOP/s',
+                                    frac=flops_per_image(Q) * value / 1e12 / peaks['tflops']))
+
+    if rank == 0:
+        cpu = cpu_baseline(Q, os.cpu_count() or 1) if (world == 1 and not args.no_cpu_baseline) else None
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic', impl='b200',
+                    config=dict(workload='configs[1]: COCO-OVIS instance decoder head, Q=%d, 9 layers, 256-d, 8 heads, '
+                                         '1024x1024, batch %d per GPU' % (Q, B),
+                                batch_per_gpu=B, global_batch=B * world, precision=args.precision,
+                                l2='inputs (%.0f MB per step) larger than L2, no explicit flush' % (h2d / 1e6),
+                                flops_per_image=flops_per_image(Q)),
+                    e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
+                    gpu_launches=int(launches), roofline=roofline, clocks=clocks)
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--queries', type=int, default=100)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == '__main__':
+    main()

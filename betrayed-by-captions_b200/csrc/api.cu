@@ -1,0 +1,445 @@
+// C-ABI layer + host-side orchestration of the decoder-head path (include/cgg_b200.h).
+// Everything here only enqueues kernels on the caller's stream.
+#include "../../include/cgg_b200.h"
+#include "kernels.h"
+#include "gemm_tc.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace cgg;
+
+struct cgg_handle {
+  cgg_config cfg;
+  std::string err;
+  bool prepared = false;
+  int H4 = 0, W4 = 0, lh[CGG_NUM_LEVELS] = {0, 0, 0}, lw[CGG_NUM_LEVELS] = {0, 0, 0};
+  int nl[CGG_NUM_LEVELS] = {0, 0, 0};  // decoder layers that read level l
+  // handle-owned device tables (fp32)
+  float* pos_level[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};  // (K_l, C)   pos + level_embed
+  float* wkv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};        // (nl*2C, C) [Wk.. | Wv..]
+  float* rk[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};         // (K_l, nl*C) key bias table
+  float* bkv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};        // (nl*2C)    0 | value bias
+  TcState* tc = nullptr;                                           // bf16 / tcgen05 side
+  void free_tables() {
+    for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+      cudaFree(pos_level[l]); cudaFree(wkv[l]); cudaFree(rk[l]); cudaFree(bkv[l]);
+      pos_level[l] = wkv[l] = rk[l] = bkv[l] = nullptr;
+    }
+  }
+};
+
+namespace {
+
+int fail(cgg_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, CGG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+#define ST(call)                       \
+  do {                                 \
+    int s__ = (call);                  \
+    if (s__ != CGG_OK) return s__;     \
+  } while (0)
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Workspace carving shared by cgg_workspace_bytes and the entry points.
+struct Workspace {
+  size_t total = 0;
+  size_t kv[CGG_NUM_LEVELS];
+  size_t z, h1, h2, me, qb, kb, vb, o, t, x1, x2, f, xs, bitmap, allm, tcws;
+  void carve(const cgg_handle* h, int B) {
+    const cgg_config& c = h->cfg;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    const size_t kv_elt = (c.precision == CGG_BF16) ? 2 : 4;
+    for (int l = 0; l < CGG_NUM_LEVELS; ++l)
+      kv[l] = take((size_t)B * h->lh[l] * h->lw[l] * h->nl[l] * 2 * c.embed_dim * kv_elt);
+    const size_t bqc = (size_t)B * c.num_queries * c.embed_dim * sizeof(float);
+    z = take(bqc); h1 = take(bqc); h2 = take(bqc); me = take(bqc); qb = take(bqc); kb = take(bqc);
+    vb = take(bqc); o = take(bqc); t = take(bqc); x1 = take(bqc); x2 = take(bqc);
+    f = take((size_t)B * c.num_queries * c.ffn_dim * sizeof(float));
+    xs = take(bqc * (c.num_layers + 1));
+    int maxk = 0;
+    for (int l = 0; l < CGG_NUM_LEVELS; ++l) maxk = max(maxk, h->lh[l] * h->lw[l]);
+    bitmap = take((size_t)B * c.num_queries * ((maxk + 31) / 32) * sizeof(uint32_t));
+    allm = take((size_t)B * c.num_queries);
+    tcws = take(tc_workspace_bytes(h->tc, B));
+    total = off;
+  }
+};
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+int check_ws(cgg_handle* h, int B, void* ws, size_t bytes, Workspace& w) {
+  if (!h->prepared) return fail(h, CGG_ERR_NOT_PREPARED, "cgg_prepare() has not been called");
+  if (B <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "batch must be positive");
+  w.carve(h, B);
+  if (!ws || bytes < w.total) return fail(h, CGG_ERR_WORKSPACE, "workspace too small");
+  return CGG_OK;
+}
+
+// y = (x [+ qe]) W^T + b, rows = B*Q
+int linear_rows(cgg_handle* h, cudaStream_t s, const float* x, const float* a2, int a2_mod, const float* W,
+                const float* bias, float* y, int rows, int N, int K, float alpha = 1.f,
+                const float* R = nullptr, bool relu = false) {
+  GemmF32 p;
+  p.A = x; p.sAm = K; p.sAk = 1;
+  if (a2) { p.A2 = a2; p.sA2m = K; p.sA2k = 1; p.a2_mod = a2_mod; }
+  p.W = W; p.sWn = K; p.sWk = 1;
+  p.bias = bias; p.alpha = alpha;
+  if (R) { p.R = R; p.sRm = N; p.sRn = 1; p.r_mod = rows; }
+  p.C = y; p.sCm = N; p.sCn = 1;
+  p.M = rows; p.N = N; p.K = K; p.batch = 1;
+  if (relu) p.relu_from = 0;
+  CU(launch_gemm_f32(p, s));
+  return CGG_OK;
+}
+
+}  // namespace
+
+// ============================================================================ lifetime
+extern "C" const char* cgg_version(void) { return "1.0 sm_100a"; }
+
+extern "C" uint64_t cgg_launch_count(void) { return (uint64_t)cgg::launch_count(); }
+
+extern "C" const char* cgg_last_error(const cgg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
+  if (!out || !cfg) return CGG_ERR_NULL;
+  *out = nullptr;
+  if (cfg->embed_dim != 256 || cfg->num_heads != 8) return CGG_ERR_UNSUPPORTED;
+  if (cfg->num_layers < 1 || cfg->num_layers > CGG_MAX_LAYERS) return CGG_ERR_BAD_SHAPE;
+  if (cfg->num_queries < 1 || cfg->num_queries > 1024 || cfg->ffn_dim < 1 || cfg->num_classes_p1 < 1 ||
+      cfg->d_lang < 1)
+    return CGG_ERR_BAD_SHAPE;
+  if (cfg->precision != CGG_FP32 && cfg->precision != CGG_BF16) return CGG_ERR_UNSUPPORTED;
+  if (cfg->pred_emb_norm) return CGG_ERR_UNSUPPORTED;  // off in every shipped config (coco_b48n17.py:151)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CGG_ERR_CUDA;  // no CPU fallback
+  cgg_handle* h = new (std::nothrow) cgg_handle();
+  if (!h) return CGG_ERR_CUDA;
+  h->cfg = *cfg;
+  if (cfg->precision == CGG_BF16) {
+    h->tc = tc_create(*cfg);
+    if (!h->tc) { delete h; return CGG_ERR_CUDA; }
+  }
+  *out = h;
+  return CGG_OK;
+}
+
+extern "C" void cgg_destroy(cgg_handle* h) {
+  if (!h) return;
+  h->free_tables();
+  if (h->tc) tc_destroy(h->tc);
+  delete h;
+}
+
+extern "C" int cgg_prepare(cgg_handle* h, const cgg_weights* w, int H4, int W4, const int level_h[CGG_NUM_LEVELS],
+                           const int level_w[CGG_NUM_LEVELS], void* stream) {
+  if (!h || !w || !level_h || !level_w) return CGG_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const cgg_config& c = h->cfg;
+  const int C = c.embed_dim;
+  if (H4 <= 0 || W4 <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad mask feature size");
+  bool same = h->prepared && h->H4 == H4 && h->W4 == W4;
+  for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+    if (level_h[l] <= 0 || level_w[l] <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad level size");
+    same = same && h->lh[l] == level_h[l] && h->lw[l] == level_w[l];
+  }
+  if (!same) {
+    // (re)allocation is the only place that may synchronise; steady-state re-prepare
+    // (new weights, same sizes) reuses the tables and stays asynchronous.
+    CU(cudaStreamSynchronize(s));
+    h->free_tables();
+    h->H4 = H4; h->W4 = W4;
+    for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+      h->lh[l] = level_h[l]; h->lw[l] = level_w[l];
+      h->nl[l] = 0;
+    }
+    for (int i = 0; i < c.num_layers; ++i) h->nl[i % CGG_NUM_LEVELS]++;
+    for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+      const size_t K = (size_t)level_h[l] * level_w[l];
+      const int n = h->nl[l] > 0 ? h->nl[l] : 1;
+      CU(cudaMalloc(&h->pos_level[l], K * C * sizeof(float)));
+      CU(cudaMalloc(&h->wkv[l], (size_t)n * 2 * C * C * sizeof(float)));
+      CU(cudaMalloc(&h->rk[l], K * n * C * sizeof(float)));
+      CU(cudaMalloc(&h->bkv[l], (size_t)n * 2 * C * sizeof(float)));
+    }
+  }
+  for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+    const int K = level_h[l] * level_w[l], n = h->nl[l];
+    CU(launch_pos_level(w->level_embed + (size_t)l * C, h->pos_level[l], level_h[l], level_w[l], C, s));
+    CU(cudaMemsetAsync(h->bkv[l], 0, (size_t)(n > 0 ? n : 1) * 2 * C * sizeof(float), s));
+    for (int sl = 0; sl < n; ++sl) {
+      const cgg_layer_weights& lw = w->layers[sl * CGG_NUM_LEVELS + l];
+      if (!lw.cross_in_w || !lw.cross_in_b) return fail(h, CGG_ERR_NULL, "missing cross-attention weights");
+      const float* Wk = lw.cross_in_w + (size_t)C * C;
+      const float* Wv = lw.cross_in_w + (size_t)2 * C * C;
+      CU(cudaMemcpyAsync(h->wkv[l] + (size_t)sl * C * C, Wk, (size_t)C * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CU(cudaMemcpyAsync(h->wkv[l] + (size_t)(n + sl) * C * C, Wv, (size_t)C * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      // key bias table: (pos + level_embed) Wk^T + bk   -> rk[l][:, sl*C:(sl+1)*C]
+      GemmF32 p;
+      p.A = h->pos_level[l]; p.sAm = C; p.sAk = 1;
+      p.W = Wk; p.sWn = C; p.sWk = 1;
+      p.bias = lw.cross_in_b + C;
+      p.C = h->rk[l] + (size_t)sl * C; p.sCm = (long)n * C; p.sCn = 1;
+      p.M = K; p.N = C; p.K = C;
+      CU(launch_gemm_f32(p, s));
+      // value bias: level_embed Wv^T + bv -> bkv[l][(n+sl)*C ...]
+      GemmF32 v;
+      v.A = w->level_embed + (size_t)l * C; v.sAm = C; v.sAk = 1;
+      v.W = Wv; v.sWn = C; v.sWk = 1;
+      v.bias = lw.cross_in_b + 2 * C;
+      v.C = h->bkv[l] + (size_t)(n + sl) * C; v.sCm = C; v.sCn = 1;
+      v.M = 1; v.N = C; v.K = C;
+      CU(launch_gemm_f32(v, s));
+    }
+  }
+  if (h->tc) {
+    int st = tc_prepare(h->tc, w, H4, W4, h->lh, h->lw, h->nl, h->wkv, h->rk, h->bkv, s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_prepare: ") + tc_last_error(h->tc));
+  }
+  h->prepared = true;
+  return CGG_OK;
+}
+
+extern "C" size_t cgg_workspace_bytes(const cgg_handle* h, int batch) {
+  if (!h || !h->prepared || batch <= 0) return 0;
+  Workspace w;
+  w.carve(h, batch);
+  return w.total;
+}
+
+// ============================================================================== stages
+extern "C" int cgg_kv_project(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !w || !memories) return CGG_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws;
+  ST(check_ws(h, batch, workspace, workspace_bytes, ws));
+  const int C = h->cfg.embed_dim;
+  for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+    if (h->nl[l] == 0) continue;
+    if (!memories[l]) return fail(h, CGG_ERR_NULL, "null memory level");
+    const int K = h->lh[l] * h->lw[l], N = h->nl[l] * 2 * C;
+    if (h->cfg.precision == CGG_BF16) {
+      int st = tc_kv_project(h->tc, l, batch, memories[l], at<void>(workspace, ws.kv[l]), s);
+      if (st != CGG_OK) return fail(h, st, std::string("tc_kv_project: ") + tc_last_error(h->tc));
+      continue;
+    }
+    GemmF32 p;
+    p.A = static_cast<const float*>(memories[l]); p.sAb = (long)C * K; p.sAm = 1; p.sAk = K; p.a_mmajor = true;
+    p.W = h->wkv[l]; p.sWn = C; p.sWk = 1;
+    p.bias = h->bkv[l];
+    p.R = h->rk[l]; p.sRm = (long)h->nl[l] * C; p.sRn = 1; p.r_mod = K; p.r_ncols = h->nl[l] * C;
+    p.C = at<float>(workspace, ws.kv[l]); p.sCb = (long)K * N; p.sCm = N; p.sCn = 1;
+    p.M = K; p.N = N; p.K = C; p.batch = batch;
+    CU(launch_gemm_f32(p, s));
+  }
+  return CGG_OK;
+}
+
+extern "C" int cgg_attn_mask_from_logits(cgg_handle* h, int batch, const float* mask_pred, int H4, int W4, int th,
+                                         int tw, uint32_t* bitmap, uint8_t* all_masked, void* stream) {
+  if (!h || !mask_pred || !bitmap || !all_masked) return CGG_ERR_NULL;
+  if (batch <= 0 || H4 <= 0 || W4 <= 0 || th <= 0 || tw <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_mask_bits(mask_pred, batch * h->cfg.num_queries, H4, W4, th, tw, bitmap, all_masked, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, const float* x, const void* mask_features,
+                             int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
+                             uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!h || !w || !x || !mask_features || !cls || !emb || !mask) return CGG_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws;
+  ST(check_ws(h, batch, workspace, workspace_bytes, ws));
+  if (bitmap && (target_level < 0 || target_level >= CGG_NUM_LEVELS)) return fail(h, CGG_ERR_BAD_SHAPE, "bad level");
+  if (bitmap && !all_masked) return CGG_ERR_NULL;
+  const cgg_config& c = h->cfg;
+  const int C = c.embed_dim, Q = c.num_queries, rows = batch * Q, HW = h->H4 * h->W4;
+  float* z = at<float>(workspace, ws.z);
+  float* h1 = at<float>(workspace, ws.h1);
+  float* h2 = at<float>(workspace, ws.h2);
+  float* me = mask_embed_out ? mask_embed_out : at<float>(workspace, ws.me);
+  // K1: post_norm + the three heads (head.py:734-746)
+  CU(launch_layernorm(x, nullptr, w->post_norm_w, w->post_norm_b, z, rows, C, 1e-5f, true, s));
+  ST(linear_rows(h, s, z, nullptr, 1, w->cls_w, w->cls_b, cls, rows, c.num_classes_p1, C));
+  ST(linear_rows(h, s, z, nullptr, 1, w->v2l_w, w->v2l_b, emb, rows, c.d_lang, C));
+  ST(linear_rows(h, s, z, nullptr, 1, w->me_w[0], w->me_b[0], h1, rows, C, C, 1.f, nullptr, true));
+  ST(linear_rows(h, s, h1, nullptr, 1, w->me_w[1], w->me_b[1], h2, rows, C, C, 1.f, nullptr, true));
+  ST(linear_rows(h, s, h2, nullptr, 1, w->me_w[2], w->me_b[2], me, rows, C, C));
+  if (c.precision == CGG_BF16) {
+    // K2 (+K3): tcgen05 mask einsum, and the attention-mask bits from the downsampled features
+    int st = tc_mask_einsum(h->tc, batch, me, mask_features, mask, bitmap ? target_level : -1, bitmap, all_masked,
+                            at<void>(workspace, ws.tcws), s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+    return CGG_OK;
+  }
+  // K2: mask_pred[b,q,p] = sum_c me[b,q,c] F[b,c,p]   (head.py:748)
+  GemmF32 p;
+  p.A = static_cast<const float*>(mask_features); p.sAb = (long)C * HW; p.sAm = 1; p.sAk = HW; p.a_mmajor = true;
+  p.W = me; p.sWb = (long)Q * C; p.sWn = C; p.sWk = 1;
+  p.C = static_cast<float*>(mask); p.sCb = (long)Q * HW; p.sCm = 1; p.sCn = HW; p.c_mmajor = true;
+  p.M = HW; p.N = Q; p.K = C; p.batch = batch;
+  CU(launch_gemm_f32(p, s));
+  // K3: downsample + threshold + bit-pack (head.py:749-759)
+  if (bitmap)
+    CU(launch_mask_bits(static_cast<const float*>(mask), rows, h->H4, h->W4, h->lh[target_level], h->lw[target_level],
+                        bitmap, all_masked, s));
+  return CGG_OK;
+}
+
+extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, const float* q, const void* k,
+                                    const void* v, long kv_stride, long kv_batch_stride, const uint32_t* bitmap,
+                                    const uint8_t* all_masked, float* out, void* stream) {
+  if (!h || !q || !k || !v || !out) return CGG_ERR_NULL;
+  if (batch <= 0 || num_keys <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.precision == CGG_BF16) {
+    int st = tc_attention(h->tc, batch, num_keys, q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_attention: ") + tc_last_error(h->tc));
+    return CGG_OK;
+  }
+  CU(launch_attention_f32(q, static_cast<const float*>(k), static_cast<const float*>(v), kv_stride, kv_batch_stride,
+                          bitmap, all_masked, out, batch, h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
+  return CGG_OK;
+}
+
+extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
+                                 const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!h || !w || !x_in || !x_out) return CGG_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws;
+  ST(check_ws(h, batch, workspace, workspace_bytes, ws));
+  const cgg_config& c = h->cfg;
+  if (layer < 0 || layer >= c.num_layers) return fail(h, CGG_ERR_BAD_SHAPE, "bad layer index");
+  const int C = c.embed_dim, Q = c.num_queries, rows = batch * Q, F = c.ffn_dim;
+  const int l = layer % CGG_NUM_LEVELS, sl = layer / CGG_NUM_LEVELS, n = h->nl[l];
+  const int K = h->lh[l] * h->lw[l];
+  const cgg_layer_weights& lw = w->layers[layer];
+  const float qscale = 1.0f / sqrtf((float)(C / c.num_heads));
+  float* qb = at<float>(workspace, ws.qb);
+  float* kb = at<float>(workspace, ws.kb);
+  float* vb = at<float>(workspace, ws.vb);
+  float* o = at<float>(workspace, ws.o);
+  float* t = at<float>(workspace, ws.t);
+  float* x1 = at<float>(workspace, ws.x1);
+  float* x2 = at<float>(workspace, ws.x2);
+  float* f = at<float>(workspace, ws.f);
+  // ---- masked cross-attention (K5): q = ((x + query_embed) Wq^T + bq) / sqrt(d)
+  ST(linear_rows(h, s, x_in, w->query_embed, Q, lw.cross_in_w, lw.cross_in_b, qb, rows, C, C, qscale));
+  const long kv_stride = (long)n * 2 * C, kv_bstride = (long)K * kv_stride;
+  if (c.precision == CGG_BF16) {
+    const __nv_bfloat16* kv = at<__nv_bfloat16>(workspace, ws.kv[l]);
+    ST(cgg_masked_attention(h, batch, K, qb, kv + (size_t)sl * C, kv + (size_t)(n + sl) * C, kv_stride, kv_bstride,
+                            bitmap, all_masked, o, stream));
+  } else {
+    const float* kv = at<float>(workspace, ws.kv[l]);
+    ST(cgg_masked_attention(h, batch, K, qb, kv + (size_t)sl * C, kv + (size_t)(n + sl) * C, kv_stride, kv_bstride,
+                            bitmap, all_masked, o, stream));
+  }
+  ST(linear_rows(h, s, o, nullptr, 1, lw.cross_out_w, lw.cross_out_b, t, rows, C, C, 1.f, x_in));
+  CU(launch_layernorm(t, nullptr, lw.norm_w[0], lw.norm_b[0], x1, rows, C, 1e-5f, true, s));
+  // ---- self-attention (K6): q = k-input = x1 + query_embed, v-input = x1
+  ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w, lw.self_in_b, qb, rows, C, C, qscale));
+  ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w + (size_t)C * C, lw.self_in_b + C, kb, rows, C, C));
+  ST(linear_rows(h, s, x1, nullptr, 1, lw.self_in_w + (size_t)2 * C * C, lw.self_in_b + 2 * C, vb, rows, C, C));
+  CU(launch_attention_f32(qb, kb, vb, C, (long)Q * C, nullptr, nullptr, o, batch, Q, Q, c.num_heads, s));
+  ST(linear_rows(h, s, o, nullptr, 1, lw.self_out_w, lw.self_out_b, t, rows, C, C, 1.f, x1));
+  CU(launch_layernorm(t, nullptr, lw.norm_w[1], lw.norm_b[1], x2, rows, C, 1e-5f, true, s));
+  // ---- FFN
+  ST(linear_rows(h, s, x2, nullptr, 1, lw.ffn_w1, lw.ffn_b1, f, rows, F, C, 1.f, nullptr, true));
+  ST(linear_rows(h, s, f, nullptr, 1, lw.ffn_w2, lw.ffn_b2, t, rows, C, F, 1.f, x2));
+  CU(launch_layernorm(t, nullptr, lw.norm_w[2], lw.norm_b[2], x_out, rows, C, 1e-5f, true, s));
+  return CGG_OK;
+}
+
+// ========================================================================== whole path
+extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batch, const void* mask_features,
+                                   const void* const memories[CGG_NUM_LEVELS], float* cls, float* emb, void* mask,
+                                   float* x_states, uint32_t* const* bitmaps, uint8_t* all_masked, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!h || !w || !mask_features || !memories || !cls || !emb || !mask) return CGG_ERR_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws;
+  ST(check_ws(h, batch, workspace, workspace_bytes, ws));
+  const cgg_config& c = h->cfg;
+  const int C = c.embed_dim, Q = c.num_queries, L = c.num_layers;
+  const size_t bqc = (size_t)batch * Q * C;
+  const size_t HW = (size_t)h->H4 * h->W4;
+  const size_t mask_elt = (c.precision == CGG_BF16) ? 2 : 4;
+  float* xs = x_states ? x_states : at<float>(workspace, ws.xs);
+  ST(cgg_kv_project(h, w, batch, memories, workspace, workspace_bytes, stream));
+  CU(launch_broadcast_rows(w->query_feat, xs, batch, Q, C, s));          // head.py:808-809
+  for (int j = 0; j <= L; ++j) {
+    const bool need_mask = j < L;                                           // the last mask is never used
+    uint32_t* bm = need_mask ? ((bitmaps && bitmaps[j]) ? bitmaps[j] : at<uint32_t>(workspace, ws.bitmap)) : nullptr;
+    uint8_t* am = need_mask ? (all_masked ? all_masked + (size_t)j * batch * Q : at<uint8_t>(workspace, ws.allm))
+                            : nullptr;
+    ST(cgg_head_call(h, w, batch, xs + j * bqc, mask_features, j % CGG_NUM_LEVELS,
+                     cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
+                     static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
+                     workspace_bytes, stream));
+    if (j < L)
+      ST(cgg_decoder_layer(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream));
+  }
+  return CGG_OK;
+}
+
+// ====================================================================== grounding side
+extern "C" int cgg_noun_embeddings(cgg_handle* h, const float* table, const float* ln_w, const float* ln_b,
+                                   const int64_t* ids, int n_ids, int d_lang, float eps, int text_emb_norm, float* out,
+                                   void* stream) {
+  if (!h || !table || !ids || !out) return CGG_ERR_NULL;
+  if (text_emb_norm && (!ln_w || !ln_b)) return CGG_ERR_NULL;
+  if (n_ids < 0 || d_lang <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_layernorm(table, ids, ln_w, ln_b, out, n_ids, d_lang, eps, text_emb_norm != 0, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_similarity(cgg_handle* h, const float* a, const float* b, int M, int N, int D, float scale,
+                              float* out, void* stream) {
+  if (!h || !a || !b || !out) return CGG_ERR_NULL;
+  if (M <= 0 || N <= 0 || D <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  GemmF32 p;
+  p.A = a; p.sAm = D; p.sAk = 1;
+  p.W = b; p.sWn = D; p.sWk = 1;
+  p.C = out; p.sCm = N; p.sCn = 1;
+  p.M = M; p.N = N; p.K = D; p.alpha = scale;
+  CU(launch_gemm_f32(p, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" size_t cgg_grounding_scratch_bytes(int Bg, int Q, int T) {
+  (void)Q; (void)T;
+  return Bg > 0 ? (size_t)2 * Bg * Bg * sizeof(float) : 0;
+}
+
+extern "C" int cgg_grounding_loss(cgg_handle* h, const float* pred, const float* cap, const int64_t* cap_mask, int Bg,
+                                  int Q, int T, int D, float temperature, float loss_weight, float* loss,
+                                  void* scratch, size_t scratch_bytes, void* stream) {
+  if (!h || !pred || !cap || !cap_mask || !loss || !scratch) return CGG_ERR_NULL;
+  if (Bg <= 0 || Bg > 96 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if ((size_t)(T * Q + T + Q) * sizeof(float) > 200 * 1024) return fail(h, CGG_ERR_BAD_SHAPE, "T*Q too large");
+  if (scratch_bytes < cgg_grounding_scratch_bytes(Bg, Q, T)) return fail(h, CGG_ERR_WORKSPACE, "scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* g1 = static_cast<float*>(scratch);
+  float* g2 = g1 + (size_t)Bg * Bg;
+  CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s));
+  CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s));
+  return CGG_OK;
+}

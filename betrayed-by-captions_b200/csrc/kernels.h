@@ -1,0 +1,66 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernels.
+// Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace cgg {
+
+// launch counter (cgg_launch_count)
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
+// ---------------------------------------------------------------------------------------
+// Generic strided fp32 SIMT GEMM (parity mode + every latency-bound small-M op):
+//   C[b,m,n] = epi( sum_k (A[b,m,k] + A2[m % a2_mod, k]) * W[b,n,k] )
+//   epi(v)   = relu_{n >= relu_from}( (v + bias[n]) * alpha + R[b, m % r_mod, n] (n < r_ncols) )
+// Element (m,k) of A lives at A + b*sAb + m*sAm + k*sAk, etc.  A_MMAJOR / C_MMAJOR only
+// select which index is walked by consecutive lanes (coalescing), never the result.
+struct GemmF32 {
+  const float* A = nullptr; long sAb = 0, sAm = 0, sAk = 0;
+  const float* A2 = nullptr; long sA2m = 0, sA2k = 0; int a2_mod = 1;
+  const float* W = nullptr; long sWb = 0, sWn = 0, sWk = 0;
+  const float* bias = nullptr;
+  const float* R = nullptr; long sRb = 0, sRm = 0, sRn = 0; int r_mod = 1; int r_ncols = 1 << 30;
+  float* C = nullptr; long sCb = 0, sCm = 0, sCn = 0;
+  int M = 0, N = 0, K = 0, batch = 1;
+  int relu_from = 1 << 30;   // relu applied to columns n >= relu_from
+  float alpha = 1.f;
+  bool a_mmajor = false, c_mmajor = false;
+};
+cudaError_t launch_gemm_f32(const GemmF32& p, cudaStream_t s);
+
+// Row LayerNorm: y[r,:] = (x[r,:]-mu)/sqrt(var+eps)*w + b ; rows of length n (n % 32 == 0 not
+// required).  gather != nullptr: row r of x is x[gather[r], :] (BERT table lookup).
+cudaError_t launch_layernorm(const float* x, const int64_t* gather, const float* w, const float* b,
+                             float* y, int rows, int n, float eps, bool apply_norm, cudaStream_t s);
+
+// x[b,q,:] = src[q,:]  (query_feat broadcast over the batch, head.py:808-809)
+cudaError_t launch_broadcast_rows(const float* src, float* dst, int batch, int rows, int n, cudaStream_t s);
+
+// mmdet SinePositionalEncoding(num_feats=C/2, normalize=True) + level embedding:
+//   out[key, c] = pos(key, c) + level_embed[c]     (K, C) fp32
+cudaError_t launch_pos_level(const float* level_embed, float* out, int h, int w, int C, cudaStream_t s);
+
+// K3: mask logits (B*Q rows of H4*W4 fp32) -> bitmap words + all_masked flags for target (th,tw)
+cudaError_t launch_mask_bits(const float* mask_pred, int rows, int H4, int W4, int th, int tw,
+                             uint32_t* bitmap, uint8_t* all_masked, cudaStream_t s);
+
+// K5/K6 attention core, fp32 SIMT flash-style.  q (B,Q,H*32) pre-scaled; k,v rows of H*32 at
+// (b*kv_bstride + key*kv_stride); bitmap (B,Q,ceil(K/32)) or nullptr.
+cudaError_t launch_attention_f32(const float* q, const float* k, const float* v, long kv_stride,
+                                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked,
+                                 float* out, int B, int Q, int K, int heads, cudaStream_t s);
+
+// K7 grounding: per (caption i, image j) pair distances, then the contrastive reduction.
+cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const int64_t* cap_mask,
+                                   int Bg, int Q, int T, int D, float temperature,
+                                   float* g_l2v, float* g_v2l, cudaStream_t s);
+cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
+                                    int Bg, int T, float loss_weight, float* loss, cudaStream_t s);
+
+// fp32 -> bf16 cast (n elements)
+cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
+
+}  // namespace cgg

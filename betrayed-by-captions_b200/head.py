@@ -1,0 +1,393 @@
+"""Host-side mirror of the reference's open-vocabulary Mask2Former head for the decoder hot path.
+
+``Mask2FormerHeadOpenB200`` keeps the forward contract of ``Mask2FormerHeadOpen``
+(open_set/models/mask2former_head.py:763-849): ``forward(feats, img_metas) ->
+(cls_pred_list, cls_emb_pred_list, mask_pred_list)``, each of length num_layers+1, and accepts
+the reference's state_dict keys unchanged, so a trained CGG checkpoint
+loads into it with ``load_state_dict``.  Everything after ``self.pixel_decoder(feats)``
+(head.py:787) runs in the CUDA library behind include/cgg_b200.h; PyTorch only owns memory
+and the stream.  There is no torch/CPU fallback: without the built library or without a CUDA
+device the forward raises.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+
+
+class _Attn(nn.Module):
+    """Parameter container with mmcv's key layout: attentions.<i>.attn.{in_proj_*,out_proj.*}."""
+
+    def __init__(self, embed, heads):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(embed, heads, 0.0)
+
+
+class _FFN(nn.Module):
+    """mmcv FFN key layout: ffns.0.layers.0.0.* and ffns.0.layers.1.*"""
+
+    def __init__(self, embed, ffn):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(embed, ffn), nn.ReLU(inplace=True), nn.Dropout(0.0)),
+                                    nn.Linear(ffn, embed), nn.Dropout(0.0))
+
+
+class _Layer(nn.Module):
+    def __init__(self, embed, heads, ffn):
+        super().__init__()
+        self.attentions = nn.ModuleList([_Attn(embed, heads), _Attn(embed, heads)])  # 0 = cross, 1 = self
+        self.ffns = nn.ModuleList([_FFN(embed, ffn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed) for _ in range(3)])
+
+
+class _Decoder(nn.Module):
+    def __init__(self, num_layers, embed, heads, ffn):
+        super().__init__()
+        self.layers = nn.ModuleList([_Layer(embed, heads, ffn) for _ in range(num_layers)])
+        self.post_norm = nn.LayerNorm(embed)
+        self.embed_dims = embed
+
+
+def _get(cfg, *path, default=None):
+    for p in path:
+        if cfg is None:
+            return default
+        cfg = cfg.get(p) if isinstance(cfg, dict) else getattr(cfg, p, None)
+    return default if cfg is None else cfg
+
+
+class Mask2FormerHeadOpenB200(nn.Module):
+    """Drop-in for ``Mask2FormerHeadOpen`` on the decoder hot path.
+
+    Constructor kwargs follow the reference (head.py:76-100 and init_kwargs :175-195); the ones
+    that only matter to losses / caption generation are accepted and ignored.  New kwargs:
+    ``precision`` ('fp32' parity mode | 'bf16' throughput mode) and ``pixel_decoder`` may be an
+    ``nn.Module`` instance (mmdet builds it from the config dict in the real stack, see
+    INTEGRATION.md)."""
+
+    def __init__(self, in_channels=None, feat_channels=256, out_channels=256, num_things_classes=80,
+                 num_stuff_classes=53, num_queries=100, num_transformer_feat_level=3, pixel_decoder=None,
+                 enforce_decoder_input_project=False, transformer_decoder=None, positional_encoding=None,
+                 precision='fp32', d_lang=768, **kwargs):
+        super().__init__()
+        if num_transformer_feat_level != 3:
+            raise ValueError('the B200 path is built for 3 feature levels (1/32, 1/16, 1/8)')
+        if enforce_decoder_input_project or feat_channels != out_channels:
+            raise ValueError('decoder_input_projs must be Identity (feat_channels == embed dims, head.py:125-131)')
+        self.num_things_classes, self.num_stuff_classes = num_things_classes, num_stuff_classes
+        self.num_classes = num_things_classes + num_stuff_classes
+        self.num_queries = num_queries
+        self.num_transformer_feat_level = 3
+        self.num_heads = _get(transformer_decoder, 'transformerlayers', 'attn_cfgs', 'num_heads', default=8)
+        self.num_transformer_decoder_layers = _get(transformer_decoder, 'num_layers', default=9)
+        ffn = _get(transformer_decoder, 'transformerlayers', 'feedforward_channels', default=2048)
+        self.feat_channels = feat_channels
+        self.ffn_channels = ffn
+        self.d_lang = d_lang
+        self.precision = precision
+        self.softmax_temperature = kwargs.get('softmax_temperature', 10.0)
+        self.pred_emb_norm = kwargs.get('pred_emb_norm', False)
+        self.text_emb_norm = kwargs.get('text_emb_norm', True)
+        self.pixel_decoder = pixel_decoder if isinstance(pixel_decoder, nn.Module) else None
+        # ---- parameters under the reference's names
+        self.transformer_decoder = _Decoder(self.num_transformer_decoder_layers, feat_channels, self.num_heads, ffn)
+        self.query_embed = nn.Embedding(num_queries, feat_channels)
+        self.query_feat = nn.Embedding(num_queries, feat_channels)
+        self.level_embed = nn.Embedding(3, feat_channels)
+        self.cls_embed = nn.Linear(feat_channels, self.num_classes + 1)
+        self.mask_embed = nn.Sequential(nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        nn.Linear(feat_channels, out_channels))
+        self.v2l_transform = nn.Linear(feat_channels, d_lang)
+        self.register_buffer('class_embs', torch.zeros(self.num_classes + 1, d_lang))
+        self._rt = None
+        self.init_weights()
+
+    def init_weights(self):
+        """head.py:231-240: xavier_normal_ on every >=2-D transformer-decoder parameter."""
+        for p in self.transformer_decoder.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)
+
+    # ------------------------------------------------------------------ runtime plumbing
+    def _runtime(self, device):
+        if self._rt is None or self._rt.device != device:
+            self._rt = _Runtime(self, device)
+        return self._rt
+
+    def decoder_forward(self, mask_features, multi_scale_memorys, return_debug=False):
+        """The seam that is replaced: head.py:787 (exclusive) .. :849.  Returns the three lists
+        (and, with return_debug, the decoder states / attention-mask bitmaps / fallback flags)."""
+        if not mask_features.is_cuda:
+            raise _lib.CggError('Mask2FormerHeadOpenB200 runs on CUDA only (no CPU fallback)')
+        rt = self._runtime(mask_features.device)
+        return rt.forward(mask_features, list(multi_scale_memorys), return_debug)
+
+    def forward(self, feats, img_metas):
+        batch_size = len(img_metas)
+        if self.pixel_decoder is None:
+            raise _lib.CggError('no pixel_decoder module attached (it is the step before the path and stays '
+                                'mmdet\'s MSDeformAttnPixelDecoder)')
+        mask_features, multi_scale_memorys = self.pixel_decoder(feats)       # head.py:787
+        assert mask_features.shape[0] == batch_size
+        with torch.no_grad():
+            return self.decoder_forward(mask_features, multi_scale_memorys)
+
+    # -------------------------------------------------------------- grounding-side helpers
+    def _get_cls_emb_logits(self, cls_emb_preds):
+        """head.py:631-648."""
+        rt = self._runtime(cls_emb_preds.device)
+        B, Q, D = cls_emb_preds.shape
+        return rt.similarity(cls_emb_preds.reshape(B * Q, D), self.class_embs,
+                             1.0 / float(self.softmax_temperature)).view(B, Q, -1)
+
+    def test_time_att(self, mask_cls_emb_results, nouns_embs):
+        """simple_test `att`, head.py:973-978."""
+        rt = self._runtime(mask_cls_emb_results.device)
+        return rt.similarity(mask_cls_emb_results[0], nouns_embs, 1.0)
+
+    def extract_word_embeddings(self, table, ln_weight, ln_bias, ids, eps=1e-12):
+        """head.py:686-698 (bert branch) for a stacked (B, max_tokens) id tensor."""
+        rt = self._runtime(ids.device)
+        return rt.noun_embeddings(table, ln_weight, ln_bias, ids, eps, self.text_emb_norm)
+
+    def grounding_loss(self, cls_emb_pred, gt_caption_embs, gt_caption_mask, loss_weight=1.0):
+        """losses/grounding_loss.py:9-77 (forward value)."""
+        rt = self._runtime(cls_emb_pred.device)
+        return rt.grounding_loss(cls_emb_pred, gt_caption_embs, gt_caption_mask,
+                                 float(self.softmax_temperature), loss_weight)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _Runtime:
+    """One C-ABI handle + packed weight pointers + workspace for a head on one device."""
+
+    def __init__(self, head, device):
+        self.lib = _lib.load()
+        self.head = head
+        self.device = device
+        self.handle = C.c_void_p()
+        prec = {'fp32': _lib.FP32, 'bf16': _lib.BF16}[head.precision]
+        self.cfg = _lib.Config(head.num_queries, head.feat_channels, head.num_heads, head.ffn_channels,
+                               head.num_transformer_decoder_layers, head.num_classes + 1, head.d_lang, prec,
+                               int(bool(head.pred_emb_norm)))
+        with torch.cuda.device(device):
+            _lib.check(self.lib.cgg_create(C.byref(self.handle), C.byref(self.cfg)), None, 'cgg_create')
+        self.weights = None
+        self.weights_key = None
+        self.sizes = None
+        self.workspace = None
+        self.batch = None
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.cgg_destroy(self.handle)
+        except Exception:
+            pass
+
+    # ---- weights
+    def _pack_weights(self):
+        h = self.head
+        keep = []
+
+        def f(t):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.Weights()
+        w.query_embed, w.query_feat, w.level_embed = f(h.query_embed.weight), f(h.query_feat.weight), f(h.level_embed.weight)
+        w.cls_w, w.cls_b = f(h.cls_embed.weight), f(h.cls_embed.bias)
+        for n, i in enumerate((0, 2, 4)):
+            w.me_w[n], w.me_b[n] = f(h.mask_embed[i].weight), f(h.mask_embed[i].bias)
+        w.v2l_w, w.v2l_b = f(h.v2l_transform.weight), f(h.v2l_transform.bias)
+        w.post_norm_w, w.post_norm_b = f(h.transformer_decoder.post_norm.weight), f(h.transformer_decoder.post_norm.bias)
+        for i, layer in enumerate(h.transformer_decoder.layers):
+            lw = w.layers[i]
+            ca, sa = layer.attentions[0].attn, layer.attentions[1].attn
+            lw.cross_in_w, lw.cross_in_b = f(ca.in_proj_weight), f(ca.in_proj_bias)
+            lw.cross_out_w, lw.cross_out_b = f(ca.out_proj.weight), f(ca.out_proj.bias)
+            lw.self_in_w, lw.self_in_b = f(sa.in_proj_weight), f(sa.in_proj_bias)
+            lw.self_out_w, lw.self_out_b = f(sa.out_proj.weight), f(sa.out_proj.bias)
+            lw.ffn_w1, lw.ffn_b1 = f(layer.ffns[0].layers[0][0].weight), f(layer.ffns[0].layers[0][0].bias)
+            lw.ffn_w2, lw.ffn_b2 = f(layer.ffns[0].layers[1].weight), f(layer.ffns[0].layers[1].bias)
+            for n in range(3):
+                lw.norm_w[n], lw.norm_b[n] = f(layer.norms[n].weight), f(layer.norms[n].bias)
+        self.weights, self._keep = w, keep
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.head.parameters())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def prepare(self, H4, W4, level_sizes, batch):
+        key = self._weights_key()
+        sizes = (H4, W4, tuple(level_sizes))
+        if self.weights is None or key != self.weights_key or sizes != self.sizes:
+            self._pack_weights()
+            lh = (C.c_int * 3)(*[s[0] for s in level_sizes])
+            lw = (C.c_int * 3)(*[s[1] for s in level_sizes])
+            _lib.check(self.lib.cgg_prepare(self.handle, C.byref(self.weights), H4, W4, lh, lw, self._stream()),
+                       self.handle, 'cgg_prepare')
+            self.weights_key, self.sizes = key, sizes
+            self.batch = None
+        if self.batch != batch:
+            nbytes = self.lib.cgg_workspace_bytes(self.handle, batch)
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.batch = batch
+
+    def _check_inputs(self, mask_features, memories):
+        want = torch.float32 if self.head.precision == 'fp32' else torch.bfloat16
+        mf = mask_features.detach()
+        if mf.dtype != want or not mf.is_contiguous():
+            mf = mf.to(want).contiguous()
+        mems = []
+        for m in memories:
+            m = m.detach()
+            if m.dtype != want or not m.is_contiguous():
+                m = m.to(want).contiguous()
+            mems.append(m)
+        return mf, mems
+
+    # ---- whole path
+    def forward(self, mask_features, memories, return_debug=False):
+        h = self.head
+        with torch.cuda.device(self.device):
+            mf, mems = self._check_inputs(mask_features, memories)
+            B, Cc, H4, W4 = mf.shape
+            assert Cc == h.feat_channels and len(mems) == 3
+            sizes = [tuple(m.shape[-2:]) for m in mems]
+            self.prepare(H4, W4, sizes, B)
+            L, Q = h.num_transformer_decoder_layers, h.num_queries
+            dev = self.device
+            cls = torch.empty((L + 1, B, Q, h.num_classes + 1), dtype=torch.float32, device=dev)
+            emb = torch.empty((L + 1, B, Q, h.d_lang), dtype=torch.float32, device=dev)
+            mask = torch.empty((L + 1, B, Q, H4, W4), dtype=mf.dtype, device=dev)
+            mem_ptrs = (C.c_void_p * 3)(*[m.data_ptr() for m in mems])
+            xs = bms = am = None
+            xs_p, bm_p, am_p = None, None, None
+            if return_debug:
+                xs = torch.empty((L + 1, B, Q, Cc), dtype=torch.float32, device=dev)
+                bms = [torch.zeros((B, Q, (s[0] * s[1] + 31) // 32), dtype=torch.int32, device=dev)
+                       for s in (sizes[j % 3] for j in range(L))]
+                am = torch.zeros((L, B, Q), dtype=torch.uint8, device=dev)
+                xs_p, am_p = _ptr(xs), _ptr(am)
+                bm_p = (C.c_void_p * L)(*[b.data_ptr() for b in bms])
+            st = self.lib.cgg_decoder_forward(self.handle, C.byref(self.weights), B, _ptr(mf), mem_ptrs, _ptr(cls),
+                                              _ptr(emb), _ptr(mask), xs_p, bm_p, am_p, _ptr(self.workspace),
+                                              self.workspace.numel(), self._stream())
+            _lib.check(st, self.handle, 'cgg_decoder_forward')
+        outs = (list(cls.unbind(0)), list(emb.unbind(0)), list(mask.unbind(0)))
+        if return_debug:
+            return outs + (dict(x=xs, bitmaps=bms, all_masked=am),)
+        return outs
+
+    # ---- stages (parity tests, teacher forcing)
+    def kv_project(self, memories):
+        mem_ptrs = (C.c_void_p * 3)(*[m.data_ptr() for m in memories])
+        _lib.check(self.lib.cgg_kv_project(self.handle, C.byref(self.weights), self.batch, mem_ptrs,
+                                           _ptr(self.workspace), self.workspace.numel(), self._stream()),
+                   self.handle, 'cgg_kv_project')
+
+    def head_call(self, x, mask_features, target_level, want_bits=True):
+        h = self.head
+        B, Q = x.shape[0], h.num_queries
+        H4, W4, sizes = self.sizes
+        dev = self.device
+        cls = torch.empty((B, Q, h.num_classes + 1), dtype=torch.float32, device=dev)
+        emb = torch.empty((B, Q, h.d_lang), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, Q, H4, W4), dtype=mask_features.dtype, device=dev)
+        me = torch.empty((B, Q, h.feat_channels), dtype=torch.float32, device=dev)
+        K = sizes[target_level][0] * sizes[target_level][1]
+        bm = torch.zeros((B, Q, (K + 31) // 32), dtype=torch.int32, device=dev) if want_bits else None
+        am = torch.zeros((B, Q), dtype=torch.uint8, device=dev) if want_bits else None
+        st = self.lib.cgg_head_call(self.handle, C.byref(self.weights), B, _ptr(x), _ptr(mask_features), target_level,
+                                    _ptr(cls), _ptr(emb), _ptr(mask), _ptr(me), _ptr(bm) if want_bits else None,
+                                    _ptr(am) if want_bits else None, _ptr(self.workspace), self.workspace.numel(),
+                                    self._stream())
+        _lib.check(st, self.handle, 'cgg_head_call')
+        return cls, emb, mask, me, bm, am
+
+    def decoder_layer(self, layer, x, bitmap, all_masked):
+        out = torch.empty_like(x)
+        st = self.lib.cgg_decoder_layer(self.handle, C.byref(self.weights), x.shape[0], layer, _ptr(x),
+                                        _ptr(bitmap) if bitmap is not None else None,
+                                        _ptr(all_masked) if all_masked is not None else None, _ptr(out),
+                                        _ptr(self.workspace), self.workspace.numel(), self._stream())
+        _lib.check(st, self.handle, 'cgg_decoder_layer')
+        return out
+
+    def attn_mask_from_logits(self, mask_pred, target_hw):
+        B, Q, H4, W4 = mask_pred.shape
+        assert Q == self.head.num_queries and mask_pred.dtype == torch.float32 and mask_pred.is_contiguous()
+        K = target_hw[0] * target_hw[1]
+        bm = torch.zeros((B, Q, (K + 31) // 32), dtype=torch.int32, device=self.device)
+        am = torch.zeros((B, Q), dtype=torch.uint8, device=self.device)
+        st = self.lib.cgg_attn_mask_from_logits(self.handle, B, _ptr(mask_pred), H4, W4, target_hw[0], target_hw[1],
+                                                _ptr(bm), _ptr(am), self._stream())
+        _lib.check(st, self.handle, 'cgg_attn_mask_from_logits')
+        return bm, am
+
+    def masked_attention(self, q, k, v, bitmap=None, all_masked=None):
+        """q (B,Q,C) pre-scaled fp32; k, v (B,K,C) contiguous (fp32 in fp32 mode, bf16 in bf16 mode)."""
+        B, Q, Cc = q.shape
+        K = k.shape[1]
+        out = torch.empty_like(q)
+        st = self.lib.cgg_masked_attention(self.handle, B, K, _ptr(q), _ptr(k), _ptr(v), Cc, K * Cc,
+                                           _ptr(bitmap) if bitmap is not None else None,
+                                           _ptr(all_masked) if all_masked is not None else None, _ptr(out),
+                                           self._stream())
+        _lib.check(st, self.handle, 'cgg_masked_attention')
+        return out
+
+    # ---- grounding side
+    def similarity(self, a, b, scale):
+        a = a.detach().float().contiguous()
+        b = b.detach().float().contiguous()
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=self.device)
+        st = self.lib.cgg_similarity(self.handle, _ptr(a), _ptr(b), a.shape[0], b.shape[0], a.shape[1], scale,
+                                     _ptr(out), self._stream())
+        _lib.check(st, self.handle, 'cgg_similarity')
+        return out
+
+    def noun_embeddings(self, table, ln_w, ln_b, ids, eps, text_emb_norm):
+        ids = ids.contiguous()
+        out = torch.empty(tuple(ids.shape) + (table.shape[1],), dtype=torch.float32, device=self.device)
+        st = self.lib.cgg_noun_embeddings(self.handle, _ptr(table), _ptr(ln_w), _ptr(ln_b), _ptr(ids), ids.numel(),
+                                          table.shape[1], eps, int(bool(text_emb_norm)), _ptr(out), self._stream())
+        _lib.check(st, self.handle, 'cgg_noun_embeddings')
+        return out
+
+    def grounding_loss(self, pred, cap, cap_mask, temperature, loss_weight):
+        pred, cap = pred.detach().float().contiguous(), cap.detach().float().contiguous()
+        cap_mask = cap_mask.to(torch.int64).contiguous()
+        Bg, Q, D = pred.shape
+        T = cap.shape[1]
+        nbytes = self.lib.cgg_grounding_scratch_bytes(Bg, Q, T)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        st = self.lib.cgg_grounding_loss(self.handle, _ptr(pred), _ptr(cap), _ptr(cap_mask), Bg, Q, T, D, temperature,
+                                         loss_weight, _ptr(loss), _ptr(scratch), nbytes, self._stream())
+        _lib.check(st, self.handle, 'cgg_grounding_loss')
+        return loss[0]
+
+
+def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9):
+    """Convenience used by tests / bench: a head carrying the given (reference-keyed) weights."""
+    head = Mask2FormerHeadOpenB200(num_things_classes=num_classes_p1 - 1, num_stuff_classes=0,
+                                   num_queries=num_queries, precision=precision,
+                                   transformer_decoder=dict(num_layers=num_layers))
+    missing = head.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return head.to(device).eval()

@@ -1,0 +1,94 @@
+"""ctypes binding of the C-ABI library (include/cgg_b200.h).  There is no fallback: if
+libcgg_b200.so is missing or a call fails, this raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libcgg_b200.so')
+
+MAX_LAYERS = 16
+NUM_LEVELS = 3
+FP32, BF16 = 0, 1
+c_float_p = C.POINTER(C.c_float)
+
+EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_launch_count', 'cgg_prepare', 'cgg_workspace_bytes',
+           'cgg_decoder_forward', 'cgg_kv_project', 'cgg_head_call', 'cgg_attn_mask_from_logits',
+           'cgg_decoder_layer', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
+           'cgg_grounding_scratch_bytes', 'cgg_grounding_loss']
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('num_queries', 'embed_dim', 'num_heads', 'ffn_dim', 'num_layers',
+                                       'num_classes_p1', 'd_lang', 'precision', 'pred_emb_norm')]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('cross_in_w', 'cross_in_b', 'cross_out_w', 'cross_out_b', 'self_in_w',
+                                          'self_in_b', 'self_out_w', 'self_out_b', 'ffn_w1', 'ffn_b1', 'ffn_w2',
+                                          'ffn_b2')] + [('norm_w', C.c_void_p * 3), ('norm_b', C.c_void_p * 3)]
+
+
+class Weights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('query_embed', 'query_feat', 'level_embed', 'cls_w', 'cls_b')] + \
+               [('me_w', C.c_void_p * 3), ('me_b', C.c_void_p * 3)] + \
+               [(n, C.c_void_p) for n in ('v2l_w', 'v2l_b', 'post_norm_w', 'post_norm_b')] + \
+               [('layers', LayerWeights * MAX_LAYERS)]
+
+
+class CggError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library; raises if it has not been built (no CPU / torch fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CggError('%s not found: build it with `python -m cgg_b200.build` '
+                       '(there is no fallback path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.cgg_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    lib.cgg_destroy.argtypes = [vp]
+    lib.cgg_destroy.restype = None
+    lib.cgg_last_error.argtypes = [vp]
+    lib.cgg_last_error.restype = C.c_char_p
+    lib.cgg_version.restype = C.c_char_p
+    lib.cgg_launch_count.restype = C.c_uint64
+    lib.cgg_prepare.argtypes = [vp, C.POINTER(Weights), i, i, C.POINTER(i), C.POINTER(i), vp]
+    lib.cgg_workspace_bytes.argtypes = [vp, i]
+    lib.cgg_workspace_bytes.restype = sz
+    lib.cgg_decoder_forward.argtypes = [vp, C.POINTER(Weights), i, vp, C.POINTER(vp), vp, vp, vp, vp,
+                                        C.POINTER(vp), vp, vp, sz, vp]
+    lib.cgg_kv_project.argtypes = [vp, C.POINTER(Weights), i, C.POINTER(vp), vp, sz, vp]
+    lib.cgg_head_call.argtypes = [vp, C.POINTER(Weights), i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.cgg_attn_mask_from_logits.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp]
+    lib.cgg_decoder_layer.argtypes = [vp, C.POINTER(Weights), i, i, vp, vp, vp, vp, vp, sz, vp]
+    lib.cgg_masked_attention.argtypes = [vp, i, i, vp, vp, vp, C.c_long, C.c_long, vp, vp, vp, vp]
+    lib.cgg_noun_embeddings.argtypes = [vp, vp, vp, vp, vp, i, i, C.c_float, i, vp, vp]
+    lib.cgg_similarity.argtypes = [vp, vp, vp, i, i, i, C.c_float, vp, vp]
+    lib.cgg_grounding_scratch_bytes.argtypes = [i, i, i]
+    lib.cgg_grounding_scratch_bytes.restype = sz
+    lib.cgg_grounding_loss.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_float, C.c_float, vp, vp, sz, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ('cgg_destroy',):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+STATUS = {0: 'CGG_OK', -1: 'CGG_ERR_BAD_SHAPE', -2: 'CGG_ERR_UNSUPPORTED', -3: 'CGG_ERR_CUDA',
+          -4: 'CGG_ERR_NOT_PREPARED', -5: 'CGG_ERR_WORKSPACE', -6: 'CGG_ERR_NULL'}
+
+
+def check(status, handle=None, what=''):
+    if status != 0:
+        msg = ''
+        if handle:
+            msg = load().cgg_last_error(handle).decode()
+        raise CggError('%s failed: %s %s' % (what, STATUS.get(status, status), msg))

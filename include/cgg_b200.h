@@ -1,0 +1,204 @@
+/*
+ * cgg_b200.h -- C ABI of the B200-native decoder-head hot path of CGG
+ * ("Betrayed by Captions", jianzongwu/betrayed-by-captions).
+ *
+ * Every entry point replaces a piece of the reference's PyTorch path; the reference
+ * location is cited beside each declaration (paths relative to the reference root,
+ * "head.py" = open_set/models/mask2former_head.py).  The reference has no FFI of its own
+ * (it is pure Python on torch/mmcv), so this header IS the boundary a maintainer binds:
+ * INTEGRATION.md shows the ctypes stub and the mmdet HEADS registration that sit on it.
+ *
+ * Conventions (all entry points)
+ *   - plain C: raw DEVICE pointers, sizes, enums, a cudaStream_t passed as void*.
+ *   - the caller allocates and owns every input, output and workspace buffer; the
+ *     library only owns what cgg_create() allocates inside the handle (cached positional
+ *     tables, per-level K/V bias tables, bf16 weight copies, TMA descriptors) and frees it
+ *     in cgg_destroy().
+ *   - all work is enqueued on the given stream; no hidden synchronisation, no global
+ *     mutable state; one handle per (device, stream); graph-capturable after cgg_prepare().
+ *   - return value: 0 = CGG_OK, negative = cgg_status; no C++ exception crosses the ABI.
+ *     cgg_last_error(handle) gives a human-readable message for the last failure.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     CGG_ERR_CUDA.
+ *
+ * Tensor layouts (row-major, innermost last)
+ *   x / decoder state        (B, Q, C)            fp32      [reference keeps (Q,B,C)]
+ *   mask_features            (B, C, H4, W4)       fp32 (CGG_FP32) or bf16 (CGG_BF16), NCHW as
+ *                                                 the pixel decoder emits it (head.py:787)
+ *   memories[l]              (B, C, h_l, w_l)     same dtype rule, l = 0..2 = 1/32,1/16,1/8
+ *   cls                      (L+1, B, Q, ncls1)   fp32
+ *   emb                      (L+1, B, Q, d_l)     fp32
+ *   mask                     (L+1, B, Q, H4, W4)  fp32 (CGG_FP32) or bf16 (CGG_BF16)
+ *   attention-mask bitmap    (B, Q, ceil(K_l/32)) u32, bit (k%32) of word (k/32) = 1  <=>
+ *                                                 reference attn_mask[b*heads+h, q, k] == True
+ *                                                 ("do not attend"), identical for all heads
+ *                                                 (head.py:756-758); tail bits are 0
+ *   all_masked               (B, Q)               u8, 1 <=> every key of the row is masked
+ *                                                 (the fallback of head.py:825-826 applies)
+ */
+#ifndef CGG_B200_H
+#define CGG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGG_MAX_LAYERS 16
+#define CGG_NUM_LEVELS 3
+
+typedef enum {
+  CGG_OK = 0,
+  CGG_ERR_BAD_SHAPE = -1,
+  CGG_ERR_UNSUPPORTED = -2,
+  CGG_ERR_CUDA = -3,
+  CGG_ERR_NOT_PREPARED = -4,
+  CGG_ERR_WORKSPACE = -5,
+  CGG_ERR_NULL = -6
+} cgg_status;
+
+typedef enum {
+  CGG_FP32 = 0, /* parity mode: fp32 operands, fp32 FFMA accumulation, fp32 masks out       */
+  CGG_BF16 = 1  /* throughput mode: bf16 operands on tcgen05, fp32 accumulate, bf16 masks out */
+} cgg_precision;
+
+/* Hyper-parameters of the head (configs/instance/coco_b48n17.py:28-100). */
+typedef struct {
+  int num_queries;   /* Q      (100..300)                                   :36  */
+  int embed_dim;     /* C      must be 256                                  :82  */
+  int num_heads;     /* must be 8 (head_dim 32)                             :83  */
+  int ffn_dim;       /* 2048                                                :90  */
+  int num_layers;    /* 9                                                   :77  */
+  int num_classes_p1;/* ncls+1: 49 (instance) / 118 (OSPS)                       */
+  int d_lang;        /* 768 (BERT width of v2l_transform, head.py:219)           */
+  int precision;     /* cgg_precision                                            */
+  int pred_emb_norm; /* head.py:743-744                                          */
+} cgg_config;
+
+/* Per-layer weights: state_dict keys transformer_decoder.layers.<i>.* (SURVEY.md 8b). */
+typedef struct {
+  const float *cross_in_w, *cross_in_b;   /* attentions.0.attn.in_proj_{weight (3C,C),bias (3C)} */
+  const float *cross_out_w, *cross_out_b; /* attentions.0.attn.out_proj.{weight (C,C),bias}     */
+  const float *self_in_w, *self_in_b;     /* attentions.1.attn.in_proj_*                        */
+  const float *self_out_w, *self_out_b;   /* attentions.1.attn.out_proj.*                       */
+  const float *ffn_w1, *ffn_b1;           /* ffns.0.layers.0.0.{weight (F,C),bias}              */
+  const float *ffn_w2, *ffn_b2;           /* ffns.0.layers.1.{weight (C,F),bias}                */
+  const float *norm_w[3], *norm_b[3];     /* norms.{0,1,2}.{weight,bias}                        */
+} cgg_layer_weights;
+
+/* All fp32 DEVICE pointers in the reference's own layouts; never retained past a call
+ * except by cgg_prepare(), which derives handle-owned tables from them. */
+typedef struct {
+  const float *query_embed;  /* query_embed.weight (Q,C)   head.py:133 */
+  const float *query_feat;   /* query_feat.weight  (Q,C)   head.py:134 */
+  const float *level_embed;  /* level_embed.weight (3,C)   head.py:136 */
+  const float *cls_w, *cls_b;        /* cls_embed (ncls1,C)        head.py:139 */
+  const float *me_w[3], *me_b[3];    /* mask_embed.{0,2,4} (C,C)   head.py:140-143 */
+  const float *v2l_w, *v2l_b;        /* v2l_transform (d_l,C)      head.py:219 */
+  const float *post_norm_w, *post_norm_b; /* transformer_decoder.post_norm */
+  cgg_layer_weights layers[CGG_MAX_LAYERS];
+} cgg_weights;
+
+typedef struct cgg_handle cgg_handle;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int cgg_create(cgg_handle **out, const cgg_config *cfg);
+void cgg_destroy(cgg_handle *h);
+const char *cgg_last_error(const cgg_handle *h);
+/* "major.minor" of this ABI and the SM arch the kernels were compiled for (sm_100a). */
+const char *cgg_version(void);
+/* Number of kernels this library has launched in this process (monotonic; bench.py reports the
+ * difference over its timed region as "gpu_launches"). */
+uint64_t cgg_launch_count(void);
+
+/* Derives, for the given weights and feature sizes, the handle-owned tables: sine
+ * positional encodings (mmdet SinePositionalEncoding, head.py:798-804), per-layer
+ * key-bias tables  PosK_i = (pos_l + level_embed[l]) Wk_i^T + bk_i,  value biases
+ * Wv_i level_embed[l] + bv_i  (head.py:792-796 folded through the cross-attention
+ * in-projection) and, in CGG_BF16 mode, bf16 copies of the GEMM weights.  Must be called
+ * again when weights or sizes change. */
+int cgg_prepare(cgg_handle *h, const cgg_weights *w, int H4, int W4,
+                const int level_h[CGG_NUM_LEVELS], const int level_w[CGG_NUM_LEVELS],
+                void *stream);
+
+/* Bytes of caller-provided workspace cgg_decoder_forward needs for this batch size. */
+size_t cgg_workspace_bytes(const cgg_handle *h, int batch);
+
+/* ---- whole path: Mask2FormerHeadOpen.forward after the pixel decoder (head.py:787-849)
+ * mask_features, memories: dtype per precision (see layouts).  Outputs as listed above.
+ * Optional (may be NULL) introspection outputs used by the parity tests:
+ *   x_states (L+1,B,Q,C) fp32  : decoder state fed to each head call
+ *   bitmaps[j], j=0..L-1       : bitmap produced by head call j (for level j%3), BEFORE
+ *                                the fallback; all_masked (L,B,Q) u8.                    */
+int cgg_decoder_forward(cgg_handle *h, const cgg_weights *w, int batch,
+                        const void *mask_features, const void *const memories[CGG_NUM_LEVELS],
+                        float *cls, float *emb, void *mask,
+                        float *x_states, uint32_t *const *bitmaps, uint8_t *all_masked,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- stages (each is what cgg_decoder_forward enqueues; exported for stage-level and
+ *      teacher-forced parity tests and for microbenchmarks) ---------------------------- */
+
+/* K4: cross-attention key/value in-projection of every layer from the three memories
+ * (torch.nn.MultiheadAttention in-proj reached from head.py:829-840) into the workspace. */
+int cgg_kv_project(cgg_handle *h, const cgg_weights *w, int batch,
+                   const void *const memories[CGG_NUM_LEVELS], void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* K1+K2+K3: forward_head (head.py:711-761) for head call `call_idx` (0..L): post_norm,
+ * cls_embed, v2l_transform, mask_embed MLP, mask einsum, and -- when bitmap != NULL -- the
+ * bilinear downsample to level `target_level`, sigmoid<0.5 threshold, bit-pack and
+ * all-masked flags.  x (B,Q,C).  cls/emb/mask point at this call's slice. */
+int cgg_head_call(cgg_handle *h, const cgg_weights *w, int batch, const float *x,
+                  const void *mask_features, int target_level, float *cls, float *emb,
+                  void *mask, float *mask_embed_out, uint32_t *bitmap, uint8_t *all_masked,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* K3 alone on given fp32 logits (stage-level bit-exactness test): mask_pred (B,Q,H4,W4)
+ * -> bitmap, all_masked for a target (h,w).  head.py:749-759. */
+int cgg_attn_mask_from_logits(cgg_handle *h, int batch, const float *mask_pred, int H4, int W4,
+                              int th, int tw, uint32_t *bitmap, uint8_t *all_masked, void *stream);
+
+/* K5+K6: one DetrTransformerDecoderLayer (cross-attn, norm, self-attn, norm, FFN, norm;
+ * head.py:829-840) with the K/V that cgg_kv_project left in the workspace.  The fallback
+ * (head.py:825-826) is applied from all_masked.  x_in, x_out (B,Q,C) fp32. */
+int cgg_decoder_layer(cgg_handle *h, const cgg_weights *w, int batch, int layer,
+                      const float *x_in, const uint32_t *bitmap, const uint8_t *all_masked,
+                      float *x_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* K5 alone: masked multi-head cross-attention core softmax(q k^T + mask) v.
+ * q (B,Q,C) fp32 already scaled by 1/sqrt(d); k, v (B,K,C) fp32 (CGG_FP32) or bf16 with row
+ * stride kv_stride elements; bitmap/all_masked may be NULL (= no mask). out (B,Q,C) fp32. */
+int cgg_masked_attention(cgg_handle *h, int batch, int num_keys, const float *q, const void *k,
+                         const void *v, long kv_stride, long kv_batch_stride,
+                         const uint32_t *bitmap, const uint8_t *all_masked,
+                         float *out, void *stream);
+
+/* ---- grounding side -------------------------------------------------------------- */
+
+/* extract_word_embeddings (head.py:686-698) + BertEmbeddings (utils/bert_embeddings.py:4-13):
+ * out[n,:] = LayerNorm_eps(table[ids[n],:]) (no LN when text_emb_norm == 0). ids int64. */
+int cgg_noun_embeddings(cgg_handle *h, const float *table, const float *ln_w, const float *ln_b,
+                        const int64_t *ids, int n_ids, int d_lang, float eps, int text_emb_norm,
+                        float *out, void *stream);
+
+/* _get_cls_emb_logits (head.py:631-648) and test-time `att` (head.py:973-978):
+ * out (M,N) = a (M,D) . b (N,D)^T * scale. */
+int cgg_similarity(cgg_handle *h, const float *a, const float *b, int M, int N, int D,
+                   float scale, float *out, void *stream);
+
+/* K7 forward: grounding_loss (losses/grounding_loss.py:9-77) for Bg images x Bg captions as one
+ * similarity contraction + fused dual softmax / masked reductions + the 4 contrastive CE terms.
+ * pred (Bg,Q,D) fp32, cap (Bg,T,D) fp32, cap_mask (Bg,T) int64 -> loss (1) fp32 = weight*loss.
+ * scratch: >= cgg_grounding_scratch_bytes(Bg) bytes. */
+size_t cgg_grounding_scratch_bytes(int Bg, int Q, int T);
+int cgg_grounding_loss(cgg_handle *h, const float *pred, const float *cap, const int64_t *cap_mask,
+                       int Bg, int Q, int T, int D, float temperature, float loss_weight,
+                       float *loss, void *scratch, size_t scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGG_B200_H */
