@@ -221,6 +221,18 @@ extern "C" size_t cgg_workspace_bytes(const cgg_handle* h, int batch) {
   return w.total;
 }
 
+extern "C" size_t cgg_workspace_offset(const cgg_handle* h, int batch, const char* what) {
+  if (!h || !h->prepared || batch <= 0 || !what) return (size_t)-1;
+  Workspace w;
+  w.carve(h, batch);
+  const std::string n(what);
+  if (n == "kv0") return w.kv[0];
+  if (n == "kv1") return w.kv[1];
+  if (n == "kv2") return w.kv[2];
+  const size_t o = tc_workspace_offset(h->tc, batch, what);
+  return o == (size_t)-1 ? o : w.tcws + o;
+}
+
 // ============================================================================== stages
 extern "C" int cgg_kv_project(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
                               void* workspace, size_t workspace_bytes, void* stream) {
@@ -258,12 +270,15 @@ extern "C" int cgg_attn_mask_from_logits(cgg_handle* h, int batch, const float* 
   return CGG_OK;
 }
 
-extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, const float* x, const void* mask_features,
-                             int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
-                             uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
-                             void* stream) {
-  if (!h || !w || !x || !mask_features || !cls || !emb || !mask) return CGG_ERR_NULL;
-  cudaStream_t s = (cudaStream_t)stream;
+// forward_head (head.py:711-761).  call_slot: row block of the all-call mask-embedding operand
+// (bf16 mode); defer_einsum: leave K2 to the batched pass at the end of cgg_decoder_forward;
+// fds_ready: the per-level downsampled features are already in the workspace.
+static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const float* x, const void* mask_features,
+                          int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
+                          uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
+                          cudaStream_t s, int call_slot, bool defer_einsum, bool fds_ready) {
+  if (!h || !w || !x || !mask_features || !cls || !emb) return CGG_ERR_NULL;
+  if (!mask && !defer_einsum) return CGG_ERR_NULL;
   Workspace ws;
   ST(check_ws(h, batch, workspace, workspace_bytes, ws));
   if (bitmap && (target_level < 0 || target_level >= CGG_NUM_LEVELS)) return fail(h, CGG_ERR_BAD_SHAPE, "bad level");
@@ -282,10 +297,19 @@ extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, con
   ST(linear_rows(h, s, h1, nullptr, 1, w->me_w[1], w->me_b[1], h2, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h2, nullptr, 1, w->me_w[2], w->me_b[2], me, rows, C, C));
   if (c.precision == CGG_BF16) {
-    // K2 (+K3): tcgen05 mask einsum, and the attention-mask bits from the downsampled features
-    int st = tc_mask_einsum(h->tc, batch, me, mask_features, mask, bitmap ? target_level : -1, bitmap, all_masked,
-                            at<void>(workspace, ws.tcws), s);
-    if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+    void* tws = at<void>(workspace, ws.tcws);
+#define TC(call)                                                                                \
+  do {                                                                                          \
+    int st__ = (call);                                                                          \
+    if (st__ != CGG_OK) return fail(h, st__, std::string(#call) + ": " + tc_last_error(h->tc)); \
+  } while (0)
+    TC(tc_store_mask_embed(h->tc, batch, call_slot, me, tws, s));
+    if (bitmap) {
+      // K3 on tensor cores: me x (mask_features resampled to the level) -> threshold -> ballot
+      if (!fds_ready) TC(tc_downsample(h->tc, batch, mask_features, tws, s));
+      TC(tc_mask_bits(h->tc, batch, call_slot, target_level, bitmap, all_masked, tws, s));
+    }
+    if (!defer_einsum) TC(tc_mask_einsum(h->tc, batch, call_slot, 1, mask_features, mask, 0, tws, s));
     return CGG_OK;
   }
   // K2: mask_pred[b,q,p] = sum_c me[b,q,c] F[b,c,p]   (head.py:748)
@@ -302,19 +326,23 @@ extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, con
   return CGG_OK;
 }
 
+extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, const float* x, const void* mask_features,
+                             int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
+                             uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!mask) return CGG_ERR_NULL;
+  return head_call_impl(h, w, batch, x, mask_features, target_level, cls, emb, mask, mask_embed_out, bitmap, all_masked,
+                        workspace, workspace_bytes, (cudaStream_t)stream, 0, false, false);
+}
+
 extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, const float* q, const void* k,
                                     const void* v, long kv_stride, long kv_batch_stride, const uint32_t* bitmap,
                                     const uint8_t* all_masked, float* out, void* stream) {
   if (!h || !q || !k || !v || !out) return CGG_ERR_NULL;
   if (batch <= 0 || num_keys <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->cfg.precision == CGG_BF16) {
-    int st = tc_attention(h->tc, batch, num_keys, q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, s);
-    if (st != CGG_OK) return fail(h, st, std::string("tc_attention: ") + tc_last_error(h->tc));
-    return CGG_OK;
-  }
-  CU(launch_attention_f32(q, static_cast<const float*>(k), static_cast<const float*>(v), kv_stride, kv_batch_stride,
-                          bitmap, all_masked, out, batch, h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
+  CU(launch_attention_f32(q, k, v, h->cfg.precision == CGG_BF16, kv_stride, kv_batch_stride, bitmap, all_masked, out,
+                          batch, h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
   return CGG_OK;
 }
 
@@ -358,7 +386,7 @@ extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch,
   ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w, lw.self_in_b, qb, rows, C, C, qscale));
   ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w + (size_t)C * C, lw.self_in_b + C, kb, rows, C, C));
   ST(linear_rows(h, s, x1, nullptr, 1, lw.self_in_w + (size_t)2 * C * C, lw.self_in_b + 2 * C, vb, rows, C, C));
-  CU(launch_attention_f32(qb, kb, vb, C, (long)Q * C, nullptr, nullptr, o, batch, Q, Q, c.num_heads, s));
+  CU(launch_attention_f32(qb, kb, vb, false, C, (long)Q * C, nullptr, nullptr, o, batch, Q, Q, c.num_heads, s));
   ST(linear_rows(h, s, o, nullptr, 1, lw.self_out_w, lw.self_out_b, t, rows, C, C, 1.f, x1));
   CU(launch_layernorm(t, nullptr, lw.norm_w[1], lw.norm_b[1], x2, rows, C, 1e-5f, true, s));
   // ---- FFN
@@ -383,19 +411,30 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
   const size_t HW = (size_t)h->H4 * h->W4;
   const size_t mask_elt = (c.precision == CGG_BF16) ? 2 : 4;
   float* xs = x_states ? x_states : at<float>(workspace, ws.xs);
+  const bool tcm = c.precision == CGG_BF16;
   ST(cgg_kv_project(h, w, batch, memories, workspace, workspace_bytes, stream));
+  if (tcm) {
+    int st = tc_downsample(h->tc, batch, mask_features, at<void>(workspace, ws.tcws), s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_downsample: ") + tc_last_error(h->tc));
+  }
   CU(launch_broadcast_rows(w->query_feat, xs, batch, Q, C, s));          // head.py:808-809
   for (int j = 0; j <= L; ++j) {
     const bool need_mask = j < L;                                           // the last mask is never used
     uint32_t* bm = need_mask ? ((bitmaps && bitmaps[j]) ? bitmaps[j] : at<uint32_t>(workspace, ws.bitmap)) : nullptr;
     uint8_t* am = need_mask ? (all_masked ? all_masked + (size_t)j * batch * Q : at<uint8_t>(workspace, ws.allm))
                             : nullptr;
-    ST(cgg_head_call(h, w, batch, xs + j * bqc, mask_features, j % CGG_NUM_LEVELS,
-                     cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
-                     static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
-                     workspace_bytes, stream));
+    ST(head_call_impl(h, w, batch, xs + j * bqc, mask_features, j % CGG_NUM_LEVELS,
+                      cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
+                      static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
+                      workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true));
     if (j < L)
       ST(cgg_decoder_layer(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream));
+  }
+  if (tcm) {
+    // K2 for all L+1 head calls in one pass: mask_features is read from HBM once (head.py:748 x10)
+    int st = tc_mask_einsum(h->tc, batch, 0, L + 1, mask_features, mask, (long)batch * Q * HW,
+                            at<void>(workspace, ws.tcws), s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
   }
   return CGG_OK;
 }

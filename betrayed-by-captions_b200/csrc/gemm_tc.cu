@@ -1,13 +1,623 @@
+// tcgen05 / TMEM / TMA GEMM of the throughput mode (CGG_BF16), sm_100a.
+//
+// One kernel serves the three dense contractions whose big operand is an NCHW feature map:
+//   K2  mask einsum      D[pixel, (call,q)] = sum_c F[c,pixel]      * me[(call,q), c]
+//   K3  attn-mask bits   D[key,   q]        = sum_c Fds_l[c,key]    * me[q, c]     -> sigmoid<0.5 -> ballot
+//   K4  K/V projection   D[key,   n]        = sum_c mem_l[c,key]    * Wkv[n, c]    (+ bias tables)
+// A (the feature map) is "MN-major": pixels contiguous, channels strided -- exactly NCHW -- so it is
+// fed to the tensor core as-is through TMA with a 128-byte swizzle, no transposition pass.
+// B (mask embeddings / weights) is K-major [rows][256].
+//
+// CTA = 128 pixels x all N.  The A tile (128 px x 256 ch bf16 = 64 KB) is loaded ONCE and stays in
+// shared memory while the CTA walks NT tiles of N (for K2: all 10 head calls, so mask_features is
+// read from HBM once per forward instead of once per call).  B tiles stream through a ring of TMA
+// stages; accumulators are double-buffered in TMEM so the epilogue warps drain tile t while the
+// single MMA-issuing thread runs tile t+1.
+//   warp 0 : TMA producer (one lane)        warp 1 : TMEM alloc + tcgen05.mma issue (one lane)
+//   warps 2..9 : epilogue (tcgen05.ld -> registers -> global), 2 warps per TMEM lane quarter
 #include "gemm_tc.h"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <string>
+
 namespace cgg {
-struct TcState { cgg_config cfg; std::string err; };
-TcState* tc_create(const cgg_config& cfg) { TcState* t = new TcState(); t->cfg = cfg; return t; }
-void tc_destroy(TcState* t) { delete t; }
-const char* tc_last_error(const TcState* t) { return t ? t->err.c_str() : ""; }
-size_t tc_workspace_bytes(const TcState* t, int) { (void)t; return 0; }
-int tc_prepare(TcState* t, const cgg_weights*, int, int, const int*, const int*, const int*, float* const*, float* const*, float* const*, cudaStream_t) { t->err = "bf16 path not built yet"; return CGG_ERR_UNSUPPORTED; }
-int tc_kv_project(TcState* t, int, int, const void*, void*, cudaStream_t) { t->err = "bf16 path not built yet"; return CGG_ERR_UNSUPPORTED; }
-int tc_mask_einsum(TcState* t, int, const float*, const void*, void*, int, uint32_t*, uint8_t*, void*, cudaStream_t) { t->err = "bf16 path not built yet"; return CGG_ERR_UNSUPPORTED; }
-int tc_attention(TcState* t, int, int, const float*, const void*, const void*, long, long, const uint32_t*, const uint8_t*, float*, cudaStream_t) { t->err = "bf16 path not built yet"; return CGG_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_BM = 128;      // pixels per CTA (UMMA M)
+constexpr int TC_BK = 64;       // channels per smem chunk (one 128B swizzle row of bf16 K... see below)
+constexpr int A_CHUNK_BYTES = 2 * 64 * 64 * 2;   // 2 pixel groups x 64 ch x 64 px x bf16 = 16 KB
+
+enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2 };
+
+struct TcGemmP {
+  int NT, N_TILE, KC, stages;
+  int b_row0;            // first B row (e.g. call_idx * q_pad)
+  int b_rows_per_batch;  // B row offset per batch index (0: weights shared by the batch)
+  int acc_stride;        // TMEM columns between the two accumulator buffers
+  int tmem_cols;         // power of two >= 32
+  int epi;
+  int M_valid;           // valid pixels / keys per batch image
+  // EPI_MASK_T
+  __nv_bfloat16* out_mask; long out_call_stride, out_batch_stride, HW; int Q, q_pad, n_calls;
+  // EPI_ROWMAJOR
+  __nv_bfloat16* out_rows; long ld_out, out_rows_batch_stride; const float* bias; const __nv_bfloat16* R;
+  long ldr; int r_ncols;
+  // EPI_BITS
+  uint32_t* bitmap; int W32;
+};
+
+__device__ __forceinline__ bool masked_from_logit(float d) {
+  // same expression as the fp32 path / torch: sigmoid(d) < 0.5
+  return (1.0f / (1.0f + expf(-d))) < 0.5f;
 }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = p.N_TILE * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.KC * A_CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = b_full + p.stages;
+  uint64_t* acc_full = b_empty + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, batch = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::mbar_init(a_full, 1);
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
+      for (int kc = 0; kc < p.KC; ++kc)
+        for (int g = 0; g < 2; ++g)
+          ptx::tma_load_3d(sA + kc * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, a_full,
+                           m_tile * TC_BM + g * 64, kc * TC_BK, batch);
+      int it = 0;
+      for (int t = 0; t < p.NT; ++t)
+        for (int kc = 0; kc < p.KC; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          ptx::mbar_wait(&b_empty[s], ph ^ 1u);
+          ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
+          ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &b_full[s], kc * TC_BK,
+                           batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer (single thread)
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
+      ptx::mbar_wait(a_full, 0);
+      ptx::tc_fence_after();
+      int it = 0;
+      for (int t = 0; t < p.NT; ++t) {
+        const int buf = t & 1;
+        const uint32_t use = (uint32_t)(t >> 1);
+        ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+        for (int kc = 0; kc < p.KC; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          ptx::mbar_wait(&b_full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(sA + kc * A_CHUNK_BYTES);
+          const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
+            // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
+            const uint64_t adesc = ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
+            const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
+            ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
+        }
+        ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
+      }
+    }
+  } else {
+    // ---------------- epilogue: 8 warps, 2 per TMEM lane quarter
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = m_tile * TC_BM + quarter * 32 + lane;     // pixel / key index inside the image
+    const bool m_ok = m < p.M_valid;
+    const int chunks = p.N_TILE / 16;
+    for (int t = 0; t < p.NT; ++t) {
+      const int buf = t & 1;
+      const uint32_t use = (uint32_t)(t >> 1);
+      ptx::mbar_wait(&acc_full[buf], use & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      for (int c = half; c < chunks; c += 2) {
+        float v[16];
+        ptx::tmem_ld16(taddr + (uint32_t)(c * 16), v);
+        const int n0 = t * p.N_TILE + c * 16;
+        if (p.epi == EPI_MASK_T) {
+          // transposed store: out[call][batch][q][pixel]; lanes = pixels.  Two columns at a time:
+          // even lanes store (own, right neighbour) for column i, odd lanes for column i+1.
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float send = (lane & 1) ? v[i] : v[i + 1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const int r = n0 + i + (lane & 1);
+            const int call = r / p.q_pad, q = r - call * p.q_pad;
+            if (m_ok && q < p.Q && call < p.n_calls) {
+              const uint32_t packed = (lane & 1) ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
+              __nv_bfloat16* dst = p.out_mask + (long)call * p.out_call_stride + (long)batch * p.out_batch_stride +
+                                   (long)q * p.HW + (m & ~1);
+              *reinterpret_cast<uint32_t*>(dst) = packed;
+            }
+          }
+        } else if (p.epi == EPI_ROWMAJOR) {
+          if (m_ok) {
+            float add[16];
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 x = __ldg(b4 + i);
+              add[4 * i] = x.x; add[4 * i + 1] = x.y; add[4 * i + 2] = x.z; add[4 * i + 3] = x.w;
+            }
+            if (n0 < p.r_ncols) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.R + (long)m * p.ldr + n0);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint4 x = __ldg(r4 + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h[j]);
+                  add[8 * i + 2 * j] += f.x;
+                  add[8 * i + 2 * j + 1] += f.y;
+                }
+              }
+            }
+            uint4 o[2];
+            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(v[2 * i] + add[2 * i], v[2 * i + 1] + add[2 * i + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(p.out_rows + (long)batch * p.out_rows_batch_stride +
+                                                  (long)m * p.ld_out + n0);
+            dst[0] = o[0];
+            dst[1] = o[1];
+          }
+        } else {  // EPI_BITS
+          const int wi = (m_tile * TC_BM + quarter * 32) >> 5;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool mk = m_ok && masked_from_logit(v[i]);
+            const uint32_t word = __ballot_sync(0xffffffffu, mk);
+            const int q = n0 + i;
+            if (lane == 0 && q < p.Q && wi < p.W32) p.bitmap[((long)batch * p.Q + q) * p.W32 + wi] = word;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------- small kernels
+// One pass over mask_features (bf16 NCHW) producing the bilinear (align_corners=False) resamples to
+// the three level sizes for the exact ratios 8/4/2: each is the mean of the central 2x2 of its
+// block, evaluated in the reference's order 0.5*(0.5a+0.5b)+0.5*(0.5c+0.5d) in fp32.
+// One thread per 8x8 block of one (image, channel) plane.
+__global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int H4,
+                                                          int W4, __nv_bfloat16* __restrict__ d8,
+                                                          __nv_bfloat16* __restrict__ d4,
+                                                          __nv_bfloat16* __restrict__ d2) {
+  const int bw = W4 >> 3, bh = H4 >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)planes * bh * bw;
+  if (idx >= total) return;
+  const int bx = (int)(idx % bw);
+  const int by = (int)((idx / bw) % bh);
+  const long plane = idx / ((long)bw * bh);
+  const __nv_bfloat16* src = F + plane * (long)H4 * W4 + (long)by * 8 * W4 + bx * 8;
+  float px[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint4 x = *reinterpret_cast<const uint4*>(src + (long)r * W4);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      px[r][2 * j] = f.x;
+      px[r][2 * j + 1] = f.y;
+    }
+  }
+  auto avg = [&](int r, int c) {
+    return 0.5f * (0.5f * px[r][c] + 0.5f * px[r][c + 1]) + 0.5f * (0.5f * px[r + 1][c] + 0.5f * px[r + 1][c + 1]);
+  };
+  // ratio 8 -> rows 3,4 cols 3,4
+  d8[plane * (long)bh * bw + (long)by * bw + bx] = __float2bfloat16_rn(avg(3, 3));
+  // ratio 4 -> centre of each 4x4: rows 1,2 / 5,6
+  {
+    const int w = W4 >> 2;
+    __nv_bfloat16* o = d4 + plane * (long)(H4 >> 2) * w + (long)(by * 2) * w + bx * 2;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      *reinterpret_cast<uint32_t*>(o + (long)r * w) = pack_bf16x2(avg(4 * r + 1, 1), avg(4 * r + 1, 5));
+  }
+  // ratio 2 -> every 2x2
+  {
+    const int w = W4 >> 1;
+    __nv_bfloat16* o = d2 + plane * (long)(H4 >> 1) * w + (long)(by * 4) * w + bx * 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint2 pk;
+      pk.x = pack_bf16x2(avg(2 * r, 0), avg(2 * r, 2));
+      pk.y = pack_bf16x2(avg(2 * r, 4), avg(2 * r, 6));
+      *reinterpret_cast<uint2*>(o + (long)r * w) = pk;
+    }
+  }
+}
+
+// me (B,Q,C) fp32 -> rows [b][call*q_pad + q][C] bf16 of the all-call B operand
+__global__ void store_me_kernel(const float* __restrict__ me, __nv_bfloat16* __restrict__ dst, int B, int Q, int C,
+                                int rows_per_batch, int row0) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Q * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long bq = i / C;
+  const int q = (int)(bq % Q);
+  const int b = (int)(bq / Q);
+  dst[((long)b * rows_per_batch + row0 + q) * C + c] = __float2bfloat16_rn(me[i]);
+}
+
+// all_masked[row] = (popcount of the row's bitmap == K)
+__global__ void __launch_bounds__(256) all_masked_kernel(const uint32_t* __restrict__ bitmap, int rows, int W32, int K,
+                                                         uint8_t* __restrict__ all_masked) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int cnt = 0;
+  for (int i = lane; i < W32; i += 32) cnt += __popc(bitmap[(long)row * W32 + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) all_masked[row] = (cnt == K) ? 1 : 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct TcState {
+  cgg_config cfg;
+  std::string err;
+  EncodeTiledFn encode = nullptr;
+  int H4 = 0, W4 = 0, lh[3] = {0, 0, 0}, lw[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
+  __nv_bfloat16* wkv[3] = {nullptr, nullptr, nullptr};   // (nl*2C, C) bf16
+  __nv_bfloat16* rk[3] = {nullptr, nullptr, nullptr};    // (K_l, nl*C) bf16 key-bias table
+  const float* bkv[3] = {nullptr, nullptr, nullptr};     // (nl*2C) fp32, owned by the handle
+  // N tiling of the mask einsum / bits GEMMs
+  int q_pad = 0, ein_ntile = 0, ein_calls_per_tile = 0, bits_ntile = 0, bits_nt = 0;
+  int rows_per_batch = 0;
+  bool smem_attr_set = false;
+  void free_all() {
+    for (int l = 0; l < 3; ++l) { cudaFree(wkv[l]); cudaFree(rk[l]); wkv[l] = rk[l] = nullptr; }
+  }
+};
+
+namespace {
+
+struct TcWs {  // carving of the caller-provided tc workspace
+  size_t me_all, fds[3], total;
+  void carve(const TcState* t, int B) {
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += align256(b); return o; };
+    const int C = t->cfg.embed_dim;
+    me_all = take((size_t)B * t->rows_per_batch * C * 2 + 64 * 1024);
+    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * C * t->lh[l] * t->lw[l] * 2);
+    total = off;
+  }
+};
+
+int tc_fail(TcState* t, int code, const std::string& m) { t->err = m; return code; }
+
+#define TCU(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return tc_fail(t, CGG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// 3-D map over an NCHW feature tensor: dims (pixels, channels, batch), box (64 px, 64 ch, 1)
+int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, int B) {
+  if ((pixels * 2) % 16 != 0)
+    return tc_fail(t, CGG_ERR_UNSUPPORTED, "bf16 mode needs a pixel count that is a multiple of 8 (TMA 16-byte stride rule)");
+  cuuint64_t dims[3] = {(cuuint64_t)pixels, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)pixels * 2, (cuuint64_t)pixels * C * 2};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = t->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r));
+  return CGG_OK;
+}
+// 2-D map over a K-major [rows][C] bf16 matrix: box (64 k, n_tile rows)
+int make_map_B(TcState* t, CUtensorMap* m, const void* base, long rows, int C, int n_tile) {
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = t->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r));
+  return CGG_OK;
+}
+
+int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcGemmP p, int m_tiles, int batch,
+                   cudaStream_t s) {
+  if (p.N_TILE % 16 != 0 || p.N_TILE < 16 || p.N_TILE > 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "bad N tile");
+  p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
+  if (p.N_TILE <= 32) p.acc_stride = 32; else if (p.N_TILE <= 64) p.acc_stride = 64;
+  p.tmem_cols = 2 * p.acc_stride;
+  const size_t a_bytes = (size_t)p.KC * A_CHUNK_BYTES;
+  const size_t b_stage = (size_t)p.N_TILE * 128;
+  const size_t budget = 200 * 1024;
+  int stages = (int)((budget - a_bytes) / b_stage);
+  if (stages > 8) stages = 8;
+  if (stages > p.NT * p.KC) stages = p.NT * p.KC;
+  if (stages < 2) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 16;
+  if (!t->smem_attr_set) {
+    TCU(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    t->smem_attr_set = true;
+  }
+  tc_gemm_kernel<<<dim3(m_tiles, batch), TC_THREADS, smem, s>>>(mA, mB, p);
+  count_launch();
+  TCU(cudaGetLastError());
+  return CGG_OK;
+}
+
+}  // namespace
+
+// =========================================================================== host interface
+TcState* tc_create(const cgg_config& cfg) {
+  TcState* t = new (std::nothrow) TcState();
+  if (!t) return nullptr;
+  t->cfg = cfg;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    delete t;
+    return nullptr;
+  }
+  t->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  const int Q = cfg.num_queries, calls = cfg.num_layers + 1;
+  // N tiling: two head calls per 2*round8(Q)-wide tile when that fits one MMA (Q=100 -> 208, 4% pad);
+  // otherwise one call per round16(Q) tile; above 256 queries, two tiles per call.
+  if (2 * round_up(Q, 8) <= 256 && calls % 2 == 0) {
+    t->q_pad = round_up(Q, 8); t->ein_ntile = 2 * t->q_pad; t->ein_calls_per_tile = 2;
+  } else if (round_up(Q, 16) <= 256) {
+    t->q_pad = round_up(Q, 16); t->ein_ntile = t->q_pad; t->ein_calls_per_tile = 1;
+  } else {
+    t->q_pad = round_up(Q, 32); t->ein_ntile = t->q_pad / 2; t->ein_calls_per_tile = 0;  // 2 tiles per call
+    if (t->ein_ntile > 256) { delete t; return nullptr; }
+  }
+  if (round_up(Q, 16) <= 256) { t->bits_ntile = round_up(Q, 16); t->bits_nt = 1; }
+  else { t->bits_ntile = round_up(Q, 32) / 2; t->bits_nt = 2; }
+  t->rows_per_batch = calls * t->q_pad;
+  return t;
+}
+
+void tc_destroy(TcState* t) {
+  if (!t) return;
+  t->free_all();
+  delete t;
+}
+
+const char* tc_last_error(const TcState* t) { return t ? t->err.c_str() : ""; }
+
+size_t tc_workspace_bytes(const TcState* t, int batch) {
+  if (!t) return 0;
+  TcWs w;
+  w.carve(t, batch);
+  return w.total;
+}
+
+size_t tc_workspace_offset(const TcState* t, int batch, const char* what) {
+  if (!t || !what) return (size_t)-1;
+  TcWs w;
+  w.carve(t, batch);
+  const std::string n(what);
+  if (n == "me_all") return w.me_all;
+  if (n == "fds0") return w.fds[0];
+  if (n == "fds1") return w.fds[1];
+  if (n == "fds2") return w.fds[2];
+  return (size_t)-1;
+}
+int tc_rows_per_batch(const TcState* t) { return t ? t->rows_per_batch : 0; }
+int tc_q_pad(const TcState* t) { return t ? t->q_pad : 0; }
+
+int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, const int* lw, const int* nl,
+               float* const* wkv_f32, float* const* rk_f32, float* const* bkv_f32, cudaStream_t s) {
+  (void)w;
+  const int C = t->cfg.embed_dim;
+  const int ratio[3] = {8, 4, 2};
+  for (int l = 0; l < 3; ++l)
+    if (lh[l] * ratio[l] != H4 || lw[l] * ratio[l] != W4)
+      return tc_fail(t, CGG_ERR_UNSUPPORTED,
+                     "bf16 mode needs level sizes at exactly 1/8, 1/4, 1/2 of the mask-feature size (inputs padded to /32)");
+  bool same = t->H4 == H4 && t->W4 == W4;
+  for (int l = 0; l < 3; ++l) same = same && t->lh[l] == lh[l] && t->lw[l] == lw[l] && t->nl[l] == nl[l] && t->wkv[l];
+  if (!same) {
+    t->free_all();
+    t->H4 = H4; t->W4 = W4;
+    for (int l = 0; l < 3; ++l) {
+      t->lh[l] = lh[l]; t->lw[l] = lw[l]; t->nl[l] = nl[l];
+      const int n = nl[l] > 0 ? nl[l] : 1;
+      TCU(cudaMalloc(&t->wkv[l], (size_t)n * 2 * C * C * 2));
+      TCU(cudaMalloc(&t->rk[l], (size_t)lh[l] * lw[l] * n * C * 2));
+    }
+  }
+  for (int l = 0; l < 3; ++l) {
+    if (nl[l] == 0) continue;
+    TCU(launch_cast_bf16(wkv_f32[l], t->wkv[l], (size_t)nl[l] * 2 * C * C, s));
+    TCU(launch_cast_bf16(rk_f32[l], t->rk[l], (size_t)lh[l] * lw[l] * nl[l] * C, s));
+    t->bkv[l] = bkv_f32[l];
+  }
+  return CGG_OK;
+}
+
+int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, cudaStream_t s) {
+  const int C = t->cfg.embed_dim, K = t->lh[level] * t->lw[level], N = t->nl[level] * 2 * C;
+  CUtensorMap mA, mB;
+  int st = make_map_A(t, &mA, mem_bf16, K, C, batch);
+  if (st != CGG_OK) return st;
+  TcGemmP p = {};
+  p.N_TILE = 256;
+  if (N % p.N_TILE != 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "K/V width not a multiple of 256");
+  st = make_map_B(t, &mB, t->wkv[level], N, C, p.N_TILE);
+  if (st != CGG_OK) return st;
+  p.NT = N / p.N_TILE; p.KC = C / TC_BK;
+  p.b_row0 = 0; p.b_rows_per_batch = 0;
+  p.epi = EPI_ROWMAJOR; p.M_valid = K;
+  p.out_rows = static_cast<__nv_bfloat16*>(kv_bf16); p.ld_out = N; p.out_rows_batch_stride = (long)K * N;
+  p.bias = t->bkv[level]; p.R = t->rk[level]; p.ldr = (long)t->nl[level] * C; p.r_ncols = t->nl[level] * C;
+  return launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s);
+}
+
+int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* ws, cudaStream_t s) {
+  TcWs w;
+  w.carve(t, batch);
+  if ((t->H4 % 8) || (t->W4 % 8)) return tc_fail(t, CGG_ERR_UNSUPPORTED, "mask feature size must be a multiple of 8");
+  const int planes = batch * t->cfg.embed_dim;
+  const long total = (long)planes * (t->H4 / 8) * (t->W4 / 8);
+  char* base = static_cast<char*>(ws);
+  downsample3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->H4, t->W4,
+      reinterpret_cast<__nv_bfloat16*>(base + w.fds[0]), reinterpret_cast<__nv_bfloat16*>(base + w.fds[1]),
+      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2]));
+  count_launch();
+  TCU(cudaGetLastError());
+  return CGG_OK;
+}
+
+int tc_store_mask_embed(TcState* t, int batch, int call_idx, const float* me_f32, void* ws, cudaStream_t s) {
+  TcWs w;
+  w.carve(t, batch);
+  const int C = t->cfg.embed_dim, Q = t->cfg.num_queries;
+  const long total = (long)batch * Q * C;
+  store_me_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      me_f32, reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + w.me_all), batch, Q, C, t->rows_per_batch,
+      call_idx * t->q_pad);
+  count_launch();
+  TCU(cudaGetLastError());
+  return CGG_OK;
+}
+
+int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitmap, uint8_t* all_masked, void* ws,
+                 cudaStream_t s) {
+  TcWs w;
+  w.carve(t, batch);
+  const int C = t->cfg.embed_dim, Q = t->cfg.num_queries, K = t->lh[level] * t->lw[level];
+  char* base = static_cast<char*>(ws);
+  CUtensorMap mA, mB;
+  int st = make_map_A(t, &mA, base + w.fds[level], K, C, batch);
+  if (st != CGG_OK) return st;
+  // rows beyond the buffer's logical end are covered by the 64 KB slack of me_all (finite garbage,
+  // columns >= Q are never stored)
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, C, t->bits_ntile);
+  if (st != CGG_OK) return st;
+  TcGemmP p = {};
+  p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = C / TC_BK;
+  p.b_row0 = call_idx * t->q_pad; p.b_rows_per_batch = t->rows_per_batch;
+  p.epi = EPI_BITS; p.M_valid = K; p.Q = Q;
+  p.bitmap = bitmap; p.W32 = (K + 31) / 32;
+  st = launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s);
+  if (st != CGG_OK) return st;
+  const int rows = batch * Q;
+  all_masked_kernel<<<(rows + 7) / 8, 256, 0, s>>>(bitmap, rows, p.W32, K, all_masked);
+  count_launch();
+  TCU(cudaGetLastError());
+  return CGG_OK;
+}
+
+int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const void* mask_features_bf16,
+                   void* mask_bf16, long call_stride, void* ws, cudaStream_t s) {
+  TcWs w;
+  w.carve(t, batch);
+  const int C = t->cfg.embed_dim, Q = t->cfg.num_queries;
+  const long HW = (long)t->H4 * t->W4;
+  char* base = static_cast<char*>(ws);
+  CUtensorMap mA, mB;
+  int st = make_map_A(t, &mA, mask_features_bf16, (int)HW, C, batch);
+  if (st != CGG_OK) return st;
+  TcGemmP p = {};
+  p.KC = C / TC_BK;
+  p.b_row0 = first_call * t->q_pad; p.b_rows_per_batch = t->rows_per_batch;
+  p.epi = EPI_MASK_T; p.M_valid = (int)HW; p.Q = Q; p.q_pad = t->q_pad; p.n_calls = num_calls;
+  p.out_mask = static_cast<__nv_bfloat16*>(mask_bf16);
+  p.out_call_stride = call_stride; p.out_batch_stride = (long)Q * HW; p.HW = HW;
+  if (t->ein_calls_per_tile == 2 && num_calls % 2 == 0) {
+    p.N_TILE = t->ein_ntile; p.NT = num_calls / 2;
+  } else if (t->ein_calls_per_tile == 0) {
+    p.N_TILE = t->ein_ntile; p.NT = 2 * num_calls;
+  } else {
+    // one call per tile; a tile may read past this call's rows (next call / slack), never stored
+    p.N_TILE = round_up(t->q_pad, 16); p.NT = num_calls;
+    if (p.N_TILE != t->q_pad && num_calls > 1) {
+      // q_pad is a multiple of 8 only: walk call by call so tiles start on call boundaries
+      for (int c = 0; c < num_calls; ++c) {
+        st = tc_mask_einsum(t, batch, first_call + c, 1, mask_features_bf16,
+                            static_cast<__nv_bfloat16*>(mask_bf16) + (long)c * call_stride, call_stride, ws, s);
+        if (st != CGG_OK) return st;
+      }
+      return CGG_OK;
+    }
+  }
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, C, p.N_TILE);
+  if (st != CGG_OK) return st;
+  return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s);
+}
+
+}  // namespace cgg

@@ -12,21 +12,34 @@ TcState* tc_create(const cgg_config& cfg);
 void tc_destroy(TcState* t);
 const char* tc_last_error(const TcState* t);
 size_t tc_workspace_bytes(const TcState* t, int batch);  // t may be null (fp32 mode) -> 0
+size_t tc_workspace_offset(const TcState* t, int batch, const char* what);  // (size_t)-1 if unknown
+int tc_rows_per_batch(const TcState* t);
+int tc_q_pad(const TcState* t);
 
-// bf16 copies of the K/V projection weights and bias tables + TMA descriptors for the given sizes.
+// bf16 copies of the K/V projection weights and key-bias tables for the given sizes.
 int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, const int* lw, const int* nl,
                float* const* wkv_f32, float* const* rk_f32, float* const* bkv_f32, cudaStream_t s);
 
 // K4: kv[b, key, :] = mem[b, :, key]^T Wkv^T + bias tables, bf16 out (B, K_l, nl*2C)
 int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, cudaStream_t s);
 
-// K2 (+K3): mask[b,q,p] = sum_c me[b,q,c] F[b,c,p] (bf16 out); when target_level >= 0 also the
-// attention-mask bitmap / all_masked flags of that level.
-int tc_mask_einsum(TcState* t, int batch, const float* me_f32, const void* mask_features_bf16, void* mask_bf16,
-                   int target_level, uint32_t* bitmap, uint8_t* all_masked, void* ws, cudaStream_t s);
+// Once per forward: the centre-2x2 averages of mask_features at the three level resolutions
+// (bf16, (B,C,K_l) each) that the attention-mask GEMMs contract against.
+int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* ws, cudaStream_t s);
 
-// K5 with bf16 K/V
-int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
-                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, cudaStream_t s);
+// Stores head call `call_idx`'s mask embeddings (fp32 (B,Q,C)) as bf16 rows of the all-layer
+// B operand in the workspace.
+int tc_store_mask_embed(TcState* t, int batch, int call_idx, const float* me_f32, void* ws, cudaStream_t s);
+
+// K3 on tensor cores: attention-mask bitmap of head call `call_idx` for `level`:
+//   bits = sigmoid( me . Fds_level ) < 0.5, ballot-packed in the epilogue; then all_masked.
+int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitmap, uint8_t* all_masked, void* ws,
+                 cudaStream_t s);
+
+// K2: mask[b,q,p] = sum_c me[b,q,c] F[b,c,p], bf16 out.  first_call..first_call+num_calls-1 head
+// calls in ONE pass over mask_features (A tile resident in shared memory across all of them).
+// mask points at call `first_call`'s slice; consecutive calls are call_stride elements apart.
+int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const void* mask_features_bf16,
+                   void* mask_bf16, long call_stride, void* ws, cudaStream_t s);
 
 }  // namespace cgg

@@ -47,9 +47,9 @@ cudaError_t launch_pos_level(const float* level_embed, float* out, int h, int w,
 cudaError_t launch_mask_bits(const float* mask_pred, int rows, int H4, int W4, int th, int tw,
                              uint32_t* bitmap, uint8_t* all_masked, cudaStream_t s);
 
-// K5/K6 attention core, fp32 SIMT flash-style.  q (B,Q,H*32) pre-scaled; k,v rows of H*32 at
+// K5/K6 attention core, fp32 SIMT flash-style (K/V fp32 or bf16).  q (B,Q,H*32) pre-scaled; k,v rows of H*32 at
 // (b*kv_bstride + key*kv_stride); bitmap (B,Q,ceil(K/32)) or nullptr.
-cudaError_t launch_attention_f32(const float* q, const float* k, const float* v, long kv_stride,
+cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, bool kv_bf16, long kv_stride,
                                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked,
                                  float* out, int B, int Q, int K, int heads, cudaStream_t s);
 

@@ -11,7 +11,7 @@ NUM_LEVELS = 3
 FP32, BF16 = 0, 1
 c_float_p = C.POINTER(C.c_float)
 
-EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_launch_count', 'cgg_prepare', 'cgg_workspace_bytes',
+EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_launch_count', 'cgg_prepare', 'cgg_workspace_bytes', 'cgg_workspace_offset',
            'cgg_decoder_forward', 'cgg_kv_project', 'cgg_head_call', 'cgg_attn_mask_from_logits',
            'cgg_decoder_layer', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
            'cgg_grounding_scratch_bytes', 'cgg_grounding_loss']
@@ -62,6 +62,8 @@ def load():
     lib.cgg_prepare.argtypes = [vp, C.POINTER(Weights), i, i, C.POINTER(i), C.POINTER(i), vp]
     lib.cgg_workspace_bytes.argtypes = [vp, i]
     lib.cgg_workspace_bytes.restype = sz
+    lib.cgg_workspace_offset.argtypes = [vp, i, C.c_char_p]
+    lib.cgg_workspace_offset.restype = sz
     lib.cgg_decoder_forward.argtypes = [vp, C.POINTER(Weights), i, vp, C.POINTER(vp), vp, vp, vp, vp,
                                         C.POINTER(vp), vp, vp, sz, vp]
     lib.cgg_kv_project.argtypes = [vp, C.POINTER(Weights), i, C.POINTER(vp), vp, sz, vp]

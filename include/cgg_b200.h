@@ -125,6 +125,11 @@ int cgg_prepare(cgg_handle *h, const cgg_weights *w, int H4, int W4,
 
 /* Bytes of caller-provided workspace cgg_decoder_forward needs for this batch size. */
 size_t cgg_workspace_bytes(const cgg_handle *h, int batch);
+/* Introspection for the stage-level parity tests: byte offset inside the workspace of a named
+ * intermediate ("kv0","kv1","kv2": projected keys/values of level l, (B,K_l,nl*2C), columns
+ * [k_0..k_{nl-1} | v_0..v_{nl-1}]; "me_all": bf16 mask embeddings of all head calls; "fds0".."fds2":
+ * mask_features resampled to level l (bf16 mode)).  Returns (size_t)-1 for an unknown name. */
+size_t cgg_workspace_offset(const cgg_handle *h, int batch, const char *what);
 
 /* ---- whole path: Mask2FormerHeadOpen.forward after the pixel decoder (head.py:787-849)
  * mask_features, memories: dtype per precision (see layouts).  Outputs as listed above.
