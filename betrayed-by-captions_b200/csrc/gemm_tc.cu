@@ -36,6 +36,9 @@ enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2 };
 
 struct TcGemmP {
   int NT, N_TILE, KC, stages;
+  int a_resident;        // 1: the whole A tile (KC chunks) stays in smem for all NT tiles; 0: A chunks stream with B
+  int a_kcoord[12];      // channel coordinate of A chunk kc   (split-precision GEMMs revisit chunks)
+  int b_kcoord[12];      // K coordinate of B chunk kc
   int b_row0;            // first B row (e.g. call_idx * q_pad)
   int b_rows_per_batch;  // B row offset per batch index (0: weights shared by the batch)
   int acc_stride;        // TMEM columns between the two accumulator buffers
@@ -65,9 +68,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_stage_bytes = p.N_TILE * 128;
+  const int b_tile_bytes = p.N_TILE * 128;
+  const int a_in_stage = p.a_resident ? 0 : A_CHUNK_BYTES;
+  const int b_stage_bytes = a_in_stage + b_tile_bytes;      // ring stage = [A chunk (if streamed)] [B chunk]
   uint8_t* sA = smem;
-  uint8_t* sB = sA + p.KC * A_CHUNK_BYTES;
+  uint8_t* sB = sA + (p.a_resident ? p.KC * A_CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + 1;
@@ -99,11 +104,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer
-      ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
-      for (int kc = 0; kc < p.KC; ++kc)
-        for (int g = 0; g < 2; ++g)
-          ptx::tma_load_3d(sA + kc * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, a_full,
-                           m_tile * TC_BM + g * 64, kc * TC_BK, batch);
+      if (p.a_resident) {
+        ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
+        for (int kc = 0; kc < p.KC; ++kc)
+          for (int g = 0; g < 2; ++g)
+            ptx::tma_load_3d(sA + kc * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, a_full,
+                             m_tile * TC_BM + g * 64, p.a_kcoord[kc], batch);
+      }
       int it = 0;
       for (int t = 0; t < p.NT; ++t)
         for (int kc = 0; kc < p.KC; ++kc, ++it) {
@@ -111,7 +118,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           ptx::mbar_wait(&b_empty[s], ph ^ 1u);
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
-          ptx::tma_load_2d(sB + s * b_stage_bytes, &tmB, &b_full[s], kc * TC_BK,
+          uint8_t* stage = sB + s * b_stage_bytes;
+          if (!p.a_resident)
+            for (int g = 0; g < 2; ++g)
+              ptx::tma_load_3d(stage + g * (A_CHUNK_BYTES / 2), &tmA, &b_full[s], m_tile * TC_BM + g * 64,
+                               p.a_kcoord[kc], batch);
+          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
     }
@@ -119,8 +131,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
       const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
-      ptx::mbar_wait(a_full, 0);
-      ptx::tc_fence_after();
+      if (p.a_resident) {
+        ptx::mbar_wait(a_full, 0);
+        ptx::tc_fence_after();
+      }
       int it = 0;
       for (int t = 0; t < p.NT; ++t) {
         const int buf = t & 1;
@@ -133,8 +147,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(sA + kc * A_CHUNK_BYTES);
-          const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes);
+          const uint32_t a_base = ptx::smem_u32(p.a_resident ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
+          const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes + a_in_stage);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
@@ -242,7 +256,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the three level sizes for the exact ratios 8/4/2: each is the mean of the central 2x2 of its
 // block, evaluated in the reference's order 0.5*(0.5a+0.5b)+0.5*(0.5c+0.5d) in fp32.
 // One thread per 8x8 block of one (image, channel) plane.
-__global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int H4,
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Outputs are hi/lo bf16 pairs (x ~= hi + lo to ~16 mantissa bits): per image the resampled map is
+// stored as (2C, K_l): channels [0,C) = hi, [C,2C) = lo.
+__global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int C, int H4,
                                                           int W4, __nv_bfloat16* __restrict__ d8,
                                                           __nv_bfloat16* __restrict__ d4,
                                                           __nv_bfloat16* __restrict__ d2) {
@@ -253,6 +277,8 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
   const int bx = (int)(idx % bw);
   const int by = (int)((idx / bw) % bh);
   const long plane = idx / ((long)bw * bh);
+  const long img = plane / C, ch = plane % C;
+  const long hi_plane = img * 2 * C + ch, lo_plane = hi_plane + C;
   const __nv_bfloat16* src = F + plane * (long)H4 * W4 + (long)by * 8 * W4 + bx * 8;
   float px[8][8];
 #pragma unroll
@@ -270,25 +296,39 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
     return 0.5f * (0.5f * px[r][c] + 0.5f * px[r][c + 1]) + 0.5f * (0.5f * px[r + 1][c] + 0.5f * px[r + 1][c + 1]);
   };
   // ratio 8 -> rows 3,4 cols 3,4
-  d8[plane * (long)bh * bw + (long)by * bw + bx] = __float2bfloat16_rn(avg(3, 3));
+  {
+    __nv_bfloat16 hi, lo;
+    split_bf16(avg(3, 3), hi, lo);
+    d8[hi_plane * (long)bh * bw + (long)by * bw + bx] = hi;
+    d8[lo_plane * (long)bh * bw + (long)by * bw + bx] = lo;
+  }
   // ratio 4 -> centre of each 4x4: rows 1,2 / 5,6
   {
     const int w = W4 >> 2;
-    __nv_bfloat16* o = d4 + plane * (long)(H4 >> 2) * w + (long)(by * 2) * w + bx * 2;
+    const long off = (long)(by * 2) * w + bx * 2, psz = (long)(H4 >> 2) * w;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-      *reinterpret_cast<uint32_t*>(o + (long)r * w) = pack_bf16x2(avg(4 * r + 1, 1), avg(4 * r + 1, 5));
+    for (int r = 0; r < 2; ++r) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(avg(4 * r + 1, 1), h0, l0);
+      split_bf16(avg(4 * r + 1, 5), h1, l1);
+      *reinterpret_cast<uint32_t*>(d4 + hi_plane * psz + off + (long)r * w) = pack2(h0, h1);
+      *reinterpret_cast<uint32_t*>(d4 + lo_plane * psz + off + (long)r * w) = pack2(l0, l1);
+    }
   }
   // ratio 2 -> every 2x2
   {
     const int w = W4 >> 1;
-    __nv_bfloat16* o = d2 + plane * (long)(H4 >> 1) * w + (long)(by * 4) * w + bx * 4;
+    const long off = (long)(by * 4) * w + bx * 4, psz = (long)(H4 >> 1) * w;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      uint2 pk;
-      pk.x = pack_bf16x2(avg(2 * r, 0), avg(2 * r, 2));
-      pk.y = pack_bf16x2(avg(2 * r, 4), avg(2 * r, 6));
-      *reinterpret_cast<uint2*>(o + (long)r * w) = pk;
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_bf16(avg(2 * r, 2 * j), h[j], l[j]);
+      uint2 ph, pl;
+      ph.x = pack2(h[0], h[1]); ph.y = pack2(h[2], h[3]);
+      pl.x = pack2(l[0], l[1]); pl.y = pack2(l[2], l[3]);
+      *reinterpret_cast<uint2*>(d2 + hi_plane * psz + off + (long)r * w) = ph;
+      *reinterpret_cast<uint2*>(d2 + lo_plane * psz + off + (long)r * w) = pl;
     }
   }
 }
@@ -303,7 +343,11 @@ __global__ void store_me_kernel(const float* __restrict__ me, __nv_bfloat16* __r
   const long bq = i / C;
   const int q = (int)(bq % Q);
   const int b = (int)(bq / Q);
-  dst[((long)b * rows_per_batch + row0 + q) * C + c] = __float2bfloat16_rn(me[i]);
+  __nv_bfloat16 hi, lo;
+  split_bf16(me[i], hi, lo);
+  __nv_bfloat16* row = dst + ((long)b * rows_per_batch + row0 + q) * 2 * C;
+  row[c] = hi;          // columns [0,C): hi  (the only part the mask einsum reads)
+  row[C + c] = lo;      // columns [C,2C): lo (third term of the split-precision attention-mask GEMM)
 }
 
 // all_masked[row] = (popcount of the row's bitmap == K)
@@ -352,8 +396,8 @@ struct TcWs {  // carving of the caller-provided tc workspace
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += align256(b); return o; };
     const int C = t->cfg.embed_dim;
-    me_all = take((size_t)B * t->rows_per_batch * C * 2 + 64 * 1024);
-    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * C * t->lh[l] * t->lw[l] * 2);
+    me_all = take((size_t)B * t->rows_per_batch * 2 * C * 2 + 128 * 1024);   // [hi|lo] rows + 128 slack rows
+    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * 2 * C * t->lh[l] * t->lw[l] * 2);   // hi, lo planes
     total = off;
   }
 };
@@ -382,6 +426,7 @@ int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, 
 }
 // 2-D map over a K-major [rows][C] bf16 matrix: box (64 k, n_tile rows)
 int make_map_B(TcState* t, CUtensorMap* m, const void* base, long rows, int C, int n_tile) {
+  // C = row length in elements (pitch == length)
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)C * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
@@ -399,8 +444,9 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
   if (p.N_TILE <= 32) p.acc_stride = 32; else if (p.N_TILE <= 64) p.acc_stride = 64;
   p.tmem_cols = 2 * p.acc_stride;
-  const size_t a_bytes = (size_t)p.KC * A_CHUNK_BYTES;
-  const size_t b_stage = (size_t)p.N_TILE * 128;
+  const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
+  const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
+  if (p.KC > 12) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
   const size_t budget = 200 * 1024;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
@@ -519,6 +565,8 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
   st = make_map_B(t, &mB, t->wkv[level], N, C, p.N_TILE);
   if (st != CGG_OK) return st;
   p.NT = N / p.N_TILE; p.KC = C / TC_BK;
+  p.a_resident = 1;
+  for (int kc = 0; kc < p.KC; ++kc) p.a_kcoord[kc] = p.b_kcoord[kc] = kc * TC_BK;
   p.b_row0 = 0; p.b_rows_per_batch = 0;
   p.epi = EPI_ROWMAJOR; p.M_valid = K;
   p.out_rows = static_cast<__nv_bfloat16*>(kv_bf16); p.ld_out = N; p.out_rows_batch_stride = (long)K * N;
@@ -534,7 +582,7 @@ int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* w
   const long total = (long)planes * (t->H4 / 8) * (t->W4 / 8);
   char* base = static_cast<char*>(ws);
   downsample3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->H4, t->W4,
+      static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->cfg.embed_dim, t->H4, t->W4,
       reinterpret_cast<__nv_bfloat16*>(base + w.fds[0]), reinterpret_cast<__nv_bfloat16*>(base + w.fds[1]),
       reinterpret_cast<__nv_bfloat16*>(base + w.fds[2]));
   count_launch();
@@ -562,14 +610,23 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
   const int C = t->cfg.embed_dim, Q = t->cfg.num_queries, K = t->lh[level] * t->lw[level];
   char* base = static_cast<char*>(ws);
   CUtensorMap mA, mB;
-  int st = make_map_A(t, &mA, base + w.fds[level], K, C, batch);
+  // split-precision contraction  logits = Fhi.me_hi + Flo.me_hi + Fhi.me_lo  (bf16 pairs, fp32
+  // accumulate: ~16 mantissa bits per operand), expressed as ONE GEMM with K = 3C by revisiting chunks
+  int st = make_map_A(t, &mA, base + w.fds[level], K, 2 * C, batch);
   if (st != CGG_OK) return st;
   // rows beyond the buffer's logical end are covered by the 64 KB slack of me_all (finite garbage,
   // columns >= Q are never stored)
-  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, C, t->bits_ntile);
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t->bits_ntile);
   if (st != CGG_OK) return st;
   TcGemmP p = {};
-  p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = C / TC_BK;
+  p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = 3 * C / TC_BK;
+  p.a_resident = 0;
+  const int cpc = C / TC_BK;   // chunks per C
+  for (int kc = 0; kc < p.KC; ++kc) {
+    const int term = kc / cpc, j = (kc % cpc) * TC_BK;
+    p.a_kcoord[kc] = (term == 1 ? C : 0) + j;     // hi, lo, hi
+    p.b_kcoord[kc] = (term == 2 ? C : 0) + j;     // hi, hi, lo
+  }
   p.b_row0 = call_idx * t->q_pad; p.b_rows_per_batch = t->rows_per_batch;
   p.epi = EPI_BITS; p.M_valid = K; p.Q = Q;
   p.bitmap = bitmap; p.W32 = (K + 31) / 32;
@@ -594,6 +651,8 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   if (st != CGG_OK) return st;
   TcGemmP p = {};
   p.KC = C / TC_BK;
+  p.a_resident = 1;
+  for (int kc = 0; kc < p.KC; ++kc) p.a_kcoord[kc] = p.b_kcoord[kc] = kc * TC_BK;
   p.b_row0 = first_call * t->q_pad; p.b_rows_per_batch = t->rows_per_batch;
   p.epi = EPI_MASK_T; p.M_valid = (int)HW; p.Q = Q; p.q_pad = t->q_pad; p.n_calls = num_calls;
   p.out_mask = static_cast<__nv_bfloat16*>(mask_bf16);
@@ -615,7 +674,7 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       return CGG_OK;
     }
   }
-  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, C, p.N_TILE);
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE);
   if (st != CGG_OK) return st;
   return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s);
 }

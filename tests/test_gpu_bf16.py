@@ -1,0 +1,122 @@
+"""GPU parity tests of the throughput mode (CGG_BF16: bf16 operands on tcgen05, fp32 accumulate)
+against the oracle's fp32 results.  Tolerances are the ones BASELINE.json states for bf16 mode:
+  * mask / class / grounding logits: max-abs error <= 1e-2 of the logit range,
+  * attention-mask bits: >= 99.9 % agreement,
+  * final mask IoU >= 0.99,
+all against the reference-equivalent fp32 path on identical inputs and weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cgg_oracle as O
+from cgg_b200 import synth
+from cgg_b200.head import build_head_from_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+REL_TOL = 1e-2
+BIT_AGREE = 0.999
+IOU_MIN = 0.99
+
+
+def _unpack(bm, K):
+    w = bm.cpu().numpy().astype(np.int32)
+    bits = np.unpackbits(w.view(np.uint8), bitorder='little').reshape(w.shape[0], w.shape[1], -1)[:, :, :K]
+    return torch.from_numpy(bits.astype(bool))
+
+
+def _rel(got, want):
+    return float((got.float().cpu() - want).abs().max()) / float(want.abs().max())
+
+
+def _setup(Q, B, H, W, pseed, iseed):
+    sd = synth.make_params(seed=pseed, num_queries=Q, perturb=True)
+    mf, mems = synth.make_inputs(iseed, B, H, W)
+    # the bf16 path consumes bf16 pixel-decoder outputs; the oracle sees the SAME (rounded) values
+    mf, mems = mf.bfloat16().float(), [m.bfloat16().float() for m in mems]
+    head = build_head_from_state_dict(sd, Q, 49, 'bf16', DEV)
+    return sd, mf, mems, head
+
+
+@pytest.mark.parametrize('Q,B,H,W', [(100, 2, 256, 256), (37, 1, 256, 320), (200, 1, 256, 256), (300, 1, 256, 256)])
+def test_bf16_teacher_forced_layers(Q, B, H, W):
+    sd, mf, mems, head = _setup(Q, B, H, W, 31, 7)
+    ref = O.decoder_forward(sd, mf, mems)
+    dev = torch.device(DEV, 0)
+    rt = head._runtime(dev)
+    sizes = [tuple(m.shape[-2:]) for m in mems]
+    rt.prepare(mf.shape[2], mf.shape[3], sizes, B)
+    mfd = mf.to(dev).bfloat16()
+    rt.kv_project([m.to(dev).bfloat16() for m in mems])
+    for i in range(9):
+        x = ref['x'][i].to(dev).contiguous()
+        cls, emb, mask, me, bm, am = rt.head_call(x, mfd, i % 3)
+        assert _rel(cls, ref['cls'][i]) < REL_TOL and _rel(emb, ref['emb'][i]) < REL_TOL
+        assert _rel(mask, ref['mask'][i]) < REL_TOL, 'mask logits, head call %d' % i
+        K = sizes[i % 3][0] * sizes[i % 3][1]
+        agree = float((_unpack(bm, K) == ref['masked'][i]).float().mean())
+        assert agree >= BIT_AGREE, 'attention-mask bit agreement %.5f at head call %d' % (agree, i)
+        want_bits = O.pack_mask_bits(ref['masked'][i]).to(dev)
+        x_out = rt.decoder_layer(i, x, want_bits, ref['masked'][i].all(-1).to(torch.uint8).to(dev))
+        assert _rel(x_out, ref['x'][i + 1]) < REL_TOL, 'decoder layer %d' % i
+
+
+def test_bf16_free_running_final_outputs():
+    Q, B, H, W = 100, 2, 256, 256
+    sd, mf, mems, head = _setup(Q, B, H, W, 33, 9)
+    ref = O.decoder_forward(sd, mf, mems)
+    cls, emb, mask, dbg = head.decoder_forward(mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems],
+                                               return_debug=True)
+    assert mask[0].dtype == torch.bfloat16 and len(mask) == 10
+    sizes = [tuple(m.shape[-2:]) for m in mems]
+    for j in (0, 1, 2):
+        K = sizes[j % 3][0] * sizes[j % 3][1]
+        agree = float((_unpack(dbg['bitmaps'][j], K) == ref['masked'][j]).float().mean())
+        assert agree >= BIT_AGREE, (j, agree)
+    # final masks: IoU of the thresholded (mask > 0) predictions, per query, averaged
+    got = mask[9].float().cpu() > 0
+    want = ref['mask'][9] > 0
+    inter = (got & want).flatten(2).sum(-1).float()
+    union = (got | want).flatten(2).sum(-1).float().clamp(min=1)
+    iou = float((inter / union).mean())
+    assert iou >= IOU_MIN, iou
+    assert _rel(mask[9], ref['mask'][9]) < 3 * REL_TOL      # free-running: compounding over 9 layers
+    assert _rel(emb[9], ref['emb'][9]) < 3 * REL_TOL
+    # grounding / class-embedding logits from the final embeddings
+    logits = head._get_cls_emb_logits(emb[9])
+    want_l = O.cls_emb_logits(ref['emb'][9], sd['class_embs'], 10.0)
+    assert _rel(logits, want_l) < 3 * REL_TOL
+
+
+def test_bf16_batched_einsum_equals_per_call_einsum():
+    """The all-calls-in-one-pass einsum (A tile resident) must equal the per-call stage output."""
+    Q, B, H, W = 100, 2, 256, 256
+    sd, mf, mems, head = _setup(Q, B, H, W, 35, 11)
+    mfd, memd = mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems]
+    cls, emb, mask, dbg = head.decoder_forward(mfd, memd, return_debug=True)
+    rt = head._runtime(torch.device(DEV, 0))
+    for j in (0, 3, 9):
+        _, _, m1, _, _, _ = rt.head_call(dbg['x'][j].contiguous(), mfd, j % 3, want_bits=False)
+        assert torch.equal(m1, mask[j]), j
+
+
+def test_bf16_full_size_1024_properties():
+    """1024x1024, Q=100, B=2: per-image independence and run-to-run determinism of the bf16 path,
+    and layer-0 parity with the oracle at full size."""
+    Q, B = 100, 2
+    sd = synth.make_params(seed=0, num_queries=Q)
+    mf, mems = synth.make_inputs(0, B, 1024, 1024)
+    mf, mems = mf.bfloat16(), [m.bfloat16() for m in mems]
+    head = build_head_from_state_dict(sd, Q, 49, 'bf16', DEV)
+    mfd, memd = mf.to(DEV), [m.to(DEV) for m in mems]
+    cls, emb, mask, dbg = head.decoder_forward(mfd, memd, return_debug=True)
+    cls2, emb2, mask2, dbg2 = head.decoder_forward(mfd, memd, return_debug=True)
+    assert all(torch.equal(a, b) for a, b in zip(mask, mask2)) and all(torch.equal(a, b) for a, b in zip(emb, emb2))
+    cls1, emb1, mask1, _ = head.decoder_forward(mfd[:1].contiguous(), [m[:1].contiguous() for m in memd],
+                                                return_debug=True)
+    for j in range(10):
+        assert torch.equal(mask1[j][0], mask[j][0]) and torch.equal(emb1[j][0], emb[j][0])
+    ref0 = O.head_call(sd, sd['query_feat.weight'][None], mf[:1].float(), (32, 32))
+    assert _rel(mask[0][:1], ref0[2]) < REL_TOL
+    agree = float((_unpack(dbg['bitmaps'][0][:1], 1024) == ref0[3]).float().mean())
+    assert agree >= BIT_AGREE, agree
