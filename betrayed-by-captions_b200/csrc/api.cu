@@ -341,8 +341,13 @@ extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, cons
   if (!h || !q || !k || !v || !out) return CGG_ERR_NULL;
   if (batch <= 0 || num_keys <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
-  CU(launch_attention_f32(q, k, v, h->cfg.precision == CGG_BF16, kv_stride, kv_batch_stride, bitmap, all_masked, out,
-                          batch, h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
+  if (h->cfg.precision == CGG_BF16) {
+    int st = tc_attention(h->tc, batch, num_keys, q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_attention: ") + tc_last_error(h->tc));
+    return CGG_OK;
+  }
+  CU(launch_attention_f32(q, k, v, false, kv_stride, kv_batch_stride, bitmap, all_masked, out, batch,
+                          h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
   return CGG_OK;
 }
 

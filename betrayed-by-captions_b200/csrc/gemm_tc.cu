@@ -18,6 +18,7 @@
 #include "gemm_tc.h"
 #include "kernels.h"
 #include "tc_ptx.cuh"
+#include "tc_state.h"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -362,31 +363,10 @@ __global__ void __launch_bounds__(256) all_masked_kernel(const uint32_t* __restr
   if (lane == 0) all_masked[row] = (cnt == K) ? 1 : 0;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
-
-struct TcState {
-  cgg_config cfg;
-  std::string err;
-  EncodeTiledFn encode = nullptr;
-  int H4 = 0, W4 = 0, lh[3] = {0, 0, 0}, lw[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
-  __nv_bfloat16* wkv[3] = {nullptr, nullptr, nullptr};   // (nl*2C, C) bf16
-  __nv_bfloat16* rk[3] = {nullptr, nullptr, nullptr};    // (K_l, nl*C) bf16 key-bias table
-  const float* bkv[3] = {nullptr, nullptr, nullptr};     // (nl*2C) fp32, owned by the handle
-  // N tiling of the mask einsum / bits GEMMs
-  int q_pad = 0, ein_ntile = 0, ein_calls_per_tile = 0, bits_ntile = 0, bits_nt = 0;
-  int rows_per_batch = 0;
-  bool smem_attr_set = false;
-  void free_all() {
-    for (int l = 0; l < 3; ++l) { cudaFree(wkv[l]); cudaFree(rk[l]); wkv[l] = rk[l] = nullptr; }
-  }
-};
 
 namespace {
 
@@ -401,14 +381,6 @@ struct TcWs {  // carving of the caller-provided tc workspace
     total = off;
   }
 };
-
-int tc_fail(TcState* t, int code, const std::string& m) { t->err = m; return code; }
-
-#define TCU(call)                                                                                  \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess) return tc_fail(t, CGG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
 
 // 3-D map over an NCHW feature tensor: dims (pixels, channels, batch), box (64 px, 64 ch, 1)
 int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, int B) {
@@ -492,12 +464,15 @@ TcState* tc_create(const cgg_config& cfg) {
   if (round_up(Q, 16) <= 256) { t->bits_ntile = round_up(Q, 16); t->bits_nt = 1; }
   else { t->bits_ntile = round_up(Q, 32) / 2; t->bits_nt = 2; }
   t->rows_per_batch = calls * t->q_pad;
+  t->live_bytes = 1 << 20;
+  if (cudaMalloc(&t->live_buf, t->live_bytes) != cudaSuccess) { delete t; return nullptr; }
   return t;
 }
 
 void tc_destroy(TcState* t) {
   if (!t) return;
   t->free_all();
+  cudaFree(t->live_buf);
   delete t;
 }
 

@@ -42,4 +42,9 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
 int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const void* mask_features_bf16,
                    void* mask_bf16, long call_stride, void* ws, cudaStream_t s);
 
+// K5 on tensor cores: masked multi-head cross-attention, flash-style over 128-key tiles.
+// q (B,Q,heads*32) fp32 pre-scaled; k, v bf16 rows (b*kv_bstride + key*kv_stride); out fp32.
+int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
+                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, cudaStream_t s);
+
 }  // namespace cgg
