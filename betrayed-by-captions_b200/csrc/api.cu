@@ -290,12 +290,17 @@ static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const 
   float* h2 = at<float>(workspace, ws.h2);
   float* me = mask_embed_out ? mask_embed_out : at<float>(workspace, ws.me);
   // K1: post_norm + the three heads (head.py:734-746)
+  if (c.precision == CGG_BF16) {
+    int st = tc_query_heads(h->tc, w, batch, x, cls, emb, me, at<void>(workspace, ws.tcws), s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_query_heads: ") + tc_last_error(h->tc));
+  } else {
   CU(launch_layernorm(x, nullptr, w->post_norm_w, w->post_norm_b, z, rows, C, 1e-5f, true, s));
   ST(linear_rows(h, s, z, nullptr, 1, w->cls_w, w->cls_b, cls, rows, c.num_classes_p1, C));
   ST(linear_rows(h, s, z, nullptr, 1, w->v2l_w, w->v2l_b, emb, rows, c.d_lang, C));
   ST(linear_rows(h, s, z, nullptr, 1, w->me_w[0], w->me_b[0], h1, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h1, nullptr, 1, w->me_w[1], w->me_b[1], h2, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h2, nullptr, 1, w->me_w[2], w->me_b[2], me, rows, C, C));
+  }
   if (c.precision == CGG_BF16) {
     void* tws = at<void>(workspace, ws.tcws);
 #define TC(call)                                                                                \
@@ -342,11 +347,11 @@ extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, cons
   if (batch <= 0 || num_keys <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   if (h->cfg.precision == CGG_BF16) {
-    int st = tc_attention(h->tc, batch, num_keys, q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, s);
+    int st = tc_attention(h->tc, batch, num_keys, q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, nullptr, s);
     if (st != CGG_OK) return fail(h, st, std::string("tc_attention: ") + tc_last_error(h->tc));
     return CGG_OK;
   }
-  CU(launch_attention_f32(q, k, v, false, kv_stride, kv_batch_stride, bitmap, all_masked, out, batch,
+  CU(launch_attention_f32(q, k, v, false, kv_stride, kv_batch_stride, bitmap, all_masked, out, nullptr, batch,
                           h->cfg.num_queries, num_keys, h->cfg.num_heads, s));
   return CGG_OK;
 }
@@ -363,6 +368,14 @@ extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch,
   const int C = c.embed_dim, Q = c.num_queries, rows = batch * Q, F = c.ffn_dim;
   const int l = layer % CGG_NUM_LEVELS, sl = layer / CGG_NUM_LEVELS, n = h->nl[l];
   const int K = h->lh[l] * h->lw[l];
+  if (c.precision == CGG_BF16) {
+    const long kvs = (long)n * 2 * C, kvb = (long)K * kvs;
+    const __nv_bfloat16* kv = at<__nv_bfloat16>(workspace, ws.kv[l]);
+    int st = tc_decoder_layer(h->tc, w, batch, layer, x_in, kv + (size_t)sl * C, kv + (size_t)(n + sl) * C, kvs, kvb, K,
+                              bitmap, all_masked, x_out, at<void>(workspace, ws.tcws), s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_decoder_layer: ") + tc_last_error(h->tc));
+    return CGG_OK;
+  }
   const cgg_layer_weights& lw = w->layers[layer];
   const float qscale = 1.0f / sqrtf((float)(C / c.num_heads));
   float* qb = at<float>(workspace, ws.qb);
@@ -391,7 +404,7 @@ extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch,
   ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w, lw.self_in_b, qb, rows, C, C, qscale));
   ST(linear_rows(h, s, x1, w->query_embed, Q, lw.self_in_w + (size_t)C * C, lw.self_in_b + C, kb, rows, C, C));
   ST(linear_rows(h, s, x1, nullptr, 1, lw.self_in_w + (size_t)2 * C * C, lw.self_in_b + 2 * C, vb, rows, C, C));
-  CU(launch_attention_f32(qb, kb, vb, false, C, (long)Q * C, nullptr, nullptr, o, batch, Q, Q, c.num_heads, s));
+  CU(launch_attention_f32(qb, kb, vb, false, C, (long)Q * C, nullptr, nullptr, o, nullptr, batch, Q, Q, c.num_heads, s));
   ST(linear_rows(h, s, o, nullptr, 1, lw.self_out_w, lw.self_out_b, t, rows, C, C, 1.f, x1));
   CU(launch_layernorm(t, nullptr, lw.norm_w[1], lw.norm_b[1], x2, rows, C, 1e-5f, true, s));
   // ---- FFN

@@ -31,7 +31,7 @@ constexpr int AT_P_BYTES = 128 * AT_KT * 2;  // 32 KB per P buffer
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnP {
-  const float* q; float* out;
+  const float* q; float* out; __nv_bfloat16* out_bf16;
   const uint32_t* bitmap; const uint8_t* all_masked; const uint8_t* live;
   int Q, K, heads, W32, ntiles, nqt;
 };
@@ -284,10 +284,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
     if (row_ok) {
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);
+      if (p.out) {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      }
+      if (p.out_bf16) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * C + h * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 pk;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(o[8 * i + 2 * j] * inv, o[8 * i + 2 * j + 1] * inv);
+            w[j] = *reinterpret_cast<uint32_t*>(&v2);
+          }
+          dst[i] = pk;
+        }
+      }
     }
   }
   ptx::tc_fence_before();
@@ -340,7 +356,8 @@ int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_str
 }  // namespace
 
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
-                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, cudaStream_t s) {
+                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, __nv_bfloat16* out_bf16,
+                 cudaStream_t s) {
   const int Q = t->cfg.num_queries, heads = t->cfg.num_heads, C = t->cfg.embed_dim;
   const int ntiles = (num_keys + AT_KT - 1) / AT_KT, nqt = (Q + 127) / 128;
   if ((size_t)batch * nqt * ntiles > t->live_bytes) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many key tiles");
@@ -354,7 +371,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   count_launch();
   TCU(cudaGetLastError());
   AttnP p;
-  p.q = q; p.out = out; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
+  p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + (2 * AT_STAGES + 6) * 8 + 16;
   if (!t->attn_attr_set) {

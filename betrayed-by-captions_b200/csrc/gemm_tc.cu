@@ -33,13 +33,20 @@ constexpr int TC_BM = 128;      // pixels per CTA (UMMA M)
 constexpr int TC_BK = 64;       // channels per smem chunk (one 128B swizzle row of bf16 K... see below)
 constexpr int A_CHUNK_BYTES = 2 * 64 * 64 * 2;   // 2 pixel groups x 64 ch x 64 px x bf16 = 16 KB
 
-enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2 };
+enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2, EPI_LINEAR = 3, EPI_LN = 4 };
 
 struct TcGemmP {
   int NT, N_TILE, KC, stages;
   int a_resident;        // 1: the whole A tile (KC chunks) stays in smem for all NT tiles; 0: A chunks stream with B
+  int a_kmajor;          // 0: A is an NCHW feature map (pixels contiguous); 1: A is [rows][K] activations (K contiguous)
+  int k_identity;        // 1: chunk kc sits at K coordinate kc*64 for both operands (kcoord tables unused)
   int a_kcoord[12];      // channel coordinate of A chunk kc   (split-precision GEMMs revisit chunks)
   int b_kcoord[12];      // K coordinate of B chunk kc
+  // EPI_LINEAR: up to 3 column segments of  (acc + bias [+ rowbias]) * alpha  [relu]
+  TcSeg seg[3]; int nseg; const float* lin_bias;
+  // EPI_LN: y = LayerNorm(acc + bias + res) over the 256 columns of the row
+  const float* ln_res; const float* ln_w; const float* ln_b; float* ln_out; __nv_bfloat16* ln_out_bf16;
+  __nv_bfloat16* ln_out_bf16_q; const float* ln_qe; int ln_Q;
   int b_row0;            // first B row (e.g. call_idx * q_pad)
   int b_rows_per_batch;  // B row offset per batch index (0: weights shared by the batch)
   int acc_stride;        // TMEM columns between the two accumulator buffers
@@ -65,6 +72,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,6 +96,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = b_empty + p.stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* ln_part = reinterpret_cast<float*>(tmem_slot + 4);   // [128 rows][2 halves][sum, sumsq] (EPI_LN)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, batch = blockIdx.y;
@@ -105,12 +121,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer
+      // A chunk = 128 rows x 64 K: an NCHW operand comes as two (64 px x 64 ch) boxes, an
+      // activation operand as one (64 k x 128 rows) box; 16 KB either way.
+      auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
+        const int kco = p.k_identity ? kc * TC_BK : p.a_kcoord[kc];
+        if (p.a_kmajor) {
+          ptx::tma_load_2d(dst, &tmA, bar, kco, m_tile * TC_BM);
+        } else {
+          for (int g = 0; g < 2; ++g)
+            ptx::tma_load_3d(dst + g * (A_CHUNK_BYTES / 2), &tmA, bar, m_tile * TC_BM + g * 64, kco, batch);
+        }
+      };
       if (p.a_resident) {
         ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
-        for (int kc = 0; kc < p.KC; ++kc)
-          for (int g = 0; g < 2; ++g)
-            ptx::tma_load_3d(sA + kc * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, a_full,
-                             m_tile * TC_BM + g * 64, p.a_kcoord[kc], batch);
+        for (int kc = 0; kc < p.KC; ++kc) load_a(sA + kc * A_CHUNK_BYTES, a_full, kc);
       }
       int it = 0;
       for (int t = 0; t < p.NT; ++t)
@@ -120,18 +144,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&b_empty[s], ph ^ 1u);
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
-          if (!p.a_resident)
-            for (int g = 0; g < 2; ++g)
-              ptx::tma_load_3d(stage + g * (A_CHUNK_BYTES / 2), &tmA, &b_full[s], m_tile * TC_BM + g * 64,
-                               p.a_kcoord[kc], batch);
-          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.b_kcoord[kc],
+          if (!p.a_resident) load_a(stage, &b_full[s], kc);
+          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? kc * TC_BK : p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
-      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !p.a_kmajor, /*B K-major*/ false);
       if (p.a_resident) {
         ptx::mbar_wait(a_full, 0);
         ptx::tc_fence_after();
@@ -154,7 +175,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < TC_BK / 16; ++k) {
             // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
             // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
-            const uint64_t adesc = ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
+            const uint64_t adesc = p.a_kmajor ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
+                                              : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
             const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
             ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
           }
@@ -176,6 +198,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&acc_full[buf], use & 1u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      float ln_s = 0.f, ln_ss = 0.f;
       for (int c = half; c < chunks; c += 2) {
         float v[16];
         ptx::tmem_ld16(taddr + (uint32_t)(c * 16), v);
@@ -228,6 +251,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[0] = o[0];
             dst[1] = o[1];
           }
+        } else if (p.epi == EPI_LINEAR) {
+          // row-major outputs in up to 3 column segments (16-aligned starts): fp32 or bf16
+          if (m_ok) {
+#pragma unroll 1
+            for (int sgi = 0; sgi < p.nseg; ++sgi) {
+              const TcSeg& sg = p.seg[sgi];
+              const int nn0 = n0 - sg.col0;
+              if (nn0 < 0 || nn0 >= sg.ncols) continue;
+              float y[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x = v[i] + __ldg(p.lin_bias + n0 + i);
+                if (sg.rowbias && nn0 + i < sg.ncols) x += __ldg(sg.rowbias + (long)(m % sg.rb_mod) * sg.rb_ld + nn0 + i);
+                x *= sg.alpha;
+                y[i] = sg.relu ? fmaxf(x, 0.f) : x;
+              }
+              const bool full = nn0 + 16 <= sg.ncols;
+              if (sg.is_bf16 && sg.split) {
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(sg.ptr) + (long)m * sg.ld + nn0;
+                uint4 oh[2], ol[2];
+                uint32_t* hw = reinterpret_cast<uint32_t*>(oh);
+                uint32_t* lw2 = reinterpret_cast<uint32_t*>(ol);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __nv_bfloat16 h0, l0, h1, l1;
+                  split_bf16(y[2 * i], h0, l0);
+                  split_bf16(y[2 * i + 1], h1, l1);
+                  hw[i] = pack2(h0, h1);
+                  lw2[i] = pack2(l0, l1);
+                }
+                reinterpret_cast<uint4*>(dst)[0] = oh[0];
+                reinterpret_cast<uint4*>(dst)[1] = oh[1];
+                reinterpret_cast<uint4*>(dst + 256)[0] = ol[0];
+                reinterpret_cast<uint4*>(dst + 256)[1] = ol[1];
+              } else if (sg.is_bf16) {
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(sg.ptr) + (long)m * sg.ld + nn0;
+                if (full && (sg.ld & 7) == 0) {
+                  uint4 o[2];
+                  uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
+                  reinterpret_cast<uint4*>(dst)[0] = o[0];
+                  reinterpret_cast<uint4*>(dst)[1] = o[1];
+                } else {
+                  for (int i = 0; i < 16; ++i)
+                    if (nn0 + i < sg.ncols) dst[i] = __float2bfloat16_rn(y[i]);
+                }
+              } else {
+                float* dst = static_cast<float*>(sg.ptr) + (long)m * sg.ld + nn0;
+                if (full && (sg.ld & 3) == 0) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4*>(dst)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                } else {
+                  for (int i = 0; i < 16; ++i)
+                    if (nn0 + i < sg.ncols) dst[i] = y[i];
+                }
+              }
+            }
+          }
+        } else if (p.epi == EPI_LN) {
+          // pass 1 of the fused residual + LayerNorm: partial sum / sum of squares of this warp's columns
+          if (m_ok) {
+            const float* res = p.ln_res + (long)m * 256 + n0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = v[i] + __ldg(p.lin_bias + n0 + i) + __ldg(res + i);
+              ln_s += x;
+              ln_ss = fmaf(x, x, ln_ss);
+            }
+          }
         } else {  // EPI_BITS
           const int wi = (m_tile * TC_BM + quarter * 32) >> 5;
 #pragma unroll
@@ -236,6 +330,57 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t word = __ballot_sync(0xffffffffu, mk);
             const int q = n0 + i;
             if (lane == 0 && q < p.Q && wi < p.W32) p.bitmap[((long)batch * p.Q + q) * p.W32 + wi] = word;
+          }
+        }
+      }
+      if (p.epi == EPI_LN) {
+        // exchange the two half-row partials between the warp pair, then pass 2: normalise + store
+        const int row = quarter * 32 + lane;
+        ln_part[(row * 2 + half) * 2] = ln_s;
+        ln_part[(row * 2 + half) * 2 + 1] = ln_ss;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float sum = ln_part[row * 4] + ln_part[row * 4 + 2];
+        const float sq = ln_part[row * 4 + 1] + ln_part[row * 4 + 3];
+        const float mean = sum * (1.0f / 256.0f);
+        const float var = fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // (tcgen05.ld is warp-collective: every lane runs the loop, only the memory traffic is guarded)
+        for (int c = half; c < chunks; c += 2) {
+          float v[16];
+          ptx::tmem_ld16(taddr + (uint32_t)(c * 16), v);
+          if (m_ok) {
+            const int n0 = c * 16;
+            const float* res = p.ln_res + (long)m * 256 + n0;
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float x = v[i] + __ldg(p.lin_bias + n0 + i) + __ldg(res + i);
+              y[i] = (x - mean) * rstd * __ldg(p.ln_w + n0 + i) + __ldg(p.ln_b + n0 + i);
+            }
+            float* dst = p.ln_out + (long)m * 256 + n0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+            if (p.ln_out_bf16) {
+              uint4 o[2];
+              uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
+              uint4* d2 = reinterpret_cast<uint4*>(p.ln_out_bf16 + (long)m * 256 + n0);
+              d2[0] = o[0];
+              d2[1] = o[1];
+            }
+            if (p.ln_out_bf16_q) {
+              const float* qe = p.ln_qe + (long)(m % p.ln_Q) * 256 + n0;
+              uint4 o[2];
+              uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                ow[i] = pack_bf16x2(y[2 * i] + __ldg(qe + 2 * i), y[2 * i + 1] + __ldg(qe + 2 * i + 1));
+              uint4* d2 = reinterpret_cast<uint4*>(p.ln_out_bf16_q + (long)m * 256 + n0);
+              d2[0] = o[0];
+              d2[1] = o[1];
+            }
           }
         }
       }
@@ -257,14 +402,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the three level sizes for the exact ratios 8/4/2: each is the mean of the central 2x2 of its
 // block, evaluated in the reference's order 0.5*(0.5a+0.5b)+0.5*(0.5c+0.5d) in fp32.
 // One thread per 8x8 block of one (image, channel) plane.
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
 // Outputs are hi/lo bf16 pairs (x ~= hi + lo to ~16 mantissa bits): per image the resampled map is
 // stored as (2C, K_l): channels [0,C) = hi, [C,2C) = lo.
 __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int C, int H4,
@@ -370,18 +507,6 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 namespace {
 
-struct TcWs {  // carving of the caller-provided tc workspace
-  size_t me_all, fds[3], total;
-  void carve(const TcState* t, int B) {
-    size_t off = 0;
-    auto take = [&](size_t b) { size_t o = off; off += align256(b); return o; };
-    const int C = t->cfg.embed_dim;
-    me_all = take((size_t)B * t->rows_per_batch * 2 * C * 2 + 128 * 1024);   // [hi|lo] rows + 128 slack rows
-    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * 2 * C * t->lh[l] * t->lw[l] * 2);   // hi, lo planes
-    total = off;
-  }
-};
-
 // 3-D map over an NCHW feature tensor: dims (pixels, channels, batch), box (64 px, 64 ch, 1)
 int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, int B) {
   if ((pixels * 2) % 16 != 0)
@@ -418,14 +543,14 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.tmem_cols = 2 * p.acc_stride;
   const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
-  if (p.KC > 12) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
+  if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
   const size_t budget = 200 * 1024;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
   if (stages < 2) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 16;
+  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 16 + 2048 + 64;
   if (!t->smem_attr_set) {
     TCU(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     t->smem_attr_set = true;
@@ -472,6 +597,7 @@ TcState* tc_create(const cgg_config& cfg) {
 void tc_destroy(TcState* t) {
   if (!t) return;
   t->free_all();
+  t->free_packed();
   cudaFree(t->live_buf);
   delete t;
 }
@@ -501,7 +627,6 @@ int tc_q_pad(const TcState* t) { return t ? t->q_pad : 0; }
 
 int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, const int* lw, const int* nl,
                float* const* wkv_f32, float* const* rk_f32, float* const* bkv_f32, cudaStream_t s) {
-  (void)w;
   const int C = t->cfg.embed_dim;
   const int ratio[3] = {8, 4, 2};
   for (int l = 0; l < 3; ++l)
@@ -526,7 +651,7 @@ int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, 
     TCU(launch_cast_bf16(rk_f32[l], t->rk[l], (size_t)lh[l] * lw[l] * nl[l] * C, s));
     t->bkv[l] = bkv_f32[l];
   }
-  return CGG_OK;
+  return tc_pack_weights(t, w, s);
 }
 
 int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, cudaStream_t s) {
@@ -652,6 +777,77 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE);
   if (st != CGG_OK) return st;
   return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s);
+}
+
+// ------------------------------------------------------------------ small-M linear layers
+// y = A[M,K] W[N,K]^T (+ bias ...) with both operands bf16 K-major through TMA.  Rows are the
+// flattened (image, query) pairs; 128 rows per CTA, N walked in tiles of <= 256.
+namespace {
+int make_map_act(TcState* t, CUtensorMap* m, const void* base, long rows, int K) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = t->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: " + std::to_string((int)r));
+  return CGG_OK;
+}
+
+int pick_ntile(int n_padded) {   // largest tile <= 256 (multiple of 16) that divides the padded width
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (n_padded % nt == 0) return nt;
+  return 16;
+}
+}  // namespace
+
+int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k) {
+  if (K % TC_BK != 0 || n_padded % 16 != 0 || nsegs < 1 || nsegs > 3) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear shape");
+  if (split_k && K != 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "split-precision linear needs K = 256");
+  const int row_len = split_k ? 2 * K : K;
+  CUtensorMap mA, mB;
+  int st = make_map_act(t, &mA, A, M, row_len);
+  if (st != CGG_OK) return st;
+  TcGemmP p = {};
+  p.N_TILE = pick_ntile(n_padded);
+  st = make_map_B(t, &mB, W, n_padded, row_len, p.N_TILE);
+  if (st != CGG_OK) return st;
+  p.NT = n_padded / p.N_TILE; p.KC = K / TC_BK;
+  p.a_kmajor = 1; p.k_identity = 1;
+  if (split_k) {
+    p.k_identity = 0; p.KC = 3 * K / TC_BK;
+    const int cpc = K / TC_BK;
+    for (int kc = 0; kc < p.KC; ++kc) {
+      const int term = kc / cpc, j = (kc % cpc) * TC_BK;
+      p.a_kcoord[kc] = (term == 1 ? K : 0) + j;     // hi, lo, hi
+      p.b_kcoord[kc] = (term == 2 ? K : 0) + j;     // hi, hi, lo
+    }
+  }
+  p.a_resident = (p.NT > 1 && p.KC <= 4) ? 1 : 0;
+  p.epi = EPI_LINEAR; p.M_valid = M;
+  p.nseg = nsegs; p.lin_bias = bias;
+  for (int i = 0; i < nsegs; ++i) p.seg[i] = segs[i];
+  return launch_tc_gemm(t, mA, mB, p, (M + TC_BM - 1) / TC_BM, 1, s);
+}
+
+int tc_linear_ln(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
+                 const float* res, const float* ln_w, const float* ln_b, float* out_f32, __nv_bfloat16* out_bf16,
+                 __nv_bfloat16* out_bf16_q, const float* qe, int Q, cudaStream_t s) {
+  if (K % TC_BK != 0 || t->cfg.embed_dim != 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear_ln shape");
+  CUtensorMap mA, mB;
+  int st = make_map_act(t, &mA, A, M, K);
+  if (st != CGG_OK) return st;
+  TcGemmP p = {};
+  p.N_TILE = 256; p.NT = 1; p.KC = K / TC_BK;
+  st = make_map_B(t, &mB, W, 256, K, 256);
+  if (st != CGG_OK) return st;
+  p.a_kmajor = 1; p.k_identity = 1; p.a_resident = 0;
+  p.epi = EPI_LN; p.M_valid = M;
+  p.lin_bias = bias; p.ln_res = res; p.ln_w = ln_w; p.ln_b = ln_b;
+  p.ln_out = out_f32; p.ln_out_bf16 = out_bf16; p.ln_out_bf16_q = out_bf16_q; p.ln_qe = qe; p.ln_Q = Q > 0 ? Q : 1;
+  return launch_tc_gemm(t, mA, mB, p, (M + TC_BM - 1) / TC_BM, 1, s);
 }
 
 }  // namespace cgg

@@ -3,10 +3,22 @@
 #pragma once
 #include "../../include/cgg_b200.h"
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 namespace cgg {
 
 struct TcState;
+
+// One column segment of a row-major GEMM output: columns [col0, col0+ncols) of
+//   y = (acc + bias[n] + rowbias[(m % rb_mod), n-col0]) * alpha, optional ReLU, fp32 or bf16.
+struct TcSeg {
+  int col0, ncols;
+  void* ptr; long ld;
+  int is_bf16, relu;
+  int split;      // bf16 only: write x as a hi/lo pair, hi at column n, lo at column 256+n of a 512-wide row
+  float alpha;
+  const float* rowbias; int rb_mod; long rb_ld;
+};
 
 TcState* tc_create(const cgg_config& cfg);
 void tc_destroy(TcState* t);
@@ -42,9 +54,28 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
 int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const void* mask_features_bf16,
                    void* mask_bf16, long call_stride, void* ws, cudaStream_t s);
 
+// Small-M linear layers on tensor cores (rows = flattened (image, query)); bf16 K-major operands.
+// split_k: A and W rows are [hi(256) | lo(256)] bf16 pairs and the contraction is evaluated as
+// hi.hi + lo.hi + hi.lo (fp32 accumulate), i.e. with ~16 mantissa bits per operand (K must be 256).
+int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false);
+// out = LayerNorm(A W^T + bias + res) with W (256,K); also bf16(out) and bf16(out + qe[m % Q]) copies.
+int tc_linear_ln(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
+                 const float* res, const float* ln_w, const float* ln_b, float* out_f32, __nv_bfloat16* out_bf16,
+                 __nv_bfloat16* out_bf16_q, const float* qe, int Q, cudaStream_t s);
+
+// The bf16-mode decoder layer (K5 + K6) and the query heads (K1) built from the pieces above.
+int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
+                     const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,
+                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s);
+int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, float* cls, float* emb, float* me,
+                   void* ws, cudaStream_t s);
+
 // K5 on tensor cores: masked multi-head cross-attention, flash-style over 128-key tiles.
-// q (B,Q,heads*32) fp32 pre-scaled; k, v bf16 rows (b*kv_bstride + key*kv_stride); out fp32.
+// q (B,Q,heads*32) fp32 pre-scaled; k, v bf16 rows (b*kv_bstride + key*kv_stride); out fp32 and/or bf16
+// (either may be null).
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
-                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, cudaStream_t s);
+                 long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out,
+                 __nv_bfloat16* out_bf16, cudaStream_t s);
 
 }  // namespace cgg

@@ -51,7 +51,7 @@ cudaError_t launch_mask_bits(const float* mask_pred, int rows, int H4, int W4, i
 // (b*kv_bstride + key*kv_stride); bitmap (B,Q,ceil(K/32)) or nullptr.
 cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, bool kv_bf16, long kv_stride,
                                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked,
-                                 float* out, int B, int Q, int K, int heads, cudaStream_t s);
+                                 float* out, __nv_bfloat16* out_bf16, int B, int Q, int K, int heads, cudaStream_t s);
 
 // K7 grounding: per (caption i, image j) pair distances, then the contrastive reduction.
 cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const int64_t* cap_mask,
@@ -60,6 +60,8 @@ cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const in
 cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
                                     int Bg, int T, float loss_weight, float* loss, cudaStream_t s);
 
+// fp32 (rows, cols) -> bf16 (rows, 2*cols) hi/lo pairs: [hi | lo] per row
+cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s);
 // fp32 -> bf16 cast (n elements)
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
 

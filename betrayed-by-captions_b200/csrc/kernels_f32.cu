@@ -244,7 +244,8 @@ template <typename KV>
 __global__ void __launch_bounds__(128) attention_f32_kernel(
     const float* __restrict__ q, const KV* __restrict__ k, const KV* __restrict__ v,
     long kv_stride, long kv_bstride, const uint32_t* __restrict__ bitmap,
-    const uint8_t* __restrict__ all_masked, float* __restrict__ out, int Q, int K, int heads) {
+    const uint8_t* __restrict__ all_masked, float* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16, int Q,
+    int K, int heads) {
   __shared__ float qs[AQT][AHD];
   __shared__ float Ks[AKT][AHD + 1];
   __shared__ __align__(16) float Vs[AKT][AHD];
@@ -339,23 +340,27 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(
   }
   if (q0 + pq < Q) {
     const float inv = (l > 0.f) ? 1.0f / l : 0.f;
-    float* op = out + ((long)b * Q + q0 + pq) * C + h * AHD + pd;
-    op[0] = o[0] * inv; op[1] = o[1] * inv; op[2] = o[2] * inv; op[3] = o[3] * inv;
+    const long off = ((long)b * Q + q0 + pq) * C + h * AHD + pd;
+    if (out) { out[off] = o[0] * inv; out[off + 1] = o[1] * inv; out[off + 2] = o[2] * inv; out[off + 3] = o[3] * inv; }
+    if (out_bf16) {
+      out_bf16[off] = __float2bfloat16_rn(o[0] * inv); out_bf16[off + 1] = __float2bfloat16_rn(o[1] * inv);
+      out_bf16[off + 2] = __float2bfloat16_rn(o[2] * inv); out_bf16[off + 3] = __float2bfloat16_rn(o[3] * inv);
+    }
   }
 }
 
 cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, bool kv_bf16, long kv_stride,
                                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked,
-                                 float* out, int B, int Q, int K, int heads, cudaStream_t s) {
+                                 float* out, __nv_bfloat16* out_bf16, int B, int Q, int K, int heads, cudaStream_t s) {
   if (B <= 0 || Q <= 0) return cudaSuccess;
   dim3 grid((Q + AQT - 1) / AQT, heads, B);
   if (kv_bf16)
     attention_f32_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(q, static_cast<const __nv_bfloat16*>(k),
                                                              static_cast<const __nv_bfloat16*>(v), kv_stride, kv_bstride,
-                                                             bitmap, all_masked, out, Q, K, heads);
+                                                             bitmap, all_masked, out, out_bf16, Q, K, heads);
   else
     attention_f32_kernel<float><<<grid, 128, 0, s>>>(q, static_cast<const float*>(k), static_cast<const float*>(v),
-                                                     kv_stride, kv_bstride, bitmap, all_masked, out, Q, K, heads);
+                                                     kv_stride, kv_bstride, bitmap, all_masked, out, out_bf16, Q, K, heads);
   count_launch();
   return cudaGetLastError();
 }
@@ -503,6 +508,24 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void cast_bf16_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n, int cols) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long r = i / cols;
+  const int c = (int)(i % cols);
+  const float x = in[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  out[r * 2 * cols + c] = hi;
+  out[r * 2 * cols + cols + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s) {
+  const long n = (long)rows * cols;
+  if (n == 0) return cudaSuccess;
+  cast_bf16_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, cols);
   count_launch();
   return cudaGetLastError();
 }

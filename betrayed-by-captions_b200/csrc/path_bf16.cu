@@ -1,0 +1,228 @@
+// Throughput-mode (CGG_BF16) orchestration of the query-side ("small-M") work: every linear layer
+// of the decoder layer and of the query heads runs on the tcgen05 GEMM (gemm_tc.cu) with bf16
+// K-major activations through TMA; bias / scale / ReLU / residual + LayerNorm live in the GEMM
+// epilogues.  The decoder state x stays fp32 between layers (residual stream); only GEMM operands
+// are rounded to bf16.
+#include "gemm_tc.h"
+#include "kernels.h"
+#include "tc_state.h"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace cgg {
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// dst = bf16(x + qe[row % Q])
+__global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __restrict__ qe,
+                                   __nv_bfloat16* __restrict__ dst, long total, int per /* Q*C */) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const float4 a = *reinterpret_cast<const float4*>(x + i);
+  const float4 b = *reinterpret_cast<const float4*>(qe + (i % per));
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x + b.x, a.y + b.y), hi = __floats2bfloat162_rn(a.z + b.z, a.w + b.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst + i) = pk;
+}
+
+// post_norm: z = LayerNorm(x) rows of 256 as bf16 hi/lo pairs, one warp per row
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ b,
+                                                             __nv_bfloat16* __restrict__ y, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)row * 256) + lane * 2;
+  const float4 a = xr[0], c = xr[1];
+  float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 256.0f) + 1e-5f);
+  const int n0 = lane * 8;
+  uint4 pk, pl;
+  uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+  uint32_t* plw = reinterpret_cast<uint32_t*>(&pl);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float y0 = (v[2 * i] - mu) * rstd * w[n0 + 2 * i] + b[n0 + 2 * i];
+    const float y1 = (v[2 * i + 1] - mu) * rstd * w[n0 + 2 * i + 1] + b[n0 + 2 * i + 1];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+    pw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    plw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  // row = [hi(256) | lo(256)]: operand of the split-precision head GEMMs
+  *reinterpret_cast<uint4*>(y + (long)row * 512 + n0) = pk;
+  *reinterpret_cast<uint4*>(y + (long)row * 512 + 256 + n0) = pl;
+}
+
+template <typename T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+TcSeg seg(int col0, int ncols, void* ptr, long ld, bool bf16, bool relu, float alpha = 1.f, const float* rowbias = nullptr,
+          int rb_mod = 1, long rb_ld = 0, bool split = false) {
+  TcSeg s;
+  s.col0 = col0; s.ncols = ncols; s.ptr = ptr; s.ld = ld; s.is_bf16 = bf16 ? 1 : 0; s.relu = relu ? 1 : 0;
+  s.split = split ? 1 : 0;
+  s.alpha = alpha; s.rowbias = rowbias; s.rb_mod = rb_mod; s.rb_ld = rb_ld;
+  return s;
+}
+
+// CGG_DEBUG_SYNC=1: synchronise after every stage so a faulting kernel is named in the error.
+inline bool debug_sync_on() {
+  static const bool on = getenv("CGG_DEBUG_SYNC") != nullptr;
+  return on;
+}
+#define TST(call)                                                                                      \
+  do {                                                                                                 \
+    int st__ = (call);                                                                                 \
+    if (st__ != CGG_OK) return st__;                                                                   \
+    if (debug_sync_on()) {                                                                             \
+      cudaError_t e2__ = cudaStreamSynchronize(s);                                                     \
+      if (e2__ != cudaSuccess)                                                                         \
+        return tc_fail(t, CGG_ERR_CUDA, std::string("after ") + #call + ": " + cudaGetErrorString(e2__)); \
+    }                                                                                                  \
+  } while (0)
+
+}  // namespace
+
+// bf16 copies of every small-M weight, in the row order the fused GEMMs want.
+int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
+  const cgg_config& c = t->cfg;
+  const int C = c.embed_dim, F = c.ffn_dim, Q = c.num_queries, L = c.num_layers;
+  const int nh = round_up(c.d_lang + C + c.num_classes_p1, 256);
+  if (c.d_lang % 16 != 0) return tc_fail(t, CGG_ERR_UNSUPPORTED, "d_lang must be a multiple of 16");
+  if (!t->packed_alloc || t->nh_padded != nh) {
+    t->free_packed();
+    for (int i = 0; i < L; ++i) {
+      TcState::LayerW& l = t->pl[i];
+      TCU(cudaMalloc(&l.wq_c, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.wo_c, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.wqkv_s, (size_t)3 * C * C * 2));
+      TCU(cudaMalloc(&l.wo_s, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.w1, (size_t)F * C * 2));
+      TCU(cudaMalloc(&l.w2, (size_t)C * F * 2));
+      TCU(cudaMalloc(&l.rowbias_v, (size_t)Q * C * 4));
+    }
+    TCU(cudaMalloc(&t->wh, (size_t)nh * 2 * C * 2));       // hi/lo rows: the head chain runs at split precision
+    TCU(cudaMalloc(&t->wme1, (size_t)C * 2 * C * 2));
+    TCU(cudaMalloc(&t->wme2, (size_t)C * 2 * C * 2));
+    TCU(cudaMalloc(&t->bias_h, (size_t)nh * 4));
+    t->nh_padded = nh;
+    t->packed_alloc = true;
+  }
+  for (int i = 0; i < L; ++i) {
+    const cgg_layer_weights& lw = w->layers[i];
+    TcState::LayerW& l = t->pl[i];
+    TCU(launch_cast_bf16(lw.cross_in_w, l.wq_c, (size_t)C * C, s));                 // Wq of the cross-attention
+    TCU(launch_cast_bf16(lw.cross_out_w, l.wo_c, (size_t)C * C, s));
+    TCU(launch_cast_bf16(lw.self_in_w, l.wqkv_s, (size_t)3 * C * C, s));            // [Wq; Wk; Wv] as stored
+    TCU(launch_cast_bf16(lw.self_out_w, l.wo_s, (size_t)C * C, s));
+    TCU(launch_cast_bf16(lw.ffn_w1, l.w1, (size_t)F * C, s));
+    TCU(launch_cast_bf16(lw.ffn_w2, l.w2, (size_t)C * F, s));
+    // v = x Wv^T + bv = (x + qe) Wv^T + bv - qe Wv^T : the last term is a per-query constant
+    GemmF32 g;
+    g.A = w->query_embed; g.sAm = C; g.sAk = 1;
+    g.W = lw.self_in_w + (size_t)2 * C * C; g.sWn = C; g.sWk = 1;
+    g.C = l.rowbias_v; g.sCm = C; g.sCn = 1;
+    g.M = Q; g.N = C; g.K = C; g.alpha = -1.f;
+    TCU(launch_gemm_f32(g, s));
+  }
+  TCU(cudaMemsetAsync(t->wh, 0, (size_t)nh * 2 * C * 2, s));
+  TCU(cudaMemsetAsync(t->bias_h, 0, (size_t)nh * 4, s));
+  TCU(launch_cast_bf16_split(w->v2l_w, t->wh, c.d_lang, C, s));
+  TCU(launch_cast_bf16_split(w->me_w[0], t->wh + (size_t)c.d_lang * 2 * C, C, C, s));
+  TCU(launch_cast_bf16_split(w->cls_w, t->wh + (size_t)(c.d_lang + C) * 2 * C, c.num_classes_p1, C, s));
+  TCU(cudaMemcpyAsync(t->bias_h, w->v2l_b, (size_t)c.d_lang * 4, cudaMemcpyDeviceToDevice, s));
+  TCU(cudaMemcpyAsync(t->bias_h + c.d_lang, w->me_b[0], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  TCU(cudaMemcpyAsync(t->bias_h + c.d_lang + C, w->cls_b, (size_t)c.num_classes_p1 * 4, cudaMemcpyDeviceToDevice, s));
+  TCU(launch_cast_bf16_split(w->me_w[1], t->wme1, C, C, s));
+  TCU(launch_cast_bf16_split(w->me_w[2], t->wme2, C, C, s));
+  return CGG_OK;
+}
+
+// K1: post_norm -> [v2l_transform | mask_embed.0 + ReLU | cls_embed] in one GEMM -> mask_embed.2 -> .4
+int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, float* cls, float* emb, float* me,
+                   void* ws, cudaStream_t s) {
+  const cgg_config& c = t->cfg;
+  const int C = c.embed_dim, M = batch * c.num_queries;
+  TcWs o;
+  o.carve(t, batch);
+  __nv_bfloat16* zb = at<__nv_bfloat16>(ws, o.zb);
+  __nv_bfloat16* h1b = at<__nv_bfloat16>(ws, o.h1b);
+  __nv_bfloat16* h2b = at<__nv_bfloat16>(ws, o.h2b);
+  layernorm_bf16_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, w->post_norm_w, w->post_norm_b, zb, M);
+  count_launch();
+  TCU(cudaGetLastError());
+  // split precision (hi/lo bf16 pairs, 3 MMAs per product): the mask embedding feeds the
+  // sigmoid<0.5 threshold, where plain bf16 operands flip ~0.15% of the attention-mask bits
+  TcSeg sh[3] = {seg(0, c.d_lang, emb, c.d_lang, false, false),
+                 seg(c.d_lang, C, h1b, 2 * C, true, true, 1.f, nullptr, 1, 0, /*split=*/true),
+                 seg(c.d_lang + C, c.num_classes_p1, cls, c.num_classes_p1, false, false)};
+  TST(tc_linear(t, zb, M, C, t->wh, t->nh_padded, t->bias_h, sh, 3, s, true));
+  TcSeg s2[1] = {seg(0, C, h2b, 2 * C, true, true, 1.f, nullptr, 1, 0, true)};
+  TST(tc_linear(t, h1b, M, C, t->wme1, C, w->me_b[1], s2, 1, s, true));
+  TcSeg s3[1] = {seg(0, C, me, C, false, false)};
+  TST(tc_linear(t, h2b, M, C, t->wme2, C, w->me_b[2], s3, 1, s, true));
+  return CGG_OK;
+}
+
+// K5 + K6: one DetrTransformerDecoderLayer (head.py:829-840), bf16 operands on tensor cores.
+int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
+                     const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,
+                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s) {
+  const cgg_config& c = t->cfg;
+  const int C = c.embed_dim, Q = c.num_queries, M = batch * Q, F = c.ffn_dim;
+  const cgg_layer_weights& lw = w->layers[layer];
+  const TcState::LayerW& pw = t->pl[layer];
+  const float qscale = 1.0f / sqrtf((float)(C / c.num_heads));
+  TcWs o;
+  o.carve(t, batch);
+  __nv_bfloat16* xqb = at<__nv_bfloat16>(ws, o.xqb);
+  __nv_bfloat16* xb = at<__nv_bfloat16>(ws, o.xb);
+  __nv_bfloat16* ob = at<__nv_bfloat16>(ws, o.ob);
+  __nv_bfloat16* fb = at<__nv_bfloat16>(ws, o.fb);
+  float* qf = at<float>(ws, o.qf);
+  float* qs = at<float>(ws, o.qs);
+  float* kvs = at<float>(ws, o.kvs);
+  float* x1 = at<float>(ws, o.x1);
+  float* x2 = at<float>(ws, o.x2);
+  // ---- cross-attention: q = ((x + query_embed) Wq^T + bq) / sqrt(d)
+  const long total = (long)M * C;
+  add_qe_cast_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(x_in, w->query_embed, xqb, total, Q * C);
+  count_launch();
+  TCU(cudaGetLastError());
+  TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
+  TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
+  TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s));
+  // x1 = LN(x + o Wo^T + bo);  also bf16(x1 + query_embed) for the self-attention projections
+  TST(tc_linear_ln(t, ob, M, C, pw.wo_c, lw.cross_out_b, x_in, lw.norm_w[0], lw.norm_b[0], x1, nullptr, xqb,
+                   w->query_embed, Q, s));
+  // ---- self-attention: q, k from x1 + query_embed, v from x1 (per-query constant folded into rowbias_v)
+  TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvs, 2 * C, false, false),
+                 seg(2 * C, C, kvs + C, 2 * C, false, false, 1.f, pw.rowbias_v, Q, C)};
+  TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s));
+  TCU(launch_attention_f32(qs, kvs, kvs + C, false, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, batch, Q, Q,
+                           c.num_heads, s));
+  TST(tc_linear_ln(t, ob, M, C, pw.wo_s, lw.self_out_b, x1, lw.norm_w[1], lw.norm_b[1], x2, xb, nullptr, nullptr, 0, s));
+  // ---- FFN
+  TcSeg sf[1] = {seg(0, F, fb, F, true, true)};
+  TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s));
+  TST(tc_linear_ln(t, fb, M, F, pw.w2, lw.ffn_b2, x2, lw.norm_w[2], lw.norm_b[2], x_out, nullptr, nullptr, nullptr, 0, s));
+  return CGG_OK;
+}
+
+}  // namespace cgg
