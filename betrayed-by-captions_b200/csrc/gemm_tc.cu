@@ -14,7 +14,7 @@
 // stages; accumulators are double-buffered in TMEM so the epilogue warps drain tile t while the
 // single MMA-issuing thread runs tile t+1.
 //   warp 0 : TMA producer (one lane)        warp 1 : TMEM alloc + tcgen05.mma issue (one lane)
-//   warps 2..9 : epilogue (tcgen05.ld -> registers -> global), 2 warps per TMEM lane quarter
+//   warps 2..17 : epilogue (tcgen05.ld -> registers -> global), 4 warps per TMEM lane quarter
 #include "gemm_tc.h"
 #include "kernels.h"
 #include "tc_ptx.cuh"
@@ -23,17 +23,19 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace cgg {
 
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps
 constexpr int TC_BM = 128;      // pixels per CTA (UMMA M)
 constexpr int TC_BK = 64;       // channels per smem chunk (one 128B swizzle row of bf16 K... see below)
 constexpr int A_CHUNK_BYTES = 2 * 64 * 64 * 2;   // 2 pixel groups x 64 ch x 64 px x bf16 = 16 KB
 
-enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2, EPI_LINEAR = 3, EPI_LN = 4 };
+enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2, EPI_LINEAR_T = 3 };
 
 struct TcGemmP {
   int NT, N_TILE, KC, stages;
@@ -42,17 +44,15 @@ struct TcGemmP {
   int k_identity;        // 1: chunk kc sits at K coordinate kc*64 for both operands (kcoord tables unused)
   int a_kcoord[12];      // channel coordinate of A chunk kc   (split-precision GEMMs revisit chunks)
   int b_kcoord[12];      // K coordinate of B chunk kc
-  // EPI_LINEAR: up to 3 column segments of  (acc + bias [+ rowbias]) * alpha  [relu]
-  TcSeg seg[3]; int nseg; const float* lin_bias;
-  // EPI_LN: y = LayerNorm(acc + bias + res) over the 256 columns of the row
-  const float* ln_res; const float* ln_w; const float* ln_b; float* ln_out; __nv_bfloat16* ln_out_bf16;
-  __nv_bfloat16* ln_out_bf16_q; const float* ln_qe; int ln_Q;
+  // EPI_LINEAR_T: up to 3 FEATURE segments (32-aligned starts) of (acc + bias [+ rowbias]) * alpha [+ res] [relu]
+  TcSeg seg[3]; int nseg; const float* lin_bias; int n_tokens;
   int b_row0;            // first B row (e.g. call_idx * q_pad)
-  int b_rows_per_batch;  // B row offset per batch index (0: weights shared by the batch)
+  int b_rows_per_batch;  // B row offset per blockIdx.y (0: weights shared by the batch)
   int acc_stride;        // TMEM columns between the two accumulator buffers
   int tmem_cols;         // power of two >= 32
   int epi;
-  int M_valid;           // valid pixels / keys per batch image
+  int dbg;
+  int M_valid;           // valid pixels / keys per batch image (features for EPI_LINEAR_T)
   // EPI_MASK_T
   __nv_bfloat16* out_mask; long out_call_stride, out_batch_stride, HW; int Q, q_pad, n_calls;
   // EPI_ROWMAJOR
@@ -80,8 +80,194 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+
+constexpr int EPI_WARPS = 16;                 // epilogue warps (4 per TMEM lane quarter)
+constexpr int EPI_PARTS = EPI_WARPS / 4;
+
+struct EpiCtx {
+  int lane, m, batch, part, chunks, wi, col0;
+  bool m_ok;
+  uint32_t taddr;
+};
+
+// K2 epilogue: out[call][image][q][pixel] bf16, lanes = pixels.  Two columns at a time: even lanes
+// store (own, right neighbour) for column i, odd lanes for column i+1 -> 4-byte stores, 64 B runs.
+__device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c) {
+  const int Q = p.Q, q_pad = p.q_pad, n_calls = p.n_calls, odd = c.lane & 1;
+  const long HW = p.HW, call_stride = p.out_call_stride;
+  __nv_bfloat16* base = p.out_mask + (long)c.batch * p.out_batch_stride + (c.m & ~1);
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
+    float v[16];
+    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+    const int r0 = c.col0 + ch * 16;
+    const int call0 = r0 / q_pad;            // one division per chunk; q_pad >= 16: at most one wrap below
+    const int q0 = r0 - call0 * q_pad + odd;
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float send = odd ? v[i] : v[i + 1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      int q = q0 + i, call = call0;
+      if (q >= q_pad) { q -= q_pad; ++call; }
+      if (c.m_ok && q < Q && call < n_calls) {
+        const uint32_t packed = odd ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
+        *reinterpret_cast<uint32_t*>(base + (long)call * call_stride + (long)q * HW) = packed;
+      }
+    }
+  }
+}
+
+// K4 epilogue: out[image][key][n] bf16 = acc + bias[n] + R[key][n]; the R / bias loads of a chunk are
+// issued before the TMEM read so their latency overlaps it.
+__device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c) {
+  const int r_ncols = p.r_ncols;
+  const __nv_bfloat16* rrow = p.R + (long)c.m * p.ldr;
+  __nv_bfloat16* orow = p.out_rows + (long)c.batch * p.out_rows_batch_stride + (long)c.m * p.ld_out;
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
+    const int n0 = c.col0 + ch * 16;
+    uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (c.m_ok && n0 < r_ncols) {
+      rr[0] = __ldg(reinterpret_cast<const uint4*>(rrow + n0));
+      rr[1] = __ldg(reinterpret_cast<const uint4*>(rrow + n0) + 1);
+    }
+    float4 bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+    float v[16];
+    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+    if (c.m_ok) {
+      const float* bf = reinterpret_cast<const float*>(bb);
+      const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(rr);
+      uint4 o[2];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 r2 = __bfloat1622float2(rh[i]);
+        ow[i] = pack_bf16x2(v[2 * i] + bf[2 * i] + r2.x, v[2 * i + 1] + bf[2 * i + 1] + r2.y);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(orow + n0);
+      dst[0] = o[0];
+      dst[1] = o[1];
+    }
+  }
+}
+
+// K3 epilogue: threshold + ballot = 32 consecutive key bits of one query per warp instruction.
+// sigmoid(x) < 0.5 in fp32 holds exactly for x <= -1.7881392e-07.
+__device__ __forceinline__ void epi_bits(const TcGemmP& p, const EpiCtx& c) {
+  const int Q = p.Q, W32 = p.W32;
+  uint32_t* brow = p.bitmap + (long)c.batch * Q * W32 + c.wi;
+  const bool w_ok = c.wi < W32;
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
+    float v[16];
+    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+    const int q0 = c.col0 + ch * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t word = __ballot_sync(0xffffffffu, c.m_ok && v[i] <= -1.7881392e-07f);
+      if (c.lane == 0 && w_ok && q0 + i < Q) brow[(long)(q0 + i) * W32] = word;
+    }
+  }
+}
+
+// Swap-AB linear layers: TMEM lanes = output FEATURES, columns = tokens; for one token a warp holds
+// 32 consecutive features, so every global access is one coalesced line.  The thread's segment is
+// resolved once (registers), and the inner loop is specialised on the output kind / extra operands.
+struct LinCtx {
+  bool on = false;
+  int f = 0, mode = 0, rb_mod = 1, split_off = 0;
+  long ld = 0, rb_ld = 0, res_ld = 0;
+  float bias = 0.f, alpha = 1.f, floor = -INFINITY;
+  void* ptr = nullptr;
+  const float* rowbias = nullptr;
+  const float* res = nullptr;
+  __device__ __forceinline__ void init(const TcGemmP& p, int m) {
+#pragma unroll
+    for (int sgi = 0; sgi < 3; ++sgi) {
+      if (sgi < p.nseg && m >= p.seg[sgi].col0 && m < p.seg[sgi].col0 + p.seg[sgi].ncols) {
+        on = true;
+        f = m - p.seg[sgi].col0;
+        mode = p.seg[sgi].is_bf16 ? (p.seg[sgi].split ? 2 : 1) : 0;
+        floor = p.seg[sgi].relu ? 0.f : -INFINITY;
+        ptr = p.seg[sgi].ptr; ld = p.seg[sgi].ld; alpha = p.seg[sgi].alpha;
+        rowbias = p.seg[sgi].rowbias; rb_mod = p.seg[sgi].rb_mod; rb_ld = p.seg[sgi].rb_ld;
+        res = p.seg[sgi].res; res_ld = p.seg[sgi].res_ld; split_off = p.seg[sgi].ncols;
+      }
+    }
+    if (on && p.lin_bias) bias = __ldg(p.lin_bias + m);
+  }
+};
+
+template <int MODE, bool HAS_RB, bool HAS_RES>
+__device__ __forceinline__ void epi_linear_t(const TcGemmP& p, const EpiCtx& c, const LinCtx& L) {
+  const int n_tokens = p.n_tokens;
+  const int tok_base = c.batch * p.NT * p.N_TILE + c.col0;
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
+    const int tok0 = tok_base + ch * 16;
+    const int nvalid = L.on ? min(16, n_tokens - tok0) : 0;      // <= 0: nothing to store
+    float rb[16], rs[16];
+    if (HAS_RB) {
+      int tq = tok0 % L.rb_mod;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        rb[i] = (i < nvalid) ? __ldg(L.rowbias + (long)tq * L.rb_ld + L.f) : 0.f;
+        if (++tq == L.rb_mod) tq = 0;
+      }
+    }
+    if (HAS_RES) {
+      const float* rp = L.res + (long)tok0 * L.res_ld + L.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rs[i] = (i < nvalid) ? __ldg(rp + (long)i * L.res_ld) : 0.f;
+    }
+    float v[16];
+    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x = v[i] + L.bias;
+      if (HAS_RB) x += rb[i];
+      x *= L.alpha;
+      if (HAS_RES) x += rs[i];
+      x = fmaxf(x, L.floor);
+      if (i < nvalid) {
+        const long off = (long)(tok0 + i) * L.ld + L.f;
+        if (MODE == 0) {
+          static_cast<float*>(L.ptr)[off] = x;
+        } else if (MODE == 1) {
+          static_cast<__nv_bfloat16*>(L.ptr)[off] = __float2bfloat16_rn(x);
+        } else {
+          __nv_bfloat16 hi, lo;
+          split_bf16(x, hi, lo);
+          static_cast<__nv_bfloat16*>(L.ptr)[off] = hi;
+          static_cast<__nv_bfloat16*>(L.ptr)[off + L.split_off] = lo;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiCtx& c, const LinCtx& L) {
+  // warp-uniform: a warp's 32 features belong to one segment (32-aligned segment starts)
+  const bool rb = L.rowbias != nullptr, rs = L.res != nullptr;
+  if (L.mode == 0) {
+    if (rb) epi_linear_t<0, true, false>(p, c, L);
+    else if (rs) epi_linear_t<0, false, true>(p, c, L);
+    else epi_linear_t<0, false, false>(p, c, L);
+  } else if (L.mode == 1) {
+    epi_linear_t<1, false, false>(p, c, L);
+  } else {
+    epi_linear_t<2, false, false>(p, c, L);
+  }
+}
+
+// Debug timeline (CGG_TC_TIMING=1): globaltimer stamps of CTA (0,0), printed by launch_tc_gemm.
+__device__ unsigned long long g_tc_stamps[16];
+#define TC_STAMP(i)                                                            \
+  do {                                                                         \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
+  } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmP p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.N_TILE * 128;
@@ -96,17 +282,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = b_empty + p.stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* ln_part = reinterpret_cast<float*>(tmem_slot + 4);   // [128 rows][2 halves][sum, sumsq] (EPI_LN)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, batch = blockIdx.y;
+  if (threadIdx.x == 0) TC_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::mbar_init(a_full, 1);
     for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -117,6 +303,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -169,6 +356,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
+          if (it == 0) TC_STAMP(2);
           const uint32_t a_base = ptx::smem_u32(p.a_resident ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
           const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes + a_in_stage);
 #pragma unroll
@@ -183,214 +371,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
         }
         ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
+        if (t == 0) TC_STAMP(3);
       }
     }
   } else {
-    // ---------------- epilogue: 8 warps, 2 per TMEM lane quarter
+    // ---------------- epilogue: EPI_WARPS warps, EPI_WARPS/4 per TMEM lane quarter; each warp takes
+    // every (EPI_WARPS/4)-th 16-column chunk.  One lean, specialised loop per epilogue kind.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int m = m_tile * TC_BM + quarter * 32 + lane;     // pixel / key index inside the image
+    const int part = (warp - 2) >> 2;                       // which share of the chunks
+    const int m = m_tile * TC_BM + quarter * 32 + lane;     // TMEM lane -> pixel / key / feature index
     const bool m_ok = m < p.M_valid;
-    const int chunks = p.N_TILE / 16;
+    EpiCtx ctx;
+    ctx.lane = lane; ctx.m = m; ctx.m_ok = m_ok; ctx.batch = batch; ctx.part = part;
+    ctx.chunks = p.N_TILE / 16; ctx.wi = (m_tile * TC_BM + quarter * 32) >> 5;
+    LinCtx lin;
+    if (p.epi == EPI_LINEAR_T) lin.init(p, m);
     for (int t = 0; t < p.NT; ++t) {
       const int buf = t & 1;
       const uint32_t use = (uint32_t)(t >> 1);
       ptx::mbar_wait(&acc_full[buf], use & 1u);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      float ln_s = 0.f, ln_ss = 0.f;
-      for (int c = half; c < chunks; c += 2) {
-        float v[16];
-        ptx::tmem_ld16(taddr + (uint32_t)(c * 16), v);
-        const int n0 = t * p.N_TILE + c * 16;
-        if (p.epi == EPI_MASK_T) {
-          // transposed store: out[call][batch][q][pixel]; lanes = pixels.  Two columns at a time:
-          // even lanes store (own, right neighbour) for column i, odd lanes for column i+1.
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float send = (lane & 1) ? v[i] : v[i + 1];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            const int r = n0 + i + (lane & 1);
-            const int call = r / p.q_pad, q = r - call * p.q_pad;
-            if (m_ok && q < p.Q && call < p.n_calls) {
-              const uint32_t packed = (lane & 1) ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
-              __nv_bfloat16* dst = p.out_mask + (long)call * p.out_call_stride + (long)batch * p.out_batch_stride +
-                                   (long)q * p.HW + (m & ~1);
-              *reinterpret_cast<uint32_t*>(dst) = packed;
-            }
-          }
-        } else if (p.epi == EPI_ROWMAJOR) {
-          if (m_ok) {
-            float add[16];
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 x = __ldg(b4 + i);
-              add[4 * i] = x.x; add[4 * i + 1] = x.y; add[4 * i + 2] = x.z; add[4 * i + 3] = x.w;
-            }
-            if (n0 < p.r_ncols) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.R + (long)m * p.ldr + n0);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const uint4 x = __ldg(r4 + i);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(h[j]);
-                  add[8 * i + 2 * j] += f.x;
-                  add[8 * i + 2 * j + 1] += f.y;
-                }
-              }
-            }
-            uint4 o[2];
-            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(v[2 * i] + add[2 * i], v[2 * i + 1] + add[2 * i + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(p.out_rows + (long)batch * p.out_rows_batch_stride +
-                                                  (long)m * p.ld_out + n0);
-            dst[0] = o[0];
-            dst[1] = o[1];
-          }
-        } else if (p.epi == EPI_LINEAR) {
-          // row-major outputs in up to 3 column segments (16-aligned starts): fp32 or bf16
-          if (m_ok) {
-#pragma unroll 1
-            for (int sgi = 0; sgi < p.nseg; ++sgi) {
-              const TcSeg& sg = p.seg[sgi];
-              const int nn0 = n0 - sg.col0;
-              if (nn0 < 0 || nn0 >= sg.ncols) continue;
-              float y[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float x = v[i] + __ldg(p.lin_bias + n0 + i);
-                if (sg.rowbias && nn0 + i < sg.ncols) x += __ldg(sg.rowbias + (long)(m % sg.rb_mod) * sg.rb_ld + nn0 + i);
-                x *= sg.alpha;
-                y[i] = sg.relu ? fmaxf(x, 0.f) : x;
-              }
-              const bool full = nn0 + 16 <= sg.ncols;
-              if (sg.is_bf16 && sg.split) {
-                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(sg.ptr) + (long)m * sg.ld + nn0;
-                uint4 oh[2], ol[2];
-                uint32_t* hw = reinterpret_cast<uint32_t*>(oh);
-                uint32_t* lw2 = reinterpret_cast<uint32_t*>(ol);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  split_bf16(y[2 * i], h0, l0);
-                  split_bf16(y[2 * i + 1], h1, l1);
-                  hw[i] = pack2(h0, h1);
-                  lw2[i] = pack2(l0, l1);
-                }
-                reinterpret_cast<uint4*>(dst)[0] = oh[0];
-                reinterpret_cast<uint4*>(dst)[1] = oh[1];
-                reinterpret_cast<uint4*>(dst + 256)[0] = ol[0];
-                reinterpret_cast<uint4*>(dst + 256)[1] = ol[1];
-              } else if (sg.is_bf16) {
-                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(sg.ptr) + (long)m * sg.ld + nn0;
-                if (full && (sg.ld & 7) == 0) {
-                  uint4 o[2];
-                  uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
-                  reinterpret_cast<uint4*>(dst)[0] = o[0];
-                  reinterpret_cast<uint4*>(dst)[1] = o[1];
-                } else {
-                  for (int i = 0; i < 16; ++i)
-                    if (nn0 + i < sg.ncols) dst[i] = __float2bfloat16_rn(y[i]);
-                }
-              } else {
-                float* dst = static_cast<float*>(sg.ptr) + (long)m * sg.ld + nn0;
-                if (full && (sg.ld & 3) == 0) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    reinterpret_cast<float4*>(dst)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-                } else {
-                  for (int i = 0; i < 16; ++i)
-                    if (nn0 + i < sg.ncols) dst[i] = y[i];
-                }
-              }
-            }
-          }
-        } else if (p.epi == EPI_LN) {
-          // pass 1 of the fused residual + LayerNorm: partial sum / sum of squares of this warp's columns
-          if (m_ok) {
-            const float* res = p.ln_res + (long)m * 256 + n0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = v[i] + __ldg(p.lin_bias + n0 + i) + __ldg(res + i);
-              ln_s += x;
-              ln_ss = fmaf(x, x, ln_ss);
-            }
-          }
-        } else {  // EPI_BITS
-          const int wi = (m_tile * TC_BM + quarter * 32) >> 5;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const bool mk = m_ok && masked_from_logit(v[i]);
-            const uint32_t word = __ballot_sync(0xffffffffu, mk);
-            const int q = n0 + i;
-            if (lane == 0 && q < p.Q && wi < p.W32) p.bitmap[((long)batch * p.Q + q) * p.W32 + wi] = word;
-          }
-        }
-      }
-      if (p.epi == EPI_LN) {
-        // exchange the two half-row partials between the warp pair, then pass 2: normalise + store
-        const int row = quarter * 32 + lane;
-        ln_part[(row * 2 + half) * 2] = ln_s;
-        ln_part[(row * 2 + half) * 2 + 1] = ln_ss;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float sum = ln_part[row * 4] + ln_part[row * 4 + 2];
-        const float sq = ln_part[row * 4 + 1] + ln_part[row * 4 + 3];
-        const float mean = sum * (1.0f / 256.0f);
-        const float var = fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        // (tcgen05.ld is warp-collective: every lane runs the loop, only the memory traffic is guarded)
-        for (int c = half; c < chunks; c += 2) {
-          float v[16];
-          ptx::tmem_ld16(taddr + (uint32_t)(c * 16), v);
-          if (m_ok) {
-            const int n0 = c * 16;
-            const float* res = p.ln_res + (long)m * 256 + n0;
-            float y[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float x = v[i] + __ldg(p.lin_bias + n0 + i) + __ldg(res + i);
-              y[i] = (x - mean) * rstd * __ldg(p.ln_w + n0 + i) + __ldg(p.ln_b + n0 + i);
-            }
-            float* dst = p.ln_out + (long)m * 256 + n0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-            if (p.ln_out_bf16) {
-              uint4 o[2];
-              uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(y[2 * i], y[2 * i + 1]);
-              uint4* d2 = reinterpret_cast<uint4*>(p.ln_out_bf16 + (long)m * 256 + n0);
-              d2[0] = o[0];
-              d2[1] = o[1];
-            }
-            if (p.ln_out_bf16_q) {
-              const float* qe = p.ln_qe + (long)(m % p.ln_Q) * 256 + n0;
-              uint4 o[2];
-              uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                ow[i] = pack_bf16x2(y[2 * i] + __ldg(qe + 2 * i), y[2 * i + 1] + __ldg(qe + 2 * i + 1));
-              uint4* d2 = reinterpret_cast<uint4*>(p.ln_out_bf16_q + (long)m * 256 + n0);
-              d2[0] = o[0];
-              d2[1] = o[1];
-            }
-          }
-        }
+      if (t == 0 && warp == 2 && lane == 0) TC_STAMP(4);
+      ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      ctx.col0 = t * p.N_TILE;
+      switch (p.epi) {
+        case EPI_MASK_T: epi_mask_t(p, ctx); break;
+        case EPI_ROWMAJOR: epi_rowmajor(p, ctx); break;
+        case EPI_BITS: epi_bits(p, ctx); break;
+        default: epi_linear_dispatch(p, ctx, lin); break;
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      if (t == p.NT - 1 && warp == 2 && lane == 0) TC_STAMP(5);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -550,14 +568,31 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
   if (stages < 2) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 16 + 2048 + 64;
+  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 64;
   if (!t->smem_attr_set) {
     TCU(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     t->smem_attr_set = true;
   }
+  static const bool timing = getenv("CGG_TC_TIMING") != nullptr;
+  p.dbg = timing ? 1 : 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
   tc_gemm_kernel<<<dim3(m_tiles, batch), TC_THREADS, smem, s>>>(mA, mB, p);
   count_launch();
   TCU(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    unsigned long long st[16];
+    cudaMemcpyFromSymbol(st, g_tc_stamps, sizeof(st));
+    fprintf(stderr, "[tc_gemm] grid %dx%d epi %d NT %d KC %d N_TILE %d stages %d smem %zu: event %.1f us | setup %.1f first-data %.1f mma-issued %.1f "
+            "acc-ready %.1f epi-done %.1f teardown %.1f (us since entry)\n", m_tiles, batch, p.epi, p.NT, p.KC, p.N_TILE, p.stages, smem,
+            ms * 1e3, (st[1] - st[0]) * 1e-3, (st[2] - st[0]) * 1e-3, (st[3] - st[0]) * 1e-3, (st[4] - st[0]) * 1e-3,
+            (st[5] - st[0]) * 1e-3, (st[6] - st[0]) * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   return CGG_OK;
 }
 
@@ -579,7 +614,7 @@ TcState* tc_create(const cgg_config& cfg) {
   // N tiling: two head calls per 2*round8(Q)-wide tile when that fits one MMA (Q=100 -> 208, 4% pad);
   // otherwise one call per round16(Q) tile; above 256 queries, two tiles per call.
   if (2 * round_up(Q, 8) <= 256 && calls % 2 == 0) {
-    t->q_pad = round_up(Q, 8); t->ein_ntile = 2 * t->q_pad; t->ein_calls_per_tile = 2;
+    t->q_pad = round_up(Q, 8) < 16 ? 16 : round_up(Q, 8); t->ein_ntile = 2 * t->q_pad; t->ein_calls_per_tile = 2;
   } else if (round_up(Q, 16) <= 256) {
     t->q_pad = round_up(Q, 16); t->ein_ntile = t->q_pad; t->ein_calls_per_tile = 1;
   } else {
@@ -795,59 +830,43 @@ int make_map_act(TcState* t, CUtensorMap* m, const void* base, long rows, int K)
   return CGG_OK;
 }
 
-int pick_ntile(int n_padded) {   // largest tile <= 256 (multiple of 16) that divides the padded width
-  for (int nt = 256; nt >= 16; nt -= 16)
-    if (n_padded % nt == 0) return nt;
-  return 16;
-}
 }  // namespace
 
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
               const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k) {
-  if (K % TC_BK != 0 || n_padded % 16 != 0 || nsegs < 1 || nsegs > 3) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear shape");
+  // swap-AB: the WEIGHTS are the UMMA A operand (128 output features per CTA on the TMEM lanes), the
+  // activations the B operand (a tile of <= 256 tokens on the columns); grid = feature tiles x token tiles.
+  if (K % TC_BK != 0 || n_padded % TC_BM != 0 || nsegs < 1 || nsegs > 3)
+    return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear shape (features must be padded to 128)");
   if (split_k && K != 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "split-precision linear needs K = 256");
+  for (int i = 0; i < nsegs; ++i)
+    if (segs[i].col0 % 32 != 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "segment start must be a multiple of 32");
   const int row_len = split_k ? 2 * K : K;
-  CUtensorMap mA, mB;
-  int st = make_map_act(t, &mA, A, M, row_len);
-  if (st != CGG_OK) return st;
   TcGemmP p = {};
-  p.N_TILE = pick_ntile(n_padded);
-  st = make_map_B(t, &mB, W, n_padded, row_len, p.N_TILE);
+  // token tile: as few CTAs-worth of padding as possible with N <= 256 (multiple of 16)
+  const int n_tok_tiles = (M + 255) / 256;
+  p.N_TILE = ((M + n_tok_tiles - 1) / n_tok_tiles + 15) / 16 * 16;
+  CUtensorMap mW, mX;
+  int st = make_map_act(t, &mW, W, n_padded, row_len);      // A operand: (64 k x 128 features) boxes
   if (st != CGG_OK) return st;
-  p.NT = n_padded / p.N_TILE; p.KC = K / TC_BK;
-  p.a_kmajor = 1; p.k_identity = 1;
+  st = make_map_B(t, &mX, A, M, row_len, p.N_TILE);          // B operand: (64 k x N_TILE tokens) boxes
+  if (st != CGG_OK) return st;
+  p.NT = 1; p.KC = K / TC_BK;
+  p.a_kmajor = 1; p.k_identity = 1; p.a_resident = 0;
   if (split_k) {
     p.k_identity = 0; p.KC = 3 * K / TC_BK;
     const int cpc = K / TC_BK;
     for (int kc = 0; kc < p.KC; ++kc) {
       const int term = kc / cpc, j = (kc % cpc) * TC_BK;
-      p.a_kcoord[kc] = (term == 1 ? K : 0) + j;     // hi, lo, hi
-      p.b_kcoord[kc] = (term == 2 ? K : 0) + j;     // hi, hi, lo
+      p.a_kcoord[kc] = (term == 2 ? K : 0) + j;     // weights:     hi, hi, lo
+      p.b_kcoord[kc] = (term == 1 ? K : 0) + j;     // activations: hi, lo, hi
     }
   }
-  p.a_resident = (p.NT > 1 && p.KC <= 4) ? 1 : 0;
-  p.epi = EPI_LINEAR; p.M_valid = M;
+  p.b_row0 = 0; p.b_rows_per_batch = p.N_TILE;       // blockIdx.y = token tile
+  p.epi = EPI_LINEAR_T; p.M_valid = n_padded; p.n_tokens = M;
   p.nseg = nsegs; p.lin_bias = bias;
   for (int i = 0; i < nsegs; ++i) p.seg[i] = segs[i];
-  return launch_tc_gemm(t, mA, mB, p, (M + TC_BM - 1) / TC_BM, 1, s);
-}
-
-int tc_linear_ln(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
-                 const float* res, const float* ln_w, const float* ln_b, float* out_f32, __nv_bfloat16* out_bf16,
-                 __nv_bfloat16* out_bf16_q, const float* qe, int Q, cudaStream_t s) {
-  if (K % TC_BK != 0 || t->cfg.embed_dim != 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear_ln shape");
-  CUtensorMap mA, mB;
-  int st = make_map_act(t, &mA, A, M, K);
-  if (st != CGG_OK) return st;
-  TcGemmP p = {};
-  p.N_TILE = 256; p.NT = 1; p.KC = K / TC_BK;
-  st = make_map_B(t, &mB, W, 256, K, 256);
-  if (st != CGG_OK) return st;
-  p.a_kmajor = 1; p.k_identity = 1; p.a_resident = 0;
-  p.epi = EPI_LN; p.M_valid = M;
-  p.lin_bias = bias; p.ln_res = res; p.ln_w = ln_w; p.ln_b = ln_b;
-  p.ln_out = out_f32; p.ln_out_bf16 = out_bf16; p.ln_out_bf16_q = out_bf16_q; p.ln_qe = qe; p.ln_Q = Q > 0 ? Q : 1;
-  return launch_tc_gemm(t, mA, mB, p, (M + TC_BM - 1) / TC_BM, 1, s);
+  return launch_tc_gemm(t, mW, mX, p, n_padded / TC_BM, n_tok_tiles, s);
 }
 
 }  // namespace cgg

@@ -10,14 +10,16 @@ namespace cgg {
 struct TcState;
 
 // One column segment of a row-major GEMM output: columns [col0, col0+ncols) of
-//   y = (acc + bias[n] + rowbias[(m % rb_mod), n-col0]) * alpha, optional ReLU, fp32 or bf16.
+//   y = (acc + bias[n] + rowbias[(m % rb_mod), n-col0]) * alpha + res[m, n-col0], optional ReLU, fp32 or bf16.
+// col0 must be a multiple of 32 (a warp of the epilogue holds 32 consecutive features).
 struct TcSeg {
   int col0, ncols;
   void* ptr; long ld;
   int is_bf16, relu;
-  int split;      // bf16 only: write x as a hi/lo pair, hi at column n, lo at column 256+n of a 512-wide row
+  int split;      // bf16 only: write x as a hi/lo pair, hi at column n, lo at column ncols+n of the row
   float alpha;
   const float* rowbias; int rb_mod; long rb_ld;
+  const float* res; long res_ld;   // fp32 residual added after the scale: res[token*res_ld + (n - col0)]
 };
 
 TcState* tc_create(const cgg_config& cfg);
@@ -59,11 +61,6 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
 // hi.hi + lo.hi + hi.lo (fp32 accumulate), i.e. with ~16 mantissa bits per operand (K must be 256).
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
               const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false);
-// out = LayerNorm(A W^T + bias + res) with W (256,K); also bf16(out) and bf16(out + qe[m % Q]) copies.
-int tc_linear_ln(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
-                 const float* res, const float* ln_w, const float* ln_b, float* out_f32, __nv_bfloat16* out_bf16,
-                 __nv_bfloat16* out_bf16_q, const float* qe, int Q, cudaStream_t s);
-
 // The bf16-mode decoder layer (K5 + K6) and the query heads (K1) built from the pieces above.
 int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
                      const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,

@@ -30,13 +30,18 @@ __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __r
   *reinterpret_cast<uint2*>(dst + i) = pk;
 }
 
-// post_norm: z = LayerNorm(x) rows of 256 as bf16 hi/lo pairs, one warp per row
-__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                             const float* __restrict__ b,
-                                                             __nv_bfloat16* __restrict__ y, int rows) {
+// Row LayerNorm over 256 channels, one warp per row, every access coalesced.  Optional outputs:
+// fp32, bf16, bf16 of (y + qe[row % Q]) and a bf16 hi/lo pair row [hi(256) | lo(256)].
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ b, int rows, float* __restrict__ out_f32,
+                                                      __nv_bfloat16* __restrict__ out_bf16,
+                                                      __nv_bfloat16* __restrict__ out_bf16_q,
+                                                      const float* __restrict__ qe, int Q,
+                                                      __nv_bfloat16* __restrict__ out_hl) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long)row * 256) + lane * 2;
+  const int n0 = lane * 8;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)row * 256 + n0);
   const float4 a = xr[0], c = xr[1];
   float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
   float s = 0.f;
@@ -51,30 +56,60 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q * (1.0f / 256.0f) + 1e-5f);
-  const int n0 = lane * 8;
-  uint4 pk, pl;
-  uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-  uint32_t* plw = reinterpret_cast<uint32_t*>(&pl);
+  float y[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float y0 = (v[2 * i] - mu) * rstd * w[n0 + 2 * i] + b[n0 + 2 * i];
-    const float y1 = (v[2 * i + 1] - mu) * rstd * w[n0 + 2 * i + 1] + b[n0 + 2 * i + 1];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-    pw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    plw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  for (int i = 0; i < 8; ++i) y[i] = (v[i] - mu) * rstd * __ldg(w + n0 + i) + __ldg(b + n0 + i);
+  if (out_f32) {
+    float4* d = reinterpret_cast<float4*>(out_f32 + (long)row * 256 + n0);
+    d[0] = make_float4(y[0], y[1], y[2], y[3]);
+    d[1] = make_float4(y[4], y[5], y[6], y[7]);
   }
-  // row = [hi(256) | lo(256)]: operand of the split-precision head GEMMs
-  *reinterpret_cast<uint4*>(y + (long)row * 512 + n0) = pk;
-  *reinterpret_cast<uint4*>(y + (long)row * 512 + 256 + n0) = pl;
+  auto pack = [](float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  };
+  if (out_bf16) {
+    uint4 pk = make_uint4(pack(y[0], y[1]), pack(y[2], y[3]), pack(y[4], y[5]), pack(y[6], y[7]));
+    *reinterpret_cast<uint4*>(out_bf16 + (long)row * 256 + n0) = pk;
+  }
+  if (out_bf16_q) {
+    const float* e = qe + (long)(row % Q) * 256 + n0;
+    uint4 pk = make_uint4(pack(y[0] + e[0], y[1] + e[1]), pack(y[2] + e[2], y[3] + e[3]), pack(y[4] + e[4], y[5] + e[5]),
+                          pack(y[6] + e[6], y[7] + e[7]));
+    *reinterpret_cast<uint4*>(out_bf16_q + (long)row * 256 + n0) = pk;
+  }
+  if (out_hl) {
+    uint4 ph, pl;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(&ph);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(&pl);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * i]), h1 = __float2bfloat16_rn(y[2 * i + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * i] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(h1));
+      hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(out_hl + (long)row * 512 + n0) = ph;
+    *reinterpret_cast<uint4*>(out_hl + (long)row * 512 + 256 + n0) = pl;
+  }
+}
+
+cudaError_t launch_ln_rows(const float* x, const float* w, const float* b, int rows, float* out_f32,
+                           __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_q, const float* qe, int Q,
+                           __nv_bfloat16* out_hl, cudaStream_t s) {
+  ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, b, rows, out_f32, out_bf16, out_bf16_q, qe, Q > 0 ? Q : 1, out_hl);
+  count_launch();
+  return cudaGetLastError();
 }
 
 template <typename T>
 T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
 TcSeg seg(int col0, int ncols, void* ptr, long ld, bool bf16, bool relu, float alpha = 1.f, const float* rowbias = nullptr,
-          int rb_mod = 1, long rb_ld = 0, bool split = false) {
+          int rb_mod = 1, long rb_ld = 0, bool split = false, const float* res = nullptr, long res_ld = 0) {
   TcSeg s;
+  s.res = res; s.res_ld = res_ld;
   s.col0 = col0; s.ncols = ncols; s.ptr = ptr; s.ld = ld; s.is_bf16 = bf16 ? 1 : 0; s.relu = relu ? 1 : 0;
   s.split = split ? 1 : 0;
   s.alpha = alpha; s.rowbias = rowbias; s.rb_mod = rb_mod; s.rb_ld = rb_ld;
@@ -164,9 +199,7 @@ int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, 
   __nv_bfloat16* zb = at<__nv_bfloat16>(ws, o.zb);
   __nv_bfloat16* h1b = at<__nv_bfloat16>(ws, o.h1b);
   __nv_bfloat16* h2b = at<__nv_bfloat16>(ws, o.h2b);
-  layernorm_bf16_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, w->post_norm_w, w->post_norm_b, zb, M);
-  count_launch();
-  TCU(cudaGetLastError());
+  TCU(launch_ln_rows(x, w->post_norm_w, w->post_norm_b, M, nullptr, nullptr, nullptr, nullptr, 0, zb, s));
   // split precision (hi/lo bf16 pairs, 3 MMAs per product): the mask embedding feeds the
   // sigmoid<0.5 threshold, where plain bf16 operands flip ~0.15% of the attention-mask bits
   TcSeg sh[3] = {seg(0, c.d_lang, emb, c.d_lang, false, false),
@@ -200,6 +233,7 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   float* kvs = at<float>(ws, o.kvs);
   float* x1 = at<float>(ws, o.x1);
   float* x2 = at<float>(ws, o.x2);
+  float* t1 = at<float>(ws, o.t1);
   // ---- cross-attention: q = ((x + query_embed) Wq^T + bq) / sqrt(d)
   const long total = (long)M * C;
   add_qe_cast_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(x_in, w->query_embed, xqb, total, Q * C);
@@ -209,19 +243,24 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
   TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s));
   // x1 = LN(x + o Wo^T + bo);  also bf16(x1 + query_embed) for the self-attention projections
-  TST(tc_linear_ln(t, ob, M, C, pw.wo_c, lw.cross_out_b, x_in, lw.norm_w[0], lw.norm_b[0], x1, nullptr, xqb,
-                   w->query_embed, Q, s));
+  TcSeg so[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x_in, C)};
+  TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s));
+  TCU(launch_ln_rows(t1, lw.norm_w[0], lw.norm_b[0], M, x1, nullptr, xqb, w->query_embed, Q, nullptr, s));
   // ---- self-attention: q, k from x1 + query_embed, v from x1 (per-query constant folded into rowbias_v)
   TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvs, 2 * C, false, false),
                  seg(2 * C, C, kvs + C, 2 * C, false, false, 1.f, pw.rowbias_v, Q, C)};
   TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s));
   TCU(launch_attention_f32(qs, kvs, kvs + C, false, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, batch, Q, Q,
                            c.num_heads, s));
-  TST(tc_linear_ln(t, ob, M, C, pw.wo_s, lw.self_out_b, x1, lw.norm_w[1], lw.norm_b[1], x2, xb, nullptr, nullptr, 0, s));
+  TcSeg so2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x1, C)};
+  TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s));
+  TCU(launch_ln_rows(t1, lw.norm_w[1], lw.norm_b[1], M, x2, xb, nullptr, nullptr, 0, nullptr, s));
   // ---- FFN
   TcSeg sf[1] = {seg(0, F, fb, F, true, true)};
   TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s));
-  TST(tc_linear_ln(t, fb, M, F, pw.w2, lw.ffn_b2, x2, lw.norm_w[2], lw.norm_b[2], x_out, nullptr, nullptr, nullptr, 0, s));
+  TcSeg sf2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x2, C)};
+  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s));
+  TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, nullptr, nullptr, 0, nullptr, s));
   return CGG_OK;
 }
 

@@ -52,7 +52,7 @@ struct TcState {
 
 // carving of the caller-provided tc workspace
 struct TcWs {
-  size_t me_all, fds[3], xqb, xb, ob, fb, zb, h1b, h2b, qf, qs, kvs, x1, x2, total;
+  size_t me_all, fds[3], xqb, xb, ob, fb, zb, h1b, h2b, qf, qs, kvs, x1, x2, t1, total;
   void carve(const TcState* t, int B) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
@@ -64,7 +64,7 @@ struct TcWs {
     fb = take(M * t->cfg.ffn_dim * 2);
     zb = take(M * 2 * C * 2); h1b = take(M * 2 * C * 2); h2b = take(M * 2 * C * 2);   // hi/lo rows
     qf = take(M * C * 4); qs = take(M * C * 4); kvs = take(M * 2 * C * 4);
-    x1 = take(M * C * 4); x2 = take(M * C * 4);
+    x1 = take(M * C * 4); x2 = take(M * C * 4); t1 = take(M * C * 4);
     total = off;
   }
 };
