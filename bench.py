@@ -225,24 +225,54 @@ def run_b200_arm(args):
     res_h = None
     h2d = mf_h.numel() * mf_h.element_size() + sum(m.numel() * m.element_size() for m in mems_h)
 
-    def step_e2e():
-        nonlocal res_h
-        a = mf_h.to(dev, non_blocking=True)
-        ms_ = [m.to(dev, non_blocking=True) for m in mems_h]
-        cls, emb, mask = head.decoder_forward(a, ms_)
-        if res_h is None:
-            res_h = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (cls[-1], emb[-1], mask[-1])]
-        for dst, src in zip(res_h, (cls[-1], emb[-1], mask[-1])):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Three streams, double-buffered device inputs: the H2D copy of step i+1 and the D2H read of
+    # step i-1 overlap the kernels of step i (PCIe is full duplex); every step still pays its own
+    # H2D + D2H, and the loop ends with a full synchronise.
+    main = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    in_bufs = [(torch.empty_like(mf_d), [torch.empty_like(m) for m in mems_d]) for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    out_free = torch.cuda.Event()
 
-    for _ in range(2):
-        step_e2e()
+    def upload(slot):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(in_free[slot])
+            in_bufs[slot][0].copy_(mf_h, non_blocking=True)
+            for d, hsrc in zip(in_bufs[slot][1], mems_h):
+                d.copy_(hsrc, non_blocking=True)
+            in_ready[slot].record(s_in)
+
+    def run_e2e(n):
+        nonlocal res_h
+        for e in in_free:
+            e.record(main)
+        out_free.record(main)
+        upload(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)
+            main.wait_event(in_ready[slot])
+            cls, emb, mask = head.decoder_forward(in_bufs[slot][0], in_bufs[slot][1])
+            in_free[slot].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            if res_h is None:
+                res_h = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (cls[-1], emb[-1], mask[-1])]
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for dst, src in zip(res_h, (cls[-1], emb[-1], mask[-1])):
+                    src.record_stream(s_out)
+                    dst.copy_(src, non_blocking=True)
+                out_free.record(s_out)
+        torch.cuda.synchronize()
+
+    run_e2e(2)
     barrier()
-    e2e_steps = max(2, args.steps // 2)
+    e2e_steps = max(4, args.steps)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
+    run_e2e(e2e_steps)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -253,23 +283,50 @@ def run_b200_arm(args):
     # ---- roofline of the dominant kernel (the mask einsum, 55% of the path's FLOPs): CUDA events
     # on the launching stream around that stage alone, same inputs, averaged over launches
     rt = head._runtime(dev)
-    x0 = torch.randn((B, Q, C), device=dev)
-    for _ in range(3):
-        rt.head_call(x0, mf_d, 0, want_bits=False)
-    torch.cuda.synchronize()
+    peaks = measured_peaks()
     reps = 10
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the small head GEMMs run inside the same stage; time them separately and subtract
-    k0.record()
-    for _ in range(reps):
-        rt.head_call(x0, mf_d, 0, want_bits=False)
-    k1.record()
-    torch.cuda.synchronize()
-    stage_ms = k0.elapsed_time(k1) / reps
-    peaks = measured_peaks()
-    ach = einsum_flops_per_launch(Q, B) / (stage_ms * 1e-3) / 1e12
+    if args.precision == 'bf16':
+        # K2 alone: ONE launch of the tcgen05 GEMM computes the mask logits of all 10 head calls
+        # (the mask embeddings of the last forward are still in the workspace); 2.1 GB of output
+        # per launch, far larger than L2.
+        mask_out = torch.empty((LAYERS + 1, B, Q, H // 4, W // 4), dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            rt.mask_einsum(mf_d, mask_out)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            rt.mask_einsum(mf_d, mask_out)
+        k1.record()
+        torch.cuda.synchronize()
+        kern_ms = k0.elapsed_time(k1) / reps
+        flops = einsum_flops_per_launch(Q, B) * (LAYERS + 1)
+        kname = 'tc_gemm_kernel / EPI_MASK_T: mask einsum of all 10 head calls, one launch (cgg_mask_einsum)'
+        del mask_out
+    else:
+        x0 = torch.randn((B, Q, C), device=dev)
+        for _ in range(3):
+            rt.head_call(x0, mf_d, 0, want_bits=False)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            rt.head_call(x0, mf_d, 0, want_bits=False)
+        k1.record()
+        torch.cuda.synchronize()
+        kern_ms = k0.elapsed_time(k1) / reps
+        flops = einsum_flops_per_launch(Q, B)
+        kname = 'cgg_head_call stage (fp32 SIMT heads + mask einsum of one head call)'
+    ach = flops / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'einsum_dram_traffic.json')
+    if args.precision == 'bf16' and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get('batch') == B and tj.get('queries') == Q:
+            traffic = tj.get('dram_bytes_per_launch')
     roofline = dict(bound='tensor', achieved=ach, peak=peaks['tflops'], unit='TFLOP/s', frac=ach / peaks['tflops'],
-                    traffic=None, kernel='mask einsum stage (cgg_head_call: K1 heads + K2 einsum)',
+                    traffic=traffic, kernel=kname, kernel_ms=kern_ms,
+                    algorithmic_bytes=(B * C * (H // 4) * (W // 4) * 2 + (LAYERS + 1) * B * Q * (H // 4) * (W // 4) * 2)
+                    if args.precision == 'bf16' else None,
                     peak_source=peaks['source'] + ' (sustained bf16)',
                     whole_path=dict(achieved=flops_per_image(Q) * value / 1e12, unit='TFLOP/s',
                                     frac=flops_per_image(Q) * value / 1e12 / peaks['tflops']))

@@ -340,6 +340,21 @@ extern "C" int cgg_head_call(cgg_handle* h, const cgg_weights* w, int batch, con
                         workspace, workspace_bytes, (cudaStream_t)stream, 0, false, false);
 }
 
+extern "C" int cgg_mask_einsum(cgg_handle* h, int batch, int first_call, int num_calls, const void* mask_features,
+                               void* mask, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !mask_features || !mask) return CGG_ERR_NULL;
+  if (h->cfg.precision != CGG_BF16) return fail(h, CGG_ERR_UNSUPPORTED, "cgg_mask_einsum is a CGG_BF16 stage");
+  Workspace ws;
+  ST(check_ws(h, batch, workspace, workspace_bytes, ws));
+  if (first_call < 0 || num_calls < 1 || first_call + num_calls > h->cfg.num_layers + 1)
+    return fail(h, CGG_ERR_BAD_SHAPE, "bad head-call range");
+  const long call_stride = (long)batch * h->cfg.num_queries * h->H4 * h->W4;
+  int st = tc_mask_einsum(h->tc, batch, first_call, num_calls, mask_features, mask, call_stride,
+                          at<void>(workspace, ws.tcws), (cudaStream_t)stream);
+  if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+  return CGG_OK;
+}
+
 extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, const float* q, const void* k,
                                     const void* v, long kv_stride, long kv_batch_stride, const uint32_t* bitmap,
                                     const uint8_t* all_masked, float* out, void* stream) {

@@ -90,29 +90,41 @@ struct EpiCtx {
   uint32_t taddr;
 };
 
-// K2 epilogue: out[call][image][q][pixel] bf16, lanes = pixels.  Two columns at a time: even lanes
-// store (own, right neighbour) for column i, odd lanes for column i+1 -> 4-byte stores, 64 B runs.
-__device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c) {
-  const int Q = p.Q, q_pad = p.q_pad, n_calls = p.n_calls, odd = c.lane & 1;
-  const long HW = p.HW, call_stride = p.out_call_stride;
-  __nv_bfloat16* base = p.out_mask + (long)c.batch * p.out_batch_stride + (c.m & ~1);
+// K2 epilogue: out[call][image][q][pixel] bf16.  TMEM lanes = pixels, columns = (call, q): the tile
+// is staged in shared memory as [column][128 pixels] and leaves through TMA stores -- one
+// (128 px x Q rows) box per head call of the tile; rows q >= Q fall outside the tensor and are clipped
+// by the TMA unit.  No per-thread global stores at all.
+__device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const CUtensorMap* tmC,
+                                           bool leader_warp, int t, int m_tile) {
+  const bool leader = leader_warp && c.lane == 0;
+  // the previous tile's stores must have finished READING the staging buffer
+  if (leader) ptx::tma_store_wait_read();
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  const int row = c.m & (TC_BM - 1);
   for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
     float v[16];
     ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
-    const int r0 = c.col0 + ch * 16;
-    const int call0 = r0 / q_pad;            // one division per chunk; q_pad >= 16: at most one wrap below
-    const int q0 = r0 - call0 * q_pad + odd;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sStage) + (long)(ch * 16) * TC_BM + row;
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float send = odd ? v[i] : v[i + 1];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-      int q = q0 + i, call = call0;
-      if (q >= q_pad) { q -= q_pad; ++call; }
-      if (c.m_ok && q < Q && call < n_calls) {
-        const uint32_t packed = odd ? pack_bf16x2(recv, v[i + 1]) : pack_bf16x2(v[i], recv);
-        *reinterpret_cast<uint32_t*>(base + (long)call * call_stride + (long)q * HW) = packed;
+    for (int i = 0; i < 16; ++i) dst[i * TC_BM] = __float2bfloat16_rn(v[i]);
+  }
+  ptx::fence_proxy_async_smem();
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  if (leader) {
+    const int r0 = c.col0;                       // first (call, q) row of this tile
+    const int N_TILE = c.chunks * 16, q_pad = p.q_pad;
+    if (N_TILE >= q_pad) {
+      for (int sidx = 0; sidx * q_pad + q_pad <= N_TILE || sidx == 0; ++sidx) {
+        const int call = r0 / q_pad + sidx;
+        if (call >= p.n_calls || sidx * q_pad >= N_TILE) break;
+        ptx::tma_store_3d(tmC, sStage + (long)sidx * q_pad * TC_BM * 2, m_tile * TC_BM, 0, call * (int)gridDim.y + c.batch);
       }
+    } else {
+      const int call = r0 / q_pad, q0 = r0 - call * q_pad;
+      if (call < p.n_calls) ptx::tma_store_3d(tmC, sStage, m_tile * TC_BM, q0, call * (int)gridDim.y + c.batch);
     }
+    ptx::tma_store_commit();
+    if (t == p.NT - 1) ptx::tma_store_wait_read();   // smem must stay valid until the last store has read it
   }
 }
 
@@ -267,7 +279,7 @@ __device__ unsigned long long g_tc_stamps[16];
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ TcGemmP p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.N_TILE * 128;
@@ -282,6 +294,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = b_empty + p.stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // EPI_MASK_T staging tile [N_TILE columns][128 pixels] bf16 for the TMA store (128-byte aligned)
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, batch = blockIdx.y;
@@ -395,7 +409,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
       ctx.col0 = t * p.N_TILE;
       switch (p.epi) {
-        case EPI_MASK_T: epi_mask_t(p, ctx); break;
+        case EPI_MASK_T: epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
         case EPI_ROWMAJOR: epi_rowmajor(p, ctx); break;
         case EPI_BITS: epi_bits(p, ctx); break;
         default: epi_linear_dispatch(p, ctx, lin); break;
@@ -554,7 +568,7 @@ int make_map_B(TcState* t, CUtensorMap* m, const void* base, long rows, int C, i
 }
 
 int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcGemmP p, int m_tiles, int batch,
-                   cudaStream_t s) {
+                   cudaStream_t s, const CUtensorMap* mC = nullptr) {
   if (p.N_TILE % 16 != 0 || p.N_TILE < 16 || p.N_TILE > 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "bad N tile");
   p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
   if (p.N_TILE <= 32) p.acc_stride = 32; else if (p.N_TILE <= 64) p.acc_stride = 64;
@@ -562,13 +576,14 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
   if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
-  const size_t budget = 200 * 1024;
+  const size_t stage_bytes = (p.epi == EPI_MASK_T) ? (size_t)p.N_TILE * TC_BM * 2 + 128 : 0;
+  const size_t budget = 204 * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
   if (stages < 2) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 64;
+  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 64 + stage_bytes;
   if (!t->smem_attr_set) {
     TCU(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     t->smem_attr_set = true;
@@ -577,7 +592,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  tc_gemm_kernel<<<dim3(m_tiles, batch), TC_THREADS, smem, s>>>(mA, mB, p);
+  tc_gemm_kernel<<<dim3(m_tiles, batch), TC_THREADS, smem, s>>>(mA, mB, mC ? *mC : mB, p);
   count_launch();
   TCU(cudaGetLastError());
   if (timing) {
@@ -811,7 +826,21 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   }
   st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE);
   if (st != CGG_OK) return st;
-  return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s);
+  // output map: (pixels, q, call*B + image); one (128 px x min(q_pad, N_TILE) rows) box per store
+  if (num_calls > 1 && call_stride != (long)batch * Q * HW)
+    return tc_fail(t, CGG_ERR_BAD_SHAPE, "mask outputs of consecutive head calls must be contiguous");
+  CUtensorMap mC;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)Q, (cuuint64_t)num_calls * batch};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)Q * HW * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BM, (cuuint32_t)(t->q_pad < p.N_TILE ? t->q_pad : p.N_TILE), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = t->encode(&mC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out) failed: " + std::to_string((int)r));
+  }
+  return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s, &mC);
 }
 
 // ------------------------------------------------------------------ small-M linear layers

@@ -319,6 +319,14 @@ class _Runtime:
         _lib.check(st, self.handle, 'cgg_head_call')
         return cls, emb, mask, me, bm, am
 
+    def mask_einsum(self, mask_features, mask_out, first_call=0, num_calls=None):
+        """K2 alone (bf16 mode) from the mask embeddings already in the workspace; mask_out
+        (num_calls, B, Q, H4, W4) bf16."""
+        n = num_calls if num_calls is not None else mask_out.shape[0]
+        st = self.lib.cgg_mask_einsum(self.handle, self.batch, first_call, n, _ptr(mask_features), _ptr(mask_out),
+                                      _ptr(self.workspace), self.workspace.numel(), self._stream())
+        _lib.check(st, self.handle, 'cgg_mask_einsum')
+
     def decoder_layer(self, layer, x, bitmap, all_masked):
         out = torch.empty_like(x)
         st = self.lib.cgg_decoder_layer(self.handle, C.byref(self.weights), x.shape[0], layer, _ptr(x),

@@ -13,7 +13,7 @@ c_float_p = C.POINTER(C.c_float)
 
 EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_launch_count', 'cgg_prepare', 'cgg_workspace_bytes', 'cgg_workspace_offset',
            'cgg_decoder_forward', 'cgg_kv_project', 'cgg_head_call', 'cgg_attn_mask_from_logits',
-           'cgg_decoder_layer', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
+           'cgg_decoder_layer', 'cgg_mask_einsum', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
            'cgg_grounding_scratch_bytes', 'cgg_grounding_loss']
 
 
@@ -68,6 +68,7 @@ def load():
                                         C.POINTER(vp), vp, vp, sz, vp]
     lib.cgg_kv_project.argtypes = [vp, C.POINTER(Weights), i, C.POINTER(vp), vp, sz, vp]
     lib.cgg_head_call.argtypes = [vp, C.POINTER(Weights), i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.cgg_mask_einsum.argtypes = [vp, i, i, i, vp, vp, vp, sz, vp]
     lib.cgg_attn_mask_from_logits.argtypes = [vp, i, vp, i, i, i, i, vp, vp, vp]
     lib.cgg_decoder_layer.argtypes = [vp, C.POINTER(Weights), i, i, vp, vp, vp, vp, vp, sz, vp]
     lib.cgg_masked_attention.argtypes = [vp, i, i, vp, vp, vp, C.c_long, C.c_long, vp, vp, vp, vp]

@@ -161,6 +161,13 @@ int cgg_head_call(cgg_handle *h, const cgg_weights *w, int batch, const float *x
                   void *mask, float *mask_embed_out, uint32_t *bitmap, uint8_t *all_masked,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* K2 alone (CGG_BF16 mode): the mask einsum of head calls first_call .. first_call+num_calls-1 in ONE
+ * pass over mask_features, from the mask embeddings that cgg_head_call / cgg_decoder_forward left in
+ * the workspace (head.py:748, x num_calls).  mask points at call `first_call`'s (B,Q,H4,W4) bf16
+ * slice; consecutive calls must be contiguous.  Used by the roofline measurement in bench.py. */
+int cgg_mask_einsum(cgg_handle *h, int batch, int first_call, int num_calls, const void *mask_features,
+                    void *mask, void *workspace, size_t workspace_bytes, void *stream);
+
 /* K3 alone on given fp32 logits (stage-level bit-exactness test): mask_pred (B,Q,H4,W4)
  * -> bitmap, all_masked for a target (h,w).  head.py:749-759. */
 int cgg_attn_mask_from_logits(cgg_handle *h, int batch, const float *mask_pred, int H4, int W4,

@@ -96,7 +96,8 @@ def bilinear_resize(x, out_hw):
         i0 = src.floor().to(torch.long).clamp(max=inn - 1)
         i1 = torch.clamp(i0 + 1, max=inn - 1)
         l1 = src - i0.to(torch.float32)
-        return i0, i1, 1.0 - l1, l1
+        dev = x.device
+        return i0.to(dev), i1.to(dev), (1.0 - l1).to(dev), l1.to(dev)
 
     r0, r1, h0, h1 = axis(H, oh)
     c0, c1, w0, w1 = axis(W, ow)
@@ -176,7 +177,7 @@ def decoder_forward(sd, mask_features, memories, num_layers=9, pred_emb_norm=Fal
     for l, mem in enumerate(memories):
         h, w = mem.shape[-2:]
         flat = mem.flatten(2).transpose(1, 2) + sd['level_embed.weight'][l]  # :792-796
-        pos = sine_pos_enc(h, w, C // 2)                                     # :798-804
+        pos = sine_pos_enc(h, w, C // 2).to(mem.device)                      # :798-804
         val_in.append(flat)
         key_in.append(flat + pos)
         sizes.append((h, w))
