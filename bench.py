@@ -104,6 +104,21 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def reduce_max(value, world, device):
+    """MAX over ranks of a per-rank scalar (the timing rule: slowest rank defines the step)."""
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_value(world, batch_per_gpu, steps, ms):
+    """images/s of the whole job: every rank processed batch_per_gpu images per step (weak scaling,
+    batch-sharded, no data-path collective -- SURVEY.md section 8e)."""
+    return world * batch_per_gpu * steps / (ms * 1e-3)
+
+
 def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
@@ -214,11 +229,8 @@ def run_b200_arm(args):
     ms = e0.elapsed_time(e1)
     launches = lib.cgg_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    ms = reduce_max(ms, world, dev)
+    value = whole_job_value(world, B, args.steps, ms)
 
     # ---- e2e: public API with HOST buffers; H2D of the step's inputs and D2H of the step's
     # result (last layer's cls / cls_emb / mask logits, what simple_test consumes, head.py:943-945)
@@ -274,10 +286,7 @@ def run_b200_arm(args):
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
     barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / float(t_e2e.item())
+    e2e_val = whole_job_value(world, B, e2e_steps, 1e3 * reduce_max(time.perf_counter() - t0, world, dev))
     d2h = sum(x.numel() * x.element_size() for x in res_h)
 
     # ---- roofline of the dominant kernel (the mask einsum, 55% of the path's FLOPs): CUDA events
