@@ -12,7 +12,9 @@
 // the projected K/V buffer.  Key tiles that are masked for EVERY query of the CTA are skipped
 // (flags from live_tiles_kernel); rows with all_masked set ignore the bitmap (the reference's
 // all-masked-row fallback, head.py:825-826).
-//   warp 0: TMA producer   warp 1: MMA issuer (1 thread)   warps 2-5: softmax / epilogue
+//   warp 0: TMA producer   warp 1: MMA issuer (1 thread)   warps 2-9: softmax / epilogue -- two
+//   groups of 4 warps, each owning 64 of the tile's 128 key columns with its OWN running max / sum /
+//   output accumulator (merged once at the end), so the groups never synchronise per tile
 #include "kernels.h"
 #include "tc_ptx.cuh"
 #include "tc_state.h"
@@ -21,7 +23,7 @@ namespace cgg {
 
 namespace {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 64 + 256;       // TMA warp + MMA warp + 8 softmax warps (two column halves)
 constexpr int AT_KT = 128;                   // keys per tile
 constexpr int AT_STAGES = 4;
 constexpr int AT_KV_TILE_BYTES = AT_KT * 64; // 128 keys x 32 dims x bf16 = 8 KB
@@ -95,14 +97,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
     for (int i = 0; i < AT_STAGES; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 128); ptx::mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 256); ptx::mbar_init(&o_full[i], 1); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     // Q tile -> bf16, core-matrix (no-swizzle) K-major layout: element (row, d) at
     // (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
     const int row = (warp & 3) * 32 + lane, qi = qt * 128 + row;
@@ -136,7 +138,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;    // 2 x 32 columns
+  const uint32_t tmem_O = tmem_base + 256;    // 2 buffers x 2 column halves x 32 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -182,10 +184,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const uint32_t p_addr = ptx::smem_u32(sP + (j & 1) * AT_P_BYTES);
         const uint32_t v_addr = ptx::smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < AT_KT / 16; ++k) {
-          const uint64_t adesc = umma_desc(p_addr + k * 256, 128, 2048, 0);         // P: core matrices
-          const uint64_t bdesc = umma_desc(v_addr + k * 1024, 512, 512, 4);         // V tile: SW64, N-major
-          ptx::mma_bf16_ss(tmem_O + (uint32_t)((j & 1) * 32), adesc, bdesc, idesc_o, k);
+        for (int hf = 0; hf < 2; ++hf) {
+          // O_half = P[:, 64 keys of this half] . V[those keys, :]  (each half has its own softmax reference)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_desc(p_addr + hf * 1024 + k * 256, 128, 2048, 0);         // P: core matrices
+            const uint64_t bdesc = umma_desc(v_addr + hf * 4096 + k * 1024, 512, 512, 4);         // V: SW64, N-major
+            ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 2 + hf) * 32), adesc, bdesc, idesc_o, k);
+          }
         }
         ptx::mma_commit(&o_full[j & 1]);
         ptx::mma_commit(&kv_empty[s]);
@@ -195,6 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   } else {
     // ------------- softmax / epilogue: thread = query row
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;             // which 64 key columns of every tile
     const int row = quarter * 32 + lane, qi = qt * 128 + row;
     const bool row_ok = qi < p.Q;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
@@ -210,21 +217,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       ptx::mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       // mask words of this row for the tile's 128 keys (bit = 1 -> masked); keys >= K are masked
-      uint32_t mw[4];
+      uint32_t mw[2];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int widx = t * 4 + w;
+      for (int w = 0; w < 2; ++w) {
+        const int widx = t * 4 + hf * 2 + w;
         uint32_t word = 0u;
         if (!ignore_mask && widx < p.W32) word = __ldg(brow + widx);
-        const int k0 = t * AT_KT + w * 32;
+        const int k0 = t * AT_KT + (hf * 2 + w) * 32;
         if (k0 + 32 > p.K) word |= (k0 >= p.K) ? 0xffffffffu : ~((1u << (p.K - k0)) - 1u);
         mw[w] = word;
       }
-      const uint32_t s_addr = tmem_S + (uint32_t)(buf * 128) + lane_off;
+      const uint32_t s_addr = tmem_S + (uint32_t)(buf * 128 + hf * 64) + lane_off;
       // pass 1: row max over unmasked keys
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(s_addr + c * 32, v);
 #pragma unroll
@@ -236,9 +243,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const float mneg = (m_new == -INFINITY) ? 0.f : -m_new * LOG2E;
       // pass 2: p = exp(s - m), bf16, into the P buffer (core-matrix layout, 16 B = 8 keys per store)
       float rowsum = 0.f;
-      uint8_t* prow = sP + buf * AT_P_BYTES + (row >> 3) * 2048 + (row & 7) * 16;
+      uint8_t* prow = sP + buf * AT_P_BYTES + (row >> 3) * 2048 + (row & 7) * 16 + hf * 1024;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(s_addr + c * 32, v);
 #pragma unroll
@@ -268,7 +275,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         ptx::mbar_wait(&o_full[pb], (uint32_t)((it - 1) >> 1) & 1u);
         ptx::tc_fence_after();
         float ov[32];
-        tmem_ld32(tmem_O + (uint32_t)(pb * 32) + lane_off, ov);
+        tmem_ld32(tmem_O + (uint32_t)((pb * 2 + hf) * 32) + lane_off, ov);
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
       }
@@ -278,11 +285,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       ptx::mbar_wait(&o_full[pb], (uint32_t)((it - 1) >> 1) & 1u);
       ptx::tc_fence_after();
       float ov[32];
-      tmem_ld32(tmem_O + (uint32_t)(pb * 32) + lane_off, ov);
+      tmem_ld32(tmem_O + (uint32_t)((pb * 2 + hf) * 32) + lane_off, ov);
 #pragma unroll
       for (int i = 0; i < 32; ++i) o[i] += ov[i];
     }
-    if (row_ok) {
+    // merge the two column halves of the row: half 1 publishes (m, l, o) through shared memory
+    // (the P buffers are idle once the last PV has been consumed), half 0 combines and stores
+    float* xch = reinterpret_cast<float*>(sP) + row * 35;
+    if (hf == 1) {
+      xch[0] = m_run;
+      xch[1] = l_run;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xch[2 + i] = o[i];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) {
+      const float m1 = xch[0], l1 = xch[1];
+      const float m = fmaxf(m_run, m1);
+      const float a0 = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m) * LOG2E);
+      const float a1 = (m1 == -INFINITY) ? 0.f : fast_exp2((m1 - m) * LOG2E);
+      l_run = l_run * a0 + l1 * a1;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * a0 + xch[2 + i] * a1;
+    }
+    if (row_ok && hf == 0) {
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       if (p.out) {
         float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);

@@ -264,7 +264,8 @@ __device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiC
     else if (rs) epi_linear_t<0, false, true>(p, c, L);
     else epi_linear_t<0, false, false>(p, c, L);
   } else if (L.mode == 1) {
-    epi_linear_t<1, false, false>(p, c, L);
+    if (rb) epi_linear_t<1, true, false>(p, c, L);
+    else epi_linear_t<1, false, false>(p, c, L);
   } else {
     epi_linear_t<2, false, false>(p, c, L);
   }

@@ -247,11 +247,12 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s));
   TCU(launch_ln_rows(t1, lw.norm_w[0], lw.norm_b[0], M, x1, nullptr, xqb, w->query_embed, Q, nullptr, s));
   // ---- self-attention: q, k from x1 + query_embed, v from x1 (per-query constant folded into rowbias_v)
-  TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvs, 2 * C, false, false),
-                 seg(2 * C, C, kvs + C, 2 * C, false, false, 1.f, pw.rowbias_v, Q, C)};
+  __nv_bfloat16* kvb = reinterpret_cast<__nv_bfloat16*>(kvs);          // (M, 2C) bf16: [k | v]
+  TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvb, 2 * C, true, false),
+                 seg(2 * C, C, kvb + C, 2 * C, true, false, 1.f, pw.rowbias_v, Q, C)};
   TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s));
-  TCU(launch_attention_f32(qs, kvs, kvs + C, false, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, batch, Q, Q,
-                           c.num_heads, s));
+  // the 100 x 100 self-attention runs on the same tcgen05 attention kernel (one key tile, no mask)
+  TST(tc_attention(t, batch, Q, qs, kvb, kvb + C, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, s));
   TcSeg so2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x1, C)};
   TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s));
   TCU(launch_ln_rows(t1, lw.norm_w[1], lw.norm_b[1], M, x2, xb, nullptr, nullptr, 0, nullptr, s));

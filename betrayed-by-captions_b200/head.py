@@ -64,15 +64,17 @@ class Mask2FormerHeadOpenB200(nn.Module):
 
     Constructor kwargs follow the reference (head.py:76-100 and init_kwargs :175-195); the ones
     that only matter to losses / caption generation are accepted and ignored.  New kwargs:
-    ``precision`` ('fp32' parity mode | 'bf16' throughput mode) and ``pixel_decoder`` may be an
+    ``precision`` ('fp32' parity mode | 'bf16' throughput mode), ``cuda_graph`` (replay the whole path
+    as one CUDA graph per set of input buffers) and ``pixel_decoder`` may be an
     ``nn.Module`` instance (mmdet builds it from the config dict in the real stack, see
     INTEGRATION.md)."""
 
     def __init__(self, in_channels=None, feat_channels=256, out_channels=256, num_things_classes=80,
                  num_stuff_classes=53, num_queries=100, num_transformer_feat_level=3, pixel_decoder=None,
                  enforce_decoder_input_project=False, transformer_decoder=None, positional_encoding=None,
-                 precision='fp32', d_lang=768, **kwargs):
+                 precision='fp32', d_lang=768, cuda_graph=False, **kwargs):
         super().__init__()
+        self.cuda_graph = bool(cuda_graph)
         if num_transformer_feat_level != 3:
             raise ValueError('the B200 path is built for 3 feature levels (1/32, 1/16, 1/8)')
         if enforce_decoder_input_project or feat_channels != out_channels:
@@ -185,6 +187,7 @@ class _Runtime:
         self.workspace = None
         self.batch = None
         self._keep = []
+        self._graphs = {}
 
     def __del__(self):
         try:
@@ -262,6 +265,40 @@ class _Runtime:
 
     # ---- whole path
     def forward(self, mask_features, memories, return_debug=False):
+        h = self.head
+        if h.cuda_graph and not return_debug:
+            return self._forward_graph(mask_features, memories)
+        return self._forward_eager(mask_features, memories, return_debug)
+
+    def _forward_graph(self, mask_features, memories):
+        """Replays a CUDA graph of the whole path (one graph per distinct set of input buffers; the
+        library call is capturable after cgg_prepare).  Outputs are graph-owned static tensors: they
+        are overwritten by the next replay of the same graph."""
+        with torch.cuda.device(self.device):
+            mf, mems = self._check_inputs(mask_features, memories)
+            sizes = [tuple(m.shape[-2:]) for m in mems]
+            self.prepare(mf.shape[2], mf.shape[3], sizes, mf.shape[0])
+            key = (mf.data_ptr(), tuple(m.data_ptr() for m in mems), tuple(mf.shape), self.weights_key)
+            entry = self._graphs.get(key)
+            if entry is None:
+                if len(self._graphs) >= 4:
+                    self._graphs.clear()
+                cur = torch.cuda.current_stream(self.device)
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self._forward_eager(mf, mems, False)          # warm-up outside capture
+                    side.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        outs = self._forward_eager(mf, mems, False)
+                cur.wait_stream(side)
+                entry = (g, outs, mf, mems)                       # keep the inputs alive with the graph
+                self._graphs[key] = entry
+            entry[0].replay()
+            return entry[1]
+
+    def _forward_eager(self, mask_features, memories, return_debug=False):
         h = self.head
         with torch.cuda.device(self.device):
             mf, mems = self._check_inputs(mask_features, memories)
@@ -391,10 +428,11 @@ class _Runtime:
         return loss[0]
 
 
-def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9):
+def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9,
+                               cuda_graph=False):
     """Convenience used by tests / bench: a head carrying the given (reference-keyed) weights."""
     head = Mask2FormerHeadOpenB200(num_things_classes=num_classes_p1 - 1, num_stuff_classes=0,
-                                   num_queries=num_queries, precision=precision,
+                                   num_queries=num_queries, precision=precision, cuda_graph=cuda_graph,
                                    transformer_decoder=dict(num_layers=num_layers))
     missing = head.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
