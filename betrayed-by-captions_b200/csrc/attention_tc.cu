@@ -27,7 +27,7 @@ constexpr int AT_THREADS = 64 + 256;       // TMA warp + MMA warp + 8 softmax wa
 constexpr int AT_KT = 128;                   // keys per tile
 constexpr int AT_STAGES = 4;
 constexpr int AT_KV_TILE_BYTES = AT_KT * 64; // 128 keys x 32 dims x bf16 = 8 KB
-constexpr int AT_STAGE_BYTES = 2 * AT_KV_TILE_BYTES;
+constexpr int AT_STAGE_BYTES = 4 * AT_KV_TILE_BYTES;   // K tile, V tile, key-bias (R) tile as hi + lo
 constexpr int AT_Q_BYTES = 128 * 64;         // 128 queries x 32 dims bf16, core-matrix layout
 constexpr int AT_P_BYTES = 128 * AT_KT * 2;  // 32 KB per P buffer
 constexpr float LOG2E = 1.4426950408889634f;
@@ -36,6 +36,7 @@ struct AttnP {
   const float* q; float* out; __nv_bfloat16* out_bf16;
   const uint32_t* bitmap; const uint8_t* all_masked; const uint8_t* live;
   int Q, K, heads, W32, ntiles, nqt;
+  int has_r, r_col0, r_lo_off;   // key-bias table term: S += Q (R_hi + R_lo)^T, R columns r_col0 + head*32
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -74,7 +75,8 @@ __device__ __forceinline__ int next_live(const uint8_t* live, int t, int n) {
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnP p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ AttnP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                   // 8 KB
@@ -96,6 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
+    if (p.has_r) ptx::prefetch_tmap(&tmR);
     for (int i = 0; i < AT_STAGES; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 256); ptx::mbar_init(&o_full[i], 1); }
     ptx::fence_mbar_init();
@@ -148,8 +151,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int s = it % AT_STAGES;
         const uint32_t ph = (uint32_t)(it / AT_STAGES) & 1u;
         ptx::mbar_wait(&kv_empty[s], ph ^ 1u);
-        ptx::mbar_expect_tx(&kv_full[s], AT_STAGE_BYTES);
+        ptx::mbar_expect_tx(&kv_full[s], (p.has_r ? 4 : 2) * AT_KV_TILE_BYTES);
         uint8_t* st = sKV + s * AT_STAGE_BYTES;
+        if (p.has_r) {
+          ptx::tma_load_2d(st + 2 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_col0 + h * 32, t * AT_KT);
+          ptx::tma_load_2d(st + 3 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_lo_off + p.r_col0 + h * 32, t * AT_KT);
+        }
         ptx::tma_load_3d(st, &tmK, &kv_full[s], h * 32, t * AT_KT, b);
         ptx::tma_load_3d(st + AT_KV_TILE_BYTES, &tmV, &kv_full[s], h * 32, t * AT_KT, b);
       }
@@ -172,6 +179,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           const uint64_t adesc = umma_desc(q_addr + k * 256, 128, 512, 0);          // Q: core matrices
           const uint64_t bdesc = umma_desc(k_addr + k * 32, 16, 512, 4);            // K tile: SW64, K-major
           ptx::mma_bf16_ss(tmem_S + (uint32_t)((j & 1) * 128), adesc, bdesc, idesc_s, k);
+        }
+        if (p.has_r) {
+          // + Q R^T: positional / level / bias part of the keys, a batch-independent table that the K/V
+          // projection therefore never has to add (K = Wk x + R  =>  q.K = q.(Wk x) + q.R)
+          // (R is kept as a bf16 hi/lo pair so that the table itself carries no bf16 rounding)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_desc(q_addr + (k & 1) * 256, 128, 512, 0);
+            const uint64_t bdesc = umma_desc(k_addr + (2 + (k >> 1)) * AT_KV_TILE_BYTES + (k & 1) * 32, 16, 512, 4);
+            ptx::mma_bf16_ss(tmem_S + (uint32_t)((j & 1) * 128), adesc, bdesc, idesc_s, 1u);
+          }
         }
         ptx::mma_commit(&s_full[j & 1]);
       };
@@ -383,7 +401,8 @@ int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_str
 
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, __nv_bfloat16* out_bf16,
-                 cudaStream_t s) {
+                 cudaStream_t s, const void* r_table, long r_cols, int r_col0) {
+  // r_table: (num_keys, r_cols) bf16 with columns [hi (r_cols/2) | lo (r_cols/2)]
   const int Q = t->cfg.num_queries, heads = t->cfg.num_heads, C = t->cfg.embed_dim;
   const int ntiles = (num_keys + AT_KT - 1) / AT_KT, nqt = (Q + 127) / 128;
   if ((size_t)batch * nqt * ntiles > t->live_bytes) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many key tiles");
@@ -392,6 +411,17 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   if (st != CGG_OK) return st;
   st = make_map_kv(t, &mV, v, num_keys, kv_stride, kv_bstride, batch, C);
   if (st != CGG_OK) return st;
+  CUtensorMap mR = mK;
+  if (r_table) {
+    cuuint64_t dims[2] = {(cuuint64_t)r_cols, (cuuint64_t)num_keys};
+    cuuint64_t strides[1] = {(cuuint64_t)r_cols * 2};
+    cuuint32_t box[2] = {32, AT_KT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = t->encode(&mR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(r_table), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(R) failed: " + std::to_string((int)r));
+  }
   const int W32 = (num_keys + 31) / 32;
   live_tiles_kernel<<<dim3(ntiles, nqt, batch), 128, 0, s>>>(bitmap, all_masked, Q, num_keys, W32, ntiles, nqt, t->live_buf);
   count_launch();
@@ -399,12 +429,13 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   AttnP p;
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
+  p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + (2 * AT_STAGES + 6) * 8 + 16;
   if (!t->attn_attr_set) {
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     t->attn_attr_set = true;
   }
-  attention_tc_kernel<<<dim3(heads * nqt, batch), AT_THREADS, smem, s>>>(mK, mV, p);
+  attention_tc_kernel<<<dim3(heads * nqt, batch), AT_THREADS, smem, s>>>(mK, mV, mR, p);
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;

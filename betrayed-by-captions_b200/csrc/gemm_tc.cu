@@ -128,38 +128,43 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
   }
 }
 
-// K4 epilogue: out[image][key][n] bf16 = acc + bias[n] + R[key][n]; the R / bias loads of a chunk are
-// issued before the TMEM read so their latency overlaps it.
-__device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c) {
-  const int r_ncols = p.r_ncols;
-  const __nv_bfloat16* rrow = p.R + (long)c.m * p.ldr;
-  __nv_bfloat16* orow = p.out_rows + (long)c.batch * p.out_rows_batch_stride + (long)c.m * p.ld_out;
+// K4 epilogue: out[image][key][n] bf16 = acc + bias[n].  The 128-key x N_TILE tile is staged in shared
+// memory as 64-column sub-tiles in the TMA 128-byte-swizzle layout (a thread owns a key row and writes
+// 16-byte chunks at chunk ^ (row & 7): conflict-free) and leaves through one TMA store per sub-tile;
+// rows past the image's last key are clipped by the TMA unit.  (The positional / level part of the keys
+// is not added here at all: the attention kernel adds Q R^T, see attention_tc.cu.)
+__device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const CUtensorMap* tmC,
+                                             bool leader_warp, int t, int m_tile) {
+  const bool leader = leader_warp && c.lane == 0;
+  if (leader) ptx::tma_store_wait_read();
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  const int row = c.m & (TC_BM - 1);
   for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
     const int n0 = c.col0 + ch * 16;
-    uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    if (c.m_ok && n0 < r_ncols) {
-      rr[0] = __ldg(reinterpret_cast<const uint4*>(rrow + n0));
-      rr[1] = __ldg(reinterpret_cast<const uint4*>(rrow + n0) + 1);
-    }
     float4 bb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
     float v[16];
     ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
-    if (c.m_ok) {
-      const float* bf = reinterpret_cast<const float*>(bb);
-      const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(rr);
-      uint4 o[2];
-      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+    const float* bf = reinterpret_cast<const float*>(bb);
+    uint4 o[2];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 r2 = __bfloat1622float2(rh[i]);
-        ow[i] = pack_bf16x2(v[2 * i] + bf[2 * i] + r2.x, v[2 * i + 1] + bf[2 * i + 1] + r2.y);
-      }
-      uint4* dst = reinterpret_cast<uint4*>(orow + n0);
-      dst[0] = o[0];
-      dst[1] = o[1];
-    }
+    for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(v[2 * i] + bf[2 * i], v[2 * i + 1] + bf[2 * i + 1]);
+    // column chunk (16 B = 8 columns) j of sub-tile `sub`, swizzled with the row
+    const int sub = ch >> 2, j = (ch & 3) * 2;
+    uint8_t* base = sStage + sub * (TC_BM * 128) + row * 128;
+    *reinterpret_cast<uint4*>(base + ((j ^ (row & 7)) << 4)) = o[0];
+    *reinterpret_cast<uint4*>(base + (((j + 1) ^ (row & 7)) << 4)) = o[1];
+  }
+  ptx::fence_proxy_async_smem();
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  if (leader) {
+    const int subs = c.chunks >> 2;
+    for (int sub = 0; sub < subs; ++sub)
+      ptx::tma_store_3d(tmC, sStage + sub * (TC_BM * 128), c.col0 + sub * 64, m_tile * TC_BM, c.batch);
+    ptx::tma_store_commit();
+    if (t == p.NT - 1) ptx::tma_store_wait_read();
   }
 }
 
@@ -296,7 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   // EPI_MASK_T staging tile [N_TILE columns][128 pixels] bf16 for the TMA store (128-byte aligned)
-  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, batch = blockIdx.y;
@@ -411,7 +416,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ctx.col0 = t * p.N_TILE;
       switch (p.epi) {
         case EPI_MASK_T: epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
-        case EPI_ROWMAJOR: epi_rowmajor(p, ctx); break;
+        case EPI_ROWMAJOR: epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
         case EPI_BITS: epi_bits(p, ctx); break;
         default: epi_linear_dispatch(p, ctx, lin); break;
       }
@@ -577,7 +582,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
   if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
-  const size_t stage_bytes = (p.epi == EPI_MASK_T) ? (size_t)p.N_TILE * TC_BM * 2 + 128 : 0;
+  const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR) ? (size_t)p.N_TILE * TC_BM * 2 + 1024 : 0;
   const size_t budget = 204 * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
@@ -673,6 +678,10 @@ size_t tc_workspace_offset(const TcState* t, int batch, const char* what) {
   if (n == "fds2") return w.fds[2];
   return (size_t)-1;
 }
+const void* tc_key_bias_table(const TcState* t, int level, long* cols) {
+  if (cols) *cols = 2L * t->nl[level] * t->cfg.embed_dim;   // [hi | lo]
+  return t->rk[level];
+}
 int tc_rows_per_batch(const TcState* t) { return t ? t->rows_per_batch : 0; }
 int tc_q_pad(const TcState* t) { return t ? t->q_pad : 0; }
 
@@ -693,13 +702,13 @@ int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, 
       t->lh[l] = lh[l]; t->lw[l] = lw[l]; t->nl[l] = nl[l];
       const int n = nl[l] > 0 ? nl[l] : 1;
       TCU(cudaMalloc(&t->wkv[l], (size_t)n * 2 * C * C * 2));
-      TCU(cudaMalloc(&t->rk[l], (size_t)lh[l] * lw[l] * n * C * 2));
+      TCU(cudaMalloc(&t->rk[l], (size_t)lh[l] * lw[l] * n * C * 2 * 2));   // hi | lo
     }
   }
   for (int l = 0; l < 3; ++l) {
     if (nl[l] == 0) continue;
     TCU(launch_cast_bf16(wkv_f32[l], t->wkv[l], (size_t)nl[l] * 2 * C * C, s));
-    TCU(launch_cast_bf16(rk_f32[l], t->rk[l], (size_t)lh[l] * lw[l] * nl[l] * C, s));
+    TCU(launch_cast_bf16_split(rk_f32[l], t->rk[l], lh[l] * lw[l], nl[l] * C, s));
     t->bkv[l] = bkv_f32[l];
   }
   return tc_pack_weights(t, w, s);
@@ -721,8 +730,21 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
   p.b_row0 = 0; p.b_rows_per_batch = 0;
   p.epi = EPI_ROWMAJOR; p.M_valid = K;
   p.out_rows = static_cast<__nv_bfloat16*>(kv_bf16); p.ld_out = N; p.out_rows_batch_stride = (long)K * N;
-  p.bias = t->bkv[level]; p.R = t->rk[level]; p.ldr = (long)t->nl[level] * C; p.r_ncols = t->nl[level] * C;
-  return launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s);
+  // the key-bias table (pos / level / bk through Wk) is NOT added here: the attention kernel adds Q R^T
+  p.bias = t->bkv[level]; p.R = t->rk[level]; p.ldr = (long)t->nl[level] * C; p.r_ncols = 0;
+  if (p.N_TILE % 64 != 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "K/V tile width must be a multiple of 64");
+  CUtensorMap mC;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)K, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)K * N * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)TC_BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = t->encode(&mC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, kv_bf16, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(kv out) failed: " + std::to_string((int)r));
+  }
+  return launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s, &mC);
 }
 
 int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* ws, cudaStream_t s) {

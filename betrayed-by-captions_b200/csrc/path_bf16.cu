@@ -241,7 +241,13 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   TCU(cudaGetLastError());
   TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
   TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
-  TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s));
+  {
+    const int level = layer % CGG_NUM_LEVELS, slot = layer / CGG_NUM_LEVELS;
+    long rcols = 0;
+    const void* rtab = tc_key_bias_table(t, level, &rcols);
+    TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s, rtab, rcols,
+                     slot * C));
+  }
   // x1 = LN(x + o Wo^T + bo);  also bf16(x1 + query_embed) for the self-attention projections
   TcSeg so[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x_in, C)};
   TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s));
