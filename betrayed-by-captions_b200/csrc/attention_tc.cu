@@ -107,6 +107,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  // barrier init / TMEM allocation above overlapped the previous kernel's tail
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   if (warp >= 2 && warp < 6) {
     // Q tile -> bf16, core-matrix (no-swizzle) K-major layout: element (row, d) at
     // (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
@@ -363,6 +366,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 __global__ void __launch_bounds__(128) live_tiles_kernel(const uint32_t* __restrict__ bitmap,
                                                          const uint8_t* __restrict__ all_masked, int Q, int K, int W32,
                                                          int ntiles, int nqt, uint8_t* __restrict__ live) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int t = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
   const int qi = qt * 128 + threadIdx.x;
   int any = 0;
@@ -423,7 +428,8 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(R) failed: " + std::to_string((int)r));
   }
   const int W32 = (num_keys + 31) / 32;
-  live_tiles_kernel<<<dim3(ntiles, nqt, batch), 128, 0, s>>>(bitmap, all_masked, Q, num_keys, W32, ntiles, nqt, t->live_buf);
+  TCU(launch_pdl(live_tiles_kernel, dim3(ntiles, nqt, batch), dim3(128), 0, s, bitmap, all_masked, Q, num_keys, W32, ntiles, nqt,
+                 t->live_buf));
   count_launch();
   TCU(cudaGetLastError());
   AttnP p;
@@ -435,7 +441,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     t->attn_attr_set = true;
   }
-  attention_tc_kernel<<<dim3(heads * nqt, batch), AT_THREADS, smem, s>>>(mK, mV, mR, p);
+  TCU(launch_pdl(attention_tc_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem, s, mK, mV, mR, p));
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;

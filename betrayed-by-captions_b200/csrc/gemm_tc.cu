@@ -324,6 +324,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TC_STAMP(1);
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -446,6 +449,8 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
                                                           int W4, __nv_bfloat16* __restrict__ d8,
                                                           __nv_bfloat16* __restrict__ d4,
                                                           __nv_bfloat16* __restrict__ d2) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int bw = W4 >> 3, bh = H4 >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)planes * bh * bw;
@@ -512,6 +517,8 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
 // me (B,Q,C) fp32 -> rows [b][call*q_pad + q][C] bf16 of the all-call B operand
 __global__ void store_me_kernel(const float* __restrict__ me, __nv_bfloat16* __restrict__ dst, int B, int Q, int C,
                                 int rows_per_batch, int row0) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Q * C;
   if (i >= total) return;
@@ -529,6 +536,8 @@ __global__ void store_me_kernel(const float* __restrict__ me, __nv_bfloat16* __r
 // all_masked[row] = (popcount of the row's bitmap == K)
 __global__ void __launch_bounds__(256) all_masked_kernel(const uint32_t* __restrict__ bitmap, int rows, int W32, int K,
                                                          uint8_t* __restrict__ all_masked) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   int cnt = 0;
@@ -598,7 +607,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  tc_gemm_kernel<<<dim3(m_tiles, batch), TC_THREADS, smem, s>>>(mA, mB, mC ? *mC : mB, p);
+  TCU(launch_pdl(tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB, mC ? *mC : mB, p));
   count_launch();
   TCU(cudaGetLastError());
   if (timing) {
@@ -754,10 +763,10 @@ int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* w
   const int planes = batch * t->cfg.embed_dim;
   const long total = (long)planes * (t->H4 / 8) * (t->W4 / 8);
   char* base = static_cast<char*>(ws);
-  downsample3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  TCU(launch_pdl(downsample3_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
       static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->cfg.embed_dim, t->H4, t->W4,
       reinterpret_cast<__nv_bfloat16*>(base + w.fds[0]), reinterpret_cast<__nv_bfloat16*>(base + w.fds[1]),
-      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2]));
+      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2])));
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;
@@ -768,9 +777,9 @@ int tc_store_mask_embed(TcState* t, int batch, int call_idx, const float* me_f32
   w.carve(t, batch);
   const int C = t->cfg.embed_dim, Q = t->cfg.num_queries;
   const long total = (long)batch * Q * C;
-  store_me_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+  TCU(launch_pdl(store_me_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
       me_f32, reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + w.me_all), batch, Q, C, t->rows_per_batch,
-      call_idx * t->q_pad);
+      call_idx * t->q_pad));
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;
@@ -806,7 +815,7 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
   st = launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s);
   if (st != CGG_OK) return st;
   const int rows = batch * Q;
-  all_masked_kernel<<<(rows + 7) / 8, 256, 0, s>>>(bitmap, rows, p.W32, K, all_masked);
+  TCU(launch_pdl(all_masked_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, (const uint32_t*)bitmap, rows, p.W32, K, all_masked));
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;

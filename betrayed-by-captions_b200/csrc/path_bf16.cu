@@ -5,6 +5,7 @@
 // are rounded to bf16.
 #include "gemm_tc.h"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 #include "tc_state.h"
 
 #include <math.h>
@@ -19,6 +20,8 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // dst = bf16(x + qe[row % Q])
 __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __restrict__ qe,
                                    __nv_bfloat16* __restrict__ dst, long total, int per /* Q*C */) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= total) return;
   const float4 a = *reinterpret_cast<const float4*>(x + i);
@@ -38,6 +41,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
                                                       __nv_bfloat16* __restrict__ out_bf16_q,
                                                       const float* __restrict__ qe, int Q,
                                                       __nv_bfloat16* __restrict__ out_hl) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int n0 = lane * 8;
@@ -98,9 +103,10 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 cudaError_t launch_ln_rows(const float* x, const float* w, const float* b, int rows, float* out_f32,
                            __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_q, const float* qe, int Q,
                            __nv_bfloat16* out_hl, cudaStream_t s) {
-  ln_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, b, rows, out_f32, out_bf16, out_bf16_q, qe, Q > 0 ? Q : 1, out_hl);
+  cudaError_t e = launch_pdl(ln_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, w, b, rows, out_f32, out_bf16, out_bf16_q,
+                             qe, Q > 0 ? Q : 1, out_hl);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <typename T>
@@ -236,7 +242,8 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   float* t1 = at<float>(ws, o.t1);
   // ---- cross-attention: q = ((x + query_embed) Wq^T + bq) / sqrt(d)
   const long total = (long)M * C;
-  add_qe_cast_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(x_in, w->query_embed, xqb, total, Q * C);
+  TCU(launch_pdl(add_qe_cast_kernel, dim3((unsigned)((total / 4 + 255) / 256)), dim3(256), 0, s, x_in, w->query_embed, xqb, total,
+                 Q * C));
   count_launch();
   TCU(cudaGetLastError());
   TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
