@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,13 @@ struct cgg_handle {
   float* rk[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};         // (K_l, nl*C) key bias table
   float* bkv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};        // (nl*2C)    0 | value bias
   TcState* tc = nullptr;                                           // bf16 / tcgen05 side
+  // Helper streams of cgg_decoder_forward (bf16 mode): throughput kernels that are off the critical
+  // chain (K/V projection of the later levels, the mask einsum of finished head calls) are forked
+  // from the caller's stream with events and joined back before the call's work ends on it.
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_kv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};
+  bool overlap = false;
   void free_tables() {
     for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
       cudaFree(pos_level[l]); cudaFree(wkv[l]); cudaFree(rk[l]); cudaFree(bkv[l]);
@@ -133,6 +141,17 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
   if (cfg->precision == CGG_BF16) {
     h->tc = tc_create(*cfg);
     if (!h->tc) { delete h; return CGG_ERR_CUDA; }
+    if (getenv("CGG_OVERLAP")) {   // opt-in: measured slower on B200 (5.33 vs 4.69 ms/step) -- the helper kernels starve the layer chain of SMs
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      bool ok = true;
+      for (int i = 0; i < 2; ++i) ok = ok && cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, lo) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 2; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < CGG_NUM_LEVELS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_kv[i], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i <= CGG_MAX_LAYERS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_me[i], cudaEventDisableTiming) == cudaSuccess;
+      h->overlap = ok;
+    }
   }
   *out = h;
   return CGG_OK;
@@ -142,6 +161,11 @@ extern "C" void cgg_destroy(cgg_handle* h) {
   if (!h) return;
   h->free_tables();
   if (h->tc) tc_destroy(h->tc);
+  for (int i = 0; i < 2; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 2; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  for (int i = 0; i < CGG_NUM_LEVELS; ++i) if (h->ev_kv[i]) cudaEventDestroy(h->ev_kv[i]);
+  for (int i = 0; i <= CGG_MAX_LAYERS; ++i) if (h->ev_me[i]) cudaEventDestroy(h->ev_me[i]);
   delete h;
 }
 
@@ -234,14 +258,13 @@ extern "C" size_t cgg_workspace_offset(const cgg_handle* h, int batch, const cha
 }
 
 // ============================================================================== stages
-extern "C" int cgg_kv_project(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
-                              void* workspace, size_t workspace_bytes, void* stream) {
+static int kv_project_levels(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
+                             void* workspace, size_t workspace_bytes, cudaStream_t s, int l_begin, int l_end) {
   if (!h || !w || !memories) return CGG_ERR_NULL;
-  cudaStream_t s = (cudaStream_t)stream;
   Workspace ws;
   ST(check_ws(h, batch, workspace, workspace_bytes, ws));
   const int C = h->cfg.embed_dim;
-  for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
+  for (int l = l_begin; l < l_end; ++l) {
     if (h->nl[l] == 0) continue;
     if (!memories[l]) return fail(h, CGG_ERR_NULL, "null memory level");
     const int K = h->lh[l] * h->lw[l], N = h->nl[l] * 2 * C;
@@ -260,6 +283,11 @@ extern "C" int cgg_kv_project(cgg_handle* h, const cgg_weights* w, int batch, co
     CU(launch_gemm_f32(p, s));
   }
   return CGG_OK;
+}
+
+extern "C" int cgg_kv_project(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, (cudaStream_t)stream, 0, CGG_NUM_LEVELS);
 }
 
 extern "C" int cgg_attn_mask_from_logits(cgg_handle* h, int batch, const float* mask_pred, int H4, int W4, int th,
@@ -445,12 +473,27 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
   const size_t mask_elt = (c.precision == CGG_BF16) ? 2 : 4;
   float* xs = x_states ? x_states : at<float>(workspace, ws.xs);
   const bool tcm = c.precision == CGG_BF16;
-  ST(cgg_kv_project(h, w, batch, memories, workspace, workspace_bytes, stream));
+  const bool ovl = tcm && h->overlap && L + 1 <= CGG_MAX_LAYERS + 1;
+  void* tws = at<void>(workspace, ws.tcws);
+  if (ovl) {
+    // fork: level 0 K/V on the caller's stream (layer 0 needs it first), levels 1 and 2 on a helper stream
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
+    CU(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
+    ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, s, 0, 1));
+    for (int l = 1; l < CGG_NUM_LEVELS; ++l) {
+      ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, h->side[0], l, l + 1));
+      CU(cudaEventRecord(h->ev_kv[l], h->side[0]));
+    }
+  } else {
+    ST(cgg_kv_project(h, w, batch, memories, workspace, workspace_bytes, stream));
+  }
   if (tcm) {
-    int st = tc_downsample(h->tc, batch, mask_features, at<void>(workspace, ws.tcws), s);
+    int st = tc_downsample(h->tc, batch, mask_features, tws, s);
     if (st != CGG_OK) return fail(h, st, std::string("tc_downsample: ") + tc_last_error(h->tc));
   }
   CU(launch_broadcast_rows(w->query_feat, xs, batch, Q, C, s));          // head.py:808-809
+  int einsum_done = 0;   // head calls whose mask einsum has been enqueued (helper stream)
   for (int j = 0; j <= L; ++j) {
     const bool need_mask = j < L;                                           // the last mask is never used
     uint32_t* bm = need_mask ? ((bitmaps && bitmaps[j]) ? bitmaps[j] : at<uint32_t>(workspace, ws.bitmap)) : nullptr;
@@ -460,14 +503,35 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
                       cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
                       static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
                       workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true));
-    if (j < L)
+    if (ovl && (j & 1) && j < L) {
+      // K2 of head calls j-1 and j (one 2-call N tile) runs on a helper stream underneath the
+      // latency-bound layer chain; only the last pair stays on the critical path
+      CU(cudaEventRecord(h->ev_me[j], s));
+      CU(cudaStreamWaitEvent(h->side[1], h->ev_me[j], 0));
+      int st = tc_mask_einsum(h->tc, batch, j - 1, 2, mask_features,
+                              static_cast<char*>(mask) + (size_t)(j - 1) * batch * Q * HW * mask_elt,
+                              (long)batch * Q * HW, tws, h->side[1]);
+      if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+      einsum_done = j + 1;
+    }
+    if (j < L) {
+      const int lvl = j % CGG_NUM_LEVELS;
+      if (ovl && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
       ST(cgg_decoder_layer(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream));
+    }
   }
   if (tcm) {
-    // K2 for all L+1 head calls in one pass: mask_features is read from HBM once (head.py:748 x10)
-    int st = tc_mask_einsum(h->tc, batch, 0, L + 1, mask_features, mask, (long)batch * Q * HW,
-                            at<void>(workspace, ws.tcws), s);
+    // K2 of the remaining head calls (all L+1 in one pass over mask_features when nothing was overlapped)
+    int st = tc_mask_einsum(h->tc, batch, einsum_done, L + 1 - einsum_done, mask_features,
+                            static_cast<char*>(mask) + (size_t)einsum_done * batch * Q * HW * mask_elt,
+                            (long)batch * Q * HW, tws, s);
     if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+  }
+  if (ovl) {
+    for (int i = 0; i < 2; ++i) {   // join
+      CU(cudaEventRecord(h->ev_join[i], h->side[i]));
+      CU(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+    }
   }
   return CGG_OK;
 }

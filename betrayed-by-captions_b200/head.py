@@ -284,7 +284,7 @@ class _Runtime:
                 if len(self._graphs) >= 4:
                     self._graphs.clear()
                 cur = torch.cuda.current_stream(self.device)
-                side = torch.cuda.Stream(self.device)
+                side = torch.cuda.Stream(self.device, priority=-1)   # the layer chain outranks the helper streams
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     self._forward_eager(mf, mems, False)          # warm-up outside capture
