@@ -39,6 +39,7 @@ enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2, EPI_LINEAR_T = 3 };
 
 struct TcGemmP {
   int NT, N_TILE, KC, stages;
+  int cluster2;          // 1: CTA pairs (cluster of 2 along x) share every B tile: each CTA loads half of it, multicast to both
   int m_halves;          // 1 or 2: the CTA owns m_halves x 128 lanes-worth of pixels (two accumulators share every B stage)
   int a_resident;        // 1: the whole A tile (KC chunks) stays in smem for all NT tiles; 0: A chunks stream with B
   int a_kmajor;          // 0: A is an NCHW feature map (pixels contiguous); 1: A is [rows][K] activations (K contiguous)
@@ -321,7 +322,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::mbar_init(a_full, 1);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], p.cluster2 ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
     ptx::fence_mbar_init();
   }
@@ -332,6 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (p.cluster2) ptx::cluster_sync_all();    // the peer's barriers must exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TC_STAMP(1);
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
@@ -366,8 +368,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
           if (!p.a_resident) load_a(stage, &b_full[s], kc, 0);
-          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? kc * TC_BK : p.b_kcoord[kc],
-                           batch * p.b_rows_per_batch + p.b_row0 + t * (p.b_tile_stride ? p.b_tile_stride : p.N_TILE));
+          const int bk = p.k_identity ? kc * TC_BK : p.b_kcoord[kc];
+          const int brow = batch * p.b_rows_per_batch + p.b_row0 + t * (p.b_tile_stride ? p.b_tile_stride : p.N_TILE);
+          if (p.cluster2) {
+            // this CTA fetches its half of the tile's rows and multicasts it to both CTAs of the pair;
+            // the other half arrives from the peer (b_empty counts BOTH consumers, so the slot is free in both)
+            const int half_rows = p.N_TILE >> 1, r = (int)ptx::cluster_ctarank();
+            ptx::tma_load_2d_mc(stage + a_in_stage + r * half_rows * 128, &tmB, &b_full[s], bk, brow + r * half_rows, 0x3);
+          } else {
+            ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], bk, brow);
+          }
         }
     }
   } else if (warp == 1) {
@@ -405,7 +415,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::mma_bf16_ss(d_tmem + (uint32_t)(hm * p.acc_stride), adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
             }
           }
-          ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
+          if (p.cluster2) ptx::mma_commit_mc(&b_empty[s], 0x3);   // frees the stage in BOTH CTAs of the pair
+          else ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
         }
         ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
         if (t == 0) TC_STAMP(3);
@@ -445,6 +456,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster2) ptx::cluster_sync_all();    // no CTA of the pair may exit while the peer can still signal it
   if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     __syncwarp();
@@ -624,7 +636,9 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  TCU(launch_pdl(tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB, mC ? *mC : mB, p));
+  if (p.cluster2) m_tiles = (m_tiles + 1) & ~1;
+  TCU(launch_pdl_cluster(p.cluster2 ? 2 : 1, tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB,
+                         mC ? *mC : mB, p));
   count_launch();
   TCU(cudaGetLastError());
   if (timing) {
@@ -885,7 +899,10 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       return CGG_OK;
     }
   }
-  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE);
+  // CTA-pair multicast of the B tiles: correct, but measured slower on B200 (1.16 vs 0.99 ms) -> opt-in
+  static const bool use_cluster = getenv("CGG_EINSUM_CLUSTER") != nullptr;
+  p.cluster2 = (use_cluster && p.m_halves <= 1 && p.N_TILE % 16 == 0) ? 1 : 0;
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.cluster2 ? p.N_TILE / 2 : p.N_TILE);
   if (st != CGG_OK) return st;
   // output map: (pixels, q, call*B + image); one (128 px x min(q_pad, N_TILE) rows) box per store
   if (num_calls > 1 && call_stride != (long)batch * Q * HW)
