@@ -30,6 +30,7 @@ constexpr int AT_KV_TILE_BYTES = AT_KT * 64; // 128 keys x 32 dims x bf16 = 8 KB
 constexpr int AT_STAGE_BYTES = 4 * AT_KV_TILE_BYTES;   // K tile, V tile, key-bias (R) tile as hi + lo
 constexpr int AT_Q_BYTES = 128 * 64;         // 128 queries x 32 dims bf16, core-matrix layout
 constexpr int AT_P_BYTES = 128 * AT_KT * 2;  // 32 KB per P buffer
+constexpr int AT_ONES_BYTES = 64 * 64;      // 64 key rows x 64 B: column 0 = 1.0 (row sums come out of the PV MMA)
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnP {
@@ -82,7 +83,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint8_t* sQ = smem;                                   // 8 KB
   uint8_t* sP = sQ + AT_Q_BYTES;                        // 2 x 32 KB
   uint8_t* sKV = sP + 2 * AT_P_BYTES;                   // stages x (K tile, V tile)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AT_STAGES * AT_STAGE_BYTES);
+  uint8_t* sOnes = sKV + AT_STAGES * AT_STAGE_BYTES;   // above every V tile (descriptor offsets are unsigned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + AT_ONES_BYTES);
   uint64_t* kv_full = bars;
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;
@@ -110,6 +112,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
+  if (warp >= 2) {
+    // "ones" tile, an extra N-group of the PV B operand in the V tiles' layout (64-byte rows, 64-byte
+    // swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)): column 0 of every key row is
+    // 1.0, so column 32 of O = P [V | 1] is the row sum of the bf16 P the tensor core actually used.
+    const int tid = threadIdx.x - 64;                       // 0..255
+    uint4 z = make_uint4(0, 0, 0, 0);
+    const int r = tid >> 2, cpos = tid & 3;                 // one 16-byte chunk per thread: 64 rows x 4 chunks
+    if (cpos == ((r >> 1) & 3)) z.x = 0x00003F80u;          // bf16 1.0 in element 0 of logical chunk 0
+    *reinterpret_cast<uint4*>(sOnes + r * 64 + cpos * 16) = z;
+    fence_async_smem();
+  }
   if (warp >= 2 && warp < 6) {
     // Q tile -> bf16, core-matrix (no-swizzle) K-major layout: element (row, d) at
     // (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
@@ -144,7 +157,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;    // 2 buffers x 2 column halves x 32 columns
+  const uint32_t tmem_O = tmem_base + 256;    // 2 buffers x 2 column halves x 64-column slots (48 used: 32 dims, sum, pad)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -168,7 +181,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (lane == 0) {
       // ------------- MMA issuer
       const uint32_t idesc_s = ptx::umma_idesc_bf16(128, AT_KT, false, false);   // S = Q K^T
-      const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 32, false, true);       // O = P V (V is N-major)
+      const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 48, false, true);       // O = P [V | 1] (N-major B, 2 N-groups)
+      const uint32_t ones_addr = ptx::smem_u32(sOnes);
       const uint32_t q_addr = ptx::smem_u32(sQ);
       int n_live = 0;
       for (int t = 0; t < p.ntiles; ++t) n_live += live[t] ? 1 : 0;
@@ -210,8 +224,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = umma_desc(p_addr + hf * 1024 + k * 256, 128, 2048, 0);         // P: core matrices
-            const uint64_t bdesc = umma_desc(v_addr + hf * 4096 + k * 1024, 512, 512, 4);         // V: SW64, N-major
-            ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 2 + hf) * 32), adesc, bdesc, idesc_o, k);
+            // V: SW64, N-major; the leading-dimension offset reaches from this V slice to the ones tile
+            const uint32_t vk = v_addr + hf * 4096 + k * 1024;
+            const uint64_t bdesc = umma_desc(vk, (ones_addr + k * 1024) - vk, 512, 4);
+            ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 2 + hf) * 64), adesc, bdesc, idesc_o, k);
           }
         }
         ptx::mma_commit(&o_full[j & 1]);
@@ -228,16 +244,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool ignore_mask = !row_ok || p.bitmap == nullptr || (p.all_masked && p.all_masked[(long)b * p.Q + qi]);
     const uint32_t* brow = p.bitmap ? p.bitmap + ((long)b * p.Q + (row_ok ? qi : 0)) * p.W32 : nullptr;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[32];
+    float m_run = -INFINITY;
+    float o[33];                                  // 32 output dims + the running row sum (column 32 of O)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    for (int i = 0; i < 33; ++i) o[i] = 0.f;
+    auto fold_o = [&](int pb, float scale) {      // o = (o + O_tile) * scale
+      float ov[32];
+      const uint32_t oa = tmem_O + (uint32_t)((pb * 2 + hf) * 64) + lane_off;
+      tmem_ld32(oa, ov);
+      uint32_t sum_bits;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sum_bits) : "r"(oa + 32));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
+      o[32] = (o[32] + __uint_as_float(sum_bits)) * scale;
+    };
     int it = 0;
     for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; t = next_live(live, t + 1, p.ntiles), ++it) {
       const int buf = it & 1;
       ptx::mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      // mask words of this row for the tile's 128 keys (bit = 1 -> masked); keys >= K are masked
+      // mask words of this row for this half's 64 keys (bit = 1 -> masked); keys >= K are masked
       uint32_t mw[2];
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
@@ -249,67 +276,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         mw[w] = word;
       }
       const uint32_t s_addr = tmem_S + (uint32_t)(buf * 128 + hf * 64) + lane_off;
-      // pass 1: row max over unmasked keys
+      // the 64 scores are read from TMEM ONCE, masked to -inf in registers, and reused for max and exp
+      float v[64];
+      tmem_ld32(s_addr, v);
+      tmem_ld32(s_addr + 32, v + 32);
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(s_addr + c * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (!((mw[c] >> i) & 1u)) mx = fmaxf(mx, v[i]);
+      for (int i = 0; i < 64; ++i) {
+        if ((mw[i >> 5] >> (i & 31)) & 1u) v[i] = -INFINITY;
+        mx = fmaxf(mx, v[i]);
       }
       const float m_new = fmaxf(m_run, mx);
       const float scale = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * LOG2E);
       const float mneg = (m_new == -INFINITY) ? 0.f : -m_new * LOG2E;
-      // pass 2: p = exp(s - m), bf16, into the P buffer (core-matrix layout, 16 B = 8 keys per store)
-      float rowsum = 0.f;
+      m_run = m_new;
+      // p = exp(s - m) as bf16 into the P buffer (core-matrix layout, 16 B = 8 keys per store); exp2(-inf) = 0
       uint8_t* prow = sP + buf * AT_P_BYTES + (row >> 3) * 2048 + (row & 7) * 16 + hf * 1024;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(s_addr + c * 32, v);
+      for (int g = 0; g < 8; ++g) {
+        uint4 pk;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i0 = g * 8 + 2 * j;
-            const float p0 = ((mw[c] >> i0) & 1u) ? 0.f : fast_exp2(fmaf(v[i0], LOG2E, mneg));
-            const float p1 = ((mw[c] >> (i0 + 1)) & 1u) ? 0.f : fast_exp2(fmaf(v[i0 + 1], LOG2E, mneg));
-            rowsum += p0 + p1;
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(p0, p1);
-            w[j] = *reinterpret_cast<uint32_t*>(&v2);
-          }
-          *reinterpret_cast<uint4*>(prow + (c * 4 + g) * 128) = pk;
+        for (int j = 0; j < 4; ++j) {
+          const int i0 = g * 8 + 2 * j;
+          __nv_bfloat162 v2 = __floats2bfloat162_rn(fast_exp2(fmaf(v[i0], LOG2E, mneg)), fast_exp2(fmaf(v[i0 + 1], LOG2E, mneg)));
+          w[j] = *reinterpret_cast<uint32_t*>(&v2);
         }
+        *reinterpret_cast<uint4*>(prow + g * 128) = pk;
       }
-      l_run = l_run * scale + rowsum;
-      m_run = m_new;
       fence_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[buf]);
-      // fold the previous tile's P V into the register accumulator, then apply this tile's rescale
+      // fold the previous tile's P [V | 1] into the register accumulator, then apply this tile's rescale
       if (it > 0) {
-        const int pb = (it - 1) & 1;
-        ptx::mbar_wait(&o_full[pb], (uint32_t)((it - 1) >> 1) & 1u);
+        ptx::mbar_wait(&o_full[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
         ptx::tc_fence_after();
-        float ov[32];
-        tmem_ld32(tmem_O + (uint32_t)((pb * 2 + hf) * 32) + lane_off, ov);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
+        fold_o((it - 1) & 1, scale);
       }
     }
     if (it > 0) {
-      const int pb = (it - 1) & 1;
-      ptx::mbar_wait(&o_full[pb], (uint32_t)((it - 1) >> 1) & 1u);
+      ptx::mbar_wait(&o_full[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
       ptx::tc_fence_after();
-      float ov[32];
-      tmem_ld32(tmem_O + (uint32_t)((pb * 2 + hf) * 32) + lane_off, ov);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] += ov[i];
+      fold_o((it - 1) & 1, 1.f);
     }
+    float l_run = o[32];
     // merge the two column halves of the row: half 1 publishes (m, l, o) through shared memory
     // (the P buffers are idle once the last PV has been consumed), half 0 combines and stores
     float* xch = reinterpret_cast<float*>(sP) + row * 35;
@@ -436,7 +446,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
-  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + (2 * AT_STAGES + 6) * 8 + 16;
+  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_ONES_BYTES + (2 * AT_STAGES + 6) * 8 + 16;
   if (!t->attn_attr_set) {
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     t->attn_attr_set = true;

@@ -39,8 +39,6 @@ enum { EPI_MASK_T = 0, EPI_ROWMAJOR = 1, EPI_BITS = 2, EPI_LINEAR_T = 3 };
 
 struct TcGemmP {
   int NT, N_TILE, KC, stages;
-  int cluster2;          // 1: CTA pairs (cluster of 2 along x) share every B tile: each CTA loads half of it, multicast to both
-  int m_halves;          // 1 or 2: the CTA owns m_halves x 128 lanes-worth of pixels (two accumulators share every B stage)
   int a_resident;        // 1: the whole A tile (KC chunks) stays in smem for all NT tiles; 0: A chunks stream with B
   int a_kmajor;          // 0: A is an NCHW feature map (pixels contiguous); 1: A is [rows][K] activations (K contiguous)
   int k_identity;        // 1: chunk kc sits at K coordinate kc*64 for both operands (kcoord tables unused)
@@ -49,7 +47,6 @@ struct TcGemmP {
   // EPI_LINEAR_T: up to 3 FEATURE segments (32-aligned starts) of (acc + bias [+ rowbias]) * alpha [+ res] [relu]
   TcSeg seg[3]; int nseg; const float* lin_bias; int n_tokens;
   int b_row0;            // first B row (e.g. call_idx * q_pad)
-  int b_tile_stride;     // B rows between consecutive N tiles (0: N_TILE)
   int b_rows_per_batch;  // B row offset per blockIdx.y (0: weights shared by the batch)
   int acc_stride;        // TMEM columns between the two accumulator buffers
   int tmem_cols;         // power of two >= 32
@@ -84,13 +81,6 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 }
 
 
-// Debug timeline (CGG_TC_TIMING=1): globaltimer stamps of CTA (0,0), printed by launch_tc_gemm.
-__device__ unsigned long long g_tc_stamps[16];
-#define TC_STAMP(i)                                                            \
-  do {                                                                         \
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
-  } while (0)
-
 constexpr int EPI_WARPS = 16;                 // epilogue warps (4 per TMEM lane quarter)
 constexpr int EPI_PARTS = EPI_WARPS / 4;
 
@@ -108,25 +98,18 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
                                            bool leader_warp, int t, int m_tile) {
   const bool leader = leader_warp && c.lane == 0;
   // the previous tile's stores must have finished READING the staging buffer
-  if (leader && t == 2) TC_STAMP(7);
   if (leader) ptx::tma_store_wait_read();
-  if (leader && t == 2) TC_STAMP(8);
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  if (leader && t == 2) TC_STAMP(9);
   const int row = c.m & (TC_BM - 1);
-  const int MT = p.m_halves * TC_BM;             // pixels per staged column
-  for (int w = c.part; w < c.chunks * p.m_halves; w += EPI_PARTS) {
-    const int hm = w / c.chunks, ch = w - hm * c.chunks;
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
     float v[16];
-    ptx::tmem_ld16(c.taddr + (uint32_t)(hm * p.acc_stride + ch * 16), v);
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sStage) + (long)(ch * 16) * MT + hm * TC_BM + row;
+    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sStage) + (long)(ch * 16) * TC_BM + row;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i * MT] = __float2bfloat16_rn(v[i]);
+    for (int i = 0; i < 16; ++i) dst[i * TC_BM] = __float2bfloat16_rn(v[i]);
   }
-  if (leader && t == 2) TC_STAMP(10);
   ptx::fence_proxy_async_smem();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  if (leader && t == 2) TC_STAMP(11);
   if (leader) {
     const int r0 = c.col0;                       // first (call, q) row of this tile
     const int N_TILE = c.chunks * 16, q_pad = p.q_pad;
@@ -134,14 +117,13 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
       for (int sidx = 0; sidx * q_pad + q_pad <= N_TILE || sidx == 0; ++sidx) {
         const int call = r0 / q_pad + sidx;
         if (call >= p.n_calls || sidx * q_pad >= N_TILE) break;
-        ptx::tma_store_3d(tmC, sStage + (long)sidx * q_pad * MT * 2, m_tile * MT, 0, call * (int)gridDim.y + c.batch);
+        ptx::tma_store_3d(tmC, sStage + (long)sidx * q_pad * TC_BM * 2, m_tile * TC_BM, 0, call * (int)gridDim.y + c.batch);
       }
     } else {
       const int call = r0 / q_pad, q0 = r0 - call * q_pad;
-      if (call < p.n_calls) ptx::tma_store_3d(tmC, sStage, m_tile * MT, q0, call * (int)gridDim.y + c.batch);
+      if (call < p.n_calls) ptx::tma_store_3d(tmC, sStage, m_tile * TC_BM, q0, call * (int)gridDim.y + c.batch);
     }
     ptx::tma_store_commit();
-    if (t == 2) TC_STAMP(12);
     if (t == p.NT - 1) ptx::tma_store_wait_read();   // smem must stay valid until the last store has read it
   }
 }
@@ -294,6 +276,13 @@ __device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiC
   }
 }
 
+// Debug timeline (CGG_TC_TIMING=1): globaltimer stamps of CTA (0,0), printed by launch_tc_gemm.
+__device__ unsigned long long g_tc_stamps[16];
+#define TC_STAMP(i)                                                            \
+  do {                                                                         \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
+  } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
@@ -303,7 +292,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_in_stage = p.a_resident ? 0 : A_CHUNK_BYTES;
   const int b_stage_bytes = a_in_stage + b_tile_bytes;      // ring stage = [A chunk (if streamed)] [B chunk]
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (p.a_resident ? p.m_halves * p.KC * A_CHUNK_BYTES : 0);
+  uint8_t* sB = sA + (p.a_resident ? p.KC * A_CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + 1;
@@ -322,7 +311,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::mbar_init(a_full, 1);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], p.cluster2 ? 2 : 1); }
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
     ptx::fence_mbar_init();
   }
@@ -333,7 +322,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (p.cluster2) ptx::cluster_sync_all();    // the peer's barriers must exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TC_STAMP(1);
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
@@ -345,19 +333,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- TMA producer
       // A chunk = 128 rows x 64 K: an NCHW operand comes as two (64 px x 64 ch) boxes, an
       // activation operand as one (64 k x 128 rows) box; 16 KB either way.
-      auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc, int hm) {
+      auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
         const int kco = p.k_identity ? kc * TC_BK : p.a_kcoord[kc];
-        const int m0 = (m_tile * p.m_halves + hm) * TC_BM;
         if (p.a_kmajor) {
-          ptx::tma_load_2d(dst, &tmA, bar, kco, m0);
+          ptx::tma_load_2d(dst, &tmA, bar, kco, m_tile * TC_BM);
         } else {
-          for (int g = 0; g < 2; ++g) ptx::tma_load_3d(dst + g * (A_CHUNK_BYTES / 2), &tmA, bar, m0 + g * 64, kco, batch);
+          for (int g = 0; g < 2; ++g)
+            ptx::tma_load_3d(dst + g * (A_CHUNK_BYTES / 2), &tmA, bar, m_tile * TC_BM + g * 64, kco, batch);
         }
       };
       if (p.a_resident) {
-        ptx::mbar_expect_tx(a_full, (uint32_t)(p.m_halves * p.KC * A_CHUNK_BYTES));
-        for (int hm = 0; hm < p.m_halves; ++hm)
-          for (int kc = 0; kc < p.KC; ++kc) load_a(sA + (hm * p.KC + kc) * A_CHUNK_BYTES, a_full, kc, hm);
+        ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
+        for (int kc = 0; kc < p.KC; ++kc) load_a(sA + kc * A_CHUNK_BYTES, a_full, kc);
       }
       int it = 0;
       for (int t = 0; t < p.NT; ++t)
@@ -367,17 +354,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&b_empty[s], ph ^ 1u);
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
-          if (!p.a_resident) load_a(stage, &b_full[s], kc, 0);
-          const int bk = p.k_identity ? kc * TC_BK : p.b_kcoord[kc];
-          const int brow = batch * p.b_rows_per_batch + p.b_row0 + t * (p.b_tile_stride ? p.b_tile_stride : p.N_TILE);
-          if (p.cluster2) {
-            // this CTA fetches its half of the tile's rows and multicasts it to both CTAs of the pair;
-            // the other half arrives from the peer (b_empty counts BOTH consumers, so the slot is free in both)
-            const int half_rows = p.N_TILE >> 1, r = (int)ptx::cluster_ctarank();
-            ptx::tma_load_2d_mc(stage + a_in_stage + r * half_rows * 128, &tmB, &b_full[s], bk, brow + r * half_rows, 0x3);
-          } else {
-            ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], bk, brow);
-          }
+          if (!p.a_resident) load_a(stage, &b_full[s], kc);
+          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? kc * TC_BK : p.b_kcoord[kc],
+                           batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
     }
   } else if (warp == 1) {
@@ -394,29 +373,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t use = (uint32_t)(t >> 1);
         ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.m_halves * p.acc_stride);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
         for (int kc = 0; kc < p.KC; ++kc, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
           if (it == 0) TC_STAMP(2);
+          const uint32_t a_base = ptx::smem_u32(p.a_resident ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
           const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes + a_in_stage);
-          for (int hm = 0; hm < p.m_halves; ++hm) {
-            const uint32_t a_base =
-                ptx::smem_u32(p.a_resident ? sA + (hm * p.KC + kc) * A_CHUNK_BYTES : sB + s * b_stage_bytes);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
-              // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
-              const uint64_t adesc = p.a_kmajor ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
-                                                : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
-              const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
-              ptx::mma_bf16_ss(d_tmem + (uint32_t)(hm * p.acc_stride), adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
-            }
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
+            // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
+            const uint64_t adesc = p.a_kmajor ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
+                                              : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
+            const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
+            ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
           }
-          if (p.cluster2) ptx::mma_commit_mc(&b_empty[s], 0x3);   // frees the stage in BOTH CTAs of the pair
-          else ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
+          ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
         }
         ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
         if (t == 0) TC_STAMP(3);
@@ -427,7 +402,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // every (EPI_WARPS/4)-th 16-column chunk.  One lean, specialised loop per epilogue kind.
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;                       // which share of the chunks
-    const int m = m_tile * p.m_halves * TC_BM + quarter * 32 + lane;     // TMEM lane -> pixel / key / feature index (half 0)
+    const int m = m_tile * TC_BM + quarter * 32 + lane;     // TMEM lane -> pixel / key / feature index
     const bool m_ok = m < p.M_valid;
     EpiCtx ctx;
     ctx.lane = lane; ctx.m = m; ctx.m_ok = m_ok; ctx.batch = batch; ctx.part = part;
@@ -440,8 +415,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&acc_full[buf], use & 1u);
       ptx::tc_fence_after();
       if (t == 0 && warp == 2 && lane == 0) TC_STAMP(4);
-      ctx.taddr = tmem_base + (uint32_t)(buf * p.m_halves * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      ctx.col0 = t * (p.b_tile_stride ? p.b_tile_stride : p.N_TILE);
+      ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      ctx.col0 = t * p.N_TILE;
       switch (p.epi) {
         case EPI_MASK_T: epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
         case EPI_ROWMAJOR: epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
@@ -456,7 +431,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (p.cluster2) ptx::cluster_sync_all();    // no CTA of the pair may exit while the peer can still signal it
   if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     __syncwarp();
@@ -613,15 +587,12 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   if (p.N_TILE % 16 != 0 || p.N_TILE < 16 || p.N_TILE > 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "bad N tile");
   p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
   if (p.N_TILE <= 32) p.acc_stride = 32; else if (p.N_TILE <= 64) p.acc_stride = 64;
-  if (p.m_halves < 1) p.m_halves = 1;
-  p.tmem_cols = 2 * p.m_halves * p.acc_stride;
-  if (p.tmem_cols > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "accumulators exceed TMEM");
-  const size_t a_bytes = p.a_resident ? (size_t)p.m_halves * p.KC * A_CHUNK_BYTES : 0;
+  p.tmem_cols = 2 * p.acc_stride;
+  const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
   if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
-  const size_t stage_bytes =
-      (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR) ? (size_t)p.N_TILE * p.m_halves * TC_BM * 2 + 1024 : 0;
-  const size_t budget = (p.m_halves > 1 ? 222 : 204) * 1024 - stage_bytes;
+  const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR) ? (size_t)p.N_TILE * TC_BM * 2 + 1024 : 0;
+  const size_t budget = 204 * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
@@ -636,9 +607,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  if (p.cluster2) m_tiles = (m_tiles + 1) & ~1;
-  TCU(launch_pdl_cluster(p.cluster2 ? 2 : 1, tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB,
-                         mC ? *mC : mB, p));
+  TCU(launch_pdl(tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB, mC ? *mC : mB, p));
   count_launch();
   TCU(cudaGetLastError());
   if (timing) {
@@ -652,10 +621,6 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
             "acc-ready %.1f epi-done %.1f teardown %.1f (us since entry)\n", m_tiles, batch, p.epi, p.NT, p.KC, p.N_TILE, p.stages, smem,
             ms * 1e3, (st[1] - st[0]) * 1e-3, (st[2] - st[0]) * 1e-3, (st[3] - st[0]) * 1e-3, (st[4] - st[0]) * 1e-3,
             (st[5] - st[0]) * 1e-3, (st[6] - st[0]) * 1e-3);
-    if (p.epi == EPI_MASK_T && p.NT > 2)
-      fprintf(stderr, "   tile 2 epilogue: enter %.2f  store-read-done %.2f  bar %.2f  drained %.2f  bar %.2f  stores issued %.2f\n",
-              (st[7] - st[0]) * 1e-3, (st[8] - st[0]) * 1e-3, (st[9] - st[0]) * 1e-3, (st[10] - st[0]) * 1e-3,
-              (st[11] - st[0]) * 1e-3, (st[12] - st[0]) * 1e-3);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
   return CGG_OK;
@@ -874,15 +839,7 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   p.epi = EPI_MASK_T; p.M_valid = (int)HW; p.Q = Q; p.q_pad = t->q_pad; p.n_calls = num_calls;
   p.out_mask = static_cast<__nv_bfloat16*>(mask_bf16);
   p.out_call_stride = call_stride; p.out_batch_stride = (long)Q * HW; p.HW = HW;
-  int px_per_cta = TC_BM;
-  static const bool wide = getenv("CGG_EINSUM_256PX") != nullptr;   // measured slower (1.37 vs 0.99 ms): only 2 B stages fit
-  if (wide && round_up(t->q_pad, 16) <= 128) {
-    // 256 pixels per CTA: two 128-lane accumulators share every B (mask-embedding) stage, which halves
-    // the L2 -> SM traffic of the re-read B operand (the measured limiter of the 128-pixel variant);
-    // one head call per N tile, tiles q_pad rows apart, 4 x 128 TMEM columns (2 halves x 2 buffers)
-    p.m_halves = 2; px_per_cta = 2 * TC_BM;
-    p.N_TILE = round_up(t->q_pad, 16); p.NT = num_calls; p.b_tile_stride = t->q_pad;
-  } else if (t->ein_calls_per_tile == 2 && num_calls % 2 == 0) {
+  if (t->ein_calls_per_tile == 2 && num_calls % 2 == 0) {
     p.N_TILE = t->ein_ntile; p.NT = num_calls / 2;
   } else if (t->ein_calls_per_tile == 0) {
     p.N_TILE = t->ein_ntile; p.NT = 2 * num_calls;
@@ -899,10 +856,7 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       return CGG_OK;
     }
   }
-  // CTA-pair multicast of the B tiles: correct, but measured slower on B200 (1.16 vs 0.99 ms) -> opt-in
-  static const bool use_cluster = getenv("CGG_EINSUM_CLUSTER") != nullptr;
-  p.cluster2 = (use_cluster && p.m_halves <= 1 && p.N_TILE % 16 == 0) ? 1 : 0;
-  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.cluster2 ? p.N_TILE / 2 : p.N_TILE);
+  st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE);
   if (st != CGG_OK) return st;
   // output map: (pixels, q, call*B + image); one (128 px x min(q_pad, N_TILE) rows) box per store
   if (num_calls > 1 && call_stride != (long)batch * Q * HW)
@@ -911,14 +865,14 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   {
     cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)Q, (cuuint64_t)num_calls * batch};
     cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)Q * HW * 2};
-    cuuint32_t box[3] = {(cuuint32_t)px_per_cta, (cuuint32_t)(t->q_pad < p.N_TILE ? t->q_pad : p.N_TILE), 1};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BM, (cuuint32_t)(t->q_pad < p.N_TILE ? t->q_pad : p.N_TILE), 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = t->encode(&mC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out) failed: " + std::to_string((int)r));
   }
-  return launch_tc_gemm(t, mA, mB, p, (int)((HW + px_per_cta - 1) / px_per_cta), batch, s, &mC);
+  return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s, &mC);
 }
 
 // ------------------------------------------------------------------ small-M linear layers
