@@ -283,16 +283,23 @@ __device__ unsigned long long g_tc_stamps[16];
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
   } while (0)
 
+// Specialised per epilogue kind: the operand layout / residency follow from it at compile time
+//   EPI_MASK_T, EPI_ROWMAJOR : A = NCHW feature map, tile resident in smem for all N tiles
+//   EPI_BITS                 : A = NCHW (hi/lo planes), streamed with B
+//   EPI_LINEAR_T             : A = weights (K-major), streamed with B
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
+  constexpr bool A_KMAJOR = (EPI == EPI_LINEAR_T);
+  constexpr bool A_RESIDENT = (EPI == EPI_MASK_T || EPI == EPI_ROWMAJOR);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.N_TILE * 128;
-  const int a_in_stage = p.a_resident ? 0 : A_CHUNK_BYTES;
+  const int a_in_stage = A_RESIDENT ? 0 : A_CHUNK_BYTES;
   const int b_stage_bytes = a_in_stage + b_tile_bytes;      // ring stage = [A chunk (if streamed)] [B chunk]
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (p.a_resident ? p.KC * A_CHUNK_BYTES : 0);
+  uint8_t* sB = sA + (A_RESIDENT ? p.KC * A_CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + 1;
@@ -335,14 +342,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // activation operand as one (64 k x 128 rows) box; 16 KB either way.
       auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
         const int kco = p.k_identity ? kc * TC_BK : p.a_kcoord[kc];
-        if (p.a_kmajor) {
+        if (A_KMAJOR) {
           ptx::tma_load_2d(dst, &tmA, bar, kco, m_tile * TC_BM);
         } else {
           for (int g = 0; g < 2; ++g)
             ptx::tma_load_3d(dst + g * (A_CHUNK_BYTES / 2), &tmA, bar, m_tile * TC_BM + g * 64, kco, batch);
         }
       };
-      if (p.a_resident) {
+      if (A_RESIDENT) {
         ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
         for (int kc = 0; kc < p.KC; ++kc) load_a(sA + kc * A_CHUNK_BYTES, a_full, kc);
       }
@@ -354,7 +361,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&b_empty[s], ph ^ 1u);
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
-          if (!p.a_resident) load_a(stage, &b_full[s], kc);
+          if (!A_RESIDENT) load_a(stage, &b_full[s], kc);
           ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? kc * TC_BK : p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
@@ -362,8 +369,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
-      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !p.a_kmajor, /*B K-major*/ false);
-      if (p.a_resident) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false);
+      if (A_RESIDENT) {
         ptx::mbar_wait(a_full, 0);
         ptx::tc_fence_after();
       }
@@ -380,13 +387,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
           if (it == 0) TC_STAMP(2);
-          const uint32_t a_base = ptx::smem_u32(p.a_resident ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
+          const uint32_t a_base = ptx::smem_u32(A_RESIDENT ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
           const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes + a_in_stage);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
             // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
-            const uint64_t adesc = p.a_kmajor ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
+            const uint64_t adesc = A_KMAJOR ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
                                               : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
             const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
             ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
@@ -408,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ctx.lane = lane; ctx.m = m; ctx.m_ok = m_ok; ctx.batch = batch; ctx.part = part;
     ctx.chunks = p.N_TILE / 16; ctx.wi = (m_tile * TC_BM + quarter * 32) >> 5;
     LinCtx lin;
-    if (p.epi == EPI_LINEAR_T) lin.init(p, m);
+    if (EPI == EPI_LINEAR_T) lin.init(p, m);
     for (int t = 0; t < p.NT; ++t) {
       const int buf = t & 1;
       const uint32_t use = (uint32_t)(t >> 1);
@@ -417,12 +424,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (t == 0 && warp == 2 && lane == 0) TC_STAMP(4);
       ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
       ctx.col0 = t * p.N_TILE;
-      switch (p.epi) {
-        case EPI_MASK_T: epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
-        case EPI_ROWMAJOR: epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, t, m_tile); break;
-        case EPI_BITS: epi_bits(p, ctx); break;
-        default: epi_linear_dispatch(p, ctx, lin); break;
-      }
+      if (EPI == EPI_MASK_T) epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile);
+      else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, t, m_tile);
+      else if (EPI == EPI_BITS) epi_bits(p, ctx);
+      else epi_linear_dispatch(p, ctx, lin);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
@@ -600,14 +605,28 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.stages = stages;
   const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 64 + stage_bytes;
   if (!t->smem_attr_set) {
-    TCU(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_MASK_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_ROWMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_LINEAR_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     t->smem_attr_set = true;
   }
+  // the kernel instantiation fixes the A-operand layout / residency: check the caller agrees
+  const bool want_res = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR), want_km = (p.epi == EPI_LINEAR_T);
+  if ((p.a_resident != 0) != want_res || (p.a_kmajor != 0) != want_km)
+    return tc_fail(t, CGG_ERR_BAD_SHAPE, "operand layout does not match the kernel specialisation");
   static const bool timing = getenv("CGG_TC_TIMING") != nullptr;
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  TCU(launch_pdl(tc_gemm_kernel, dim3(m_tiles, batch), dim3(TC_THREADS), smem, s, mA, mB, mC ? *mC : mB, p));
+  const dim3 grid(m_tiles, batch), block(TC_THREADS);
+  const CUtensorMap& mCC = mC ? *mC : mB;
+  switch (p.epi) {
+    case EPI_MASK_T: TCU(launch_pdl(tc_gemm_kernel<EPI_MASK_T>, grid, block, smem, s, mA, mB, mCC, p)); break;
+    case EPI_ROWMAJOR: TCU(launch_pdl(tc_gemm_kernel<EPI_ROWMAJOR>, grid, block, smem, s, mA, mB, mCC, p)); break;
+    case EPI_BITS: TCU(launch_pdl(tc_gemm_kernel<EPI_BITS>, grid, block, smem, s, mA, mB, mCC, p)); break;
+    default: TCU(launch_pdl(tc_gemm_kernel<EPI_LINEAR_T>, grid, block, smem, s, mA, mB, mCC, p)); break;
+  }
   count_launch();
   TCU(cudaGetLastError());
   if (timing) {
