@@ -170,9 +170,8 @@ __device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, 
 
 // K3 epilogue: threshold + ballot = 32 consecutive key bits of one query per warp instruction.
 // sigmoid(x) < 0.5 in fp32 holds exactly for x <= -1.7881392e-07.
-__device__ __forceinline__ void epi_bits(const TcGemmP& p, const EpiCtx& c) {
-  const int Q = p.Q, W32 = p.W32;
-  uint32_t* brow = p.bitmap + (long)c.batch * Q * W32 + c.wi;
+__device__ __forceinline__ void epi_bits_impl(int Q, int W32, uint32_t* bitmap, const EpiCtx& c) {
+  uint32_t* brow = bitmap + (long)c.batch * Q * W32 + c.wi;
   const bool w_ok = c.wi < W32;
   for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
     float v[16];
@@ -185,6 +184,7 @@ __device__ __forceinline__ void epi_bits(const TcGemmP& p, const EpiCtx& c) {
     }
   }
 }
+__device__ __forceinline__ void epi_bits(const TcGemmP& p, const EpiCtx& c) { epi_bits_impl(p.Q, p.W32, p.bitmap, c); }
 
 // Swap-AB linear layers: TMEM lanes = output FEATURES, columns = tokens; for one token a warp holds
 // 32 consecutive features, so every global access is one coalesced line.  The thread's segment is
@@ -437,6 +437,128 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(6);
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------- K3, persistent variant
+// Attention-mask bits with the B operand RESIDENT: the head call's mask embeddings (hi and lo planes,
+// 8 chunks of N_TILE x 64) are loaded once per CTA and stay in shared memory while the CTA walks its
+// share of the image's 128-key tiles; per tile only the resampled features stream in (4 hi + 4 lo
+// chunks, each used for the terms hi.me_hi + hi.me_lo resp. lo.me_hi), so every byte is fetched once.
+struct TcBitsP {
+  int N_TILE, b_row, m_tiles, K_valid, Q, W32, stages, acc_stride, tmem_cols, C;
+  uint32_t* bitmap;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcBitsP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int bt = p.N_TILE * 128;                 // bytes of one resident B chunk
+  uint8_t* sBres = smem;                         // 8 chunks: me_hi k-chunks 0..3, me_lo k-chunks 0..3
+  uint8_t* sA = sBres + 8 * bt;                  // ring of 16 KB feature chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * A_CHUNK_BYTES);
+  uint64_t* b_res_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = a_full + p.stages;
+  uint64_t* acc_full = a_empty + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int batch = blockIdx.y;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::mbar_init(b_res_full, 1);
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(b_res_full, (uint32_t)(8 * bt));
+      for (int j = 0; j < 8; ++j)
+        ptx::tma_load_3d(sBres + j * bt, &tmB, b_res_full, (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C), p.b_row, batch);
+      int it = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
+        for (int j = 0; j < 8; ++j, ++it) {
+          const int s = it % p.stages;
+          ptx::mbar_wait(&a_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+          ptx::mbar_expect_tx(&a_full[s], A_CHUNK_BYTES);
+          const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
+          for (int g = 0; g < 2; ++g)
+            ptx::tma_load_3d(sA + s * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s], mt * TC_BM + g * 64, ch, batch);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, true, false);
+      ptx::mbar_wait(b_res_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t bres = ptx::smem_u32(sBres);
+      int it = 0, t = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++t) {
+        const int buf = t & 1;
+        ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+        for (int j = 0; j < 8; ++j, ++it) {
+          const int s = it % p.stages;
+          ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(sA + s * A_CHUNK_BYTES);
+          // hi feature chunk k: x me_hi[k] and x me_lo[k];   lo feature chunk k: x me_hi[k]
+          const int nb = j < 4 ? 2 : 1;
+          for (int bsel = 0; bsel < nb; ++bsel) {
+            const uint32_t b_base = bres + (uint32_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t adesc = ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
+              const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
+              ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (j | bsel | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(&a_empty[s]);
+        }
+        ptx::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    EpiCtx ctx;
+    ctx.lane = lane; ctx.batch = batch; ctx.part = (warp - 2) >> 2; ctx.chunks = p.N_TILE / 16; ctx.col0 = 0;
+    int t = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++t) {
+      const int buf = t & 1;
+      ptx::mbar_wait(&acc_full[buf], ((uint32_t)(t >> 1)) & 1u);
+      ptx::tc_fence_after();
+      ctx.m = mt * TC_BM + quarter * 32 + lane;
+      ctx.m_ok = ctx.m < p.K_valid;
+      ctx.wi = (mt * TC_BM + quarter * 32) >> 5;
+      ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      epi_bits_impl(p.Q, p.W32, p.bitmap, ctx);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
   if (warp == 1) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -819,6 +941,52 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
   // columns >= Q are never stored)
   st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t->bits_ntile);
   if (st != CGG_OK) return st;
+  if (t->bits_nt == 1 && 8 * t->bits_ntile * 128 + 4 * A_CHUNK_BYTES <= 200 * 1024) {
+    // persistent, B-resident variant (Q <= 128)
+    TcBitsP bp = {};
+    bp.N_TILE = t->bits_ntile; bp.b_row = 0; bp.m_tiles = (K + TC_BM - 1) / TC_BM; bp.K_valid = K; bp.Q = Q;
+    bp.W32 = (K + 31) / 32; bp.C = C; bp.bitmap = bitmap;
+    bp.acc_stride = bp.N_TILE <= 32 ? 32 : bp.N_TILE <= 64 ? 64 : 128;
+    bp.tmem_cols = 2 * bp.acc_stride;
+    bp.stages = (int)((200 * 1024 - 8 * bp.N_TILE * 128) / A_CHUNK_BYTES);
+    if (bp.stages > 6) bp.stages = 6;
+    // per-image B rows differ: one map per launch over all rows, row coordinate = image base + call offset
+    // (blockIdx.y = image) -> the kernel needs the per-image row: pass through b_row and rows_per_batch
+    bp.b_row = call_idx * t->q_pad;
+    const size_t smem = 1024 + 8 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TCU(cudaFuncSetAttribute(tc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int gx = sms / batch;
+    if (gx < 1) gx = 1;
+    if (gx > bp.m_tiles) gx = bp.m_tiles;
+    bp.m_tiles = bp.m_tiles;
+    // B map: rows of ONE image only (the image's row block is selected by offsetting the base pointer per launch
+    // would need one map per image) -> use a 3-D map (k, row-in-image, image)
+    CUtensorMap mB3;
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)(2 * C), (cuuint64_t)t->rows_per_batch, (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)(2 * C) * 2, (cuuint64_t)t->rows_per_batch * (2 * C) * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)bp.N_TILE, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = t->encode(&mB3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base + w.me_all, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(me) failed: " + std::to_string((int)r));
+    }
+    TCU(launch_pdl(tc_bits_kernel, dim3(gx, batch), dim3(TC_THREADS), smem, s, mA, mB3, bp));
+    count_launch();
+    TCU(cudaGetLastError());
+    const int rows = batch * Q;
+    TCU(launch_pdl(all_masked_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, (const uint32_t*)bitmap, rows, bp.W32, K, all_masked));
+    count_launch();
+    TCU(cudaGetLastError());
+    return CGG_OK;
+  }
   TcGemmP p = {};
   p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = 3 * C / TC_BK;
   p.a_resident = 0;
