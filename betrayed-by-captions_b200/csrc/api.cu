@@ -304,7 +304,7 @@ extern "C" int cgg_attn_mask_from_logits(cgg_handle* h, int batch, const float* 
 static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const float* x, const void* mask_features,
                           int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
                           uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
-                          cudaStream_t s, int call_slot, bool defer_einsum, bool fds_ready) {
+                          cudaStream_t s, int call_slot, bool defer_einsum, bool fds_ready, bool z_ready = false) {
   if (!h || !w || !x || !mask_features || !cls || !emb) return CGG_ERR_NULL;
   if (!mask && !defer_einsum) return CGG_ERR_NULL;
   Workspace ws;
@@ -319,7 +319,7 @@ static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const 
   float* me = mask_embed_out ? mask_embed_out : at<float>(workspace, ws.me);
   // K1: post_norm + the three heads (head.py:734-746)
   if (c.precision == CGG_BF16) {
-    int st = tc_query_heads(h->tc, w, batch, x, cls, emb, me, at<void>(workspace, ws.tcws), s);
+    int st = tc_query_heads(h->tc, w, batch, x, cls, emb, me, at<void>(workspace, ws.tcws), s, call_slot, z_ready);
     if (st != CGG_OK) return fail(h, st, std::string("tc_query_heads: ") + tc_last_error(h->tc));
   } else {
   CU(launch_layernorm(x, nullptr, w->post_norm_w, w->post_norm_b, z, rows, C, 1e-5f, true, s));
@@ -399,9 +399,20 @@ extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, cons
   return CGG_OK;
 }
 
+static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
+                              const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
+                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out);
+
 extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
                                  const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
                                  size_t workspace_bytes, void* stream) {
+  return decoder_layer_impl(h, w, batch, layer, x_in, bitmap, all_masked, x_out, workspace, workspace_bytes, stream, false,
+                            false);
+}
+
+static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
+                              const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
+                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out) {
   if (!h || !w || !x_in || !x_out) return CGG_ERR_NULL;
   cudaStream_t s = (cudaStream_t)stream;
   Workspace ws;
@@ -415,7 +426,7 @@ extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch,
     const long kvs = (long)n * 2 * C, kvb = (long)K * kvs;
     const __nv_bfloat16* kv = at<__nv_bfloat16>(workspace, ws.kv[l]);
     int st = tc_decoder_layer(h->tc, w, batch, layer, x_in, kv + (size_t)sl * C, kv + (size_t)(n + sl) * C, kvs, kvb, K,
-                              bitmap, all_masked, x_out, at<void>(workspace, ws.tcws), s);
+                              bitmap, all_masked, x_out, at<void>(workspace, ws.tcws), s, chained_in, chained_out);
     if (st != CGG_OK) return fail(h, st, std::string("tc_decoder_layer: ") + tc_last_error(h->tc));
     return CGG_OK;
   }
@@ -502,7 +513,7 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     ST(head_call_impl(h, w, batch, xs + j * bqc, mask_features, j % CGG_NUM_LEVELS,
                       cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
                       static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
-                      workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true));
+                      workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true, /*z_ready=*/tcm && j > 0));
     if (ovl && (j & 1) && j < L) {
       // K2 of head calls j-1 and j (one 2-call N tile) runs on a helper stream underneath the
       // latency-bound layer chain; only the last pair stays on the critical path
@@ -517,7 +528,8 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     if (j < L) {
       const int lvl = j % CGG_NUM_LEVELS;
       if (ovl && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
-      ST(cgg_decoder_layer(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream));
+      ST(decoder_layer_impl(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream,
+                            /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm));
     }
   }
   if (tcm) {

@@ -1092,7 +1092,8 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   const int row_len = split_k ? 2 * K : K;
   TcGemmP p = {};
   // token tile: as few CTAs-worth of padding as possible with N <= 256 (multiple of 16)
-  const int n_tok_tiles = (M + 255) / 256;
+  static const int tok_cap = getenv("CGG_TOK_TILE") ? atoi(getenv("CGG_TOK_TILE")) : 128;   // 128: measured best (3.93 vs 4.29 ms/step at 256)
+  const int n_tok_tiles = (M + tok_cap - 1) / tok_cap;
   p.N_TILE = ((M + n_tok_tiles - 1) / n_tok_tiles + 15) / 16 * 16;
   CUtensorMap mW, mX;
   int st = make_map_act(t, &mW, W, n_padded, row_len);      // A operand: (64 k x 128 features) boxes

@@ -20,6 +20,8 @@ struct TcSeg {
   float alpha;
   const float* rowbias; int rb_mod; long rb_ld;
   const float* res; long res_ld;   // fp32 residual added after the scale: res[token*res_ld + (n - col0)]
+  // optional output-row remap (split outputs): row = (token / remap_q) * remap_rows + remap_row0 + token % remap_q
+  int remap_q, remap_rows, remap_row0;
 };
 
 TcState* tc_create(const cgg_config& cfg);
@@ -62,11 +64,17 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
               const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false);
 // The bf16-mode decoder layer (K5 + K6) and the query heads (K1) built from the pieces above.
+// chained_in: the workspace already holds bf16(x_in + query_embed) (written by the previous layer's last
+// LayerNorm); chained_out: the last LayerNorm also emits bf16(x_out + query_embed) and post_norm(x_out) as
+// hi/lo pairs for the next head call / layer, which then skip their own preparation kernels.
 int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
                      const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,
-                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s);
-int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, float* cls, float* emb, float* me,
-                   void* ws, cudaStream_t s);
+                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s, bool chained_in = false,
+                     bool chained_out = false);
+// me_f32 == nullptr: the mask embeddings go straight into the all-call hi/lo operand (slot call_slot)
+// from the last GEMM's epilogue; z_ready: post_norm(x) is already in the workspace.
+int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, float* cls, float* emb, float* me_f32,
+                   void* ws, cudaStream_t s, int call_slot = 0, bool z_ready = false);
 
 // K5 on tensor cores: masked multi-head cross-attention, flash-style over 128-key tiles.
 // q (B,Q,heads*32) fp32 pre-scaled; k, v bf16 rows (b*kv_bstride + key*kv_stride); out fp32 and/or bf16

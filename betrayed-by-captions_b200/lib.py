@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libcgg_b200.so')
+LIB_PATH = os.environ.get('CGG_LIB', os.path.join(HERE, 'libcgg_b200.so'))   # CGG_LIB: A/B another build of the same ABI
 
 MAX_LAYERS = 16
 NUM_LEVELS = 3
