@@ -46,6 +46,7 @@ struct TcGemmP {
   int b_kcoord[12];      // K coordinate of B chunk kc
   // EPI_LINEAR_T: up to 3 FEATURE segments (32-aligned starts) of (acc + bias [+ rowbias]) * alpha [+ res] [relu]
   TcSeg seg[3]; int nseg; const float* lin_bias; int n_tokens;
+  long kpart_stride;     // EPI_LINEAR_T with gridDim.z K-parts: part z writes its partial sums at ptr + z*kpart_stride (fp32)
   int b_row0;            // first B row (e.g. call_idx * q_pad)
   int b_rows_per_batch;  // B row offset per blockIdx.y (0: weights shared by the batch)
   int acc_stride;        // TMEM columns between the two accumulator buffers
@@ -211,6 +212,10 @@ struct LinCtx {
       }
     }
     if (on && p.lin_bias) bias = __ldg(p.lin_bias + m);
+    if (blockIdx.z > 0) {   // K-split partial: bias / residual belong to part 0 only
+      bias = 0.f; res = nullptr; rowbias = nullptr;
+      ptr = static_cast<float*>(ptr) + (long)blockIdx.z * p.kpart_stride;
+    }
   }
 };
 
@@ -341,7 +346,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // A chunk = 128 rows x 64 K: an NCHW operand comes as two (64 px x 64 ch) boxes, an
       // activation operand as one (64 k x 128 rows) box; 16 KB either way.
       auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
-        const int kco = p.k_identity ? kc * TC_BK : p.a_kcoord[kc];
+        const int kco = p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.a_kcoord[kc];
         if (A_KMAJOR) {
           ptx::tma_load_2d(dst, &tmA, bar, kco, m_tile * TC_BM);
         } else {
@@ -362,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
           if (!A_RESIDENT) load_a(stage, &b_full[s], kc);
-          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? kc * TC_BK : p.b_kcoord[kc],
+          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
     }
@@ -710,7 +715,7 @@ int make_map_B(TcState* t, CUtensorMap* m, const void* base, long rows, int C, i
 }
 
 int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcGemmP p, int m_tiles, int batch,
-                   cudaStream_t s, const CUtensorMap* mC = nullptr) {
+                   cudaStream_t s, const CUtensorMap* mC = nullptr, int kparts = 1) {
   if (p.N_TILE % 16 != 0 || p.N_TILE < 16 || p.N_TILE > 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "bad N tile");
   p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
   if (p.N_TILE <= 32) p.acc_stride = 32; else if (p.N_TILE <= 64) p.acc_stride = 64;
@@ -741,7 +746,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.dbg = timing ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  const dim3 grid(m_tiles, batch), block(TC_THREADS);
+  const dim3 grid(m_tiles, batch, kparts), block(TC_THREADS);
   const CUtensorMap& mCC = mC ? *mC : mB;
   switch (p.epi) {
     case EPI_MASK_T: TCU(launch_pdl(tc_gemm_kernel<EPI_MASK_T>, grid, block, smem, s, mA, mB, mCC, p)); break;
@@ -1081,7 +1086,10 @@ int make_map_act(TcState* t, CUtensorMap* m, const void* base, long rows, int K)
 }  // namespace
 
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
-              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k) {
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k, int kparts, long kpart_stride) {
+  if (kparts < 1) kparts = 1;
+  if (kparts > 1 && (split_k || nsegs != 1 || segs[0].is_bf16 || segs[0].relu || (K / TC_BK) % kparts != 0))
+    return tc_fail(t, CGG_ERR_BAD_SHAPE, "K-parts need one plain fp32 output segment");
   // swap-AB: the WEIGHTS are the UMMA A operand (128 output features per CTA on the TMEM lanes), the
   // activations the B operand (a tile of <= 256 tokens on the columns); grid = feature tiles x token tiles.
   if (K % TC_BK != 0 || n_padded % TC_BM != 0 || nsegs < 1 || nsegs > 3)
@@ -1100,7 +1108,7 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   if (st != CGG_OK) return st;
   st = make_map_B(t, &mX, A, M, row_len, p.N_TILE);          // B operand: (64 k x N_TILE tokens) boxes
   if (st != CGG_OK) return st;
-  p.NT = 1; p.KC = K / TC_BK;
+  p.NT = 1; p.KC = K / TC_BK / kparts; p.kpart_stride = kpart_stride;
   p.a_kmajor = 1; p.k_identity = 1; p.a_resident = 0;
   if (split_k) {
     p.k_identity = 0; p.KC = 3 * K / TC_BK;
@@ -1115,7 +1123,7 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   p.epi = EPI_LINEAR_T; p.M_valid = n_padded; p.n_tokens = M;
   p.nseg = nsegs; p.lin_bias = bias;
   for (int i = 0; i < nsegs; ++i) p.seg[i] = segs[i];
-  return launch_tc_gemm(t, mW, mX, p, n_padded / TC_BM, n_tok_tiles, s);
+  return launch_tc_gemm(t, mW, mX, p, n_padded / TC_BM, n_tok_tiles, s, nullptr, kparts);
 }
 
 }  // namespace cgg

@@ -62,7 +62,9 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
 // split_k: A and W rows are [hi(256) | lo(256)] bf16 pairs and the contraction is evaluated as
 // hi.hi + lo.hi + hi.lo (fp32 accumulate), i.e. with ~16 mantissa bits per operand (K must be 256).
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
-              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false);
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false, int kparts = 1, long kpart_stride = 0);
+// kparts > 1: the K range is split over gridDim.z CTAs; part z writes fp32 partial sums at ptr + z*kpart_stride
+// (bias / residual added by part 0); the consumer (LayerNorm) adds the parts.
 // The bf16-mode decoder layer (K5 + K6) and the query heads (K1) built from the pieces above.
 // chained_in: the workspace already holds bf16(x_in + query_embed) (written by the previous layer's last
 // LayerNorm); chained_out: the last LayerNorm also emits bf16(x_out + query_embed) and post_norm(x_out) as

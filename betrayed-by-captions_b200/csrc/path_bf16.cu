@@ -35,7 +35,8 @@ __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __r
 
 // Row LayerNorm over 256 channels, one warp per row, every access coalesced.  Optional outputs:
 // fp32, bf16, bf16 of (y + qe[row % Q]) and a bf16 hi/lo pair row [hi(256) | lo(256)].
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int nparts, long part_stride,
+                                                      const float* __restrict__ w,
                                                       const float* __restrict__ b, int rows, float* __restrict__ out_f32,
                                                       __nv_bfloat16* __restrict__ out_bf16,
                                                       __nv_bfloat16* __restrict__ out_bf16_q,
@@ -50,6 +51,11 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   const float4* xr = reinterpret_cast<const float4*>(x + (long)row * 256 + n0);
   const float4 a = xr[0], c = xr[1];
   float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  for (int pt = 1; pt < nparts; ++pt) {      // K-split partial sums of the producing GEMM, fixed order
+    const float4* xp = reinterpret_cast<const float4*>(x + pt * part_stride + (long)row * 256 + n0);
+    const float4 e = xp[0], f = xp[1];
+    v[0] += e.x; v[1] += e.y; v[2] += e.z; v[3] += e.w; v[4] += f.x; v[5] += f.y; v[6] += f.z; v[7] += f.w;
+  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += v[i];
@@ -120,8 +126,9 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 
 cudaError_t launch_ln_rows(const float* x, const float* w, const float* b, int rows, float* out_f32,
                            __nv_bfloat16* out_bf16, __nv_bfloat16* out_bf16_q, const float* qe, int Q,
-                           __nv_bfloat16* out_hl, cudaStream_t s, const float* w2 = nullptr, const float* b2 = nullptr) {
-  cudaError_t e = launch_pdl(ln_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, w, b, rows, out_f32, out_bf16, out_bf16_q,
+                           __nv_bfloat16* out_hl, cudaStream_t s, const float* w2 = nullptr, const float* b2 = nullptr,
+                           int nparts = 1, long part_stride = 0) {
+  cudaError_t e = launch_pdl(ln_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, nparts, part_stride, w, b, rows, out_f32, out_bf16, out_bf16_q,
                              qe, Q > 0 ? Q : 1, out_hl, w2, b2);
   count_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
@@ -298,12 +305,16 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   TcSeg sf[1] = {seg(0, F, fb, F, true, true)};
   TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s));
   TcSeg sf2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x2, C)};
-  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s));
+  // K = 2048 over 4 K-parts (4x the CTAs, each a quarter of the chunk chain); the LayerNorm adds the parts
+  const int kparts = (F / 64) % 4 == 0 ? 4 : 1;
+  const long pstride = (long)M * C;
+  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s, false, kparts, pstride));
   if (chained_out)   // also bf16(x_out + query_embed) for the next layer and post_norm(x_out) for the next head call
     TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, xqb, w->query_embed, Q, at<__nv_bfloat16>(ws, o.zb), s,
-                       w->post_norm_w, w->post_norm_b));
+                       w->post_norm_w, w->post_norm_b, kparts, pstride));
   else
-    TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, nullptr, nullptr, 0, nullptr, s));
+    TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, nullptr, nullptr, 0, nullptr, s, nullptr, nullptr,
+                       kparts, pstride));
   return CGG_OK;
 }
 

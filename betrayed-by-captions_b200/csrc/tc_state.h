@@ -64,7 +64,7 @@ struct TcWs {
     fb = take(M * t->cfg.ffn_dim * 2);
     zb = take(M * 2 * C * 2); h1b = take(M * 2 * C * 2); h2b = take(M * 2 * C * 2);   // hi/lo rows
     qf = take(M * C * 4); qs = take(M * C * 4); kvs = take(M * 2 * C * 4);
-    x1 = take(M * C * 4); x2 = take(M * C * 4); t1 = take(M * C * 4);
+    x1 = take(M * C * 4); x2 = take(M * C * 4); t1 = take(4 * M * C * 4);   // t1: up to 4 K-split partial sums
     total = off;
   }
 };
