@@ -84,7 +84,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint8_t* sP = sQ + AT_Q_BYTES;                        // 2 x 32 KB
   uint8_t* sKV = sP + 2 * AT_P_BYTES;                   // stages x (K tile, V tile)
   uint8_t* sOnes = sKV + AT_STAGES * AT_STAGE_BYTES;   // above every V tile (descriptor offsets are unsigned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + AT_ONES_BYTES);
+  uint8_t* sLive = sOnes + AT_ONES_BYTES;               // this CTA's live-tile flags (<= 512 key tiles)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLive + 512);
   uint64_t* kv_full = bars;
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;
@@ -94,7 +95,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.heads, qt = blockIdx.x / p.heads, b = blockIdx.y;
-  const uint8_t* live = p.live + ((long)b * p.nqt + qt) * p.ntiles;
+  const uint8_t* live_g = p.live + ((long)b * p.nqt + qt) * p.ntiles;
+  const uint8_t* live = sLive;
   const int C = p.heads * 32;
 
   if (warp == 0 && lane == 0) {
@@ -123,6 +125,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     *reinterpret_cast<uint4*>(sOnes + r * 64 + cpos * 16) = z;
     fence_async_smem();
   }
+  // the live-tile flags are read by three roles every tile: one copy into shared memory
+  for (int i = threadIdx.x; i < p.ntiles; i += AT_THREADS) sLive[i] = live_g[i];
   if (warp >= 2 && warp < 6) {
     // Q tile -> bf16, core-matrix (no-swizzle) K-major layout: element (row, d) at
     // (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
@@ -259,13 +263,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
       o[32] = (o[32] + __uint_as_float(sum_bits)) * scale;
     };
-    int it = 0;
-    for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; t = next_live(live, t + 1, p.ntiles), ++it) {
-      const int buf = it & 1;
-      ptx::mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u);
-      ptx::tc_fence_after();
-      // mask words of this row for this half's 64 keys (bit = 1 -> masked); keys >= K are masked
-      uint32_t mw[2];
+    // mask words of this row for this half's 64 keys of tile t (bit = 1 -> masked); keys >= K are masked.
+    // They are fetched one live tile AHEAD so the global-load latency hides behind the current tile.
+    auto load_mask = [&](int t, uint32_t* mw) {
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         const int widx = t * 4 + hf * 2 + w;
@@ -275,6 +275,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         if (k0 + 32 > p.K) word |= (k0 >= p.K) ? 0xffffffffu : ~((1u << (p.K - k0)) - 1u);
         mw[w] = word;
       }
+    };
+    int it = 0;
+    uint32_t mw_next[2] = {0u, 0u};
+    {
+      const int t0 = next_live(live, 0, p.ntiles);
+      if (t0 < p.ntiles) load_mask(t0, mw_next);
+    }
+    for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; ++it) {
+      const int buf = it & 1;
+      const int t_next = next_live(live, t + 1, p.ntiles);
+      uint32_t mw[2] = {mw_next[0], mw_next[1]};
+      if (t_next < p.ntiles) load_mask(t_next, mw_next);
+      ptx::mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
       const uint32_t s_addr = tmem_S + (uint32_t)(buf * 128 + hf * 64) + lane_off;
       // the 64 scores are read from TMEM ONCE, masked to -inf in registers, and reused for max and exp
       float v[64];
@@ -313,6 +327,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         ptx::tc_fence_after();
         fold_o((it - 1) & 1, scale);
       }
+      t = t_next;
     }
     if (it > 0) {
       ptx::mbar_wait(&o_full[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
@@ -446,7 +461,8 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
-  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_ONES_BYTES + (2 * AT_STAGES + 6) * 8 + 16;
+  if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");
+  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_ONES_BYTES + 512 + (2 * AT_STAGES + 6) * 8 + 16;
   if (!t->attn_attr_set) {
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     t->attn_attr_set = true;
