@@ -269,7 +269,7 @@ static int kv_project_levels(cgg_handle* h, const cgg_weights* w, int batch, con
     if (!memories[l]) return fail(h, CGG_ERR_NULL, "null memory level");
     const int K = h->lh[l] * h->lw[l], N = h->nl[l] * 2 * C;
     if (h->cfg.precision == CGG_BF16) {
-      int st = tc_kv_project(h->tc, l, batch, memories[l], at<void>(workspace, ws.kv[l]), s);
+      int st = tc_kv_project(h->tc, l, batch, memories[l], at<void>(workspace, ws.kv[l]), at<void>(workspace, ws.tcws), s);
       if (st != CGG_OK) return fail(h, st, std::string("tc_kv_project: ") + tc_last_error(h->tc));
       continue;
     }
@@ -589,5 +589,38 @@ extern "C" int cgg_grounding_loss(cgg_handle* h, const float* pred, const float*
   float* g2 = g1 + (size_t)Bg * Bg;
   CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s));
   CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s));
+  return CGG_OK;
+}
+
+extern "C" size_t cgg_grounding_bwd_scratch_bytes(int Bg, int Q, int T) {
+  if (Bg <= 0 || Q <= 0 || T <= 0) return 0;
+  return ((size_t)4 * Bg * Bg + (size_t)Bg * Bg * T * Q + 1) * sizeof(float);
+}
+
+extern "C" int cgg_grounding_loss_backward(cgg_handle* h, const float* pred, const float* cap, const int64_t* cap_mask,
+                                           int Bg, int Q, int T, int D, float temperature, float loss_weight,
+                                           float grad_out, float* dpred, void* scratch, size_t scratch_bytes,
+                                           void* stream) {
+  if (!h || !pred || !cap || !cap_mask || !dpred || !scratch) return CGG_ERR_NULL;
+  if (Bg <= 0 || Bg > 96 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if ((size_t)(T * Q + 3 * T + 3 * Q) * sizeof(float) > 200 * 1024) return fail(h, CGG_ERR_BAD_SHAPE, "T*Q too large");
+  if (scratch_bytes < cgg_grounding_bwd_scratch_bytes(Bg, Q, T)) return fail(h, CGG_ERR_WORKSPACE, "scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* g1 = static_cast<float*>(scratch);
+  float* g2 = g1 + (size_t)Bg * Bg;
+  float* d1 = g2 + (size_t)Bg * Bg;
+  float* d2 = d1 + (size_t)Bg * Bg;
+  float* loss = d2 + (size_t)Bg * Bg;
+  float* dS = loss + 1;
+  // recompute the pair distances, then d loss / d cost, d loss / d S, and dpred_j = sum_{i,t} dS[j][i][t][:]^T cap[i][t][:]
+  CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s));
+  CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s, d1, d2));
+  CU(launch_grounding_bwd_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, d1, d2, grad_out, dS, s));
+  GemmF32 p;
+  p.A = dS; p.sAb = (long)Bg * T * Q; p.sAm = 1; p.sAk = Q; p.a_mmajor = true;     // A[q, (i,t)]
+  p.W = cap; p.sWn = 1; p.sWk = D;                                                  // W[d, (i,t)]
+  p.C = dpred; p.sCb = (long)Q * D; p.sCm = D; p.sCn = 1;
+  p.M = Q; p.N = D; p.K = Bg * T; p.batch = Bg;
+  CU(launch_gemm_f32(p, s));
   return CGG_OK;
 }

@@ -580,7 +580,7 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int C, int H4,
                                                           int W4, __nv_bfloat16* __restrict__ d8,
                                                           __nv_bfloat16* __restrict__ d4,
-                                                          __nv_bfloat16* __restrict__ d2) {
+                                                          __nv_bfloat16* __restrict__ d2, int p8, int p4, int p2) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
   const int bw = W4 >> 3, bh = H4 >> 3;
@@ -612,13 +612,13 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
   {
     __nv_bfloat16 hi, lo;
     split_bf16(avg(3, 3), hi, lo);
-    d8[hi_plane * (long)bh * bw + (long)by * bw + bx] = hi;
-    d8[lo_plane * (long)bh * bw + (long)by * bw + bx] = lo;
+    d8[hi_plane * (long)p8 + (long)by * bw + bx] = hi;
+    d8[lo_plane * (long)p8 + (long)by * bw + bx] = lo;
   }
   // ratio 4 -> centre of each 4x4: rows 1,2 / 5,6
   {
     const int w = W4 >> 2;
-    const long off = (long)(by * 2) * w + bx * 2, psz = (long)(H4 >> 2) * w;
+    const long off = (long)(by * 2) * w + bx * 2, psz = p4;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       __nv_bfloat16 h0, l0, h1, l1;
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
   // ratio 2 -> every 2x2
   {
     const int w = W4 >> 1;
-    const long off = (long)(by * 4) * w + bx * 4, psz = (long)(H4 >> 1) * w;
+    const long off = (long)(by * 4) * w + bx * 4, psz = p2;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       __nv_bfloat16 h[4], l[4];
@@ -644,6 +644,18 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
       *reinterpret_cast<uint2*>(d2 + lo_plane * psz + off + (long)r * w) = pl;
     }
   }
+}
+
+// (rows, K) bf16 -> (rows, pitch) bf16, zero padded
+__global__ void repitch_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows, int K,
+                               int pitch) {
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * pitch) return;
+  const int k = (int)(i % pitch);
+  const long r = i / pitch;
+  dst[i] = k < K ? src[r * K + k] : __float2bfloat16(0.f);
 }
 
 // me (B,Q,C) fp32 -> rows [b][call*q_pad + q][C] bf16 of the all-call B operand
@@ -687,11 +699,14 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 namespace {
 
 // 3-D map over an NCHW feature tensor: dims (pixels, channels, batch), box (64 px, 64 ch, 1)
-int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, int B) {
-  if ((pixels * 2) % 16 != 0)
-    return tc_fail(t, CGG_ERR_UNSUPPORTED, "bf16 mode needs a pixel count that is a multiple of 8 (TMA 16-byte stride rule)");
+// `pitch` = elements between consecutive channel planes (>= pixels, multiple of 8); columns in [pixels, pitch)
+// are never read: the map's extent is `pixels`, TMA zero-fills beyond it.
+int make_map_A(TcState* t, CUtensorMap* m, const void* base, int pixels, int C, int B, int pitch = -1) {
+  if (pitch < 0) pitch = pixels;
+  if ((pitch * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15))
+    return tc_fail(t, CGG_ERR_UNSUPPORTED, "TMA needs 16-byte aligned channel planes (pixel pitch multiple of 8)");
   cuuint64_t dims[3] = {(cuuint64_t)pixels, (cuuint64_t)C, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)pixels * 2, (cuuint64_t)pixels * C * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * C * 2};
   cuuint32_t box[3] = {64, 64, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = t->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
@@ -869,10 +884,23 @@ int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, 
   return tc_pack_weights(t, w, s);
 }
 
-int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, cudaStream_t s) {
+int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, void* ws, cudaStream_t s) {
   const int C = t->cfg.embed_dim, K = t->lh[level] * t->lw[level], N = t->nl[level] * 2 * C;
   CUtensorMap mA, mB;
-  int st = make_map_A(t, &mA, mem_bf16, K, C, batch);
+  int pitch = K;
+  if (K % 8) {
+    // ragged level (e.g. 33x25 keys of a 1056x800 input): copy to 16-byte aligned channel planes first
+    TcWs w;
+    w.carve(t, batch);
+    pitch = pitch8(K);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + w.memp[level]);
+    const long total = (long)batch * C * pitch;
+    TCU(launch_pdl(repitch_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
+                   static_cast<const __nv_bfloat16*>(mem_bf16), dst, (long)batch * C, K, pitch));
+    count_launch();
+    mem_bf16 = dst;
+  }
+  int st = make_map_A(t, &mA, mem_bf16, K, C, batch, pitch);
   if (st != CGG_OK) return st;
   TcGemmP p = {};
   p.N_TILE = 256;
@@ -912,7 +940,8 @@ int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* w
   TCU(launch_pdl(downsample3_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
       static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->cfg.embed_dim, t->H4, t->W4,
       reinterpret_cast<__nv_bfloat16*>(base + w.fds[0]), reinterpret_cast<__nv_bfloat16*>(base + w.fds[1]),
-      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2])));
+      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2]), pitch8(t->lh[0] * t->lw[0]), pitch8(t->lh[1] * t->lw[1]),
+      pitch8(t->lh[2] * t->lw[2])));
   count_launch();
   TCU(cudaGetLastError());
   return CGG_OK;
@@ -940,7 +969,7 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
   CUtensorMap mA, mB;
   // split-precision contraction  logits = Fhi.me_hi + Flo.me_hi + Fhi.me_lo  (bf16 pairs, fp32
   // accumulate: ~16 mantissa bits per operand), expressed as ONE GEMM with K = 3C by revisiting chunks
-  int st = make_map_A(t, &mA, base + w.fds[level], K, 2 * C, batch);
+  int st = make_map_A(t, &mA, base + w.fds[level], K, 2 * C, batch, pitch8(K));
   if (st != CGG_OK) return st;
   // rows beyond the buffer's logical end are covered by the 64 KB slack of me_all (finite garbage,
   // columns >= Q are never stored)

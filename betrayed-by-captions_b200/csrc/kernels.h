@@ -58,7 +58,12 @@ cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const in
                                    int Bg, int Q, int T, int D, float temperature,
                                    float* g_l2v, float* g_v2l, cudaStream_t s);
 cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
-                                    int Bg, int T, float loss_weight, float* loss, cudaStream_t s);
+                                    int Bg, int T, float loss_weight, float* loss, cudaStream_t s,
+                                    float* dg_l2v = nullptr, float* dg_v2l = nullptr);
+// backward: dS[j][i][t][q] = d loss / d (cap_i[t].pred_j[q]) (already divided by the temperature)
+cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, const int64_t* cap_mask, int Bg, int Q, int T,
+                                       int D, float temperature, const float* dg_l2v, const float* dg_v2l,
+                                       float grad_scale, float* dS, cudaStream_t s);
 
 // fp32 (rows, cols) -> bf16 (rows, 2*cols) hi/lo pairs: [hi | lo] per row
 cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s);

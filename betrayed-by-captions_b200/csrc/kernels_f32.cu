@@ -446,7 +446,7 @@ cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const in
 // log-softmax diagonals (grounding_loss.py:52-75).
 __global__ void __launch_bounds__(256) grounding_finish_kernel(
     const float* __restrict__ g_l2v, const float* __restrict__ g_v2l, const int64_t* __restrict__ cap_mask,
-    int Bg, int T, float loss_weight, float* __restrict__ loss) {
+    int Bg, int T, float loss_weight, float* __restrict__ loss, float* __restrict__ dg_l2v, float* __restrict__ dg_v2l) {
   extern __shared__ float sm[];
   float* cost = sm;                 // Bg*Bg
   float* diag = cost + Bg * Bg;     // Bg (per-row loss terms)
@@ -485,17 +485,123 @@ __global__ void __launch_bounds__(256) grounding_finish_kernel(
       for (int d = 0; d < Bg; ++d) a += diag[d];
       total += a / (float)Bg;
     }
+    float* dg = which == 0 ? dg_l2v : dg_v2l;
+    if (dg) {
+      // d loss / d cost[i,j] = w/(4 Bg) * (2 delta_ij - softmax_dim0(-cost)[i,j] - softmax_dim1(-cost)[i,j]); rows of
+      // empty captions were replaced by a detached constant (grounding_loss.py:52-61) -> zero gradient
+      __syncthreads();
+      for (int x = t; x < Bg * Bg; x += 256) {
+        const int i = x / Bg, j = x % Bg;
+        long ntok = 0;
+        for (int tt = 0; tt < T; ++tt) ntok += (cap_mask[(long)i * T + tt] != 0);
+        float m0 = -INFINITY, m1 = -INFINITY;
+        for (int y = 0; y < Bg; ++y) { m0 = fmaxf(m0, cost[y * Bg + j]); m1 = fmaxf(m1, cost[i * Bg + y]); }
+        float s0 = 0.f, s1 = 0.f;
+        for (int y = 0; y < Bg; ++y) { s0 += expf(cost[y * Bg + j] - m0); s1 += expf(cost[i * Bg + y] - m1); }
+        const float p0 = expf(cost[x] - m0) / s0, p1 = expf(cost[x] - m1) / s1;
+        dg[x] = ntok > 0 ? loss_weight / (4.0f * (float)Bg) * ((i == j ? 2.0f : 0.0f) - p0 - p1) : 0.f;
+      }
+    }
   }
   __syncthreads();
   if (t == 0) loss[0] = loss_weight * total / 4.0f;
 }
 
 cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
-                                    int Bg, int T, float loss_weight, float* loss, cudaStream_t s) {
+                                    int Bg, int T, float loss_weight, float* loss, cudaStream_t s, float* dg_l2v,
+                                    float* dg_v2l) {
   const size_t smem = (size_t)(Bg * Bg + Bg) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(grounding_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  grounding_finish_kernel<<<1, 256, smem, s>>>(g_l2v, g_v2l, cap_mask, Bg, T, loss_weight, loss);
+  grounding_finish_kernel<<<1, 256, smem, s>>>(g_l2v, g_v2l, cap_mask, Bg, T, loss_weight, loss, dg_l2v, dg_v2l);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// Backward of the pair distances w.r.t. the similarities: one CTA per (caption i, image j) recomputes
+// S in shared memory and writes dS[j][i][t][q] * (1/temperature) (image-major so that the following
+// batched GEMM  dpred_j = dS_j^T . cap  is deterministic).
+//   l2v: f_t = -sum_q a_tq S_tq, a = softmax_q  ->  d f_t / d S_tq = -a_tq (1 + S_tq + f_t)
+//   v2l: g_q = -sum_t b_tq S_tq, b = softmax_t  ->  d g_q / d S_tq = -b_tq (1 + S_tq + g_q)
+__global__ void __launch_bounds__(256) grounding_bwd_pairs_kernel(
+    const float* __restrict__ pred, const float* __restrict__ cap, const int64_t* __restrict__ cap_mask,
+    int Bg, int Q, int T, int D, float inv_temp, const float* __restrict__ dg_l2v, const float* __restrict__ dg_v2l,
+    float grad_scale, float* __restrict__ dS) {
+  extern __shared__ float sm[];
+  float* S = sm;                   // T*Q
+  float* st_max = S + T * Q;       // per token: max, 1/sum, f_t
+  float* st_inv = st_max + T;
+  float* st_f = st_inv + T;
+  float* sq_max = st_f + T;        // per query: max, 1/sum, g_q
+  float* sq_inv = sq_max + Q;
+  float* sq_g = sq_inv + Q;
+  const int i = blockIdx.y, j = blockIdx.x, t = threadIdx.x;
+  const float* ci = cap + (long)i * T * D;
+  const float* pj = pred + (long)j * Q * D;
+  for (int idx = t; idx < T * Q; idx += 256) {
+    const int tt = idx / Q, qq = idx % Q;
+    const float4* a = reinterpret_cast<const float4*>(ci + (long)tt * D);
+    const float4* bq = reinterpret_cast<const float4*>(pj + (long)qq * D);
+    float acc = 0.f;
+    for (int d = 0; d < D / 4; ++d) {
+      const float4 x = a[d], y = bq[d];
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+      acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    S[idx] = acc * inv_temp;
+  }
+  __syncthreads();
+  const int lane = t & 31, warp = t >> 5;
+  for (int tt = warp; tt < T; tt += 8) {
+    float mx = -INFINITY;
+    for (int qq = lane; qq < Q; qq += 32) mx = fmaxf(mx, S[tt * Q + qq]);
+    mx = warp_max(mx);
+    float se = 0.f, sd = 0.f;
+    for (int qq = lane; qq < Q; qq += 32) {
+      const float sv = S[tt * Q + qq], e = expf(sv - mx);
+      se += e;
+      sd = fmaf(e, -sv, sd);
+    }
+    se = warp_sum(se);
+    sd = warp_sum(sd);
+    if (lane == 0) { st_max[tt] = mx; st_inv[tt] = 1.0f / se; st_f[tt] = sd / se; }
+  }
+  for (int qq = t; qq < Q; qq += 256) {
+    float mx = -INFINITY;
+    for (int tt = 0; tt < T; ++tt) mx = fmaxf(mx, S[tt * Q + qq]);
+    float se = 0.f, sd = 0.f;
+    for (int tt = 0; tt < T; ++tt) {
+      const float sv = S[tt * Q + qq], e = expf(sv - mx);
+      se += e;
+      sd = fmaf(e, -sv, sd);
+    }
+    sq_max[qq] = mx; sq_inv[qq] = 1.0f / se; sq_g[qq] = sd / se;
+  }
+  __syncthreads();
+  long ntok = 0;
+  for (int tt = 0; tt < T; ++tt) ntok += (cap_mask[(long)i * T + tt] != 0);
+  const float gl = dg_l2v[i * Bg + j] * grad_scale / (float)(ntok > 0 ? ntok : 1);
+  const float gv = dg_v2l[i * Bg + j] * grad_scale / (float)Q;
+  float* out = dS + (((long)j * Bg + i) * T) * Q;
+  for (int idx = t; idx < T * Q; idx += 256) {
+    const int tt = idx / Q, qq = idx % Q;
+    const float sv = S[idx];
+    const float a = expf(sv - st_max[tt]) * st_inv[tt];
+    const float b = expf(sv - sq_max[qq]) * sq_inv[qq];
+    const float m = (cap_mask[(long)i * T + tt] != 0) ? 1.f : 0.f;
+    const float d = gl * m * (-a) * (1.0f + sv + st_f[tt]) + gv * (-b) * (1.0f + sv + sq_g[qq]);
+    out[idx] = d * inv_temp;
+  }
+}
+
+cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, const int64_t* cap_mask, int Bg, int Q, int T,
+                                       int D, float temperature, const float* dg_l2v, const float* dg_v2l,
+                                       float grad_scale, float* dS, cudaStream_t s) {
+  const size_t smem = (size_t)(T * Q + 3 * T + 3 * Q) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(grounding_bwd_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  grounding_bwd_pairs_kernel<<<dim3(Bg, Bg), 256, smem, s>>>(pred, cap, cap_mask, Bg, Q, T, D, 1.0f / temperature, dg_l2v,
+                                                             dg_v2l, grad_scale, dS);
   count_launch();
   return cudaGetLastError();
 }

@@ -51,15 +51,23 @@ struct TcState {
 
 
 // carving of the caller-provided tc workspace
+inline int pitch8(int k) { return (k + 7) & ~7; }
+
 struct TcWs {
-  size_t me_all, fds[3], xqb, xb, ob, fb, zb, h1b, h2b, qf, qs, kvs, x1, x2, t1, total;
+  size_t me_all, fds[3], memp[3], xqb, xb, ob, fb, zb, h1b, h2b, qf, qs, kvs, x1, x2, t1, total;
   void carve(const TcState* t, int B) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
     const int C = t->cfg.embed_dim;
     const size_t M = (size_t)B * t->cfg.num_queries;
     me_all = take((size_t)B * t->rows_per_batch * 2 * C * 2 + 128 * 1024);   // [hi|lo] rows + 128 slack rows
-    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * 2 * C * t->lh[l] * t->lw[l] * 2);   // hi, lo planes
+    // hi, lo planes; the plane pitch is the key count rounded up to 8 (TMA 16-byte stride rule)
+    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * 2 * C * pitch8(t->lh[l] * t->lw[l]) * 2);
+    // re-pitched copy of a memory level whose key count is not a multiple of 8 (tc_kv_project)
+    for (int l = 0; l < 3; ++l) {
+      const int K = t->lh[l] * t->lw[l];
+      memp[l] = take((K % 8) ? (size_t)B * C * pitch8(K) * 2 : 0);
+    }
     xqb = take(M * C * 2); xb = take(M * C * 2); ob = take(M * C * 2);
     fb = take(M * t->cfg.ffn_dim * 2);
     zb = take(M * 2 * C * 2); h1b = take(M * 2 * C * 2); h2b = take(M * 2 * C * 2);   // hi/lo rows

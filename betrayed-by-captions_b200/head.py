@@ -157,10 +157,10 @@ class Mask2FormerHeadOpenB200(nn.Module):
         return rt.noun_embeddings(table, ln_weight, ln_bias, ids, eps, self.text_emb_norm)
 
     def grounding_loss(self, cls_emb_pred, gt_caption_embs, gt_caption_mask, loss_weight=1.0):
-        """losses/grounding_loss.py:9-77 (forward value)."""
-        rt = self._runtime(cls_emb_pred.device)
-        return rt.grounding_loss(cls_emb_pred, gt_caption_embs, gt_caption_mask,
-                                 float(self.softmax_temperature), loss_weight)
+        """losses/grounding_loss.py:9-77; differentiable w.r.t. cls_emb_pred (grounding.py)."""
+        from .grounding import grounding_loss
+        return grounding_loss(cls_emb_pred, gt_caption_embs, gt_caption_mask, float(self.softmax_temperature),
+                              loss_weight)
 
 
 def _ptr(t):

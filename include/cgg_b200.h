@@ -210,6 +210,14 @@ int cgg_grounding_loss(cgg_handle *h, const float *pred, const float *cap, const
                        int Bg, int Q, int T, int D, float temperature, float loss_weight,
                        float *loss, void *scratch, size_t scratch_bytes, void *stream);
 
+/* K7 backward: d loss / d pred (Bg,Q,D) fp32 of the same loss, times grad_out (the upstream scalar gradient).
+ * Captions are frozen BERT embeddings in the reference (head.py:251-254), so no caption gradient is produced.
+ * scratch: >= cgg_grounding_bwd_scratch_bytes(Bg,Q,T) bytes. */
+size_t cgg_grounding_bwd_scratch_bytes(int Bg, int Q, int T);
+int cgg_grounding_loss_backward(cgg_handle *h, const float *pred, const float *cap, const int64_t *cap_mask,
+                                int Bg, int Q, int T, int D, float temperature, float loss_weight, float grad_out,
+                                float *dpred, void *scratch, size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,6 +213,30 @@ def test_grounding_loss_matches_reference_golden(name):
     assert abs(float(loss) - float(O.grounding_loss(pred, cap, m, 10.0, 2.0))) < 1e-4 * max(1.0, abs(want))
 
 
+@pytest.mark.parametrize('name', list(cases.GROUNDING_CASES))
+def test_grounding_loss_gradient_matches_reference_golden(name):
+    """d loss / d cls_emb_pred from cgg_grounding_loss_backward against the gradients the unmodified reference
+    produced (tests/golden/make_golden.py: strided sample + abs-sum) and the oracle's autograd."""
+    from cgg_b200.grounding import GroundingLossB200
+    gold = np.load(os.path.join(GOLD, 'grounding.npz'))
+    pred, cap, m = cases.grounding_tensors(name)
+    p_dev = pred.to(DEV).requires_grad_(True)
+    loss = GroundingLossB200(loss_weight=2.0)(p_dev, cap.to(DEV), m.to(DEV), 10.0)
+    (loss * 1.0).backward()
+    g = p_dev.grad.cpu()
+    p_ref = pred.clone().requires_grad_(True)
+    O.grounding_loss(p_ref, cap, m, 10.0, 2.0).backward()
+    scale = float(p_ref.grad.abs().max())
+    assert float((g - p_ref.grad).abs().max()) <= 2e-5 * scale
+    want = gold[name + '_grad_sample']
+    np.testing.assert_allclose(g.flatten()[::cases.GRAD_SAMPLE_STRIDE].numpy(), want, atol=2e-5 * scale, rtol=0)
+    assert abs(float(g.double().abs().sum()) - float(gold[name + '_grad_abssum'])) <= 1e-4 * float(gold[name + '_grad_abssum'])
+    # upstream scaling goes through
+    p2 = pred.to(DEV).requires_grad_(True)
+    (GroundingLossB200(loss_weight=2.0)(p2, cap.to(DEV), m.to(DEV), 10.0) * 0.25).backward()
+    torch.testing.assert_close(p2.grad, p_dev.grad * 0.25, rtol=1e-6, atol=0)
+
+
 def test_embedding_side_matches_reference_golden():
     gold = np.load(os.path.join(GOLD, 'embeddings.npz'))
     sd = synth.make_params(seed=9, num_queries=16)

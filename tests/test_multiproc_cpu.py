@@ -47,6 +47,58 @@ def test_two_rank_timing_and_sharding():
     assert abs(v0 - 2 * 16 * 10 / 15e-3) < 1e-6 and v0 == v1
 
 
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from cgg_b200.grounding import gather_captions_and_preds
+    from oracle import cgg_oracle as O
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    pred_all, cap_all, mask_all = _gather_data(world)
+    B = 2
+    sl = slice(rank * B, (rank + 1) * B)
+    pred = pred_all[:, sl].clone().requires_grad_(True)              # (L, B, Q, D): all head calls stacked
+    embs, mask, preds = gather_captions_and_preds(list(cap_all[sl]), list(mask_all[sl]), pred)
+    loss = sum(O.grounding_loss(preds[l], embs, mask, 10.0, 2.0) for l in range(preds.shape[0]))
+    loss.backward()
+    q.put((rank, embs.clone(), mask.clone(), preds.detach().clone(), float(loss), pred.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _gather_data(world, L=3, B=2, Q=5, T=4, D=8):
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn((L, world * B, Q, D), generator=g)
+    cap = torch.randn((world * B, T, D), generator=g)
+    mask = torch.tensor([[1, 1, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [1, 0, 0, 0]])[:world * B]
+    return pred, cap, mask
+
+
+def test_batched_caption_gather_matches_single_process():
+    """mask2former_head.py:650-684: rank-major concatenation, cross-rank negatives in the loss, gradient only
+    into the local slot -- with the 10 head calls' predictions travelling in one collective."""
+    sys.path.insert(0, ROOT)
+    from oracle import cgg_oracle as O
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pred_all, cap_all, mask_all = _gather_data(2)
+    full = pred_all.clone().requires_grad_(True)
+    want = sum(O.grounding_loss(full[l], cap_all, mask_all, 10.0, 2.0) for l in range(full.shape[0]))
+    want.backward()
+    for rank, embs, mask, preds, loss, grad in res:
+        assert torch.equal(embs, cap_all) and torch.equal(mask, mask_all) and mask.dtype == mask_all.dtype
+        assert torch.equal(preds, pred_all)
+        assert abs(loss - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+        torch.testing.assert_close(grad, full.grad[:, rank * 2:(rank + 1) * 2], rtol=1e-5, atol=1e-7)
+
+
 def test_reference_arm_runs_on_rank0_only():
     env = dict(os.environ, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
