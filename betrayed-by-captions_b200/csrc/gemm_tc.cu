@@ -54,6 +54,7 @@ struct TcGemmP {
   int epi;
   int dbg;
   int M_valid;           // valid pixels / keys per batch image (features for EPI_LINEAR_T)
+  int m_tiles, n_batch, n_work;   // A-resident kinds are persistent: CTA c walks work items c, c+grid, ... of m_tiles*n_batch
   // EPI_MASK_T
   __nv_bfloat16* out_mask; long out_call_stride, out_batch_stride, HW; int Q, q_pad, n_calls;
   // EPI_ROWMAJOR
@@ -82,11 +83,18 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 }
 
 
+// Debug trace (CGG_TC_TIMING=1): SM clock stamps of N tiles 16..23 of CTA 0 of the pair kernel.
+__device__ long long g_tc_trace[64];
+#define TC_TRACE(gi, slot)                                                                         \
+  do {                                                                                             \
+    if ((p.dbg & 1) && blockIdx.x == 0 && (gi) >= 16 && (gi) < 24) g_tc_trace[((gi) - 16) * 8 + (slot)] = clock64(); \
+  } while (0)
+
 constexpr int EPI_WARPS = 16;                 // epilogue warps (4 per TMEM lane quarter)
 constexpr int EPI_PARTS = EPI_WARPS / 4;
 
 struct EpiCtx {
-  int lane, m, batch, part, chunks, wi, col0;
+  int lane, m, batch, part, chunks, wi, col0, g = -1;
   bool m_ok;
   uint32_t taddr;
 };
@@ -96,36 +104,64 @@ struct EpiCtx {
 // (128 px x Q rows) box per head call of the tile; rows q >= Q fall outside the tensor and are clipped
 // by the TMA unit.  No per-thread global stores at all.
 __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const CUtensorMap* tmC,
-                                           bool leader_warp, int t, int m_tile) {
+                                           bool leader_warp, bool last, int m_tile, uint64_t* acc_empty_bar,
+                                           bool arrive_on_leader) {
   const bool leader = leader_warp && c.lane == 0;
-  // the previous tile's stores must have finished READING the staging buffer
+  // 1. accumulator -> registers (up to 4 chunks of 16 columns per warp, loads in flight together).
+  //    This overlaps the TMA engine still reading the previous tile out of the staging buffer.
+  static_assert(EPI_PARTS == 4, "four chunk slots per warp below");
+  uint32_t r0[16], r1[16], r2[16], r3[16];
+  const int ch0 = c.part, ch1 = c.part + 4, ch2 = c.part + 8, ch3 = c.part + 12;
+  const bool on0 = ch0 < c.chunks, on1 = ch1 < c.chunks, on2 = ch2 < c.chunks, on3 = ch3 < c.chunks;   // warp-uniform
+  if (on0) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch0 * 16), r0);
+  if (on1) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch1 * 16), r1);
+  if (on2) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch2 * 16), r2);
+  if (on3) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch3 * 16), r3);
+  if (on0) ptx::tmem_ld_wait16(r0);
+  if (on1) ptx::tmem_ld_wait16(r1);
+  if (on2) ptx::tmem_ld_wait16(r2);
+  if (on3) ptx::tmem_ld_wait16(r3);
+  // 2. the accumulator buffer is free again: the MMAs of the tile after next may start
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) {
+    if (arrive_on_leader) ptx::mbar_arrive_leader(acc_empty_bar);
+    else ptx::mbar_arrive(acc_empty_bar);
+  }
+  // 3. the previous tile's stores must have finished READING the staging buffer
   if (leader) ptx::tma_store_wait_read();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  if (leader) TC_TRACE(c.g, 6);
   const int row = c.m & (TC_BM - 1);
-  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
-    float v[16];
-    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
+  auto stage16 = [&](const uint32_t (&r)[16], int ch) {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sStage) + (long)(ch * 16) * TC_BM + row;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dst[i * TC_BM] = __float2bfloat16_rn(v[i]);
+    for (int i = 0; i < 16; ++i) dst[i * TC_BM] = __float2bfloat16_rn(__uint_as_float(r[i]));
+  };
+  if (!(p.dbg & 256)) {
+    if (on0) stage16(r0, ch0);
+    if (on1) stage16(r1, ch1);
+    if (on2) stage16(r2, ch2);
+    if (on3) stage16(r3, ch3);
   }
+  if (leader) TC_TRACE(c.g, 7);
   ptx::fence_proxy_async_smem();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  if (leader) {
+  if (leader && !(p.dbg & (256 | 1024))) {
     const int r0 = c.col0;                       // first (call, q) row of this tile
     const int N_TILE = c.chunks * 16, q_pad = p.q_pad;
     if (N_TILE >= q_pad) {
       for (int sidx = 0; sidx * q_pad + q_pad <= N_TILE || sidx == 0; ++sidx) {
         const int call = r0 / q_pad + sidx;
         if (call >= p.n_calls || sidx * q_pad >= N_TILE) break;
-        ptx::tma_store_3d(tmC, sStage + (long)sidx * q_pad * TC_BM * 2, m_tile * TC_BM, 0, call * (int)gridDim.y + c.batch);
+        ptx::tma_store_3d(tmC, sStage + (long)sidx * q_pad * TC_BM * 2, m_tile * TC_BM, 0, call * p.n_batch + c.batch);
       }
     } else {
       const int call = r0 / q_pad, q0 = r0 - call * q_pad;
-      if (call < p.n_calls) ptx::tma_store_3d(tmC, sStage, m_tile * TC_BM, q0, call * (int)gridDim.y + c.batch);
+      if (call < p.n_calls) ptx::tma_store_3d(tmC, sStage, m_tile * TC_BM, q0, call * p.n_batch + c.batch);
     }
     ptx::tma_store_commit();
-    if (t == p.NT - 1) ptx::tma_store_wait_read();   // smem must stay valid until the last store has read it
+    if (last) ptx::tma_store_wait_read();   // smem must stay valid until the last store has read it
   }
 }
 
@@ -135,7 +171,7 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
 // rows past the image's last key are clipped by the TMA unit.  (The positional / level part of the keys
 // is not added here at all: the attention kernel adds Q R^T, see attention_tc.cu.)
 __device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const CUtensorMap* tmC,
-                                             bool leader_warp, int t, int m_tile) {
+                                             bool leader_warp, bool last, int m_tile) {
   const bool leader = leader_warp && c.lane == 0;
   if (leader) ptx::tma_store_wait_read();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -165,7 +201,7 @@ __device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, 
     for (int sub = 0; sub < subs; ++sub)
       ptx::tma_store_3d(tmC, sStage + sub * (TC_BM * 128), c.col0 + sub * 64, m_tile * TC_BM, c.batch);
     ptx::tma_store_commit();
-    if (t == p.NT - 1) ptx::tma_store_wait_read();
+    if (last) ptx::tma_store_wait_read();
   }
 }
 
@@ -285,7 +321,7 @@ __device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiC
 __device__ unsigned long long g_tc_stamps[16];
 #define TC_STAMP(i)                                                            \
   do {                                                                         \
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
+    if ((p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0) g_tc_stamps[i] = ptx::global_timer_ns(); \
   } while (0)
 
 // Specialised per epilogue kind: the operand layout / residency follow from it at compile time
@@ -306,8 +342,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + (A_RESIDENT ? p.KC * A_CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
-  uint64_t* a_full = bars;
-  uint64_t* b_full = bars + 1;
+  uint64_t* a_full = bars;            // [4] per A chunk (resident kinds)
+  uint64_t* a_empty = bars + 4;       // [4] the last N tile's MMAs of a work item are done with A chunk kc
+  uint64_t* b_full = bars + 8;
   uint64_t* b_empty = b_full + p.stages;
   uint64_t* acc_full = b_empty + p.stages;
   uint64_t* acc_empty = acc_full + 2;
@@ -316,13 +353,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, batch = blockIdx.y;
+  // A-resident kinds: persistent CTAs over (pixel tile, image) work items; the others: one tile per CTA
+  const int n_work = A_RESIDENT ? p.n_work : 1;
+  const int w_first = A_RESIDENT ? (int)blockIdx.x : 0;
+  const int w_stride = A_RESIDENT ? (int)gridDim.x : 1;
+  auto tile_of = [&](int w, int& m_tile, int& batch) {
+    if (A_RESIDENT) { batch = w / p.m_tiles; m_tile = w - batch * p.m_tiles; }
+    else { m_tile = blockIdx.x; batch = blockIdx.y; }
+  };
   if (threadIdx.x == 0) TC_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    ptx::mbar_init(a_full, 1);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
     ptx::fence_mbar_init();
@@ -345,6 +389,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- TMA producer
       // A chunk = 128 rows x 64 K: an NCHW operand comes as two (64 px x 64 ch) boxes, an
       // activation operand as one (64 k x 128 rows) box; 16 KB either way.
+      int m_tile = 0, batch = 0;
       auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
         const int kco = p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.a_kcoord[kc];
         if (A_KMAJOR) {
@@ -354,13 +399,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tma_load_3d(dst + g * (A_CHUNK_BYTES / 2), &tmA, bar, m_tile * TC_BM + g * 64, kco, batch);
         }
       };
-      if (A_RESIDENT) {
-        ptx::mbar_expect_tx(a_full, (uint32_t)(p.KC * A_CHUNK_BYTES));
-        for (int kc = 0; kc < p.KC; ++kc) load_a(sA + kc * A_CHUNK_BYTES, a_full, kc);
-      }
-      int it = 0;
-      for (int t = 0; t < p.NT; ++t)
+      int it = 0, tl = 0;
+      for (int w = w_first; w < n_work; w += w_stride, ++tl) {
+       tile_of(w, m_tile, batch);
+       if (A_RESIDENT && tl == 0)
+         for (int kc = 0; kc < p.KC; ++kc) {
+           ptx::mbar_expect_tx(&a_full[kc], (uint32_t)A_CHUNK_BYTES);
+           load_a(sA + kc * A_CHUNK_BYTES, &a_full[kc], kc);
+         }
+       for (int t = 0; t < p.NT; ++t)
         for (int kc = 0; kc < p.KC; ++kc, ++it) {
+          if (A_RESIDENT && t == 0 && tl > 0) {
+            // the previous work item's last N tile has finished reading chunk kc: refill it while that
+            // tile's remaining MMAs and epilogue still run
+            ptx::mbar_wait(&a_empty[kc], (uint32_t)(tl & 1) ^ 1u);
+            ptx::mbar_expect_tx(&a_full[kc], (uint32_t)A_CHUNK_BYTES);
+            load_a(sA + kc * A_CHUNK_BYTES, &a_full[kc], kc);
+          }
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           ptx::mbar_wait(&b_empty[s], ph ^ 1u);
@@ -370,25 +425,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
       const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false);
-      if (A_RESIDENT) {
-        ptx::mbar_wait(a_full, 0);
-        ptx::tc_fence_after();
-      }
-      int it = 0;
-      for (int t = 0; t < p.NT; ++t) {
-        const int buf = t & 1;
-        const uint32_t use = (uint32_t)(t >> 1);
+      int it = 0, g = 0, tl = 0;
+      for (int w = w_first; w < n_work; w += w_stride, ++tl)
+      for (int t = 0; t < p.NT; ++t, ++g) {
+        const int buf = g & 1;
+        const uint32_t use = (uint32_t)(g >> 1);
         ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
         for (int kc = 0; kc < p.KC; ++kc, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          if (A_RESIDENT && t == 0) ptx::mbar_wait(&a_full[kc], (uint32_t)(tl & 1));
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
           if (it == 0) TC_STAMP(2);
@@ -401,12 +455,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t adesc = A_KMAJOR ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
                                               : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
             const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
-            ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+            if (!(p.dbg & 512)) ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
           }
           ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
+          if (A_RESIDENT && t == p.NT - 1) ptx::mma_commit(&a_empty[kc]);
         }
         ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
-        if (t == 0) TC_STAMP(3);
+        if (g == 0) TC_STAMP(3);
       }
     }
   } else {
@@ -414,6 +469,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // every (EPI_WARPS/4)-th 16-column chunk.  One lean, specialised loop per epilogue kind.
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;                       // which share of the chunks
+    int g = 0;
+    for (int w = w_first; w < n_work; w += w_stride) {
+    int m_tile, batch;
+    tile_of(w, m_tile, batch);
+    const bool last_work = w + w_stride >= n_work;
     const int m = m_tile * TC_BM + quarter * 32 + lane;     // TMEM lane -> pixel / key / feature index
     const bool m_ok = m < p.M_valid;
     EpiCtx ctx;
@@ -421,22 +481,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ctx.chunks = p.N_TILE / 16; ctx.wi = (m_tile * TC_BM + quarter * 32) >> 5;
     LinCtx lin;
     if (EPI == EPI_LINEAR_T) lin.init(p, m);
-    for (int t = 0; t < p.NT; ++t) {
-      const int buf = t & 1;
-      const uint32_t use = (uint32_t)(t >> 1);
+    for (int t = 0; t < p.NT; ++t, ++g) {
+      const int buf = g & 1;
+      const uint32_t use = (uint32_t)(g >> 1);
       ptx::mbar_wait(&acc_full[buf], use & 1u);
       ptx::tc_fence_after();
-      if (t == 0 && warp == 2 && lane == 0) TC_STAMP(4);
+      if (g == 0 && warp == 2 && lane == 0) TC_STAMP(4);
       ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
       ctx.col0 = t * p.N_TILE;
-      if (EPI == EPI_MASK_T) epi_mask_t(p, ctx, sStage, &tmC, warp == 2, t, m_tile);
-      else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, t, m_tile);
+      const bool last = last_work && t == p.NT - 1;
+      if (EPI == EPI_MASK_T) epi_mask_t(p, ctx, sStage, &tmC, warp == 2, last, m_tile, &acc_empty[buf], false);
+      else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, last, m_tile);
       else if (EPI == EPI_BITS) epi_bits(p, ctx);
       else epi_linear_dispatch(p, ctx, lin);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-      if (t == p.NT - 1 && warp == 2 && lane == 0) TC_STAMP(5);
+      if (EPI != EPI_MASK_T) {       // (the mask epilogue releases the accumulator itself, as soon as it is in registers)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      }
+      if (last && warp == 2 && lane == 0) TC_STAMP(5);
+    }
     }
   }
   ptx::tc_fence_before();
@@ -446,6 +510,155 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+}
+
+// ------------------------------------------------------------------- K2, CTA-pair variant
+// The mask einsum with cta_group::2 MMAs (M = 256: two 128-pixel tiles, one per CTA of the pair; N =
+// N_TILE).  Each CTA streams only HALF of every B chunk (N_TILE/2 mask-embedding rows), which makes room
+// for TWO whole N tiles of B in shared memory (2 x 4 chunks).  That matters because the single MMA-issuing
+// thread, not the tensor pipe, paces the single-CTA kernel: every tcgen05.commit costs it ~300-400
+// cycles, and a 4-stage ring needs one per chunk.  Here ONE commit per N tile (acc_full) tells the
+// epilogue "accumulator ready" and the producer "these four B slots are free".
+// Otherwise the same persistent pipeline as tc_gemm_kernel<EPI_MASK_T>: A tile resident and refilled chunk
+// by chunk under the last N tile, double-buffered accumulators, staged TMA-store epilogue (each CTA stores
+// its own 128 pixels).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_einsum_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int KC = 4;
+  const int half_n = p.N_TILE / 2;
+  const int b_chunk_bytes = half_n * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + KC * A_CHUNK_BYTES;                  // [2 N-tile slots][KC chunks]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * KC * b_chunk_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 4;
+  uint64_t* b_full = bars + 8;                            // [2][KC]
+  uint64_t* acc_full = b_full + 2 * KC;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int mt2 = p.m_tiles >> 1;                         // pixel-tile pairs per image
+  const int n_work = mt2 * p.n_batch;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2 * KC; ++i) ptx::mbar_init(&b_full[i], 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish_2sm();
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();        // the peer's barriers exist before anything arrives on them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs: own pixel tile, own half of B; tx bytes land on the leader)
+      int g = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl) {
+        const int batch = w / mt2, m_tile = (w - batch * mt2) * 2 + (int)rank;
+        for (int t = 0; t < p.NT; ++t, ++g) {
+          const int slot = g & 1;
+          // the MMAs of N tile g-2 (same slot) have completed: its accumulator commit doubles as "B slot free"
+          if (g >= 2) ptx::mbar_wait(&acc_full[slot], (uint32_t)((g - 2) >> 1) & 1u);
+          for (int kc = 0; kc < KC; ++kc) {
+            if (t == 0) {
+              if (tl > 0) ptx::mbar_wait(&a_empty[kc], (uint32_t)(tl & 1) ^ 1u);
+              if (rank == 0) ptx::mbar_expect_tx(&a_full[kc], 2u * A_CHUNK_BYTES);
+              for (int h = 0; h < 2; ++h)
+                ptx::tma_load_3d_2sm(sA + kc * A_CHUNK_BYTES + h * (A_CHUNK_BYTES / 2), &tmA, &a_full[kc],
+                                     m_tile * TC_BM + h * 64, kc * TC_BK, batch);
+            }
+            uint64_t* bar = &b_full[slot * KC + kc];
+            if (rank == 0) ptx::mbar_expect_tx(bar, 2u * (uint32_t)b_chunk_bytes);
+            ptx::tma_load_2d_2sm(sB + (slot * KC + kc) * b_chunk_bytes, &tmB, bar, kc * TC_BK,
+                                 batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE + (int)rank * half_n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer: one thread of the leader CTA drives both SMs
+      const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
+      // descriptors differ by a constant in the 14-bit address field (units of 16 bytes)
+      uint64_t adesc0[KC], bdesc0[2 * KC];
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc)
+        adesc0[kc] = ptx::umma_desc_sw128(ptx::smem_u32(sA + kc * A_CHUNK_BYTES), A_CHUNK_BYTES / 2, 1024);
+#pragma unroll
+      for (int i = 0; i < 2 * KC; ++i) bdesc0[i] = ptx::umma_desc_sw128(ptx::smem_u32(sB + i * b_chunk_bytes), 16, 1024);
+      int g = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl)
+        for (int t = 0; t < p.NT; ++t, ++g) {
+          const int buf = g & 1;
+          const uint32_t use = (uint32_t)(g >> 1);
+          ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          TC_TRACE(g, 0);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+            if (t == 0) ptx::mbar_wait(&a_full[kc], (uint32_t)(tl & 1));
+            ptx::mbar_wait(&b_full[buf * KC + kc], use & 1u);
+            ptx::tc_fence_after();
+            if (kc == 0) TC_TRACE(g, 1);
+            const uint64_t ad = adesc0[kc], bd = buf ? bdesc0[KC + kc] : bdesc0[kc];
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (32 >> 4)), idesc,
+                                   (kc | k) != 0 ? 1u : 0u);
+            if (t == p.NT - 1) ptx::mma_commit_2sm(&a_empty[kc]);   // A chunk kc may be refilled for the next work item
+          }
+          ptx::mma_commit_2sm(&acc_full[buf]);   // accumulator ready (epilogue) + B slot free (producer), both CTAs
+          TC_TRACE(g, 2);
+        }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own 128 accumulator lanes)
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    int g = 0;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      const int batch = w / mt2, m_tile = (w - batch * mt2) * 2 + (int)rank;
+      const bool last_work = w + n_pairs >= n_work;
+      const int m = m_tile * TC_BM + quarter * 32 + lane;
+      EpiCtx ctx;
+      ctx.lane = lane; ctx.m = m; ctx.m_ok = m < p.M_valid; ctx.batch = batch; ctx.part = part;
+      ctx.chunks = p.N_TILE / 16; ctx.wi = 0;
+      for (int t = 0; t < p.NT; ++t, ++g) {
+        const int buf = g & 1;
+        const uint32_t use = (uint32_t)(g >> 1);
+        ptx::mbar_wait(&acc_full[buf], use & 1u);
+        ptx::tc_fence_after();
+        if (warp == 2 && lane == 0) TC_TRACE(g, 3);
+        ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+        ctx.col0 = t * p.N_TILE; ctx.g = g;
+        epi_mask_t(p, ctx, sStage, &tmC, warp == 2, last_work && t == p.NT - 1, m_tile, &acc_empty[buf], true);
+        if (warp == 2 && lane == 0) TC_TRACE(g, 4);
+      }
+    }
+  }
+  __syncwarp();                   // the single-lane roles rejoin their warps (cluster barrier is .aligned)
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();        // both CTAs are done with both TMEMs and with each other's barriers
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------- K3, persistent variant
@@ -739,13 +952,14 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
   if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
   const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR) ? (size_t)p.N_TILE * TC_BM * 2 + 1024 : 0;
-  const size_t budget = 204 * 1024 - stage_bytes;
+  static const int smem_kb = getenv("CGG_TC_SMEM_KB") ? atoi(getenv("CGG_TC_SMEM_KB")) : 204;
+  const size_t budget = (size_t)smem_kb * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
   if (stages < 2) return tc_fail(t, CGG_ERR_BAD_SHAPE, "tile does not fit shared memory");
   p.stages = stages;
-  const size_t smem = 1024 + a_bytes + stages * b_stage + (1 + 2 * stages + 4) * 8 + 64 + stage_bytes;
+  const size_t smem = 1024 + a_bytes + stages * b_stage + (8 + 2 * stages + 4) * 8 + 64 + stage_bytes;
   if (!t->smem_attr_set) {
     TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_MASK_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TCU(cudaFuncSetAttribute(tc_gemm_kernel<EPI_ROWMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -755,13 +969,28 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   }
   // the kernel instantiation fixes the A-operand layout / residency: check the caller agrees
   const bool want_res = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR), want_km = (p.epi == EPI_LINEAR_T);
+  if (want_res && p.KC > 4) return tc_fail(t, CGG_ERR_BAD_SHAPE, "resident A tile limited to 4 K chunks");
   if ((p.a_resident != 0) != want_res || (p.a_kmajor != 0) != want_km)
     return tc_fail(t, CGG_ERR_BAD_SHAPE, "operand layout does not match the kernel specialisation");
   static const bool timing = getenv("CGG_TC_TIMING") != nullptr;
   p.dbg = timing ? 1 : 0;
+  static const int dbgmode = getenv("CGG_TC_DBGMODE") ? atoi(getenv("CGG_TC_DBGMODE")) : 0;
+  p.dbg |= dbgmode;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
-  const dim3 grid(m_tiles, batch, kparts), block(TC_THREADS);
+  dim3 grid(m_tiles, batch, kparts);
+  const dim3 block(TC_THREADS);
+  p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
+  if (want_res) {
+    static const int persist = getenv("CGG_TC_PERSIST") ? atoi(getenv("CGG_TC_PERSIST")) : 1;
+    if (t->num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int ctas = persist ? (p.n_work < t->num_sms ? p.n_work : t->num_sms) : p.n_work;
+    grid = dim3(ctas, 1, 1);
+  }
   const CUtensorMap& mCC = mC ? *mC : mB;
   switch (p.epi) {
     case EPI_MASK_T: TCU(launch_pdl(tc_gemm_kernel<EPI_MASK_T>, grid, block, smem, s, mA, mB, mCC, p)); break;
@@ -1093,7 +1322,52 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out) failed: " + std::to_string((int)r));
   }
-  return launch_tc_gemm(t, mA, mB, p, (int)((HW + TC_BM - 1) / TC_BM), batch, s, &mC);
+  const int m_tiles = (int)((HW + TC_BM - 1) / TC_BM);
+  static const int use_pair = getenv("CGG_EIN_PAIR") ? atoi(getenv("CGG_EIN_PAIR")) : 1;
+  if (use_pair && m_tiles % 2 == 0 && HW % TC_BM == 0 && p.N_TILE % 16 == 0 && p.KC == 4) {
+    // CTA-pair kernel: each CTA loads N_TILE/2 rows of every B chunk
+    st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE / 2);
+    if (st != CGG_OK) return st;
+    p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_stride;
+    p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
+    p.dbg = getenv("CGG_TC_DBGMODE") ? atoi(getenv("CGG_TC_DBGMODE")) : 0;
+    const size_t stage_bytes = (size_t)p.N_TILE * TC_BM * 2 + 1024;
+    const size_t b_chunk = (size_t)(p.N_TILE / 2) * 128;
+    const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * b_chunk + 24 * 8 + 64 + stage_bytes;
+    if (smem <= 227 * 1024) {
+      p.stages = 8;
+      static bool attr_set = false;
+      if (!attr_set) {
+        TCU(cudaFuncSetAttribute(tc_einsum_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+      }
+      if (t->num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      int pairs = t->num_sms / 2;
+      if (pairs > p.n_work / 2) pairs = p.n_work / 2;
+      if (getenv("CGG_TC_TIMING")) p.dbg |= 1;
+      TCU(launch_pdl_cluster(2, tc_einsum_pair_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem, s, mA, mB, mC, p));
+      count_launch();
+      TCU(cudaGetLastError());
+      if (p.dbg & 1) {
+        cudaStreamSynchronize(s);
+        long long tr[64];
+        cudaMemcpyFromSymbol(tr, g_tc_trace, sizeof(tr));
+        fprintf(stderr, "[pair einsum trace] cycles rel. to N-tile 16: mma(acc_empty ok, first B ok, committed) epi(acc_full ok, epi done, arrived) epi-inner(after bar1, after chunk loop)\n");
+        for (int i = 0; i < 8; ++i) {
+          fprintf(stderr, "  g=%d:", 16 + i);
+          for (int j = 0; j < 8; ++j) fprintf(stderr, " %7lld", tr[i * 8 + j] - tr[0]);
+          fprintf(stderr, "\n");
+        }
+      }
+      return CGG_OK;
+    }
+  }
+  return launch_tc_gemm(t, mA, mB, p, m_tiles, batch, s, &mC);
 }
 
 // ------------------------------------------------------------------ small-M linear layers
