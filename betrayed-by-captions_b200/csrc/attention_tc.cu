@@ -2,19 +2,24 @@
 //
 // One CTA per (image, head, 128-query tile).  Keys stream in 128-key tiles:
 //   S = Q K^T      tcgen05.mma  M=128 (queries) x N=128 (keys) x K=32 (head dim), S in TMEM
-//   softmax        4 warps, thread = query row (TMEM lane): the row's 128 scores are read with
-//                  tcgen05.ld, the attention-mask BITMAP words of that row are applied
-//                  (bit = 1 -> -inf), row max / sum are thread-local (no shuffles), P is written
+//   softmax        16 warps, thread = query row (TMEM lane) x one 32-key quarter of the tile: the scores
+//                  are read with tcgen05.ld, the row's attention-mask BITMAP word for those 32 keys is
+//                  applied (bit = 1 -> -inf), row max / sum are thread-local (no shuffles), P is written
 //                  to shared memory as bf16 in the UMMA core-matrix layout
-//   O_j = P V      tcgen05.mma  M=128 x N=32 x K=128, into a fresh TMEM tile; the softmax thread
-//                  folds it into its register accumulator with the online-softmax rescale
+//   O_j = P V      tcgen05.mma  M=128 x N=32 x K=32 per key quarter, into fresh TMEM tiles; the softmax
+//                  thread folds its quarter's tile into its register accumulator with the online-softmax
+//                  rescale
 // K and V tiles arrive by TMA (64-byte swizzle, one head's 32 dims = 64-byte rows) straight from
 // the projected K/V buffer.  Key tiles that are masked for EVERY query of the CTA are skipped
 // (flags from live_tiles_kernel); rows with all_masked set ignore the bitmap (the reference's
 // all-masked-row fallback, head.py:825-826).
-//   warp 0: TMA producer   warp 1: MMA issuer (1 thread)   warps 2-9: softmax / epilogue -- two
-//   groups of 4 warps, each owning 64 of the tile's 128 key columns with its OWN running max / sum /
-//   output accumulator (merged once at the end), so the groups never synchronise per tile
+//   warp 0: TMA producer   warp 1: MMA issuer (1 thread)   warps 2-17: softmax / epilogue -- four
+//   groups of 4 warps, each owning 32 of the tile's 128 key columns with its OWN running max / sum /
+//   output accumulator (merged once at the end), so the groups never synchronise per tile.
+//   The MMA thread issues P V of tile j and Q K^T of tile j+2 back to back and commits ONCE: that one
+//   mbarrier phase means "O(j) ready" and "S(j+2) ready" (a tcgen05.commit costs the issuing thread
+//   several hundred cycles); a softmax thread that has seen O(j) hands tile j's K/V stage back to the producer.
+#include <cstdio>
 #include "kernels.h"
 #include "tc_ptx.cuh"
 #include "tc_state.h"
@@ -23,20 +28,20 @@ namespace cgg {
 
 namespace {
 
-constexpr int AT_THREADS = 64 + 256;       // TMA warp + MMA warp + 8 softmax warps (two column halves)
+constexpr int AT_THREADS = 64 + 512;       // TMA warp + MMA warp + 16 softmax warps (four key-column quarters)
 constexpr int AT_KT = 128;                   // keys per tile
 constexpr int AT_STAGES = 4;
 constexpr int AT_KV_TILE_BYTES = AT_KT * 64; // 128 keys x 32 dims x bf16 = 8 KB
 constexpr int AT_STAGE_BYTES = 4 * AT_KV_TILE_BYTES;   // K tile, V tile, key-bias (R) tile as hi + lo
 constexpr int AT_Q_BYTES = 128 * 64;         // 128 queries x 32 dims bf16, core-matrix layout
 constexpr int AT_P_BYTES = 128 * AT_KT * 2;  // 32 KB per P buffer
-constexpr int AT_ONES_BYTES = 64 * 64;      // 64 key rows x 64 B: column 0 = 1.0 (row sums come out of the PV MMA)
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnP {
   const float* q; float* out; __nv_bfloat16* out_bf16;
   const uint32_t* bitmap; const uint8_t* all_masked; const uint8_t* live;
   int Q, K, heads, W32, ntiles, nqt;
+  int trace;
   int has_r, r_col0, r_lo_off;   // key-bias table term: S += Q (R_hi + R_lo)^T, R columns r_col0 + head*32
 };
 
@@ -75,6 +80,20 @@ __device__ __forceinline__ int next_live(const uint8_t* live, int t, int n) {
   return t;
 }
 
+// Debug trace (build with -DCGG_AT_TRACING, run with CGG_AT_TRACE=<softmax warp>): SM clock stamps of live
+// tiles 16..23 of CTA (0,0).
+__device__ long long g_at_trace[64];
+#ifdef CGG_AT_TRACING
+#define AT_TRACE(ti, slot)                                                                                   \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (ti) >= 16 && (ti) < 24) g_at_trace[((ti) - 16) * 8 + (slot)] = clock64(); \
+  } while (0)
+#define AT_TRACE_W(ti, slot) do { if (warp == p.trace && lane == 0) AT_TRACE(ti, slot); } while (0)
+#else
+#define AT_TRACE(ti, slot) do { } while (0)
+#define AT_TRACE_W(ti, slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ AttnP p) {
@@ -83,15 +102,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint8_t* sQ = smem;                                   // 8 KB
   uint8_t* sP = sQ + AT_Q_BYTES;                        // 2 x 32 KB
   uint8_t* sKV = sP + 2 * AT_P_BYTES;                   // stages x (K tile, V tile)
-  uint8_t* sOnes = sKV + AT_STAGES * AT_STAGE_BYTES;   // above every V tile (descriptor offsets are unsigned)
-  uint8_t* sLive = sOnes + AT_ONES_BYTES;               // this CTA's live-tile flags (<= 512 key tiles)
+  uint8_t* sLive = sKV + AT_STAGES * AT_STAGE_BYTES;   // this CTA's live-tile flags (<= 512 key tiles)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLive + 512);
   uint64_t* kv_full = bars;
   uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* step = kv_empty + AT_STAGES;    // [2] phase n of step[b]: S(2n+b) ready; phase n+1: O(2n+b) ready
+  uint64_t* p_full = step + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.heads, qt = blockIdx.x / p.heads, b = blockIdx.y;
@@ -104,7 +121,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     ptx::prefetch_tmap(&tmV);
     if (p.has_r) ptx::prefetch_tmap(&tmR);
     for (int i = 0; i < AT_STAGES; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 256); ptx::mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&step[i], 1); ptx::mbar_init(&p_full[i], 512); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -114,17 +131,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
-  if (warp >= 2) {
-    // "ones" tile, an extra N-group of the PV B operand in the V tiles' layout (64-byte rows, 64-byte
-    // swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)): column 0 of every key row is
-    // 1.0, so column 32 of O = P [V | 1] is the row sum of the bf16 P the tensor core actually used.
-    const int tid = threadIdx.x - 64;                       // 0..255
-    uint4 z = make_uint4(0, 0, 0, 0);
-    const int r = tid >> 2, cpos = tid & 3;                 // one 16-byte chunk per thread: 64 rows x 4 chunks
-    if (cpos == ((r >> 1) & 3)) z.x = 0x00003F80u;          // bf16 1.0 in element 0 of logical chunk 0
-    *reinterpret_cast<uint4*>(sOnes + r * 64 + cpos * 16) = z;
-    fence_async_smem();
-  }
   // the live-tile flags are read by three roles every tile: one copy into shared memory
   for (int i = threadIdx.x; i < p.ntiles; i += AT_THREADS) sLive[i] = live_g[i];
   if (warp >= 2 && warp < 6) {
@@ -161,7 +167,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;    // 2 buffers x 2 column halves x 64-column slots (48 used: 32 dims, sum, pad)
+  const uint32_t tmem_O = tmem_base + 256;    // 2 buffers x 4 key quarters x 32 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -169,8 +175,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       int it = 0;
       for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; t = next_live(live, t + 1, p.ntiles), ++it) {
         const int s = it % AT_STAGES;
-        const uint32_t ph = (uint32_t)(it / AT_STAGES) & 1u;
-        ptx::mbar_wait(&kv_empty[s], ph ^ 1u);
+        // stage s was last used by live tile it-4: a softmax thread releases it once that tile's P V has completed
+        ptx::mbar_wait(&kv_empty[s], ((uint32_t)(it / AT_STAGES) & 1u) ^ 1u);
         ptx::mbar_expect_tx(&kv_full[s], (p.has_r ? 4 : 2) * AT_KV_TILE_BYTES);
         uint8_t* st = sKV + s * AT_STAGE_BYTES;
         if (p.has_r) {
@@ -185,174 +191,188 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (lane == 0) {
       // ------------- MMA issuer
       const uint32_t idesc_s = ptx::umma_idesc_bf16(128, AT_KT, false, false);   // S = Q K^T
-      const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 48, false, true);       // O = P [V | 1] (N-major B, 2 N-groups)
-      const uint32_t ones_addr = ptx::smem_u32(sOnes);
+      const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 32, false, true);       // O = P V (N-major B)
       const uint32_t q_addr = ptx::smem_u32(sQ);
       int n_live = 0;
       for (int t = 0; t < p.ntiles; ++t) n_live += live[t] ? 1 : 0;
+      // descriptors: base + constant increments of the 14-bit address field (16-byte units); the smem window is
+      // < 256 KB so the field never carries
+      const uint64_t qd0 = umma_desc(q_addr, 128, 512, 0);                                  // Q: core matrices
+      const uint64_t kd0 = umma_desc(ptx::smem_u32(sKV), 16, 512, 4);                       // K / R tiles: SW64, K-major
+      const uint64_t vd0 = umma_desc(ptx::smem_u32(sKV + AT_KV_TILE_BYTES), 1024, 512, 4);  // V: SW64, N-major (one N group)
+      const uint64_t pd0 = umma_desc(ptx::smem_u32(sP), 128, 2048, 0);                      // P: core matrices
       auto issue_qk = [&](int j) {
         const int s = j % AT_STAGES;
         ptx::mbar_wait(&kv_full[s], (uint32_t)(j / AT_STAGES) & 1u);
         ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(sKV + s * AT_STAGE_BYTES);
+        const uint64_t kd = kd0 + (uint64_t)(s * (AT_STAGE_BYTES >> 4));
+        const uint32_t d = tmem_S + (uint32_t)((j & 1) * 128);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint64_t adesc = umma_desc(q_addr + k * 256, 128, 512, 0);          // Q: core matrices
-          const uint64_t bdesc = umma_desc(k_addr + k * 32, 16, 512, 4);            // K tile: SW64, K-major
-          ptx::mma_bf16_ss(tmem_S + (uint32_t)((j & 1) * 128), adesc, bdesc, idesc_s, k);
-        }
+        for (int k = 0; k < 2; ++k) ptx::mma_bf16_ss(d, qd0 + (uint64_t)(k * 16), kd + (uint64_t)(k * 2), idesc_s, k);
         if (p.has_r) {
           // + Q R^T: positional / level / bias part of the keys, a batch-independent table that the K/V
           // projection therefore never has to add (K = Wk x + R  =>  q.K = q.(Wk x) + q.R)
           // (R is kept as a bf16 hi/lo pair so that the table itself carries no bf16 rounding)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc(q_addr + (k & 1) * 256, 128, 512, 0);
-            const uint64_t bdesc = umma_desc(k_addr + (2 + (k >> 1)) * AT_KV_TILE_BYTES + (k & 1) * 32, 16, 512, 4);
-            ptx::mma_bf16_ss(tmem_S + (uint32_t)((j & 1) * 128), adesc, bdesc, idesc_s, 1u);
-          }
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
+                             kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
         }
-        ptx::mma_commit(&s_full[j & 1]);
       };
-      if (n_live > 0) issue_qk(0);
-      if (n_live > 1) issue_qk(1);
+      if (n_live > 0) { issue_qk(0); ptx::mma_commit(&step[0]); }
+      if (n_live > 1) { issue_qk(1); ptx::mma_commit(&step[1]); }
       for (int j = 0; j < n_live; ++j) {
         const int s = j % AT_STAGES;
         ptx::mbar_wait(&p_full[j & 1], (uint32_t)(j >> 1) & 1u);
         ptx::tc_fence_after();
-        const uint32_t p_addr = ptx::smem_u32(sP + (j & 1) * AT_P_BYTES);
-        const uint32_t v_addr = ptx::smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_TILE_BYTES);
+        AT_TRACE(j, 0);
+        const uint64_t pd = pd0 + (uint64_t)((j & 1) * (AT_P_BYTES >> 4));
+        const uint64_t vd = vd0 + (uint64_t)(s * (AT_STAGE_BYTES >> 4));
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          // O_half = P[:, 64 keys of this half] . V[those keys, :]  (each half has its own softmax reference)
+        for (int cq = 0; cq < 4; ++cq) {
+          // O_quarter = P[:, 32 keys of this quarter] . V[those keys, :]  (each quarter has its own softmax reference)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc(p_addr + hf * 1024 + k * 256, 128, 2048, 0);         // P: core matrices
-            // V: SW64, N-major; the leading-dimension offset reaches from this V slice to the ones tile
-            const uint32_t vk = v_addr + hf * 4096 + k * 1024;
-            const uint64_t bdesc = umma_desc(vk, (ones_addr + k * 1024) - vk, 512, 4);
-            ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 2 + hf) * 64), adesc, bdesc, idesc_o, k);
-          }
+          for (int k = 0; k < 2; ++k)
+            ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 4 + cq) * 32), pd + (uint64_t)((cq * 512 + k * 256) >> 4),
+                             vd + (uint64_t)((cq * 2048 + k * 1024) >> 4), idesc_o, k);
         }
-        ptx::mma_commit(&o_full[j & 1]);
-        ptx::mma_commit(&kv_empty[s]);
+        AT_TRACE(j, 1);
+        // S(j) was consumed before P(j) arrived: its buffer takes Q K^T of tile j+2 right away
         if (j + 2 < n_live) issue_qk(j + 2);
+        ptx::mma_commit(&step[j & 1]);
+        AT_TRACE(j, 2);
       }
     }
   } else {
-    // ------------- softmax / epilogue: thread = query row
+    // ------------- softmax / epilogue: thread = query row x key quarter
     const int quarter = warp & 3;
-    const int hf = (warp - 2) >> 2;             // which 64 key columns of every tile
+    const int cq = (warp - 2) >> 2;             // which 32 key columns of every tile
     const int row = quarter * 32 + lane, qi = qt * 128 + row;
     const bool row_ok = qi < p.Q;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool ignore_mask = !row_ok || p.bitmap == nullptr || (p.all_masked && p.all_masked[(long)b * p.Q + qi]);
     const uint32_t* brow = p.bitmap ? p.bitmap + ((long)b * p.Q + (row_ok ? qi : 0)) * p.W32 : nullptr;
-    float m_run = -INFINITY;
-    float o[33];                                  // 32 output dims + the running row sum (column 32 of O)
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 33; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     auto fold_o = [&](int pb, float scale) {      // o = (o + O_tile) * scale
       float ov[32];
-      const uint32_t oa = tmem_O + (uint32_t)((pb * 2 + hf) * 64) + lane_off;
-      tmem_ld32(oa, ov);
-      uint32_t sum_bits;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sum_bits) : "r"(oa + 32));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(tmem_O + (uint32_t)((pb * 4 + cq) * 32) + lane_off, ov);
+      if (__all_sync(0xffffffffu, scale == 1.f)) {    // no row of the warp raised its running max: the common case
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
-      o[32] = (o[32] + __uint_as_float(sum_bits)) * scale;
-    };
-    // mask words of this row for this half's 64 keys of tile t (bit = 1 -> masked); keys >= K are masked.
-    // They are fetched one live tile AHEAD so the global-load latency hides behind the current tile.
-    auto load_mask = [&](int t, uint32_t* mw) {
+        for (int i = 0; i < 32; ++i) o[i] += ov[i];
+      } else {
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int widx = t * 4 + hf * 2 + w;
-        uint32_t word = 0u;
-        if (!ignore_mask && widx < p.W32) word = __ldg(brow + widx);
-        const int k0 = t * AT_KT + (hf * 2 + w) * 32;
-        if (k0 + 32 > p.K) word |= (k0 >= p.K) ? 0xffffffffu : ~((1u << (p.K - k0)) - 1u);
-        mw[w] = word;
+        for (int i = 0; i < 32; ++i) o[i] = (o[i] + ov[i]) * scale;
       }
     };
+    // mask word of this row for this quarter's 32 keys of tile t (bit = 1 -> masked); keys >= K are masked.
+    // It is fetched one live tile AHEAD so the global-load latency hides behind the current tile.
+    auto load_mask = [&](int t) -> uint32_t {
+      const int widx = t * 4 + cq;
+      uint32_t word = 0u;
+      if (!ignore_mask && widx < p.W32) word = __ldg(brow + widx);
+      const int k0 = t * AT_KT + cq * 32;
+      if (k0 + 32 > p.K) word |= (k0 >= p.K) ? 0xffffffffu : ~((1u << (p.K - k0)) - 1u);
+      return word;
+    };
     int it = 0;
-    uint32_t mw_next[2] = {0u, 0u};
+    uint32_t mw_next = 0u;
     {
       const int t0 = next_live(live, 0, p.ntiles);
-      if (t0 < p.ntiles) load_mask(t0, mw_next);
+      if (t0 < p.ntiles) mw_next = load_mask(t0);
     }
     for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; ++it) {
       const int buf = it & 1;
       const int t_next = next_live(live, t + 1, p.ntiles);
-      uint32_t mw[2] = {mw_next[0], mw_next[1]};
-      if (t_next < p.ntiles) load_mask(t_next, mw_next);
-      ptx::mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u);
+      const uint32_t mw = mw_next;
+      if (t_next < p.ntiles) mw_next = load_mask(t_next);
+      ptx::mbar_wait(&step[buf], (uint32_t)(it >> 1) & 1u);          // S(it) ready
       ptx::tc_fence_after();
-      const uint32_t s_addr = tmem_S + (uint32_t)(buf * 128 + hf * 64) + lane_off;
-      // the 64 scores are read from TMEM ONCE, masked to -inf in registers, and reused for max and exp
-      float v[64];
-      tmem_ld32(s_addr, v);
-      tmem_ld32(s_addr + 32, v + 32);
+      AT_TRACE_W(it, 3);
+      // the 32 scores are read from TMEM ONCE, masked to -inf in registers, and reused for max and exp
+      float v[32];
+      tmem_ld32(tmem_S + (uint32_t)(buf * 128 + cq * 32) + lane_off, v);
+      AT_TRACE_W(it, 4);
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        if ((mw[i >> 5] >> (i & 31)) & 1u) v[i] = -INFINITY;
+      for (int i = 0; i < 32; ++i) {
+        if ((mw >> i) & 1u) v[i] = -INFINITY;
         mx = fmaxf(mx, v[i]);
       }
       const float m_new = fmaxf(m_run, mx);
       const float scale = (m_new == -INFINITY) ? 1.f : fast_exp2((m_run - m_new) * LOG2E);
       const float mneg = (m_new == -INFINITY) ? 0.f : -m_new * LOG2E;
       m_run = m_new;
-      // p = exp(s - m) as bf16 into the P buffer (core-matrix layout, 16 B = 8 keys per store); exp2(-inf) = 0
-      uint8_t* prow = sP + buf * AT_P_BYTES + (row >> 3) * 2048 + (row & 7) * 16 + hf * 1024;
+      // p = exp(s - m) as bf16 into the P buffer (core-matrix layout, 16 B = 8 keys per store); exp2(-inf) = 0.
+      // The row sum adds the fp32 values (the bf16 rounding of P is zero-mean noise in the numerator either way).
+      uint8_t* prow = sP + buf * AT_P_BYTES + (row >> 3) * 2048 + (row & 7) * 16 + cq * 512;
+      float psum = 0.f;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 pk;
         uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int i0 = g * 8 + 2 * j;
-          __nv_bfloat162 v2 = __floats2bfloat162_rn(fast_exp2(fmaf(v[i0], LOG2E, mneg)), fast_exp2(fmaf(v[i0 + 1], LOG2E, mneg)));
+          const float e0 = fast_exp2(fmaf(v[i0], LOG2E, mneg)), e1 = fast_exp2(fmaf(v[i0 + 1], LOG2E, mneg));
+          __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
           w[j] = *reinterpret_cast<uint32_t*>(&v2);
+          psum += e0 + e1;
         }
         *reinterpret_cast<uint4*>(prow + g * 128) = pk;
       }
+      l_run = l_run * scale + psum;
       fence_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[buf]);
-      // fold the previous tile's P [V | 1] into the register accumulator, then apply this tile's rescale
+      AT_TRACE_W(it, 5);
+      // fold the previous tile's P V into the register accumulator, then apply this tile's rescale
       if (it > 0) {
-        ptx::mbar_wait(&o_full[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
+        ptx::mbar_wait(&step[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) + 1) & 1u);      // O(it-1) ready
         ptx::tc_fence_after();
+        if (warp == 2 && lane == 0) ptx::mbar_arrive(&kv_empty[(it - 1) % AT_STAGES]);   // P V (it-1) done: K/V stage free
+        AT_TRACE_W(it, 6);
         fold_o((it - 1) & 1, scale);
       }
+      AT_TRACE_W(it, 7);
       t = t_next;
     }
     if (it > 0) {
-      ptx::mbar_wait(&o_full[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);
+      ptx::mbar_wait(&step[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) + 1) & 1u);
       ptx::tc_fence_after();
       fold_o((it - 1) & 1, 1.f);
     }
-    float l_run = o[32];
-    // merge the two column halves of the row: half 1 publishes (m, l, o) through shared memory
-    // (the P buffers are idle once the last PV has been consumed), half 0 combines and stores
-    float* xch = reinterpret_cast<float*>(sP) + row * 35;
-    if (hf == 1) {
-      xch[0] = m_run;
-      xch[1] = l_run;
+    // merge the four key quarters of the row: quarters 1..3 publish (m, l, o) through shared memory
+    // (the P buffers are idle once the last PV has been consumed), quarter 0 combines and stores
+    float* xch = reinterpret_cast<float*>(sP);
+    if (cq > 0) {
+      float* dst = xch + ((cq - 1) * 128 + row) * 35;
+      dst[0] = m_run;
+      dst[1] = l_run;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xch[2 + i] = o[i];
+      for (int i = 0; i < 32; ++i) dst[2 + i] = o[i];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (hf == 0) {
-      const float m1 = xch[0], l1 = xch[1];
-      const float m = fmaxf(m_run, m1);
-      const float a0 = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m) * LOG2E);
-      const float a1 = (m1 == -INFINITY) ? 0.f : fast_exp2((m1 - m) * LOG2E);
-      l_run = l_run * a0 + l1 * a1;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int hf = cq;      // (only quarter 0 stores)
+    if (cq == 0) {
+      float m = m_run;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * a0 + xch[2 + i] * a1;
+      for (int c2 = 0; c2 < 3; ++c2) m = fmaxf(m, xch[(c2 * 128 + row) * 35]);
+      const float a0 = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m) * LOG2E);
+      l_run *= a0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] *= a0;
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) {
+        const float* src = xch + (c2 * 128 + row) * 35;
+        const float m1 = src[0];
+        const float a1 = (m1 == -INFINITY) ? 0.f : fast_exp2((m1 - m) * LOG2E);
+        l_run += src[1] * a1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] += src[2 + i] * a1;
+      }
     }
     if (row_ok && hf == 0) {
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
@@ -462,14 +482,27 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");
-  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_ONES_BYTES + 512 + (2 * AT_STAGES + 6) * 8 + 16;
+  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + 512 + (2 * AT_STAGES + 4) * 8 + 16;
   if (!t->attn_attr_set) {
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     t->attn_attr_set = true;
   }
+  static const bool trace = getenv("CGG_AT_TRACE") != nullptr;
+  p.trace = trace ? atoi(getenv("CGG_AT_TRACE")) : 0;
   TCU(launch_pdl(attention_tc_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem, s, mK, mV, mR, p));
   count_launch();
   TCU(cudaGetLastError());
+  if (trace && ntiles >= 24) {
+    cudaStreamSynchronize(s);
+    long long tr[64];
+    cudaMemcpyFromSymbol(tr, g_at_trace, sizeof(tr));
+    fprintf(stderr, "[attention trace] K=%d cycles rel. to tile 16: mma(P ready, PV committed, QK(j+2) committed) softmax(S ready, S loaded, P arrived, O(j-1) ready, folded)\n", num_keys);
+    for (int i = 0; i < 8; ++i) {
+      fprintf(stderr, "  j=%d:", 16 + i);
+      for (int j = 0; j < 8; ++j) fprintf(stderr, " %7lld", tr[i * 8 + j] - tr[0]);
+      fprintf(stderr, "\n");
+    }
+  }
   return CGG_OK;
 }
 
