@@ -31,7 +31,9 @@ struct cgg_handle {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_kv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};
-  bool overlap = false;
+  bool overlap = false;      // CGG_OVERLAP: K/V levels 1,2 and the early mask einsums on helper streams (slower, debug)
+  bool overlap_kv = false;   // K/V levels 1,2 on a helper stream on a capped number of SMs
+  int kv_cta_cap = 0;
   void free_tables() {
     for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
       cudaFree(pos_level[l]); cudaFree(wkv[l]); cudaFree(rk[l]); cudaFree(bkv[l]);
@@ -141,7 +143,12 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
   if (cfg->precision == CGG_BF16) {
     h->tc = tc_create(*cfg);
     if (!h->tc) { delete h; return CGG_ERR_CUDA; }
-    if (getenv("CGG_OVERLAP")) {   // opt-in: measured slower on B200 (5.33 vs 4.69 ms/step) -- the helper kernels starve the layer chain of SMs
+    // CGG_KV_OVERLAP=0 disables the helper-stream K/V projection, =N>1 caps it at N CTAs (measured on B200 at
+    // B=16, 1024^2: off 3.536 ms/step, cap 64 3.516, cap 96 3.479, cap 120 3.470, no cap 3.468)
+    const char* kvo = getenv("CGG_KV_OVERLAP");
+    const bool want_kvo = kvo ? atoi(kvo) > 0 : true;
+    h->kv_cta_cap = kvo && atoi(kvo) > 1 ? atoi(kvo) : 0;
+    if (getenv("CGG_OVERLAP") || want_kvo) {   // CGG_OVERLAP: measured slower on B200 (5.33 vs 4.69 ms/step) -- the helper kernels starve the layer chain of SMs
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
       bool ok = true;
@@ -150,7 +157,8 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
       for (int i = 0; i < 2; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < CGG_NUM_LEVELS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_kv[i], cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i <= CGG_MAX_LAYERS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_me[i], cudaEventDisableTiming) == cudaSuccess;
-      h->overlap = ok;
+      h->overlap = ok && getenv("CGG_OVERLAP") != nullptr;
+      h->overlap_kv = ok && !h->overlap && want_kvo;
     }
   }
   *out = h;
@@ -259,7 +267,8 @@ extern "C" size_t cgg_workspace_offset(const cgg_handle* h, int batch, const cha
 
 // ============================================================================== stages
 static int kv_project_levels(cgg_handle* h, const cgg_weights* w, int batch, const void* const memories[CGG_NUM_LEVELS],
-                             void* workspace, size_t workspace_bytes, cudaStream_t s, int l_begin, int l_end) {
+                             void* workspace, size_t workspace_bytes, cudaStream_t s, int l_begin, int l_end,
+                             int cta_cap = 0) {
   if (!h || !w || !memories) return CGG_ERR_NULL;
   Workspace ws;
   ST(check_ws(h, batch, workspace, workspace_bytes, ws));
@@ -269,7 +278,7 @@ static int kv_project_levels(cgg_handle* h, const cgg_weights* w, int batch, con
     if (!memories[l]) return fail(h, CGG_ERR_NULL, "null memory level");
     const int K = h->lh[l] * h->lw[l], N = h->nl[l] * 2 * C;
     if (h->cfg.precision == CGG_BF16) {
-      int st = tc_kv_project(h->tc, l, batch, memories[l], at<void>(workspace, ws.kv[l]), at<void>(workspace, ws.tcws), s);
+      int st = tc_kv_project(h->tc, l, batch, memories[l], at<void>(workspace, ws.kv[l]), at<void>(workspace, ws.tcws), s, cta_cap);
       if (st != CGG_OK) return fail(h, st, std::string("tc_kv_project: ") + tc_last_error(h->tc));
       continue;
     }
@@ -485,8 +494,20 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
   float* xs = x_states ? x_states : at<float>(workspace, ws.xs);
   const bool tcm = c.precision == CGG_BF16;
   const bool ovl = tcm && h->overlap && L + 1 <= CGG_MAX_LAYERS + 1;
+  const bool ovl_kv = tcm && h->overlap_kv && L >= CGG_NUM_LEVELS;
   void* tws = at<void>(workspace, ws.tcws);
-  if (ovl) {
+  if (ovl_kv) {
+    // Level 0 K/V on the caller's stream (layer 0 needs it first).  Levels 1 and 2 -- 5/6 of the projection
+    // work, first needed by layers 1 and 2 -- run on a helper stream on a capped number of persistent CTAs,
+    // underneath head call 0 / layer 0 / head call 1 / layer 1, which are latency-bound and leave most SMs idle.
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
+    ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, s, 0, 1));
+    for (int l = 1; l < CGG_NUM_LEVELS; ++l) {
+      ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, h->side[0], l, l + 1, h->kv_cta_cap));
+      CU(cudaEventRecord(h->ev_kv[l], h->side[0]));
+    }
+  } else if (ovl) {
     // fork: level 0 K/V on the caller's stream (layer 0 needs it first), levels 1 and 2 on a helper stream
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
@@ -527,7 +548,7 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     }
     if (j < L) {
       const int lvl = j % CGG_NUM_LEVELS;
-      if (ovl && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
+      if ((ovl || ovl_kv) && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
       ST(decoder_layer_impl(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream,
                             /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm));
     }

@@ -255,26 +255,70 @@ struct LinCtx {
   }
 };
 
+// Per-token operands of the epilogue (row bias or residual) do not depend on the accumulator: they are
+// fetched while the MMAs still run (up to 2 chunks of 16 tokens per warp, the N_TILE = 128 case).
+struct LinPre {
+  float a[16], b[16];
+};
+__device__ __forceinline__ void lin_prefetch(const TcGemmP& p, const EpiCtx& c, const LinCtx& L, LinPre& pre) {
+  const int tok_base = c.batch * p.NT * p.N_TILE;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pre.a[i] = pre.b[i] = 0.f;
+  if (!L.on || (L.rowbias == nullptr && L.res == nullptr)) return;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ch = c.part + j * EPI_PARTS;
+    if (ch >= c.chunks) break;
+    const int tok0 = tok_base + ch * 16;
+    const int nvalid = min(16, p.n_tokens - tok0);
+    float* dst = j ? pre.b : pre.a;
+    if (L.rowbias) {
+      int tq = tok0 % L.rb_mod;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < nvalid) dst[i] = __ldg(L.rowbias + (long)tq * L.rb_ld + L.f);
+        if (++tq == L.rb_mod) tq = 0;
+      }
+    } else {
+      const float* rp = L.res + (long)tok0 * L.res_ld + L.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nvalid) dst[i] = __ldg(rp + (long)i * L.res_ld);
+    }
+  }
+}
+
 template <int MODE, bool HAS_RB, bool HAS_RES>
-__device__ __forceinline__ void epi_linear_t(const TcGemmP& p, const EpiCtx& c, const LinCtx& L) {
+__device__ __forceinline__ void epi_linear_t(const TcGemmP& p, const EpiCtx& c, const LinCtx& L, const LinPre* pre) {
   const int n_tokens = p.n_tokens;
   const int tok_base = c.batch * p.NT * p.N_TILE + c.col0;
-  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
+  int j = 0;
+  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS, ++j) {
     const int tok0 = tok_base + ch * 16;
     const int nvalid = L.on ? min(16, n_tokens - tok0) : 0;      // <= 0: nothing to store
     float rb[16], rs[16];
     if (HAS_RB) {
-      int tq = tok0 % L.rb_mod;
+      if (pre && j < 2) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        rb[i] = (i < nvalid) ? __ldg(L.rowbias + (long)tq * L.rb_ld + L.f) : 0.f;
-        if (++tq == L.rb_mod) tq = 0;
+        for (int i = 0; i < 16; ++i) rb[i] = j ? pre->b[i] : pre->a[i];
+      } else {
+        int tq = tok0 % L.rb_mod;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          rb[i] = (i < nvalid) ? __ldg(L.rowbias + (long)tq * L.rb_ld + L.f) : 0.f;
+          if (++tq == L.rb_mod) tq = 0;
+        }
       }
     }
     if (HAS_RES) {
-      const float* rp = L.res + (long)tok0 * L.res_ld + L.f;
+      if (pre && j < 2) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) rs[i] = (i < nvalid) ? __ldg(rp + (long)i * L.res_ld) : 0.f;
+        for (int i = 0; i < 16; ++i) rs[i] = j ? pre->b[i] : pre->a[i];
+      } else {
+        const float* rp = L.res + (long)tok0 * L.res_ld + L.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rs[i] = (i < nvalid) ? __ldg(rp + (long)i * L.res_ld) : 0.f;
+      }
     }
     float v[16];
     ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
@@ -302,18 +346,18 @@ __device__ __forceinline__ void epi_linear_t(const TcGemmP& p, const EpiCtx& c, 
   }
 }
 
-__device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiCtx& c, const LinCtx& L) {
+__device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiCtx& c, const LinCtx& L, const LinPre* pre) {
   // warp-uniform: a warp's 32 features belong to one segment (32-aligned segment starts)
   const bool rb = L.rowbias != nullptr, rs = L.res != nullptr;
   if (L.mode == 0) {
-    if (rb) epi_linear_t<0, true, false>(p, c, L);
-    else if (rs) epi_linear_t<0, false, true>(p, c, L);
-    else epi_linear_t<0, false, false>(p, c, L);
+    if (rb) epi_linear_t<0, true, false>(p, c, L, pre);
+    else if (rs) epi_linear_t<0, false, true>(p, c, L, pre);
+    else epi_linear_t<0, false, false>(p, c, L, pre);
   } else if (L.mode == 1) {
-    if (rb) epi_linear_t<1, true, false>(p, c, L);
-    else epi_linear_t<1, false, false>(p, c, L);
+    if (rb) epi_linear_t<1, true, false>(p, c, L, pre);
+    else epi_linear_t<1, false, false>(p, c, L, pre);
   } else {
-    epi_linear_t<2, false, false>(p, c, L);
+    epi_linear_t<2, false, false>(p, c, L, pre);
   }
 }
 
@@ -480,7 +524,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ctx.lane = lane; ctx.m = m; ctx.m_ok = m_ok; ctx.batch = batch; ctx.part = part;
     ctx.chunks = p.N_TILE / 16; ctx.wi = (m_tile * TC_BM + quarter * 32) >> 5;
     LinCtx lin;
-    if (EPI == EPI_LINEAR_T) lin.init(p, m);
+    LinPre pre;
+    const bool use_pre = EPI == EPI_LINEAR_T && p.NT == 1;
+    if (EPI == EPI_LINEAR_T) {
+      lin.init(p, m);
+      if (use_pre) lin_prefetch(p, ctx, lin, pre);
+    }
     for (int t = 0; t < p.NT; ++t, ++g) {
       const int buf = g & 1;
       const uint32_t use = (uint32_t)(g >> 1);
@@ -493,7 +542,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (EPI == EPI_MASK_T) epi_mask_t(p, ctx, sStage, &tmC, warp == 2, last, m_tile, &acc_empty[buf], false);
       else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, last, m_tile);
       else if (EPI == EPI_BITS) epi_bits(p, ctx);
-      else epi_linear_dispatch(p, ctx, lin);
+      else epi_linear_dispatch(p, ctx, lin, use_pre ? &pre : nullptr);
       if (EPI != EPI_MASK_T) {       // (the mask epilogue releases the accumulator itself, as soon as it is in registers)
         ptx::tc_fence_before();
         __syncwarp();
@@ -988,7 +1037,8 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int ctas = persist ? (p.n_work < t->num_sms ? p.n_work : t->num_sms) : p.n_work;
+    int ctas = persist ? (p.n_work < t->num_sms ? p.n_work : t->num_sms) : p.n_work;
+    if (persist && t->cta_cap > 0 && ctas > t->cta_cap) ctas = t->cta_cap;   // leave SMs to a concurrent latency-bound chain
     grid = dim3(ctas, 1, 1);
   }
   const CUtensorMap& mCC = mC ? *mC : mB;
@@ -1113,7 +1163,8 @@ int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, 
   return tc_pack_weights(t, w, s);
 }
 
-int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, void* ws, cudaStream_t s) {
+int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, void* ws, cudaStream_t s,
+                  int cta_cap) {
   const int C = t->cfg.embed_dim, K = t->lh[level] * t->lw[level], N = t->nl[level] * 2 * C;
   CUtensorMap mA, mB;
   int pitch = K;
@@ -1156,7 +1207,10 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(kv out) failed: " + std::to_string((int)r));
   }
-  return launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s, &mC);
+  t->cta_cap = cta_cap;
+  st = launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s, &mC);
+  t->cta_cap = 0;
+  return st;
 }
 
 int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* ws, cudaStream_t s) {

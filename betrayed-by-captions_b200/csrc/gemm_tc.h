@@ -37,7 +37,9 @@ int tc_prepare(TcState* t, const cgg_weights* w, int H4, int W4, const int* lh, 
                float* const* wkv_f32, float* const* rk_f32, float* const* bkv_f32, cudaStream_t s);
 
 // K4: kv[b, key, :] = mem[b, :, key]^T Wkv^T + bias tables, bf16 out (B, K_l, nl*2C)
-int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, void* ws, cudaStream_t s);
+// cta_cap > 0: run on at most that many (persistent) CTAs, for launches that overlap a latency-bound chain
+int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* kv_bf16, void* ws, cudaStream_t s,
+                  int cta_cap = 0);
 
 // Once per forward: the centre-2x2 averages of mask_features at the three level resolutions
 // (bf16, (B,C,K_l) each) that the attention-mask GEMMs contract against.

@@ -16,7 +16,7 @@ struct TcState {
   cgg_config cfg;
   std::string err;
   EncodeTiledFn encode = nullptr;
-  int num_sms = 0;
+  int num_sms = 0, cta_cap = 0;
   int H4 = 0, W4 = 0, lh[3] = {0, 0, 0}, lw[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
   __nv_bfloat16* wkv[3] = {nullptr, nullptr, nullptr};   // (nl*2C, C) bf16
   __nv_bfloat16* rk[3] = {nullptr, nullptr, nullptr};    // (K_l, nl*C) bf16 key-bias table
