@@ -727,8 +727,9 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bt = p.N_TILE * 128;                 // bytes of one resident B chunk
   uint8_t* sBres = smem;                         // 8 chunks: me_hi k-chunks 0..3, me_lo k-chunks 0..3
-  uint8_t* sA = sBres + 8 * bt;                  // ring of 16 KB feature chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * A_CHUNK_BYTES);
+  uint8_t* sA = sBres + 8 * bt;                  // ring of stages, each TWO 16 KB feature chunks (one commit frees both)
+  constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE_BYTES);
   uint64_t* b_res_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* a_empty = a_full + p.stages;
@@ -763,46 +764,56 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tma_load_3d(sBres + j * bt, &tmB, b_res_full, (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C), p.b_row, batch);
       int it = 0;
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-        for (int j = 0; j < 8; ++j, ++it) {
+        for (int j2 = 0; j2 < 4; ++j2, ++it) {
           const int s = it % p.stages;
           ptx::mbar_wait(&a_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-          ptx::mbar_expect_tx(&a_full[s], A_CHUNK_BYTES);
-          const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
-          for (int g = 0; g < 2; ++g)
-            ptx::tma_load_3d(sA + s * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s], mt * TC_BM + g * 64, ch, batch);
+          ptx::mbar_expect_tx(&a_full[s], STAGE_BYTES);
+          for (int c = 0; c < 2; ++c) {
+            const int j = 2 * j2 + c;
+            const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
+            for (int g = 0; g < 2; ++g)
+              ptx::tma_load_3d(sA + s * STAGE_BYTES + c * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s],
+                               mt * TC_BM + g * 64, ch, batch);
+          }
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, true, false);
-      ptx::mbar_wait(b_res_full, 0);
+    // MMA issuer.  The whole warp walks the loop (uniform control flow: descriptors stay in uniform registers);
+    // one elected lane issues.  Descriptors = base + constant increments of the 14-bit address field.
+    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, true, false);
+    ptx::mbar_wait(b_res_full, 0);
+    ptx::tc_fence_after();
+    const uint64_t ad0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), A_CHUNK_BYTES / 2, 1024);
+    const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sBres), 16, 1024);
+    const uint32_t bt16 = (uint32_t)bt >> 4;
+    int it = 0, t = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++t) {
+      const int buf = t & 1;
+      ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t bres = ptx::smem_u32(sBres);
-      int it = 0, t = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++t) {
-        const int buf = t & 1;
-        ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+      for (int j2 = 0; j2 < 4; ++j2, ++it) {
+        const int s = it % p.stages;
+        ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
-        for (int j = 0; j < 8; ++j, ++it) {
-          const int s = it % p.stages;
-          ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
-          ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(sA + s * A_CHUNK_BYTES);
-          // hi feature chunk k: x me_hi[k] and x me_lo[k];   lo feature chunk k: x me_hi[k]
-          const int nb = j < 4 ? 2 : 1;
-          for (int bsel = 0; bsel < nb; ++bsel) {
-            const uint32_t b_base = bres + (uint32_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt);
+        if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t adesc = ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
-              const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
-              ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (j | bsel | k) != 0 ? 1u : 0u);
+          for (int c = 0; c < 2; ++c) {
+            const int j = 2 * j2 + c;
+            const uint64_t ad = ad0 + (uint64_t)(s * (STAGE_BYTES >> 4) + c * (A_CHUNK_BYTES >> 4));
+            // hi feature chunk k: x me_hi[k] and x me_lo[k];   lo feature chunk k: x me_hi[k]
+            const int nb = j < 4 ? 2 : 1;
+            for (int bsel = 0; bsel < nb; ++bsel) {
+              const uint64_t bd = bd0 + (uint64_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt16);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc, (j | bsel | k) != 0 ? 1u : 0u);
             }
           }
           ptx::mma_commit(&a_empty[s]);
+          if (j2 == 3) ptx::mma_commit(&acc_full[buf]);
         }
-        ptx::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
   } else {
@@ -1265,12 +1276,12 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
     bp.W32 = (K + 31) / 32; bp.C = C; bp.bitmap = bitmap;
     bp.acc_stride = bp.N_TILE <= 32 ? 32 : bp.N_TILE <= 64 ? 64 : 128;
     bp.tmem_cols = 2 * bp.acc_stride;
-    bp.stages = (int)((200 * 1024 - 8 * bp.N_TILE * 128) / A_CHUNK_BYTES);
-    if (bp.stages > 6) bp.stages = 6;
+    bp.stages = (int)((225 * 1024 - 8 * bp.N_TILE * 128) / (2 * A_CHUNK_BYTES));   // stages of two feature chunks
+    if (bp.stages > 4) bp.stages = 4;
     // per-image B rows differ: one map per launch over all rows, row coordinate = image base + call offset
     // (blockIdx.y = image) -> the kernel needs the per-image row: pass through b_row and rows_per_batch
     bp.b_row = call_idx * t->q_pad;
-    const size_t smem = 1024 + 8 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
+    const size_t smem = 1024 + 8 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * 2 * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
     static bool attr_set = false;
     if (!attr_set) {
       TCU(cudaFuncSetAttribute(tc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
