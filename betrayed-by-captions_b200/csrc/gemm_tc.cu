@@ -472,11 +472,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer (single thread)
-      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false);
-      int it = 0, g = 0, tl = 0;
-      for (int w = w_first; w < n_work; w += w_stride, ++tl)
+    // ---------------- MMA issuer: the whole warp walks the loop (uniform control flow keeps the descriptors in
+    // uniform registers), one elected lane issues.  Descriptors = base + constant increments of the 14-bit
+    // address field (16-byte units).
+    //   A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO), 8-row groups 1 KB apart (SBO).
+    //   A / B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
+    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false);
+    const uint64_t ad0 = A_KMAJOR ? ptx::umma_desc_sw128(ptx::smem_u32(A_RESIDENT ? sA : sB), 16, 1024)
+                                  : ptx::umma_desc_sw128(ptx::smem_u32(A_RESIDENT ? sA : sB), A_CHUNK_BYTES / 2, 1024);
+    const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sB + a_in_stage), 16, 1024);
+    const uint32_t a_step = A_KMAJOR ? 2u : (2048u >> 4);
+    const uint32_t stage16 = (uint32_t)b_stage_bytes >> 4;
+    int it = 0, g = 0, tl = 0;
+    for (int w = w_first; w < n_work; w += w_stride, ++tl)
       for (int t = 0; t < p.NT; ++t, ++g) {
         const int buf = g & 1;
         const uint32_t use = (uint32_t)(g >> 1);
@@ -489,25 +497,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (A_RESIDENT && t == 0) ptx::mbar_wait(&a_full[kc], (uint32_t)(tl & 1));
           ptx::mbar_wait(&b_full[s], ph);
           ptx::tc_fence_after();
-          if (it == 0) TC_STAMP(2);
-          const uint32_t a_base = ptx::smem_u32(A_RESIDENT ? sA + kc * A_CHUNK_BYTES : sB + s * b_stage_bytes);
-          const uint32_t b_base = ptx::smem_u32(sB + s * b_stage_bytes + a_in_stage);
+          if (it == 0 && lane == 0) TC_STAMP(2);
+          if (ptx::elect_one()) {
+            const uint64_t ad = ad0 + (uint64_t)(A_RESIDENT ? (uint32_t)kc * (A_CHUNK_BYTES >> 4) : (uint32_t)s * stage16);
+            const uint64_t bd = bd0 + (uint64_t)((uint32_t)s * stage16);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO),
-            // 8-row groups 1 KB apart (SBO).   B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
-            const uint64_t adesc = A_KMAJOR ? ptx::umma_desc_sw128(a_base + k * 32, 16, 1024)
-                                              : ptx::umma_desc_sw128(a_base + k * 2048, A_CHUNK_BYTES / 2, 1024);
-            const uint64_t bdesc = ptx::umma_desc_sw128(b_base + k * 32, 16, 1024);
-            if (!(p.dbg & 512)) ptx::mma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k)
+              if (!(p.dbg & 512)) ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * a_step), bd + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+            ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
+            if (A_RESIDENT && t == p.NT - 1) ptx::mma_commit(&a_empty[kc]);
+            if (kc == p.KC - 1) ptx::mma_commit(&acc_full[buf]);     // accumulator tile complete
           }
-          ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
-          if (A_RESIDENT && t == p.NT - 1) ptx::mma_commit(&a_empty[kc]);
+          __syncwarp();
         }
-        ptx::mma_commit(&acc_full[buf]);     // accumulator tile t complete
-        if (g == 0) TC_STAMP(3);
+        if (g == 0 && lane == 0) TC_STAMP(3);
       }
-    }
   } else {
     // ---------------- epilogue: EPI_WARPS warps, EPI_WARPS/4 per TMEM lane quarter; each warp takes
     // every (EPI_WARPS/4)-th 16-column chunk.  One lean, specialised loop per epilogue kind.
