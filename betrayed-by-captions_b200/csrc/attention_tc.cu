@@ -188,44 +188,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------- MMA issuer
-      const uint32_t idesc_s = ptx::umma_idesc_bf16(128, AT_KT, false, false);   // S = Q K^T
-      const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 32, false, true);       // O = P V (N-major B)
-      const uint32_t q_addr = ptx::smem_u32(sQ);
-      int n_live = 0;
-      for (int t = 0; t < p.ntiles; ++t) n_live += live[t] ? 1 : 0;
-      // descriptors: base + constant increments of the 14-bit address field (16-byte units); the smem window is
-      // < 256 KB so the field never carries
-      const uint64_t qd0 = umma_desc(q_addr, 128, 512, 0);                                  // Q: core matrices
-      const uint64_t kd0 = umma_desc(ptx::smem_u32(sKV), 16, 512, 4);                       // K / R tiles: SW64, K-major
-      const uint64_t vd0 = umma_desc(ptx::smem_u32(sKV + AT_KV_TILE_BYTES), 1024, 512, 4);  // V: SW64, N-major (one N group)
-      const uint64_t pd0 = umma_desc(ptx::smem_u32(sP), 128, 2048, 0);                      // P: core matrices
-      auto issue_qk = [&](int j) {
-        const int s = j % AT_STAGES;
-        ptx::mbar_wait(&kv_full[s], (uint32_t)(j / AT_STAGES) & 1u);
-        ptx::tc_fence_after();
-        const uint64_t kd = kd0 + (uint64_t)(s * (AT_STAGE_BYTES >> 4));
-        const uint32_t d = tmem_S + (uint32_t)((j & 1) * 128);
+    // ------------- MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues
+    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, AT_KT, false, false);   // S = Q K^T
+    const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 32, false, true);       // O = P V (N-major B)
+    int n_live = 0;
+    for (int t = 0; t < p.ntiles; ++t) n_live += live[t] ? 1 : 0;
+    // descriptors: base + constant increments of the 14-bit address field (16-byte units); the smem window is
+    // < 256 KB so the field never carries
+    const uint64_t qd0 = umma_desc(ptx::smem_u32(sQ), 128, 512, 0);                        // Q: core matrices
+    const uint64_t kd0 = umma_desc(ptx::smem_u32(sKV), 16, 512, 4);                       // K / R tiles: SW64, K-major
+    const uint64_t vd0 = umma_desc(ptx::smem_u32(sKV + AT_KV_TILE_BYTES), 1024, 512, 4);  // V: SW64, N-major (one N group)
+    const uint64_t pd0 = umma_desc(ptx::smem_u32(sP), 128, 2048, 0);                      // P: core matrices
+    auto wait_kv = [&](int j) {
+      ptx::mbar_wait(&kv_full[j % AT_STAGES], (uint32_t)(j / AT_STAGES) & 1u);
+      ptx::tc_fence_after();
+    };
+    auto issue_qk = [&](int j) {                // elected lane only
+      const uint64_t kd = kd0 + (uint64_t)((j % AT_STAGES) * (AT_STAGE_BYTES >> 4));
+      const uint32_t d = tmem_S + (uint32_t)((j & 1) * 128);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) ptx::mma_bf16_ss(d, qd0 + (uint64_t)(k * 16), kd + (uint64_t)(k * 2), idesc_s, k);
-        if (p.has_r) {
-          // + Q R^T: positional / level / bias part of the keys, a batch-independent table that the K/V
-          // projection therefore never has to add (K = Wk x + R  =>  q.K = q.(Wk x) + q.R)
-          // (R is kept as a bf16 hi/lo pair so that the table itself carries no bf16 rounding)
+      for (int k = 0; k < 2; ++k) ptx::mma_bf16_ss(d, qd0 + (uint64_t)(k * 16), kd + (uint64_t)(k * 2), idesc_s, k);
+      if (p.has_r) {
+        // + Q R^T: positional / level / bias part of the keys, a batch-independent table that the K/V
+        // projection therefore never has to add (K = Wk x + R  =>  q.K = q.(Wk x) + q.R)
+        // (R is kept as a bf16 hi/lo pair so that the table itself carries no bf16 rounding)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
-                             kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
-        }
-      };
-      if (n_live > 0) { issue_qk(0); ptx::mma_commit(&step[0]); }
-      if (n_live > 1) { issue_qk(1); ptx::mma_commit(&step[1]); }
-      for (int j = 0; j < n_live; ++j) {
-        const int s = j % AT_STAGES;
-        ptx::mbar_wait(&p_full[j & 1], (uint32_t)(j >> 1) & 1u);
-        ptx::tc_fence_after();
-        AT_TRACE(j, 0);
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
+                           kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
+      }
+    };
+    for (int j = 0; j < 2 && j < n_live; ++j) {
+      wait_kv(j);
+      if (ptx::elect_one()) { issue_qk(j); ptx::mma_commit(&step[j]); }
+      __syncwarp();
+    }
+    for (int j = 0; j < n_live; ++j) {
+      const int s = j % AT_STAGES;
+      ptx::mbar_wait(&p_full[j & 1], (uint32_t)(j >> 1) & 1u);
+      if (j + 2 < n_live) wait_kv(j + 2);
+      ptx::tc_fence_after();
+      if (lane == 0) AT_TRACE(j, 0);
+      if (ptx::elect_one()) {
         const uint64_t pd = pd0 + (uint64_t)((j & 1) * (AT_P_BYTES >> 4));
         const uint64_t vd = vd0 + (uint64_t)(s * (AT_STAGE_BYTES >> 4));
 #pragma unroll
@@ -236,12 +240,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             ptx::mma_bf16_ss(tmem_O + (uint32_t)(((j & 1) * 4 + cq) * 32), pd + (uint64_t)((cq * 512 + k * 256) >> 4),
                              vd + (uint64_t)((cq * 2048 + k * 1024) >> 4), idesc_o, k);
         }
-        AT_TRACE(j, 1);
         // S(j) was consumed before P(j) arrived: its buffer takes Q K^T of tile j+2 right away
         if (j + 2 < n_live) issue_qk(j + 2);
         ptx::mma_commit(&step[j & 1]);
-        AT_TRACE(j, 2);
       }
+      __syncwarp();
+      if (lane == 0) AT_TRACE(j, 2);
     }
   } else {
     // ------------- softmax / epilogue: thread = query row x key quarter

@@ -647,8 +647,8 @@ tc_einsum_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ---------------- MMA issuer: one thread of the leader CTA drives both SMs
+    if (rank == 0) {
+      // ---------------- MMA issuer: the leader CTA's warp walks the loop, one elected lane drives both SMs
       const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
       // descriptors differ by a constant in the 14-bit address field (units of 16 bytes)
       uint64_t adesc0[KC], bdesc0[2 * KC];
@@ -664,23 +664,26 @@ tc_einsum_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t use = (uint32_t)(g >> 1);
           ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
           ptx::tc_fence_after();
-          TC_TRACE(g, 0);
+          if (lane == 0) TC_TRACE(g, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc) {
             if (t == 0) ptx::mbar_wait(&a_full[kc], (uint32_t)(tl & 1));
             ptx::mbar_wait(&b_full[buf * KC + kc], use & 1u);
             ptx::tc_fence_after();
-            if (kc == 0) TC_TRACE(g, 1);
-            const uint64_t ad = adesc0[kc], bd = buf ? bdesc0[KC + kc] : bdesc0[kc];
+            if (kc == 0 && lane == 0) TC_TRACE(g, 1);
+            if (ptx::elect_one()) {
+              const uint64_t ad = adesc0[kc], bd = buf ? bdesc0[KC + kc] : bdesc0[kc];
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k)
-              ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (32 >> 4)), idesc,
-                                   (kc | k) != 0 ? 1u : 0u);
-            if (t == p.NT - 1) ptx::mma_commit_2sm(&a_empty[kc]);   // A chunk kc may be refilled for the next work item
+              for (int k = 0; k < TC_BK / 16; ++k)
+                ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (32 >> 4)), idesc,
+                                     (kc | k) != 0 ? 1u : 0u);
+              if (t == p.NT - 1) ptx::mma_commit_2sm(&a_empty[kc]);   // A chunk kc may be refilled for the next work item
+              if (kc == KC - 1) ptx::mma_commit_2sm(&acc_full[buf]);  // accumulator ready (epilogue) + B slot free (producer), both CTAs
+            }
+            __syncwarp();
           }
-          ptx::mma_commit_2sm(&acc_full[buf]);   // accumulator ready (epilogue) + B slot free (producer), both CTAs
-          TC_TRACE(g, 2);
+          if (lane == 0) TC_TRACE(g, 2);
         }
     }
   } else {
