@@ -170,30 +170,49 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
 // 16-byte chunks at chunk ^ (row & 7): conflict-free) and leaves through one TMA store per sub-tile;
 // rows past the image's last key are clipped by the TMA unit.  (The positional / level part of the keys
 // is not added here at all: the attention kernel adds Q R^T, see attention_tc.cu.)
-__device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const CUtensorMap* tmC,
-                                             bool leader_warp, bool last, int m_tile) {
+__device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const float* sBias,
+                                             const CUtensorMap* tmC, bool leader_warp, bool last, int m_tile,
+                                             uint64_t* acc_empty_bar) {
   const bool leader = leader_warp && c.lane == 0;
+  static_assert(EPI_PARTS == 4, "four chunk slots per warp below");
+  // 1. accumulator -> registers (up to 4 chunks of 16 columns per warp, loads in flight together); this overlaps
+  //    the TMA engine still reading the previous tile out of the staging buffer
+  uint32_t r0[16], r1[16], r2[16], r3[16];
+  const int ch0 = c.part, ch1 = c.part + 4, ch2 = c.part + 8, ch3 = c.part + 12;
+  const bool on0 = ch0 < c.chunks, on1 = ch1 < c.chunks, on2 = ch2 < c.chunks, on3 = ch3 < c.chunks;   // warp-uniform
+  if (on0) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch0 * 16), r0);
+  if (on1) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch1 * 16), r1);
+  if (on2) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch2 * 16), r2);
+  if (on3) ptx::tmem_ld16_issue(c.taddr + (uint32_t)(ch3 * 16), r3);
+  if (on0) ptx::tmem_ld_wait16(r0);
+  if (on1) ptx::tmem_ld_wait16(r1);
+  if (on2) ptx::tmem_ld_wait16(r2);
+  if (on3) ptx::tmem_ld_wait16(r3);
+  // 2. the accumulator buffer is free again
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) ptx::mbar_arrive(acc_empty_bar);
+  // 3. the previous tile's stores must have finished READING the staging buffer
   if (leader) ptx::tma_store_wait_read();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
   const int row = c.m & (TC_BM - 1);
-  for (int ch = c.part; ch < c.chunks; ch += EPI_PARTS) {
-    const int n0 = c.col0 + ch * 16;
-    float4 bb[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-    float v[16];
-    ptx::tmem_ld16(c.taddr + (uint32_t)(ch * 16), v);
-    const float* bf = reinterpret_cast<const float*>(bb);
+  auto stage16 = [&](const uint32_t (&r)[16], int ch) {
+    const float* bf = sBias + c.col0 + ch * 16;       // same address for the whole warp: shared-memory broadcast
     uint4 o[2];
     uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(v[2 * i] + bf[2 * i], v[2 * i + 1] + bf[2 * i + 1]);
+    for (int i = 0; i < 8; ++i)
+      ow[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + bf[2 * i], __uint_as_float(r[2 * i + 1]) + bf[2 * i + 1]);
     // column chunk (16 B = 8 columns) j of sub-tile `sub`, swizzled with the row
     const int sub = ch >> 2, j = (ch & 3) * 2;
     uint8_t* base = sStage + sub * (TC_BM * 128) + row * 128;
     *reinterpret_cast<uint4*>(base + ((j ^ (row & 7)) << 4)) = o[0];
     *reinterpret_cast<uint4*>(base + (((j + 1) ^ (row & 7)) << 4)) = o[1];
-  }
+  };
+  if (on0) stage16(r0, ch0);
+  if (on1) stage16(r1, ch1);
+  if (on2) stage16(r2, ch2);
+  if (on3) stage16(r3, ch3);
   ptx::fence_proxy_async_smem();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
   if (leader) {
@@ -395,6 +414,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   // EPI_MASK_T staging tile [N_TILE columns][128 pixels] bf16 for the TMA store (128-byte aligned)
   uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+  // EPI_ROWMAJOR: the bias vector of all NT * N_TILE output columns, behind the staging tile
+  float* sBias = reinterpret_cast<float*>(sStage + (size_t)p.N_TILE * TC_BM * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // A-resident kinds: persistent CTAs over (pixel tile, image) work items; the others: one tile per CTA
@@ -517,6 +538,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // every (EPI_WARPS/4)-th 16-column chunk.  One lean, specialised loop per epilogue kind.
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;                       // which share of the chunks
+    if (EPI == EPI_ROWMAJOR) {
+      for (int i = threadIdx.x - 64; i < p.NT * p.N_TILE; i += EPI_WARPS * 32) sBias[i] = __ldg(p.bias + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    }
     int g = 0;
     for (int w = w_first; w < n_work; w += w_stride) {
     int m_tile, batch;
@@ -544,10 +569,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ctx.col0 = t * p.N_TILE;
       const bool last = last_work && t == p.NT - 1;
       if (EPI == EPI_MASK_T) epi_mask_t(p, ctx, sStage, &tmC, warp == 2, last, m_tile, &acc_empty[buf], false);
-      else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, &tmC, warp == 2, last, m_tile);
+      else if (EPI == EPI_ROWMAJOR) epi_rowmajor(p, ctx, sStage, sBias, &tmC, warp == 2, last, m_tile, &acc_empty[buf]);
       else if (EPI == EPI_BITS) epi_bits(p, ctx);
       else epi_linear_dispatch(p, ctx, lin, use_pre ? &pre : nullptr);
-      if (EPI != EPI_MASK_T) {       // (the mask epilogue releases the accumulator itself, as soon as it is in registers)
+      if (EPI != EPI_MASK_T && EPI != EPI_ROWMAJOR) {   // (those epilogues release the accumulator themselves, as soon as it is in registers)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
@@ -1018,7 +1043,8 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
   if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
-  const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR) ? (size_t)p.N_TILE * TC_BM * 2 + 1024 : 0;
+  const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR)
+                                 ? (size_t)p.N_TILE * TC_BM * 2 + 1024 + (p.epi == EPI_ROWMAJOR ? (size_t)p.NT * p.N_TILE * 4 : 0) : 0;
   static const int smem_kb = getenv("CGG_TC_SMEM_KB") ? atoi(getenv("CGG_TC_SMEM_KB")) : 204;
   const size_t budget = (size_t)smem_kb * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
