@@ -11,7 +11,7 @@
 //                  rescale
 // K and V tiles arrive by TMA (64-byte swizzle, one head's 32 dims = 64-byte rows) straight from
 // the projected K/V buffer.  Key tiles that are masked for EVERY query of the CTA are skipped
-// (flags from live_tiles_kernel); rows with all_masked set ignore the bitmap (the reference's
+// (flags computed by the CTA itself from the bitmap, in its prologue); rows with all_masked set ignore the bitmap (the reference's
 // all-masked-row fallback, head.py:825-826).
 //   warp 0: TMA producer   warp 1: MMA issuer (1 thread)   warps 2-17: softmax / epilogue -- four
 //   groups of 4 warps, each owning 32 of the tile's 128 key columns with its OWN running max / sum /
@@ -112,7 +112,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.heads, qt = blockIdx.x / p.heads, b = blockIdx.y;
-  const uint8_t* live_g = p.live + ((long)b * p.nqt + qt) * p.ntiles;
   const uint8_t* live = sLive;
   const int C = p.heads * 32;
 
@@ -131,8 +130,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
-  // the live-tile flags are read by three roles every tile: one copy into shared memory
-  for (int i = threadIdx.x; i < p.ntiles; i += AT_THREADS) sLive[i] = live_g[i];
+  // Live-tile flags (read by all three roles every tile): key tile t is dead when every query row of this CTA
+  // masks all of its keys; rows under the all-masked fallback attend everywhere.  One warp per key tile, a lane
+  // covers 4 query rows and reads the tile's four bitmap words of each.
+  {
+    const int q0 = qt * 128, nrows = min(128, p.Q - q0);
+    bool all_live = p.bitmap == nullptr;
+    if (!all_live && p.all_masked)
+      for (int r = lane; r < nrows; r += 32) all_live = all_live || p.all_masked[(long)b * p.Q + q0 + r] != 0;
+    all_live = __any_sync(0xffffffffu, all_live);
+    for (int t = warp; t < p.ntiles; t += AT_THREADS / 32) {
+      bool any = all_live;
+      if (!all_live) {
+        for (int r = lane; r < nrows; r += 32) {
+          const uint32_t* brow = p.bitmap + ((long)b * p.Q + q0 + r) * p.W32;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int widx = t * 4 + w, k0 = t * AT_KT + w * 32;
+            if (widx < p.W32 && k0 < p.K) {
+              const uint32_t valid = (k0 + 32 > p.K) ? ((1u << (p.K - k0)) - 1u) : 0xffffffffu;
+              any = any || ((~__ldg(brow + widx)) & valid) != 0u;
+            }
+          }
+        }
+      }
+      any = __any_sync(0xffffffffu, any);
+      if (lane == 0) sLive[t] = any ? 1 : 0;
+    }
+  }
   if (warp >= 2 && warp < 6) {
     // Q tile -> bf16, core-matrix (no-swizzle) K-major layout: element (row, d) at
     // (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
@@ -410,33 +435,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
 }
 
-// live[b][qt][tile] = 1 iff some query row of the tile attends to some key of the key tile
-// (rows under the all-masked fallback attend everywhere).
-__global__ void __launch_bounds__(128) live_tiles_kernel(const uint32_t* __restrict__ bitmap,
-                                                         const uint8_t* __restrict__ all_masked, int Q, int K, int W32,
-                                                         int ntiles, int nqt, uint8_t* __restrict__ live) {
-  ptx::grid_dep_launch();
-  ptx::grid_dep_wait();
-  const int t = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
-  const int qi = qt * 128 + threadIdx.x;
-  int any = 0;
-  if (qi < Q) {
-    if (bitmap == nullptr || (all_masked && all_masked[(long)b * Q + qi])) {
-      any = 1;
-    } else {
-      const uint32_t* brow = bitmap + ((long)b * Q + qi) * W32;
-      for (int w = 0; w < 4; ++w) {
-        const int widx = t * 4 + w, k0 = t * AT_KT + w * 32;
-        if (widx >= W32 || k0 >= K) break;
-        uint32_t valid = (k0 + 32 > K) ? ((1u << (K - k0)) - 1u) : 0xffffffffu;
-        if ((~brow[widx]) & valid) any = 1;
-      }
-    }
-  }
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) live[((long)b * nqt + qt) * ntiles + t] = any ? 1 : 0;
-}
-
 int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_stride, long kv_bstride, int B, int C) {
   if ((kv_stride * 2) % 16 != 0 || (kv_bstride * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15))
     return tc_fail(t, CGG_ERR_UNSUPPORTED, "K/V rows must be 16-byte aligned");
@@ -459,7 +457,6 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   // r_table: (num_keys, r_cols) bf16 with columns [hi (r_cols/2) | lo (r_cols/2)]
   const int Q = t->cfg.num_queries, heads = t->cfg.num_heads, C = t->cfg.embed_dim;
   const int ntiles = (num_keys + AT_KT - 1) / AT_KT, nqt = (Q + 127) / 128;
-  if ((size_t)batch * nqt * ntiles > t->live_bytes) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many key tiles");
   CUtensorMap mK, mV;
   int st = make_map_kv(t, &mK, k, num_keys, kv_stride, kv_bstride, batch, C);
   if (st != CGG_OK) return st;
@@ -477,12 +474,8 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(R) failed: " + std::to_string((int)r));
   }
   const int W32 = (num_keys + 31) / 32;
-  TCU(launch_pdl(live_tiles_kernel, dim3(ntiles, nqt, batch), dim3(128), 0, s, bitmap, all_masked, Q, num_keys, W32, ntiles, nqt,
-                 t->live_buf));
-  count_launch();
-  TCU(cudaGetLastError());
   AttnP p;
-  p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = t->live_buf;
+  p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = nullptr;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");

@@ -447,6 +447,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) TC_STAMP(1);
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   ptx::grid_dep_launch();
+  // Linear layers: the A operand is a WEIGHT matrix, independent of the previous kernel -- its first ring-full of
+  // chunks is requested before waiting for the previous grid (the activations, operand B, follow after the wait).
+  int n_pre = 0;
+  if (EPI == EPI_LINEAR_T && warp == 0 && lane == 0) {
+    const int total = p.NT * p.KC;
+    n_pre = total < p.stages ? total : p.stages;
+    for (int i = 0; i < n_pre; ++i) {
+      const int kc = i % p.KC;
+      const int kco = p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.a_kcoord[kc];
+      ptx::mbar_expect_tx(&b_full[i], (uint32_t)b_stage_bytes);
+      ptx::tma_load_2d(sB + i * b_stage_bytes, &tmA, &b_full[i], kco, (int)blockIdx.x * TC_BM);
+    }
+  }
   ptx::grid_dep_wait();
 
   if (warp == 0) {
@@ -483,10 +496,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          ptx::mbar_wait(&b_empty[s], ph ^ 1u);
-          ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
           uint8_t* stage = sB + s * b_stage_bytes;
-          if (!A_RESIDENT) load_a(stage, &b_full[s], kc);
+          if (it >= n_pre) {      // (the first n_pre stages of a linear layer already have their weights on the way)
+            ptx::mbar_wait(&b_empty[s], ph ^ 1u);
+            ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
+            if (!A_RESIDENT) load_a(stage, &b_full[s], kc);
+          }
           ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.b_kcoord[kc],
                            batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
