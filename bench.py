@@ -317,7 +317,7 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / reps
         flops = einsum_flops_per_launch(Q, B) * (LAYERS + 1)
-        kname = 'tc_einsum_pair_kernel (cta_group::2): mask einsum of all 10 head calls, one launch (cgg_mask_einsum)'
+        kname = 'tc_einsum_t_kernel (cta_group::2, queries on TMEM lanes): mask einsum of all 10 head calls, one launch (cgg_mask_einsum)'
         del mask_out
     else:
         x0 = torch.randn((B, Q, C), device=dev)

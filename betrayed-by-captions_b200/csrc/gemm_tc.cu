@@ -757,6 +757,191 @@ tc_einsum_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------- K2, transposed CTA-pair variant
+// D^T = E . F^T: the TMEM lanes are the QUERIES of a head call, the columns are PIXELS.  A thread of the
+// epilogue then holds 16 consecutive pixels of one (call, query) row -- exactly the output's contiguous
+// dimension -- and stages them with two 16-byte shared-memory stores (the pixel-on-lane form needs sixteen
+// 2-byte stores for the same data); the staging tiles are 128-byte-swizzled (64 px x q_pad rows), so a warp's
+// 32 rows hit 32 distinct bank groups, and leave through TMA stores.
+//   cta_group::2, M = 256 = two head calls (CTA r of the pair provides the 128-row block of call 2t+r),
+//   N = 256 pixels (CTA r holds the features of pixels [128 r, 128 r + 128) of the tile, resident, MN-major),
+//   K = 256 channels.  Per step t each CTA streams ONE call's mask embeddings (q_pad rows per chunk; the MMA
+//   reads 128 rows, the extra lanes are never stored), two steps of chunks fit the ring, and ONE commit per step
+//   signals "accumulator ready" + "ring slots free".  Both accumulators (2 x 256 columns) fill the TMEM.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmE,
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int KC = 4;
+  const int e_chunk_bytes = p.q_pad * 128;                // q_pad rows x 64 k
+  const int sub_bytes = p.q_pad * 128;                    // staging sub-tile: q_pad rows x 64 px
+  uint8_t* sF = smem;                                     // features of this CTA's 128 pixels: 4 chunks of 16 KB
+  uint8_t* sE = sF + KC * A_CHUNK_BYTES;                  // [2 step slots][KC chunks]
+  uint8_t* sStage = sE + 2 * KC * e_chunk_bytes;          // 4 sub-tiles (q_pad * 128 is a multiple of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * sub_bytes);
+  uint64_t* f_full = bars;
+  uint64_t* f_empty = bars + 4;
+  uint64_t* e_full = bars + 8;                            // [2][KC]
+  uint64_t* acc_full = e_full + 2 * KC;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int mt2 = p.m_tiles >> 1;                         // 256-pixel tiles per image
+  const int n_work = mt2 * p.n_batch;
+  const int NS = (p.n_calls + 1) >> 1;                    // steps: two head calls each
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmF);
+    ptx::prefetch_tmap(&tmE);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&f_full[i], 1); ptx::mbar_init(&f_empty[i], 1); }
+    for (int i = 0; i < 2 * KC; ++i) ptx::mbar_init(&e_full[i], 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512u);
+    ptx::tmem_relinquish_2sm();
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs: own 128 pixels, own head call; tx bytes land on the leader)
+      int g = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl) {
+        const int batch = w / mt2, px0 = ((w - batch * mt2) * 2 + (int)rank) * TC_BM;
+        for (int t = 0; t < NS; ++t, ++g) {
+          const int slot = g & 1;
+          if (g >= 2) ptx::mbar_wait(&acc_full[slot], (uint32_t)((g - 2) >> 1) & 1u);   // MMAs of step g-2 done
+          const int call = 2 * t + (int)rank;
+          for (int kc = 0; kc < KC; ++kc) {
+            if (t == 0) {
+              if (tl > 0) ptx::mbar_wait(&f_empty[kc], (uint32_t)(tl & 1) ^ 1u);
+              if (rank == 0) ptx::mbar_expect_tx(&f_full[kc], 2u * A_CHUNK_BYTES);
+              for (int h = 0; h < 2; ++h)
+                ptx::tma_load_3d_2sm(sF + kc * A_CHUNK_BYTES + h * (A_CHUNK_BYTES / 2), &tmF, &f_full[kc], px0 + h * 64,
+                                     kc * TC_BK, batch);
+            }
+            uint64_t* bar = &e_full[slot * KC + kc];
+            if (rank == 0) ptx::mbar_expect_tx(bar, 2u * (uint32_t)e_chunk_bytes);
+            ptx::tma_load_2d_2sm(sE + (slot * KC + kc) * e_chunk_bytes, &tmE, bar, kc * TC_BK,
+                                 batch * p.b_rows_per_batch + p.b_row0 + call * p.q_pad);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---------------- MMA issuer: the leader CTA's warp walks the loop, one elected lane drives both SMs
+      const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, 256, /*A = E, K-major*/ false, /*B = F, MN-major*/ true);
+      const uint64_t ed0 = ptx::umma_desc_sw128(ptx::smem_u32(sE), 16, 1024);
+      const uint64_t fd0 = ptx::umma_desc_sw128(ptx::smem_u32(sF), A_CHUNK_BYTES / 2, 1024);
+      const uint32_t e16 = (uint32_t)e_chunk_bytes >> 4;
+      int g = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl)
+        for (int t = 0; t < NS; ++t, ++g) {
+          const int buf = g & 1;
+          const uint32_t use = (uint32_t)(g >> 1);
+          ptx::mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+            if (t == 0) ptx::mbar_wait(&f_full[kc], (uint32_t)(tl & 1));
+            ptx::mbar_wait(&e_full[buf * KC + kc], use & 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t ed = ed0 + (uint64_t)((uint32_t)(buf * KC + kc) * e16);
+              const uint64_t fd = fd0 + (uint64_t)(kc * (A_CHUNK_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                ptx::mma_bf16_ss_2sm(d_tmem, ed + (uint64_t)(k * 2), fd + (uint64_t)(k * (2048 >> 4)), idesc, (kc | k) != 0 ? 1u : 0u);
+              if (t == NS - 1) ptx::mma_commit_2sm(&f_empty[kc]);     // feature chunk kc may be refilled for the next tile
+              if (kc == KC - 1) ptx::mma_commit_2sm(&acc_full[buf]);  // accumulator ready + ring slots free, both CTAs
+            }
+            __syncwarp();
+          }
+        }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): lane = query row of this CTA's head call, 256 pixel columns
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;                       // 16-pixel chunk `part` of every 64-pixel sub-tile
+    const int row = quarter * 32 + lane;
+    const bool row_ok = row < p.q_pad;
+    const bool leader = warp == 2 && lane == 0;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    int g = 0;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      const int batch = w / mt2, px_pair = (w - batch * mt2) * 2 * TC_BM;
+      const bool last_work = w + n_pairs >= n_work;
+      for (int t = 0; t < NS; ++t, ++g) {
+        const int buf = g & 1;
+        const uint32_t use = (uint32_t)(g >> 1);
+        const int call = 2 * t + (int)rank;
+        ptx::mbar_wait(&acc_full[buf], use & 1u);
+        ptx::tc_fence_after();
+        // 1. accumulator -> registers: sub-tile j, pixels 64 j + 16 part .. + 15
+        const uint32_t ta = tmem_base + (uint32_t)(buf * 256 + part * 16) + lane_off;
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        ptx::tmem_ld16_issue(ta, r0);
+        ptx::tmem_ld16_issue(ta + 64, r1);
+        ptx::tmem_ld16_issue(ta + 128, r2);
+        ptx::tmem_ld16_issue(ta + 192, r3);
+        ptx::tmem_ld_wait16(r0);
+        ptx::tmem_ld_wait16(r1);
+        ptx::tmem_ld_wait16(r2);
+        ptx::tmem_ld_wait16(r3);
+        // 2. the accumulator buffer is free again
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
+        // 3. the previous step's stores must have finished READING the staging tiles
+        if (leader) ptx::tma_store_wait_read();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        auto stage16 = [&](const uint32_t (&r)[16], int j) {
+          uint4 o[2];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          uint8_t* base = sStage + j * sub_bytes + row * 128;
+          *reinterpret_cast<uint4*>(base + (((2 * part) ^ (row & 7)) << 4)) = o[0];
+          *reinterpret_cast<uint4*>(base + (((2 * part + 1) ^ (row & 7)) << 4)) = o[1];
+        };
+        if (row_ok) {
+          stage16(r0, 0);
+          stage16(r1, 1);
+          stage16(r2, 2);
+          stage16(r3, 3);
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (leader) {
+          if (call < p.n_calls)
+            for (int j = 0; j < 4; ++j)
+              ptx::tma_store_3d(&tmC, sStage + j * sub_bytes, px_pair + j * 64, 0, call * p.n_batch + batch);
+          ptx::tma_store_commit();
+          if (last_work && t == NS - 1) ptx::tma_store_wait_read();
+        }
+      }
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, 512u);
+}
+
 // ------------------------------------------------------------------- K3, persistent variant
 // Attention-mask bits with the B operand RESIDENT: the head call's mask embeddings (hi and lo planes,
 // 8 chunks of N_TILE x 64) are loaded once per CTA and stay in shared memory while the CTA walks its
@@ -1436,6 +1621,45 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out) failed: " + std::to_string((int)r));
   }
   const int m_tiles = (int)((HW + TC_BM - 1) / TC_BM);
+  static const int use_t = getenv("CGG_EIN_T") ? atoi(getenv("CGG_EIN_T")) : 1;
+  if (use_t && m_tiles % 2 == 0 && HW % (2 * TC_BM) == 0 && t->q_pad <= 128 && t->q_pad % 8 == 0 && p.KC == 4 && C == 256) {
+    // transposed CTA-pair kernel: queries on the TMEM lanes, pixels on the columns
+    const size_t e_chunk = (size_t)t->q_pad * 128;
+    const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * e_chunk + 4 * e_chunk + 24 * 8 + 64;
+    if (smem <= 227 * 1024) {
+      CUtensorMap mE, mCt;
+      st = make_map_B(t, &mE, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t->q_pad);
+      if (st != CGG_OK) return st;
+      {
+        cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)Q, (cuuint64_t)num_calls * batch};
+        cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)Q * HW * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)t->q_pad, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = t->encode(&mCt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out, swizzled) failed: " + std::to_string((int)r));
+      }
+      p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
+      p.dbg = 0;
+      static bool attr_set_t = false;
+      if (!attr_set_t) {
+        TCU(cudaFuncSetAttribute(tc_einsum_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set_t = true;
+      }
+      if (t->num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      int pairs = t->num_sms / 2;
+      if (pairs > p.n_work / 2) pairs = p.n_work / 2;
+      TCU(launch_pdl_cluster(2, tc_einsum_t_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem, s, mA, mE, mCt, p));
+      count_launch();
+      TCU(cudaGetLastError());
+      return CGG_OK;
+    }
+  }
   static const int use_pair = getenv("CGG_EIN_PAIR") ? atoi(getenv("CGG_EIN_PAIR")) : 1;
   if (use_pair && m_tiles % 2 == 0 && HW % TC_BM == 0 && p.N_TILE % 16 == 0 && p.KC == 4) {
     // CTA-pair kernel: each CTA loads N_TILE/2 rows of every B chunk
