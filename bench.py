@@ -204,16 +204,50 @@ def run_b200_arm(args):
     mems_d = [m.to(dev, non_blocking=True) for m in mems_h]
     lib = clib.load()
 
+    # `value` keeps args.in_flight batches in flight: one head (own workspace, own CUDA graph) and one stream per
+    # slot, steps issued round-robin.  The layer chain of a step is latency-bound, so the
+    # chain of one batch fills the SMs the other leaves idle; every step is still a full forward of B images.
+    n_fly = max(1, args.in_flight)
+    heads = [head] + [build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph)
+                      for _ in range(n_fly - 1)]
+    fly_in = [(mf_d, mems_d)] + [(mf_d.clone(), [m.clone() for m in mems_d]) for _ in range(n_fly - 1)]
+    fly_streams = [torch.cuda.Stream() for _ in range(n_fly)]
+    step_no = [0]
+
     def step_resident():
-        return head.decoder_forward(mf_d, mems_d)
+        i = step_no[0] % n_fly
+        step_no[0] += 1
+        with torch.cuda.stream(fly_streams[i]):
+            return heads[i].decoder_forward(*fly_in[i])
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        for st in fly_streams:
+            st.wait_event(ev)
+
+    def join():
+        for st in fly_streams:
+            torch.cuda.current_stream().wait_stream(st)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    fork()
+    for _ in range(max(args.warmup, 3) * n_fly):
         out = step_resident()
+    join()
+    barrier()
+    # single-batch latency of one step (one stream, nothing else in flight), reported next to the throughput
+    l0_, l1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0_.record()
+    for _ in range(5):
+        head.decoder_forward(mf_d, mems_d)
+    l1_.record()
+    torch.cuda.synchronize()
+    latency_ms = l0_.elapsed_time(l1_) / 5
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -222,8 +256,10 @@ def run_b200_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    fork()
     for _ in range(args.steps):
         out = step_resident()
+    join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -355,7 +391,8 @@ def run_b200_arm(args):
                     config=dict(workload='configs[1]: COCO-OVIS instance decoder head, Q=%d, 9 layers, 256-d, 8 heads, '
                                          '1024x1024, batch %d per GPU' % (Q, B),
                                 batch_per_gpu=B, global_batch=B * world, precision=args.precision,
-                                cuda_graph=not args.no_graph,
+                                cuda_graph=not args.no_graph, in_flight_batches=n_fly,
+                                single_batch_latency_ms=latency_ms,
                                 l2='inputs (%.0f MB per step) larger than L2, no explicit flush' % (h2d / 1e6),
                                 flops_per_image=flops_per_image(Q)),
                     e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
@@ -378,6 +415,8 @@ def main():
     ap.add_argument('--queries', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the path eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--in-flight', type=int, default=2,
+                    help='batches in flight in the device-resident throughput leg (one head + stream each)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
