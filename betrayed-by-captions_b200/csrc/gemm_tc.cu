@@ -949,6 +949,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
 // chunks, each used for the terms hi.me_hi + hi.me_lo resp. lo.me_hi), so every byte is fetched once.
 struct TcBitsP {
   int N_TILE, b_row, m_tiles, K_valid, Q, W32, stages, acc_stride, tmem_cols, C;
+  int n_items, per_pair;      // CTA-pair variant: (image, key-tile pair) work items, a contiguous range per pair
   uint32_t* bitmap;
 };
 
@@ -1073,6 +1074,157 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+}
+
+// ------------------------------------------------------------------- K3, CTA-pair variant
+// Same contraction with cta_group::2 MMAs: M = 256 = two 128-key tiles (one per CTA of the pair), each CTA keeps
+// HALF of the head call's mask-embedding rows resident.  The kernel is paced by the MMA-issuing thread (48 small
+// MMAs per key tile), so one instruction covering two tiles halves its time.  Each pair walks a contiguous range of
+// (image, key-tile pair) items, so the resident embeddings are reloaded only when the image changes.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_bits_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ TcBitsP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int half_n = p.N_TILE / 2;
+  const int bt = half_n * 128;                   // bytes of one resident B chunk (this CTA's half of the rows)
+  constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES;
+  uint8_t* sBres = smem;                         // 8 chunks: me_hi k-chunks 0..3, me_lo k-chunks 0..3
+  uint8_t* sA = sBres + 8 * bt;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE_BYTES);
+  uint64_t* b_res_full = bars;
+  uint64_t* b_res_empty = bars + 1;
+  uint64_t* a_full = bars + 2;
+  uint64_t* a_empty = a_full + p.stages;
+  uint64_t* acc_full = a_empty + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int tp = p.m_tiles >> 1;                 // key-tile pairs per image
+  const int i0 = pair * p.per_pair, i1 = min(i0 + p.per_pair, p.n_items);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::mbar_init(b_res_full, 1);
+    ptx::mbar_init(b_res_empty, 1);
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish_2sm();
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, cur_img = -1, nchg = 0;
+      for (int item = i0; item < i1; ++item) {
+        const int img = item / tp, mt = (item - img * tp) * 2 + (int)rank;
+        if (img != cur_img) {
+          if (nchg > 0) ptx::mbar_wait(b_res_empty, (uint32_t)(nchg - 1) & 1u);   // the previous image's MMAs are done
+          if (rank == 0) ptx::mbar_expect_tx(b_res_full, 2u * 8u * (uint32_t)bt);
+          for (int j = 0; j < 8; ++j)
+            ptx::tma_load_3d_2sm(sBres + j * bt, &tmB, b_res_full, (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C),
+                                 p.b_row + (int)rank * half_n, img);
+          cur_img = img;
+          ++nchg;
+        }
+        for (int j2 = 0; j2 < 4; ++j2, ++it) {
+          const int s = it % p.stages;
+          ptx::mbar_wait(&a_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+          if (rank == 0) ptx::mbar_expect_tx(&a_full[s], 2u * STAGE_BYTES);
+          for (int c = 0; c < 2; ++c) {
+            const int j = 2 * j2 + c;
+            const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
+            for (int g = 0; g < 2; ++g)
+              ptx::tma_load_3d_2sm(sA + s * STAGE_BYTES + c * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s],
+                                   mt * TC_BM + g * 64, ch, img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, p.N_TILE, true, false);
+      const uint64_t ad0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), A_CHUNK_BYTES / 2, 1024);
+      const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sBres), 16, 1024);
+      const uint32_t bt16 = (uint32_t)bt >> 4;
+      int it = 0, t = 0, cur_img = -1, nchg = 0;
+      for (int item = i0; item < i1; ++item, ++t) {
+        const int img = item / tp;
+        if (img != cur_img) {
+          ptx::mbar_wait(b_res_full, (uint32_t)nchg & 1u);
+          cur_img = img;
+          ++nchg;
+        }
+        const bool img_ends = item + 1 < i1 && (item + 1) / tp != img;
+        const int buf = t & 1;
+        ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+        for (int j2 = 0; j2 < 4; ++j2, ++it) {
+          const int s = it % p.stages;
+          ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int j = 2 * j2 + c;
+              const uint64_t ad = ad0 + (uint64_t)(s * (STAGE_BYTES >> 4) + c * (A_CHUNK_BYTES >> 4));
+              const int nb = j < 4 ? 2 : 1;       // hi chunk k: x me_hi[k], x me_lo[k];  lo chunk k: x me_hi[k]
+              for (int bsel = 0; bsel < nb; ++bsel) {
+                const uint64_t bd = bd0 + (uint64_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt16);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc,
+                                       (j | bsel | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::mma_commit_2sm(&a_empty[s]);
+            if (j2 == 3) {
+              ptx::mma_commit_2sm(&acc_full[buf]);
+              if (img_ends) ptx::mma_commit_2sm(b_res_empty);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    EpiCtx ctx;
+    ctx.lane = lane; ctx.part = (warp - 2) >> 2; ctx.chunks = p.N_TILE / 16; ctx.col0 = 0;
+    int t = 0;
+    for (int item = i0; item < i1; ++item, ++t) {
+      const int img = item / tp, mt = (item - img * tp) * 2 + (int)rank;
+      const int buf = t & 1;
+      ptx::mbar_wait(&acc_full[buf], ((uint32_t)(t >> 1)) & 1u);
+      ptx::tc_fence_after();
+      ctx.batch = img;
+      ctx.m = mt * TC_BM + quarter * 32 + lane;
+      ctx.m_ok = ctx.m < p.K_valid;
+      ctx.wi = (mt * TC_BM + quarter * 32) >> 5;
+      ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      epi_bits_impl(p.Q, p.W32, p.bitmap, ctx);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------- small kernels
@@ -1539,7 +1691,38 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(me) failed: " + std::to_string((int)r));
     }
-    TCU(launch_pdl(tc_bits_kernel, dim3(gx, batch), dim3(TC_THREADS), smem, s, mA, mB3, bp));
+    // opt-in: parity-green but not faster on B200 (5625 vs 5680 images/s) -- the bits kernel is bound by its ballot /
+    // scattered 4-byte store epilogue, not by MMA issue
+    static const int bits_pair = getenv("CGG_BITS_PAIR") ? atoi(getenv("CGG_BITS_PAIR")) : 0;
+    bool launched = false;
+    if (bits_pair && bp.m_tiles % 2 == 0 && bp.N_TILE % 16 == 0 && (bp.N_TILE / 2) % 8 == 0) {
+      CUtensorMap mB3h;
+      cuuint64_t dims[3] = {(cuuint64_t)(2 * C), (cuuint64_t)t->rows_per_batch, (cuuint64_t)batch};
+      cuuint64_t strides[2] = {(cuuint64_t)(2 * C) * 2, (cuuint64_t)t->rows_per_batch * (2 * C) * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)(bp.N_TILE / 2), 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = t->encode(&mB3h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base + w.me_all, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(me half) failed: " + std::to_string((int)r));
+      TcBitsP pp = bp;
+      pp.n_items = batch * (bp.m_tiles / 2);
+      int pairs = sms / 2;
+      if (pairs > pp.n_items) pairs = pp.n_items;
+      pp.per_pair = (pp.n_items + pairs - 1) / pairs;
+      pairs = (pp.n_items + pp.per_pair - 1) / pp.per_pair;
+      pp.stages = (int)((225 * 1024 - 8 * (bp.N_TILE / 2) * 128) / (2 * A_CHUNK_BYTES));
+      if (pp.stages > 4) pp.stages = 4;
+      const size_t smem2 = 1024 + 8 * (size_t)(bp.N_TILE / 2) * 128 + (size_t)pp.stages * 2 * A_CHUNK_BYTES + (2 + 2 * pp.stages + 4) * 8 + 64;
+      static bool attr_set2 = false;
+      if (!attr_set2) {
+        TCU(cudaFuncSetAttribute(tc_bits_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set2 = true;
+      }
+      TCU(launch_pdl_cluster(2, tc_bits_pair_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem2, s, mA, mB3h, pp));
+      launched = true;
+    }
+    if (!launched) TCU(launch_pdl(tc_bits_kernel, dim3(gx, batch), dim3(TC_THREADS), smem, s, mA, mB3, bp));
     count_launch();
     TCU(cudaGetLastError());
     const int rows = batch * Q;
