@@ -17,6 +17,7 @@
 //   warps 2..17 : epilogue (tcgen05.ld -> registers -> global), 4 warps per TMEM lane quarter
 #include "gemm_tc.h"
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include "tc_ptx.cuh"
 #include "tc_state.h"
 
@@ -53,6 +54,7 @@ struct TcGemmP {
   int tmem_cols;         // power of two >= 32
   int epi;
   int dbg;
+  int f16;               // 1: operands are IEEE half instead of bf16 (attention-mask GEMM)
   int M_valid;           // valid pixels / keys per batch image (features for EPI_LINEAR_T)
   int m_tiles, n_batch, n_work;   // A-resident kinds are persistent: CTA c walks work items c, c+grid, ... of m_tiles*n_batch
   // EPI_MASK_T
@@ -513,7 +515,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // address field (16-byte units).
     //   A, MN-major SW128: 16 channel rows of 128 B per MMA; pixel groups 8 KB apart (LBO), 8-row groups 1 KB apart (SBO).
     //   A / B, K-major SW128: 32 B along K per MMA, SBO 1 KB.
-    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false);
+    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, /*A MN-major*/ !A_KMAJOR, /*B K-major*/ false, p.f16 != 0);
     const uint64_t ad0 = A_KMAJOR ? ptx::umma_desc_sw128(ptx::smem_u32(A_RESIDENT ? sA : sB), 16, 1024)
                                   : ptx::umma_desc_sw128(ptx::smem_u32(A_RESIDENT ? sA : sB), A_CHUNK_BYTES / 2, 1024);
     const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sB + a_in_stage), 16, 1024);
@@ -943,13 +945,14 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
 }
 
 // ------------------------------------------------------------------- K3, persistent variant
-// Attention-mask bits with the B operand RESIDENT: the head call's mask embeddings (hi and lo planes,
-// 8 chunks of N_TILE x 64) are loaded once per CTA and stay in shared memory while the CTA walks its
-// share of the image's 128-key tiles; per tile only the resampled features stream in (4 hi + 4 lo
-// chunks, each used for the terms hi.me_hi + hi.me_lo resp. lo.me_hi), so every byte is fetched once.
+// Attention-mask bits with the B operand RESIDENT: the head call's mask embeddings (fp16, 4 chunks of
+// N_TILE x 64) are loaded once per CTA and stay in shared memory while the CTA walks its share of the
+// image's 128-key tiles; per tile only the resampled features (fp16, 4 chunks) stream in.
+// Both operands are IEEE half: the resampled features are means of four bf16 values (10 significand bits,
+// exact in fp16 for 3 of 4 values), and rounding the mask embeddings to 11 bits flips 0.02 % of the bits --
+// plain bf16 operands flip 0.12 %, outside the 99.9 % bar (CPU study in DESIGN.md).
 struct TcBitsP {
   int N_TILE, b_row, m_tiles, K_valid, Q, W32, stages, acc_stride, tmem_cols, C;
-  int n_items, per_pair;      // CTA-pair variant: (image, key-tile pair) work items, a contiguous range per pair
   uint32_t* bitmap;
 };
 
@@ -959,8 +962,8 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bt = p.N_TILE * 128;                 // bytes of one resident B chunk
-  uint8_t* sBres = smem;                         // 8 chunks: me_hi k-chunks 0..3, me_lo k-chunks 0..3
-  uint8_t* sA = sBres + 8 * bt;                  // ring of stages, each TWO 16 KB feature chunks (one commit frees both)
+  uint8_t* sBres = smem;                         // 4 chunks: mask-embedding k-chunks 0..3 (fp16)
+  uint8_t* sA = sBres + 4 * bt;                  // ring of stages, each TWO 16 KB feature chunks (one commit frees both)
   constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE_BYTES);
   uint64_t* b_res_full = bars;
@@ -992,18 +995,17 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(b_res_full, (uint32_t)(8 * bt));
-      for (int j = 0; j < 8; ++j)
-        ptx::tma_load_3d(sBres + j * bt, &tmB, b_res_full, (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C), p.b_row, batch);
+      ptx::mbar_expect_tx(b_res_full, (uint32_t)(4 * bt));
+      for (int j = 0; j < 4; ++j)      // the fp16 copy of the mask embeddings sits in columns [C, 2C) of the rows
+        ptx::tma_load_3d(sBres + j * bt, &tmB, b_res_full, p.C + j * TC_BK, p.b_row, batch);
       int it = 0;
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x)
-        for (int j2 = 0; j2 < 4; ++j2, ++it) {
+        for (int j2 = 0; j2 < 2; ++j2, ++it) {
           const int s = it % p.stages;
           ptx::mbar_wait(&a_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
           ptx::mbar_expect_tx(&a_full[s], STAGE_BYTES);
           for (int c = 0; c < 2; ++c) {
-            const int j = 2 * j2 + c;
-            const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
+            const int ch = (2 * j2 + c) * TC_BK;
             for (int g = 0; g < 2; ++g)
               ptx::tma_load_3d(sA + s * STAGE_BYTES + c * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s],
                                mt * TC_BM + g * 64, ch, batch);
@@ -1013,7 +1015,7 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // MMA issuer.  The whole warp walks the loop (uniform control flow: descriptors stay in uniform registers);
     // one elected lane issues.  Descriptors = base + constant increments of the 14-bit address field.
-    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, true, false);
+    const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, p.N_TILE, true, false, /*f16*/ true);
     ptx::mbar_wait(b_res_full, 0);
     ptx::tc_fence_after();
     const uint64_t ad0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), A_CHUNK_BYTES / 2, 1024);
@@ -1025,7 +1027,7 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
-      for (int j2 = 0; j2 < 4; ++j2, ++it) {
+      for (int j2 = 0; j2 < 2; ++j2, ++it) {
         const int s = it % p.stages;
         ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
         ptx::tc_fence_after();
@@ -1034,17 +1036,13 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = 0; c < 2; ++c) {
             const int j = 2 * j2 + c;
             const uint64_t ad = ad0 + (uint64_t)(s * (STAGE_BYTES >> 4) + c * (A_CHUNK_BYTES >> 4));
-            // hi feature chunk k: x me_hi[k] and x me_lo[k];   lo feature chunk k: x me_hi[k]
-            const int nb = j < 4 ? 2 : 1;
-            for (int bsel = 0; bsel < nb; ++bsel) {
-              const uint64_t bd = bd0 + (uint64_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt16);
+            const uint64_t bd = bd0 + (uint64_t)(j * bt16);
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
-                ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc, (j | bsel | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < TC_BK / 16; ++k)
+              ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc, (j | k) != 0 ? 1u : 0u);
           }
           ptx::mma_commit(&a_empty[s]);
-          if (j2 == 3) ptx::mma_commit(&acc_full[buf]);
+          if (j2 == 1) ptx::mma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
@@ -1076,168 +1074,16 @@ tc_bits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ------------------------------------------------------------------- K3, CTA-pair variant
-// Same contraction with cta_group::2 MMAs: M = 256 = two 128-key tiles (one per CTA of the pair), each CTA keeps
-// HALF of the head call's mask-embedding rows resident.  The kernel is paced by the MMA-issuing thread (48 small
-// MMAs per key tile), so one instruction covering two tiles halves its time.  Each pair walks a contiguous range of
-// (image, key-tile pair) items, so the resident embeddings are reloaded only when the image changes.
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_bits_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ TcBitsP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int half_n = p.N_TILE / 2;
-  const int bt = half_n * 128;                   // bytes of one resident B chunk (this CTA's half of the rows)
-  constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES;
-  uint8_t* sBres = smem;                         // 8 chunks: me_hi k-chunks 0..3, me_lo k-chunks 0..3
-  uint8_t* sA = sBres + 8 * bt;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE_BYTES);
-  uint64_t* b_res_full = bars;
-  uint64_t* b_res_empty = bars + 1;
-  uint64_t* a_full = bars + 2;
-  uint64_t* a_empty = a_full + p.stages;
-  uint64_t* acc_full = a_empty + p.stages;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const int pair = blockIdx.x >> 1;
-  const int tp = p.m_tiles >> 1;                 // key-tile pairs per image
-  const int i0 = pair * p.per_pair, i1 = min(i0 + p.per_pair, p.n_items);
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
-    ptx::mbar_init(b_res_full, 1);
-    ptx::mbar_init(b_res_empty, 1);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish_2sm();
-  }
-  __syncwarp();
-  ptx::tc_fence_before();
-  ptx::cluster_sync_all();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  ptx::grid_dep_launch();
-  ptx::grid_dep_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int it = 0, cur_img = -1, nchg = 0;
-      for (int item = i0; item < i1; ++item) {
-        const int img = item / tp, mt = (item - img * tp) * 2 + (int)rank;
-        if (img != cur_img) {
-          if (nchg > 0) ptx::mbar_wait(b_res_empty, (uint32_t)(nchg - 1) & 1u);   // the previous image's MMAs are done
-          if (rank == 0) ptx::mbar_expect_tx(b_res_full, 2u * 8u * (uint32_t)bt);
-          for (int j = 0; j < 8; ++j)
-            ptx::tma_load_3d_2sm(sBres + j * bt, &tmB, b_res_full, (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C),
-                                 p.b_row + (int)rank * half_n, img);
-          cur_img = img;
-          ++nchg;
-        }
-        for (int j2 = 0; j2 < 4; ++j2, ++it) {
-          const int s = it % p.stages;
-          ptx::mbar_wait(&a_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-          if (rank == 0) ptx::mbar_expect_tx(&a_full[s], 2u * STAGE_BYTES);
-          for (int c = 0; c < 2; ++c) {
-            const int j = 2 * j2 + c;
-            const int ch = (j < 4 ? j : j - 4) * TC_BK + (j < 4 ? 0 : p.C);     // hi planes, then lo planes
-            for (int g = 0; g < 2; ++g)
-              ptx::tma_load_3d_2sm(sA + s * STAGE_BYTES + c * A_CHUNK_BYTES + g * (A_CHUNK_BYTES / 2), &tmA, &a_full[s],
-                                   mt * TC_BM + g * 64, ch, img);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, p.N_TILE, true, false);
-      const uint64_t ad0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), A_CHUNK_BYTES / 2, 1024);
-      const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sBres), 16, 1024);
-      const uint32_t bt16 = (uint32_t)bt >> 4;
-      int it = 0, t = 0, cur_img = -1, nchg = 0;
-      for (int item = i0; item < i1; ++item, ++t) {
-        const int img = item / tp;
-        if (img != cur_img) {
-          ptx::mbar_wait(b_res_full, (uint32_t)nchg & 1u);
-          cur_img = img;
-          ++nchg;
-        }
-        const bool img_ends = item + 1 < i1 && (item + 1) / tp != img;
-        const int buf = t & 1;
-        ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
-        for (int j2 = 0; j2 < 4; ++j2, ++it) {
-          const int s = it % p.stages;
-          ptx::mbar_wait(&a_full[s], (uint32_t)(it / p.stages) & 1u);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int j = 2 * j2 + c;
-              const uint64_t ad = ad0 + (uint64_t)(s * (STAGE_BYTES >> 4) + c * (A_CHUNK_BYTES >> 4));
-              const int nb = j < 4 ? 2 : 1;       // hi chunk k: x me_hi[k], x me_lo[k];  lo chunk k: x me_hi[k]
-              for (int bsel = 0; bsel < nb; ++bsel) {
-                const uint64_t bd = bd0 + (uint64_t)(((j < 4 ? j : j - 4) + (bsel ? 4 : 0)) * bt16);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                  ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc,
-                                       (j | bsel | k) != 0 ? 1u : 0u);
-              }
-            }
-            ptx::mma_commit_2sm(&a_empty[s]);
-            if (j2 == 3) {
-              ptx::mma_commit_2sm(&acc_full[buf]);
-              if (img_ends) ptx::mma_commit_2sm(b_res_empty);
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    EpiCtx ctx;
-    ctx.lane = lane; ctx.part = (warp - 2) >> 2; ctx.chunks = p.N_TILE / 16; ctx.col0 = 0;
-    int t = 0;
-    for (int item = i0; item < i1; ++item, ++t) {
-      const int img = item / tp, mt = (item - img * tp) * 2 + (int)rank;
-      const int buf = t & 1;
-      ptx::mbar_wait(&acc_full[buf], ((uint32_t)(t >> 1)) & 1u);
-      ptx::tc_fence_after();
-      ctx.batch = img;
-      ctx.m = mt * TC_BM + quarter * 32 + lane;
-      ctx.m_ok = ctx.m < p.K_valid;
-      ctx.wi = (mt * TC_BM + quarter * 32) >> 5;
-      ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      epi_bits_impl(p.Q, p.W32, p.bitmap, ctx);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
-    }
-  }
-  __syncwarp();
-  ptx::tc_fence_before();
-  ptx::cluster_sync_all();
-  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
-}
-
 // ---------------------------------------------------------------------------- small kernels
 // One pass over mask_features (bf16 NCHW) producing the bilinear (align_corners=False) resamples to
 // the three level sizes for the exact ratios 8/4/2: each is the mean of the central 2x2 of its
 // block, evaluated in the reference's order 0.5*(0.5a+0.5b)+0.5*(0.5c+0.5d) in fp32.
 // One thread per 8x8 block of one (image, channel) plane.
-// Outputs are hi/lo bf16 pairs (x ~= hi + lo to ~16 mantissa bits): per image the resampled map is
-// stored as (2C, K_l): channels [0,C) = hi, [C,2C) = lo.
+// Outputs are IEEE half (a mean of four bf16 values has 10 significand bits: fp16 holds it exactly unless the
+// four exponents differ): per image the resampled map is stored as (C, pitch_l).
 __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* __restrict__ F, int planes, int C, int H4,
-                                                          int W4, __nv_bfloat16* __restrict__ d8,
-                                                          __nv_bfloat16* __restrict__ d4,
-                                                          __nv_bfloat16* __restrict__ d2, int p8, int p4, int p2) {
+                                                          int W4, __half* __restrict__ d8, __half* __restrict__ d4,
+                                                          __half* __restrict__ d2, int p8, int p4, int p2) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
   const int bw = W4 >> 3, bh = H4 >> 3;
@@ -1247,8 +1093,6 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
   const int bx = (int)(idx % bw);
   const int by = (int)((idx / bw) % bh);
   const long plane = idx / ((long)bw * bh);
-  const long img = plane / C, ch = plane % C;
-  const long hi_plane = img * 2 * C + ch, lo_plane = hi_plane + C;
   const __nv_bfloat16* src = F + plane * (long)H4 * W4 + (long)by * 8 * W4 + bx * 8;
   float px[8][8];
 #pragma unroll
@@ -1265,40 +1109,30 @@ __global__ void __launch_bounds__(256) downsample3_kernel(const __nv_bfloat16* _
   auto avg = [&](int r, int c) {
     return 0.5f * (0.5f * px[r][c] + 0.5f * px[r][c + 1]) + 0.5f * (0.5f * px[r + 1][c] + 0.5f * px[r + 1][c + 1]);
   };
+  auto h2 = [](float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  };
   // ratio 8 -> rows 3,4 cols 3,4
-  {
-    __nv_bfloat16 hi, lo;
-    split_bf16(avg(3, 3), hi, lo);
-    d8[hi_plane * (long)p8 + (long)by * bw + bx] = hi;
-    d8[lo_plane * (long)p8 + (long)by * bw + bx] = lo;
-  }
+  d8[plane * (long)p8 + (long)by * bw + bx] = __float2half_rn(avg(3, 3));
   // ratio 4 -> centre of each 4x4: rows 1,2 / 5,6
   {
     const int w = W4 >> 2;
-    const long off = (long)(by * 2) * w + bx * 2, psz = p4;
+    const long off = (long)(by * 2) * w + bx * 2;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(avg(4 * r + 1, 1), h0, l0);
-      split_bf16(avg(4 * r + 1, 5), h1, l1);
-      *reinterpret_cast<uint32_t*>(d4 + hi_plane * psz + off + (long)r * w) = pack2(h0, h1);
-      *reinterpret_cast<uint32_t*>(d4 + lo_plane * psz + off + (long)r * w) = pack2(l0, l1);
-    }
+    for (int r = 0; r < 2; ++r)
+      *reinterpret_cast<uint32_t*>(d4 + plane * (long)p4 + off + (long)r * w) = h2(avg(4 * r + 1, 1), avg(4 * r + 1, 5));
   }
   // ratio 2 -> every 2x2
   {
     const int w = W4 >> 1;
-    const long off = (long)(by * 4) * w + bx * 4, psz = p2;
+    const long off = (long)(by * 4) * w + bx * 4;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      __nv_bfloat16 h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_bf16(avg(2 * r, 2 * j), h[j], l[j]);
-      uint2 ph, pl;
-      ph.x = pack2(h[0], h[1]); ph.y = pack2(h[2], h[3]);
-      pl.x = pack2(l[0], l[1]); pl.y = pack2(l[2], l[3]);
-      *reinterpret_cast<uint2*>(d2 + hi_plane * psz + off + (long)r * w) = ph;
-      *reinterpret_cast<uint2*>(d2 + lo_plane * psz + off + (long)r * w) = pl;
+      uint2 ph;
+      ph.x = h2(avg(2 * r, 0), avg(2 * r, 2));
+      ph.y = h2(avg(2 * r, 4), avg(2 * r, 6));
+      *reinterpret_cast<uint2*>(d2 + plane * (long)p2 + off + (long)r * w) = ph;
     }
   }
 }
@@ -1327,11 +1161,9 @@ __global__ void store_me_kernel(const float* __restrict__ me, __nv_bfloat16* __r
   const long bq = i / C;
   const int q = (int)(bq % Q);
   const int b = (int)(bq / Q);
-  __nv_bfloat16 hi, lo;
-  split_bf16(me[i], hi, lo);
   __nv_bfloat16* row = dst + ((long)b * rows_per_batch + row0 + q) * 2 * C;
-  row[c] = hi;          // columns [0,C): hi  (the only part the mask einsum reads)
-  row[C + c] = lo;      // columns [C,2C): lo (third term of the split-precision attention-mask GEMM)
+  row[c] = __float2bfloat16_rn(me[i]);                                   // columns [0,C): bf16, read by the mask einsum
+  reinterpret_cast<__half*>(row)[C + c] = __float2half_rn(me[i]);        // columns [C,2C): fp16, read by the attention-mask GEMM
 }
 
 // all_masked[row] = (popcount of the row's bitmap == K)
@@ -1618,8 +1450,8 @@ int tc_downsample(TcState* t, int batch, const void* mask_features_bf16, void* w
   char* base = static_cast<char*>(ws);
   TCU(launch_pdl(downsample3_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
       static_cast<const __nv_bfloat16*>(mask_features_bf16), planes, t->cfg.embed_dim, t->H4, t->W4,
-      reinterpret_cast<__nv_bfloat16*>(base + w.fds[0]), reinterpret_cast<__nv_bfloat16*>(base + w.fds[1]),
-      reinterpret_cast<__nv_bfloat16*>(base + w.fds[2]), pitch8(t->lh[0] * t->lw[0]), pitch8(t->lh[1] * t->lw[1]),
+      reinterpret_cast<__half*>(base + w.fds[0]), reinterpret_cast<__half*>(base + w.fds[1]),
+      reinterpret_cast<__half*>(base + w.fds[2]), pitch8(t->lh[0] * t->lw[0]), pitch8(t->lh[1] * t->lw[1]),
       pitch8(t->lh[2] * t->lw[2])));
   count_launch();
   TCU(cudaGetLastError());
@@ -1646,27 +1478,26 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
   const int C = t->cfg.embed_dim, Q = t->cfg.num_queries, K = t->lh[level] * t->lw[level];
   char* base = static_cast<char*>(ws);
   CUtensorMap mA, mB;
-  // split-precision contraction  logits = Fhi.me_hi + Flo.me_hi + Fhi.me_lo  (bf16 pairs, fp32
-  // accumulate: ~16 mantissa bits per operand), expressed as ONE GEMM with K = 3C by revisiting chunks
-  int st = make_map_A(t, &mA, base + w.fds[level], K, 2 * C, batch, pitch8(K));
+  // logits = F_ds . me with both operands in IEEE half (fp32 accumulate)
+  int st = make_map_A(t, &mA, base + w.fds[level], K, C, batch, pitch8(K));
   if (st != CGG_OK) return st;
   // rows beyond the buffer's logical end are covered by the 64 KB slack of me_all (finite garbage,
   // columns >= Q are never stored)
   st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t->bits_ntile);
   if (st != CGG_OK) return st;
-  if (t->bits_nt == 1 && 8 * t->bits_ntile * 128 + 4 * A_CHUNK_BYTES <= 200 * 1024) {
+  if (t->bits_nt == 1 && 4 * t->bits_ntile * 128 + 4 * A_CHUNK_BYTES <= 200 * 1024) {
     // persistent, B-resident variant (Q <= 128)
     TcBitsP bp = {};
     bp.N_TILE = t->bits_ntile; bp.b_row = 0; bp.m_tiles = (K + TC_BM - 1) / TC_BM; bp.K_valid = K; bp.Q = Q;
     bp.W32 = (K + 31) / 32; bp.C = C; bp.bitmap = bitmap;
     bp.acc_stride = bp.N_TILE <= 32 ? 32 : bp.N_TILE <= 64 ? 64 : 128;
     bp.tmem_cols = 2 * bp.acc_stride;
-    bp.stages = (int)((225 * 1024 - 8 * bp.N_TILE * 128) / (2 * A_CHUNK_BYTES));   // stages of two feature chunks
+    bp.stages = (int)((225 * 1024 - 4 * bp.N_TILE * 128) / (2 * A_CHUNK_BYTES));   // stages of two feature chunks
     if (bp.stages > 4) bp.stages = 4;
     // per-image B rows differ: one map per launch over all rows, row coordinate = image base + call offset
     // (blockIdx.y = image) -> the kernel needs the per-image row: pass through b_row and rows_per_batch
     bp.b_row = call_idx * t->q_pad;
-    const size_t smem = 1024 + 8 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * 2 * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
+    const size_t smem = 1024 + 4 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * 2 * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
     static bool attr_set = false;
     if (!attr_set) {
       TCU(cudaFuncSetAttribute(tc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1691,38 +1522,7 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(me) failed: " + std::to_string((int)r));
     }
-    // opt-in: parity-green but not faster on B200 (5625 vs 5680 images/s) -- the bits kernel is bound by its ballot /
-    // scattered 4-byte store epilogue, not by MMA issue
-    static const int bits_pair = getenv("CGG_BITS_PAIR") ? atoi(getenv("CGG_BITS_PAIR")) : 0;
-    bool launched = false;
-    if (bits_pair && bp.m_tiles % 2 == 0 && bp.N_TILE % 16 == 0 && (bp.N_TILE / 2) % 8 == 0) {
-      CUtensorMap mB3h;
-      cuuint64_t dims[3] = {(cuuint64_t)(2 * C), (cuuint64_t)t->rows_per_batch, (cuuint64_t)batch};
-      cuuint64_t strides[2] = {(cuuint64_t)(2 * C) * 2, (cuuint64_t)t->rows_per_batch * (2 * C) * 2};
-      cuuint32_t box[3] = {64, (cuuint32_t)(bp.N_TILE / 2), 1};
-      cuuint32_t es[3] = {1, 1, 1};
-      CUresult r = t->encode(&mB3h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base + w.me_all, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(me half) failed: " + std::to_string((int)r));
-      TcBitsP pp = bp;
-      pp.n_items = batch * (bp.m_tiles / 2);
-      int pairs = sms / 2;
-      if (pairs > pp.n_items) pairs = pp.n_items;
-      pp.per_pair = (pp.n_items + pairs - 1) / pairs;
-      pairs = (pp.n_items + pp.per_pair - 1) / pp.per_pair;
-      pp.stages = (int)((225 * 1024 - 8 * (bp.N_TILE / 2) * 128) / (2 * A_CHUNK_BYTES));
-      if (pp.stages > 4) pp.stages = 4;
-      const size_t smem2 = 1024 + 8 * (size_t)(bp.N_TILE / 2) * 128 + (size_t)pp.stages * 2 * A_CHUNK_BYTES + (2 + 2 * pp.stages + 4) * 8 + 64;
-      static bool attr_set2 = false;
-      if (!attr_set2) {
-        TCU(cudaFuncSetAttribute(tc_bits_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set2 = true;
-      }
-      TCU(launch_pdl_cluster(2, tc_bits_pair_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem2, s, mA, mB3h, pp));
-      launched = true;
-    }
-    if (!launched) TCU(launch_pdl(tc_bits_kernel, dim3(gx, batch), dim3(TC_THREADS), smem, s, mA, mB3, bp));
+    TCU(launch_pdl(tc_bits_kernel, dim3(gx, batch), dim3(TC_THREADS), smem, s, mA, mB3, bp));
     count_launch();
     TCU(cudaGetLastError());
     const int rows = batch * Q;
@@ -1732,13 +1532,12 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
     return CGG_OK;
   }
   TcGemmP p = {};
-  p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = 3 * C / TC_BK;
+  p.N_TILE = t->bits_ntile; p.NT = t->bits_nt; p.KC = C / TC_BK;
   p.a_resident = 0;
-  const int cpc = C / TC_BK;   // chunks per C
+  p.f16 = 1;                                       // both operands are IEEE half
   for (int kc = 0; kc < p.KC; ++kc) {
-    const int term = kc / cpc, j = (kc % cpc) * TC_BK;
-    p.a_kcoord[kc] = (term == 1 ? C : 0) + j;     // hi, lo, hi
-    p.b_kcoord[kc] = (term == 2 ? C : 0) + j;     // hi, hi, lo
+    p.a_kcoord[kc] = kc * TC_BK;                   // resampled features (fp16 planes)
+    p.b_kcoord[kc] = C + kc * TC_BK;               // fp16 copy of the mask embeddings: columns [C, 2C) of the rows
   }
   p.b_row0 = call_idx * t->q_pad; p.b_rows_per_batch = t->rows_per_batch;
   p.epi = EPI_BITS; p.M_valid = K; p.Q = Q;

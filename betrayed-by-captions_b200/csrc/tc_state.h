@@ -62,8 +62,8 @@ struct TcWs {
     const int C = t->cfg.embed_dim;
     const size_t M = (size_t)B * t->cfg.num_queries;
     me_all = take((size_t)B * t->rows_per_batch * 2 * C * 2 + 128 * 1024);   // [hi|lo] rows + 128 slack rows
-    // hi, lo planes; the plane pitch is the key count rounded up to 8 (TMA 16-byte stride rule)
-    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * 2 * C * pitch8(t->lh[l] * t->lw[l]) * 2);
+    // resampled features, one fp16 plane per channel; the plane pitch is the key count rounded up to 8 (TMA 16-byte stride rule)
+    for (int l = 0; l < 3; ++l) fds[l] = take((size_t)B * C * pitch8(t->lh[l] * t->lw[l]) * 2);
     // re-pitched copy of a memory level whose key count is not a multiple of 8 (tc_kv_project)
     for (int l = 0; l < 3; ++l) {
       const int K = t->lh[l] * t->lw[l];
