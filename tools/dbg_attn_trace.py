@@ -1,7 +1,7 @@
 """Debug helper (GPU box): per-tile pipeline trace of the tc attention kernel during one bf16 forward."""
 import os, sys
 os.environ.setdefault('CGG_AT_TRACE', '2')
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth

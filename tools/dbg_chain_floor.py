@@ -1,7 +1,7 @@
 """Debug helper (GPU box): graph-mode forward time vs image size -- the small-image time is the floor set by
 the latency-bound linears / LayerNorms / launches of the layer chain."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth

@@ -1,7 +1,7 @@
-"""Debug helper (GPU box): kernel-internal timeline of the tc GEMM launches of one bf16 forward."""
+"""Debug helper (GPU box): one bf16 forward, then the all-calls mask einsum alone three times
+(tc_gemm launches #97..#99 of the process) -- target for `ncu -k regex:tc_gemm_kernel --launch-skip 98`."""
 import os, sys
-os.environ['CGG_TC_TIMING'] = '1'
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth
@@ -14,6 +14,9 @@ head = build_head_from_state_dict(sd, Q, 49, 'bf16', dev)
 mfd, memd = mf.to(dev), [m.to(dev) for m in mems]
 head.decoder_forward(mfd, memd)
 torch.cuda.synchronize()
-sys.stderr.write('==== second forward ====\n')
-head.decoder_forward(mfd, memd)
+rt = head._runtime(dev)
+out = torch.empty((10, B, Q, 256, 256), dtype=torch.bfloat16, device=dev)
+for _ in range(3):
+    rt.mask_einsum(mfd, out)
 torch.cuda.synchronize()
+print('done')

@@ -1,6 +1,6 @@
 """Debug helper (GPU box): time cgg_mask_einsum alone under the CGG_TC_DBGMODE experiments."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth

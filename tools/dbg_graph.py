@@ -1,6 +1,6 @@
 """Debug helper (GPU box): eager vs CUDA-graph replay of one bf16 forward (launch-gap check)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth

@@ -1,7 +1,7 @@
 """Debug helper (GPU box): one bf16 decoder layer at a small batch with CGG_DEBUG_SYNC=1."""
 import os, sys
 os.environ['CGG_DEBUG_SYNC'] = '1'
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits next to tests/)
 sys.path.insert(0, ROOT)
 import torch
 from cgg_b200 import synth
