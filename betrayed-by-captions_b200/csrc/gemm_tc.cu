@@ -174,7 +174,7 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
 // is not added here at all: the attention kernel adds Q R^T, see attention_tc.cu.)
 __device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, uint8_t* sStage, const float* sBias,
                                              const CUtensorMap* tmC, bool leader_warp, bool last, int m_tile,
-                                             uint64_t* acc_empty_bar) {
+                                             uint64_t* acc_empty_bar, bool arrive_on_leader = false) {
   const bool leader = leader_warp && c.lane == 0;
   static_assert(EPI_PARTS == 4, "four chunk slots per warp below");
   // 1. accumulator -> registers (up to 4 chunks of 16 columns per warp, loads in flight together); this overlaps
@@ -193,7 +193,10 @@ __device__ __forceinline__ void epi_rowmajor(const TcGemmP& p, const EpiCtx& c, 
   // 2. the accumulator buffer is free again
   ptx::tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) ptx::mbar_arrive(acc_empty_bar);
+  if (c.lane == 0) {
+    if (arrive_on_leader) ptx::mbar_arrive_leader(acc_empty_bar);
+    else ptx::mbar_arrive(acc_empty_bar);
+  }
   // 3. the previous tile's stores must have finished READING the staging buffer
   if (leader) ptx::tma_store_wait_read();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -756,6 +759,139 @@ tc_einsum_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncwarp();                   // the single-lane roles rejoin their warps (cluster barrier is .aligned)
   ptx::tc_fence_before();
   ptx::cluster_sync_all();        // both CTAs are done with both TMEMs and with each other's barriers
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------- K4, CTA-pair variant
+// K/V projection with cta_group::2 MMAs: M = 256 = two 128-token tiles (one per CTA, resident, refilled chunk by
+// chunk under the last N tile), N = N_TILE weight rows of which each CTA streams HALF per chunk.  The single-CTA
+// kernel is bound by that stream (128 KB of weights per N tile through a two-stage ring); halving it per CTA and
+// doubling the ring depth moves the kernel to its HBM-write / epilogue bound.  Epilogue = epi_rowmajor.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_kv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int KC = 4;
+  const int half_n = p.N_TILE / 2;
+  const int b_stage_bytes = half_n * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + KC * A_CHUNK_BYTES;
+  uint8_t* sStage = sB + p.stages * b_stage_bytes;                       // N_TILE x 128 tokens bf16 (1024-aligned)
+  float* sBias = reinterpret_cast<float*>(sStage + (size_t)p.N_TILE * TC_BM * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.NT * p.N_TILE);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 4;
+  uint64_t* b_full = bars + 8;
+  uint64_t* b_empty = b_full + p.stages;
+  uint64_t* acc_full = b_empty + p.stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int mt2 = p.m_tiles >> 1;
+  const int n_work = mt2 * p.n_batch;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish_2sm();
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl) {
+        const int batch = w / mt2, m_tile = (w - batch * mt2) * 2 + (int)rank;
+        for (int t = 0; t < p.NT; ++t)
+          for (int kc = 0; kc < KC; ++kc, ++it) {
+            if (t == 0) {
+              if (tl > 0) ptx::mbar_wait(&a_empty[kc], (uint32_t)(tl & 1) ^ 1u);
+              if (rank == 0) ptx::mbar_expect_tx(&a_full[kc], 2u * A_CHUNK_BYTES);
+              for (int h = 0; h < 2; ++h)
+                ptx::tma_load_3d_2sm(sA + kc * A_CHUNK_BYTES + h * (A_CHUNK_BYTES / 2), &tmA, &a_full[kc],
+                                     m_tile * TC_BM + h * 64, kc * TC_BK, batch);
+            }
+            const int s = it % p.stages;
+            ptx::mbar_wait(&b_empty[s], ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+            if (rank == 0) ptx::mbar_expect_tx(&b_full[s], 2u * (uint32_t)b_stage_bytes);
+            ptx::tma_load_2d_2sm(sB + s * b_stage_bytes, &tmB, &b_full[s], kc * TC_BK, t * p.N_TILE + (int)rank * half_n);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(2 * TC_BM, p.N_TILE, /*A MN-major*/ true, /*B K-major*/ false);
+      const uint64_t ad0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), A_CHUNK_BYTES / 2, 1024);
+      const uint64_t bd0 = ptx::umma_desc_sw128(ptx::smem_u32(sB), 16, 1024);
+      const uint32_t stage16 = (uint32_t)b_stage_bytes >> 4;
+      int it = 0, g = 0, tl = 0;
+      for (int w = pair; w < n_work; w += n_pairs, ++tl)
+        for (int t = 0; t < p.NT; ++t, ++g) {
+          const int buf = g & 1;
+          ptx::mbar_wait(&acc_empty[buf], (((uint32_t)(g >> 1)) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+          for (int kc = 0; kc < KC; ++kc, ++it) {
+            const int s = it % p.stages;
+            if (t == 0) ptx::mbar_wait(&a_full[kc], (uint32_t)(tl & 1));
+            ptx::mbar_wait(&b_full[s], (uint32_t)(it / p.stages) & 1u);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t ad = ad0 + (uint64_t)(kc * (A_CHUNK_BYTES >> 4));
+              const uint64_t bd = bd0 + (uint64_t)((uint32_t)s * stage16);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                ptx::mma_bf16_ss_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+              ptx::mma_commit_2sm(&b_empty[s]);
+              if (t == p.NT - 1) ptx::mma_commit_2sm(&a_empty[kc]);
+              if (kc == KC - 1) ptx::mma_commit_2sm(&acc_full[buf]);
+            }
+            __syncwarp();
+          }
+        }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    for (int i = threadIdx.x - 64; i < p.NT * p.N_TILE; i += EPI_WARPS * 32) sBias[i] = __ldg(p.bias + i);
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    int g = 0;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      const int batch = w / mt2, m_tile = (w - batch * mt2) * 2 + (int)rank;
+      const bool last_work = w + n_pairs >= n_work;
+      EpiCtx ctx;
+      ctx.lane = lane; ctx.m = m_tile * TC_BM + quarter * 32 + lane; ctx.m_ok = ctx.m < p.M_valid; ctx.batch = batch;
+      ctx.part = part; ctx.chunks = p.N_TILE / 16; ctx.wi = 0;
+      for (int t = 0; t < p.NT; ++t, ++g) {
+        const int buf = g & 1;
+        ptx::mbar_wait(&acc_full[buf], ((uint32_t)(g >> 1)) & 1u);
+        ptx::tc_fence_after();
+        ctx.taddr = tmem_base + (uint32_t)(buf * p.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+        ctx.col0 = t * p.N_TILE;
+        epi_rowmajor(p, ctx, sStage, sBias, &tmC, warp == 2, last_work && t == p.NT - 1, m_tile, &acc_empty[buf], true);
+      }
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
   if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -1435,8 +1571,42 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(kv out) failed: " + std::to_string((int)r));
   }
+  const int m_tiles = (K + TC_BM - 1) / TC_BM;
+  static const int kv_pair = getenv("CGG_KV_PAIR") ? atoi(getenv("CGG_KV_PAIR")) : 1;
+  if (kv_pair && m_tiles % 2 == 0 && K % TC_BM == 0 && p.KC == 4) {
+    CUtensorMap mBh;
+    st = make_map_B(t, &mBh, t->wkv[level], N, C, p.N_TILE / 2);
+    if (st != CGG_OK) return st;
+    p.acc_stride = 256; p.tmem_cols = 512;
+    p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
+    const size_t stage_bytes = (size_t)p.N_TILE * TC_BM * 2, bias_bytes = (size_t)p.NT * p.N_TILE * 4;
+    const size_t b_stage = (size_t)(p.N_TILE / 2) * 128;
+    int stages = (int)((224 * 1024 - 4 * A_CHUNK_BYTES - stage_bytes - bias_bytes - 512) / b_stage);
+    if (stages > 8) stages = 8;
+    if (stages >= 3) {
+      p.stages = stages;
+      const size_t smem = 1024 + 4 * A_CHUNK_BYTES + stages * b_stage + stage_bytes + bias_bytes + (8 + 2 * stages + 4) * 8 + 64;
+      static bool attr_set = false;
+      if (!attr_set) {
+        TCU(cudaFuncSetAttribute(tc_kv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+      }
+      if (t->num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      int pairs = t->num_sms / 2;
+      if (cta_cap > 0 && pairs > cta_cap / 2) pairs = cta_cap / 2;
+      if (pairs > p.n_work / 2) pairs = p.n_work / 2;
+      TCU(launch_pdl_cluster(2, tc_kv_pair_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem, s, mA, mBh, mC, p));
+      count_launch();
+      TCU(cudaGetLastError());
+      return CGG_OK;
+    }
+  }
   t->cta_cap = cta_cap;
-  st = launch_tc_gemm(t, mA, mB, p, (K + TC_BM - 1) / TC_BM, batch, s, &mC);
+  st = launch_tc_gemm(t, mA, mB, p, m_tiles, batch, s, &mC);
   t->cta_cap = 0;
   return st;
 }
