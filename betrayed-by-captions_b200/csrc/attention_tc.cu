@@ -202,11 +202,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int s = it % AT_STAGES;
         // stage s was last used by live tile it-4: a softmax thread releases it once that tile's P V has completed
         ptx::mbar_wait(&kv_empty[s], ((uint32_t)(it / AT_STAGES) & 1u) ^ 1u);
-        ptx::mbar_expect_tx(&kv_full[s], (p.has_r ? 4 : 2) * AT_KV_TILE_BYTES);
+        ptx::mbar_expect_tx(&kv_full[s], (p.has_r ? (p.has_r > 1 ? 4 : 3) : 2) * AT_KV_TILE_BYTES);
         uint8_t* st = sKV + s * AT_STAGE_BYTES;
         if (p.has_r) {
           ptx::tma_load_2d(st + 2 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_col0 + h * 32, t * AT_KT);
-          ptx::tma_load_2d(st + 3 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_lo_off + p.r_col0 + h * 32, t * AT_KT);
+          if (p.has_r > 1) ptx::tma_load_2d(st + 3 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_lo_off + p.r_col0 + h * 32, t * AT_KT);
         }
         ptx::tma_load_3d(st, &tmK, &kv_full[s], h * 32, t * AT_KT, b);
         ptx::tma_load_3d(st + AT_KV_TILE_BYTES, &tmV, &kv_full[s], h * 32, t * AT_KT, b);
@@ -239,8 +239,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         // (R is kept as a bf16 hi/lo pair so that the table itself carries no bf16 rounding)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
-                           kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
+          if (k < 2 || p.has_r > 1)      // has_r == 1: hi part of the table only
+            ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
+                             kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
       }
     };
     for (int j = 0; j < 2 && j < n_live; ++j) {
@@ -477,7 +478,8 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   AttnP p;
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = nullptr;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
-  p.has_r = r_table ? 1 : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
+  static const int r_lo = getenv("CGG_ATTN_R_LO") ? atoi(getenv("CGG_ATTN_R_LO")) : 1;
+  p.has_r = r_table ? (r_lo ? 2 : 1) : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");
   const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + 512 + (2 * AT_STAGES + 4) * 8 + 16;
   if (!t->attn_attr_set) {
