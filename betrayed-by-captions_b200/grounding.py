@@ -96,6 +96,45 @@ class GroundingLossB200(torch.nn.Module):
         return grounding_loss(cls_emb_pred, gt_caption_embs, gt_caption_mask, temperature, self.loss_weight)
 
 
+class _SimilarityFn(torch.autograd.Function):
+    """out = scale * a @ b^T through `cgg_similarity`; both gradients are the same contraction on transposed
+    operands (da = scale * dout @ b, db = scale * dout^T @ a), so the backward uses the same entry point."""
+
+    @staticmethod
+    def _sim(a, b, scale):
+        lib, h = _Handle.get(a.device)
+        a = a.detach().float().contiguous()
+        b = b.detach().float().contiguous()
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+        stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        st = lib.cgg_similarity(h, _ptr(a), _ptr(b), a.shape[0], b.shape[0], a.shape[1], float(scale), _ptr(out), stream)
+        _lib.check(st, h, 'cgg_similarity')
+        return out
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        if not a.is_cuda:
+            raise RuntimeError('similarity runs on a CUDA device only (no CPU path)')
+        ctx.save_for_backward(a, b)
+        ctx.scale = float(scale)
+        return _SimilarityFn._sim(a, b, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _SimilarityFn._sim(g, b.t(), ctx.scale).to(a.dtype)          # (M,N) x (D,N)^T -> (M,D)
+        if ctx.needs_input_grad[1]:
+            db = _SimilarityFn._sim(g.t(), a.t(), ctx.scale).to(b.dtype)      # (N,M) x (D,M)^T -> (N,D)
+        return da, db, None
+
+
+def similarity(a, b, scale=1.0):
+    """scale * a @ b^T (`_get_cls_emb_logits`, head.py:631-648; test-time `att`, :973-978), differentiable."""
+    return _SimilarityFn.apply(a, b, scale)
+
+
 class _GatherKeepLocalGrad(torch.autograd.Function):
     """all_gather along dim `dim`; backward hands the local slot's gradient back (the other slots are
     detached copies, exactly like the re-insertion at `mask2former_head.py:678`)."""

@@ -141,10 +141,10 @@ class Mask2FormerHeadOpenB200(nn.Module):
     # -------------------------------------------------------------- grounding-side helpers
     def _get_cls_emb_logits(self, cls_emb_preds):
         """head.py:631-648."""
-        rt = self._runtime(cls_emb_preds.device)
+        from .grounding import similarity
         B, Q, D = cls_emb_preds.shape
-        return rt.similarity(cls_emb_preds.reshape(B * Q, D), self.class_embs,
-                             1.0 / float(self.softmax_temperature)).view(B, Q, -1)
+        return similarity(cls_emb_preds.reshape(B * Q, D), self.class_embs,
+                          1.0 / float(self.softmax_temperature)).view(B, Q, -1)
 
     def test_time_att(self, mask_cls_emb_results, nouns_embs):
         """simple_test `att`, head.py:973-978."""

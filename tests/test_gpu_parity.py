@@ -237,6 +237,23 @@ def test_grounding_loss_gradient_matches_reference_golden(name):
     torch.testing.assert_close(p2.grad, p_dev.grad * 0.25, rtol=1e-6, atol=0)
 
 
+def test_class_embedding_logits_are_differentiable():
+    """`_get_cls_emb_logits` (head.py:631-648) through cgg_similarity: value and both gradients vs torch."""
+    from cgg_b200.grounding import similarity
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn((200, 768), generator=g)
+    b = torch.randn((49, 768), generator=g)
+    w = torch.randn((200, 49), generator=g)
+    a_ref, b_ref = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ((a_ref @ b_ref.t()) * 0.1 * w).sum().backward()
+    a_d, b_d = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    out = similarity(a_d, b_d, 0.1)
+    (out * w.to(DEV)).sum().backward()
+    torch.testing.assert_close(out.detach().cpu(), (a @ b.t()) * 0.1, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(a_d.grad.cpu(), a_ref.grad, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(b_d.grad.cpu(), b_ref.grad, rtol=1e-5, atol=1e-4)
+
+
 def test_embedding_side_matches_reference_golden():
     gold = np.load(os.path.join(GOLD, 'embeddings.npz'))
     sd = synth.make_params(seed=9, num_queries=16)
