@@ -55,6 +55,7 @@ struct TcGemmP {
   int epi;
   int dbg;
   int f16;               // 1: operands are IEEE half instead of bf16 (attention-mask GEMM)
+  int ein_split, q_rows; // transposed einsum: 0 = two head calls per step (q_rows = q_pad rows each CTA), 1 = one call per step, CTA r takes rows [r q_rows, (r+1) q_rows)
   int M_valid;           // valid pixels / keys per batch image (features for EPI_LINEAR_T)
   int m_tiles, n_batch, n_work;   // A-resident kinds are persistent: CTA c walks work items c, c+grid, ... of m_tiles*n_batch
   // EPI_MASK_T
@@ -912,8 +913,8 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = 4;
-  const int e_chunk_bytes = p.q_pad * 128;                // q_pad rows x 64 k
-  const int sub_bytes = p.q_pad * 128;                    // staging sub-tile: q_pad rows x 64 px
+  const int e_chunk_bytes = p.q_rows * 128;               // this CTA's query rows x 64 k
+  const int sub_bytes = p.q_rows * 128;                   // staging sub-tile: query rows x 64 px
   uint8_t* sF = smem;                                     // features of this CTA's 128 pixels: 4 chunks of 16 KB
   uint8_t* sE = sF + KC * A_CHUNK_BYTES;                  // [2 step slots][KC chunks]
   uint8_t* sStage = sE + 2 * KC * e_chunk_bytes;          // 4 sub-tiles (q_pad * 128 is a multiple of 1024)
@@ -930,7 +931,8 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int mt2 = p.m_tiles >> 1;                         // 256-pixel tiles per image
   const int n_work = mt2 * p.n_batch;
-  const int NS = (p.n_calls + 1) >> 1;                    // steps: two head calls each
+  const int NS = p.ein_split ? p.n_calls : (p.n_calls + 1) >> 1;   // steps: two head calls each (or one, split over the pair)
+  const int q0 = p.ein_split ? (int)rank * p.q_rows : 0;  // first query row of this CTA within its call
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmF);
@@ -961,7 +963,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         for (int t = 0; t < NS; ++t, ++g) {
           const int slot = g & 1;
           if (g >= 2) ptx::mbar_wait(&acc_full[slot], (uint32_t)((g - 2) >> 1) & 1u);   // MMAs of step g-2 done
-          const int call = 2 * t + (int)rank;
+          const int call = p.ein_split ? t : 2 * t + (int)rank;
           for (int kc = 0; kc < KC; ++kc) {
             if (t == 0) {
               if (tl > 0) ptx::mbar_wait(&f_empty[kc], (uint32_t)(tl & 1) ^ 1u);
@@ -973,7 +975,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
             uint64_t* bar = &e_full[slot * KC + kc];
             if (rank == 0) ptx::mbar_expect_tx(bar, 2u * (uint32_t)e_chunk_bytes);
             ptx::tma_load_2d_2sm(sE + (slot * KC + kc) * e_chunk_bytes, &tmE, bar, kc * TC_BK,
-                                 batch * p.b_rows_per_batch + p.b_row0 + call * p.q_pad);
+                                 batch * p.b_rows_per_batch + p.b_row0 + call * p.q_pad + q0);
           }
         }
       }
@@ -1016,7 +1018,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;                       // 16-pixel chunk `part` of every 64-pixel sub-tile
     const int row = quarter * 32 + lane;
-    const bool row_ok = row < p.q_pad;
+    const bool row_ok = row < p.q_rows;
     const bool leader = warp == 2 && lane == 0;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     int g = 0;
@@ -1026,7 +1028,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
       for (int t = 0; t < NS; ++t, ++g) {
         const int buf = g & 1;
         const uint32_t use = (uint32_t)(g >> 1);
-        const int call = 2 * t + (int)rank;
+        const int call = p.ein_split ? t : 2 * t + (int)rank;
         ptx::mbar_wait(&acc_full[buf], use & 1u);
         ptx::tc_fence_after();
         // 1. accumulator -> registers: sub-tile j, pixels 64 j + 16 part .. + 15
@@ -1067,7 +1069,7 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         if (leader) {
           if (call < p.n_calls)
             for (int j = 0; j < 4; ++j)
-              ptx::tma_store_3d(&tmC, sStage + j * sub_bytes, px_pair + j * 64, 0, call * p.n_batch + batch);
+              ptx::tma_store_3d(&tmC, sStage + j * sub_bytes, px_pair + j * 64, q0, call * p.n_batch + batch);
           ptx::tma_store_commit();
           if (last_work && t == NS - 1) ptx::tma_store_wait_read();
         }
@@ -1774,18 +1776,20 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
   }
   const int m_tiles = (int)((HW + TC_BM - 1) / TC_BM);
   static const int use_t = getenv("CGG_EIN_T") ? atoi(getenv("CGG_EIN_T")) : 1;
-  if (use_t && m_tiles % 2 == 0 && HW % (2 * TC_BM) == 0 && t->q_pad <= 128 && t->q_pad % 8 == 0 && p.KC == 4 && C == 256) {
+  const bool t_split = t->q_pad > 128;      // one head call per step, its rows split over the CTA pair (Q up to 256)
+  const int t_rows = t_split ? t->q_pad / 2 : t->q_pad;
+  if (use_t && m_tiles % 2 == 0 && HW % (2 * TC_BM) == 0 && t->q_pad <= 256 && t_rows % 8 == 0 && t_rows <= 128 && p.KC == 4 && C == 256) {
     // transposed CTA-pair kernel: queries on the TMEM lanes, pixels on the columns
-    const size_t e_chunk = (size_t)t->q_pad * 128;
+    const size_t e_chunk = (size_t)t_rows * 128;
     const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * e_chunk + 4 * e_chunk + 24 * 8 + 64;
     if (smem <= 227 * 1024) {
       CUtensorMap mE, mCt;
-      st = make_map_B(t, &mE, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t->q_pad);
+      st = make_map_B(t, &mE, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t_rows);
       if (st != CGG_OK) return st;
       {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)Q, (cuuint64_t)num_calls * batch};
         cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)Q * HW * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)t->q_pad, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)t_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = t->encode(&mCt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1793,7 +1797,7 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
         if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out, swizzled) failed: " + std::to_string((int)r));
       }
       p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
-      p.dbg = 0;
+      p.dbg = 0; p.ein_split = t_split ? 1 : 0; p.q_rows = t_rows;
       static bool attr_set_t = false;
       if (!attr_set_t) {
         TCU(cudaFuncSetAttribute(tc_einsum_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
