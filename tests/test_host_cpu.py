@@ -43,6 +43,15 @@ def test_sass_is_sm100a_only():
     assert archs == {'100a'}, archs
 
 
+def test_sass_uses_blackwell_tensor_and_tma_paths():
+    """The library's SASS carries tcgen05 MMAs (single-CTA and CTA-pair), TMEM loads, TMA loads and stores."""
+    import subprocess
+    sass = subprocess.run(['cuobjdump', '-sass', clib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'UTCHMMA.2CTA', 'UTCBAR.2CTA.MULTICAST', 'LDTM', 'UTMALDG.3D', 'UTMALDG.2D.2CTA', 'UTMASTG.3D'):
+        assert mnemonic in sass, mnemonic
+    assert 'HMMA.16816' not in sass and 'WGMMA' not in sass      # no mma.sync / wgmma fallbacks
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
 def test_no_cpu_fallback(lib):
     h = C.c_void_p()
