@@ -195,7 +195,8 @@ def run_b200_arm(args):
     Q, B = args.queries, args.batch
     dt_in = torch.bfloat16 if args.precision == 'bf16' else torch.float32
     sd = synth.make_params(seed=0, num_queries=Q)
-    head = build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph)
+    head = build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph,
+                                      final_mask_only=args.final_mask_only)
     # synthetic pixel-decoder outputs, per-rank seed; kept in PINNED host memory for the e2e leg
     mf_h, mems_h = synth.make_inputs(rank, B, H, W, dtype=dt_in)
     mf_h = mf_h.pin_memory()
@@ -208,7 +209,8 @@ def run_b200_arm(args):
     # slot, steps issued round-robin.  The layer chain of a step is latency-bound, so the
     # chain of one batch fills the SMs the other leaves idle; every step is still a full forward of B images.
     n_fly = max(1, args.in_flight)
-    heads = [head] + [build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph)
+    heads = [head] + [build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph,
+                                                 final_mask_only=args.final_mask_only)
                       for _ in range(n_fly - 1)]
     fly_in = [(mf_d, mems_d)] + [(mf_d.clone(), [m.clone() for m in mems_d]) for _ in range(n_fly - 1)]
     fly_streams = [torch.cuda.Stream() for _ in range(n_fly)]
@@ -392,6 +394,7 @@ def run_b200_arm(args):
                                          '1024x1024, batch %d per GPU' % (Q, B),
                                 batch_per_gpu=B, global_batch=B * world, precision=args.precision,
                                 cuda_graph=not args.no_graph, in_flight_batches=n_fly,
+                                final_mask_only=bool(args.final_mask_only),
                                 single_batch_latency_ms=latency_ms,
                                 l2='inputs (%.0f MB per step) larger than L2, no explicit flush' % (h2d / 1e6),
                                 flops_per_image=flops_per_image(Q)),
@@ -415,6 +418,8 @@ def main():
     ap.add_argument('--queries', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the path eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--final-mask-only', action='store_true',
+                    help='opt-in inference shortcut: produce the last head call mask only (NOT the headline contract)')
     ap.add_argument('--in-flight', type=int, default=2,
                     help='batches in flight in the device-resident throughput leg (one head + stream each)')
     args = ap.parse_args()

@@ -34,6 +34,7 @@ struct cgg_handle {
   bool overlap = false;      // CGG_OVERLAP: K/V levels 1,2 and the early mask einsums on helper streams (slower, debug)
   bool overlap_kv = false;   // K/V levels 1,2 on a helper stream on a capped number of SMs
   int kv_cta_cap = 0;
+  bool final_mask_only = false;   // cgg_set_final_mask_only
   void free_tables() {
     for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
       cudaFree(pos_level[l]); cudaFree(wkv[l]); cudaFree(rk[l]); cudaFree(bkv[l]);
@@ -477,6 +478,14 @@ static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, in
   return CGG_OK;
 }
 
+extern "C" int cgg_set_final_mask_only(cgg_handle* h, int on) {
+  if (!h) return CGG_ERR_NULL;
+  if (on && h->cfg.precision != CGG_BF16) return fail(h, CGG_ERR_UNSUPPORTED, "final-mask-only is a CGG_BF16 option");
+  if (on && h->overlap) return fail(h, CGG_ERR_UNSUPPORTED, "final-mask-only excludes CGG_OVERLAP");
+  h->final_mask_only = on != 0;
+  return CGG_OK;
+}
+
 // ========================================================================== whole path
 extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batch, const void* mask_features,
                                    const void* const memories[CGG_NUM_LEVELS], float* cls, float* emb, void* mask,
@@ -553,7 +562,11 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
                             /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm));
     }
   }
-  if (tcm) {
+  if (tcm && h->final_mask_only) {
+    // inference shortcut: the last head call's logits only, into a (B,Q,H4,W4) buffer
+    int st = tc_mask_einsum(h->tc, batch, L, 1, mask_features, mask, (long)batch * Q * HW, tws, s);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
+  } else if (tcm) {
     // K2 of the remaining head calls (all L+1 in one pass over mask_features when nothing was overlapped)
     int st = tc_mask_einsum(h->tc, batch, einsum_done, L + 1 - einsum_done, mask_features,
                             static_cast<char*>(mask) + (size_t)einsum_done * batch * Q * HW * mask_elt,

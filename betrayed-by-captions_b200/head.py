@@ -72,9 +72,12 @@ class Mask2FormerHeadOpenB200(nn.Module):
     def __init__(self, in_channels=None, feat_channels=256, out_channels=256, num_things_classes=80,
                  num_stuff_classes=53, num_queries=100, num_transformer_feat_level=3, pixel_decoder=None,
                  enforce_decoder_input_project=False, transformer_decoder=None, positional_encoding=None,
-                 precision='fp32', d_lang=768, cuda_graph=False, **kwargs):
+                 precision='fp32', d_lang=768, cuda_graph=False, final_mask_only=False, **kwargs):
         super().__init__()
         self.cuda_graph = bool(cuda_graph)
+        # inference shortcut (opt-in, bf16 mode): only the last head call's mask logits are produced; the mask list
+        # then holds None for the intermediate head calls (only [-1] is consumed at test time, head.py:943-945)
+        self.final_mask_only = bool(final_mask_only)
         if num_transformer_feat_level != 3:
             raise ValueError('the B200 path is built for 3 feature levels (1/32, 1/16, 1/8)')
         if enforce_decoder_input_project or feat_channels != out_channels:
@@ -310,7 +313,10 @@ class _Runtime:
             dev = self.device
             cls = torch.empty((L + 1, B, Q, h.num_classes + 1), dtype=torch.float32, device=dev)
             emb = torch.empty((L + 1, B, Q, h.d_lang), dtype=torch.float32, device=dev)
-            mask = torch.empty((L + 1, B, Q, H4, W4), dtype=mf.dtype, device=dev)
+            n_maps = 1 if (h.final_mask_only and not return_debug) else L + 1
+            mask = torch.empty((n_maps, B, Q, H4, W4), dtype=mf.dtype, device=dev)
+            _lib.check(self.lib.cgg_set_final_mask_only(self.handle, int(n_maps == 1)), self.handle,
+                       'cgg_set_final_mask_only')
             mem_ptrs = (C.c_void_p * 3)(*[m.data_ptr() for m in mems])
             xs = bms = am = None
             xs_p, bm_p, am_p = None, None, None
@@ -325,7 +331,8 @@ class _Runtime:
                                               _ptr(emb), _ptr(mask), xs_p, bm_p, am_p, _ptr(self.workspace),
                                               self.workspace.numel(), self._stream())
             _lib.check(st, self.handle, 'cgg_decoder_forward')
-        outs = (list(cls.unbind(0)), list(emb.unbind(0)), list(mask.unbind(0)))
+        masks = list(mask.unbind(0)) if mask.shape[0] == L + 1 else [None] * L + [mask[0]]
+        outs = (list(cls.unbind(0)), list(emb.unbind(0)), masks)
         if return_debug:
             return outs + (dict(x=xs, bitmaps=bms, all_masked=am),)
         return outs
@@ -429,10 +436,11 @@ class _Runtime:
 
 
 def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9,
-                               cuda_graph=False):
+                               cuda_graph=False, final_mask_only=False):
     """Convenience used by tests / bench: a head carrying the given (reference-keyed) weights."""
     head = Mask2FormerHeadOpenB200(num_things_classes=num_classes_p1 - 1, num_stuff_classes=0,
                                    num_queries=num_queries, precision=precision, cuda_graph=cuda_graph,
+                                   final_mask_only=final_mask_only,
                                    transformer_decoder=dict(num_layers=num_layers))
     missing = head.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys

@@ -15,7 +15,7 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            'cgg_decoder_forward', 'cgg_kv_project', 'cgg_head_call', 'cgg_attn_mask_from_logits',
            'cgg_decoder_layer', 'cgg_mask_einsum', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
            'cgg_grounding_scratch_bytes', 'cgg_grounding_loss', 'cgg_grounding_bwd_scratch_bytes',
-           'cgg_grounding_loss_backward']
+           'cgg_grounding_loss_backward', 'cgg_set_final_mask_only']
 
 
 class Config(C.Structure):
@@ -78,6 +78,7 @@ def load():
     lib.cgg_grounding_scratch_bytes.argtypes = [i, i, i]
     lib.cgg_grounding_scratch_bytes.restype = sz
     lib.cgg_grounding_loss.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_float, C.c_float, vp, vp, sz, vp]
+    lib.cgg_set_final_mask_only.argtypes = [vp, i]
     lib.cgg_grounding_bwd_scratch_bytes.argtypes = [i, i, i]
     lib.cgg_grounding_bwd_scratch_bytes.restype = sz
     lib.cgg_grounding_loss_backward.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_float, C.c_float, C.c_float, vp, vp, sz, vp]

@@ -210,6 +210,12 @@ int cgg_grounding_loss(cgg_handle *h, const float *pred, const float *cap, const
                        int Bg, int Q, int T, int D, float temperature, float loss_weight,
                        float *loss, void *scratch, size_t scratch_bytes, void *stream);
 
+/* Inference shortcut (opt-in, changes the output contract): only the LAST head call's mask
+ * logits are consumed at test time (mask2former_head.py:943-945).  With the option on, cgg_decoder_forward writes
+ * that one map only -- `mask` then points to a (B,Q,H4,W4) buffer -- and the mask einsum of the nine intermediate
+ * head calls is skipped (their attention-mask bits never needed full-resolution logits).  CGG_BF16 only. */
+int cgg_set_final_mask_only(cgg_handle *h, int on);
+
 /* K7 backward: d loss / d pred (Bg,Q,D) fp32 of the same loss, times grad_out (the upstream scalar gradient).
  * Captions are frozen BERT embeddings in the reference (head.py:251-254), so no caption gradient is produced.
  * scratch: >= cgg_grounding_bwd_scratch_bytes(Bg,Q,T) bytes. */

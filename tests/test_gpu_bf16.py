@@ -94,6 +94,21 @@ def test_bf16_free_running_final_outputs():
     assert _rel(logits, want_l) < 3 * REL_TOL
 
 
+def test_bf16_final_mask_only_matches_full_forward():
+    """Opt-in inference shortcut: same class / embedding outputs and the same final mask, bit for bit; the nine
+    intermediate masks are not produced."""
+    Q, B, H, W = 100, 2, 256, 256
+    sd, mf, mems, head = _setup(Q, B, H, W, 35, 11)
+    mfd, memd = mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems]
+    cls, emb, mask = head.decoder_forward(mfd, memd)
+    fast = build_head_from_state_dict(sd, Q, 49, 'bf16', DEV, final_mask_only=True)
+    cls2, emb2, mask2 = fast.decoder_forward(mfd, memd)
+    assert all(m is None for m in mask2[:-1]) and len(mask2) == 10
+    assert torch.equal(mask2[-1], mask[-1])
+    for a, b in zip(cls + emb, cls2 + emb2):
+        assert torch.equal(a, b)
+
+
 def test_bf16_batched_einsum_equals_per_call_einsum():
     """The all-calls-in-one-pass einsum (A tile resident) must equal the per-call stage output."""
     Q, B, H, W = 100, 2, 256, 256
