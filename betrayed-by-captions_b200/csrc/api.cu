@@ -135,7 +135,6 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
       cfg->d_lang < 1)
     return CGG_ERR_BAD_SHAPE;
   if (cfg->precision != CGG_FP32 && cfg->precision != CGG_BF16) return CGG_ERR_UNSUPPORTED;
-  if (cfg->pred_emb_norm) return CGG_ERR_UNSUPPORTED;  // off in every shipped config (coco_b48n17.py:151)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CGG_ERR_CUDA;  // no CPU fallback
   cgg_handle* h = new (std::nothrow) cgg_handle();
@@ -339,6 +338,7 @@ static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const 
   ST(linear_rows(h, s, h1, nullptr, 1, w->me_w[1], w->me_b[1], h2, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h2, nullptr, 1, w->me_w[2], w->me_b[2], me, rows, C, C));
   }
+  if (c.pred_emb_norm) CU(launch_l2norm_rows(emb, rows, c.d_lang, s));   // head.py:743-744 (off in every shipped config)
   if (c.precision == CGG_BF16) {
     void* tws = at<void>(workspace, ws.tcws);
 #define TC(call)                                                                                \

@@ -57,6 +57,8 @@ cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, b
 cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const int64_t* cap_mask,
                                    int Bg, int Q, int T, int D, float temperature,
                                    float* g_l2v, float* g_v2l, cudaStream_t s);
+// in-place L2 normalisation of rows (pred_emb_norm, head.py:743-744)
+cudaError_t launch_l2norm_rows(float* x, int rows, int D, cudaStream_t s);
 cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
                                     int Bg, int T, float loss_weight, float* loss, cudaStream_t s,
                                     float* dg_l2v = nullptr, float* dg_v2l = nullptr);

@@ -606,6 +606,24 @@ cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, cons
   return cudaGetLastError();
 }
 
+// x[row, :] /= ||x[row, :]||_2 in place (pred_emb_norm, head.py:743-744); one warp per row
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x, int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = x + (long)row * D;
+  float ss = 0.f;
+  for (int i = lane; i < D; i += 32) ss = fmaf(r[i], r[i], ss);
+  ss = warp_sum(ss);
+  const float n = sqrtf(ss);
+  for (int i = lane; i < D; i += 32) r[i] = r[i] / n;
+}
+
+cudaError_t launch_l2norm_rows(float* x, int rows, int D, cudaStream_t s) {
+  l2norm_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, D);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------- cast
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -436,11 +436,11 @@ class _Runtime:
 
 
 def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9,
-                               cuda_graph=False, final_mask_only=False):
+                               cuda_graph=False, final_mask_only=False, **kwargs):
     """Convenience used by tests / bench: a head carrying the given (reference-keyed) weights."""
     head = Mask2FormerHeadOpenB200(num_things_classes=num_classes_p1 - 1, num_stuff_classes=0,
                                    num_queries=num_queries, precision=precision, cuda_graph=cuda_graph,
-                                   final_mask_only=final_mask_only,
+                                   final_mask_only=final_mask_only, **kwargs,
                                    transformer_decoder=dict(num_layers=num_layers))
     missing = head.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys

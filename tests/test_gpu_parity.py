@@ -237,6 +237,26 @@ def test_grounding_loss_gradient_matches_reference_golden(name):
     torch.testing.assert_close(p2.grad, p_dev.grad * 0.25, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_pred_emb_norm(precision):
+    """head.py:743-744: unit-norm embedding predictions, both modes, against the oracle."""
+    Q, B = 32, 2
+    sd = synth.make_params(seed=12, num_queries=Q, perturb=True)
+    mf, mems = synth.make_inputs(12, B, 256, 256)
+    if precision == 'bf16':
+        mf, mems = mf.bfloat16().float(), [m.bfloat16().float() for m in mems]
+    ref = O.decoder_forward(sd, mf, mems, pred_emb_norm=True)
+    head = build_head_from_state_dict(sd, Q, 49, precision, DEV, pred_emb_norm=True)
+    dt = torch.float32 if precision == 'fp32' else torch.bfloat16
+    cls, emb, mask = head.decoder_forward(mf.to(DEV).to(dt), [m.to(DEV).to(dt) for m in mems])
+    for j in (0, 9):
+        scale = float(ref['emb'][j].abs().max())
+        # fp32: absolute; bf16: relative to the largest component (free-running at j = 9, hence the wider band)
+        tol = 2e-5 if precision == 'fp32' else (1e-2 if j == 0 else 5e-2) * scale
+        assert float((emb[j].cpu() - ref['emb'][j]).abs().max()) <= tol
+        assert float((emb[j].norm(dim=-1) - 1).abs().max()) < 1e-5
+
+
 def test_class_embedding_logits_are_differentiable():
     """`_get_cls_emb_logits` (head.py:631-648) through cgg_similarity: value and both gradients vs torch."""
     from cgg_b200.grounding import similarity

@@ -126,3 +126,21 @@ def test_oracle_matches_live_reference():
         assert float((ref[0][j] - out['cls'][j]).abs().max()) < TOL
         assert float((ref[1][j] - out['emb'][j]).abs().max()) < TOL
         assert float((ref[2][j] - out['mask'][j]).abs().max()) < 5e-5
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='reference tree only exists in the build container')
+def test_oracle_pred_emb_norm_matches_live_reference():
+    """head.py:743-744: the optional L2 normalisation of the embedding predictions."""
+    R = ref_shim.REF_ROOT
+    head = ref_shim.build_reference_head(num_queries=24, known_file=R + '/datasets/unknown/known_65.txt',
+                                         unknown_file=R + '/datasets/unknown/unknown_17.txt')
+    sd = synth.make_params(seed=22, num_queries=24, perturb=True)
+    head.load_state_dict(sd, strict=True)
+    head.pred_emb_norm = True
+    mf, mems = synth.make_inputs(10, 1, 64, 64)
+    ref = ref_shim.run_reference_head(head, mf, mems)
+    out = O.decoder_forward(sd, mf, mems, pred_emb_norm=True)
+    for j in range(10):
+        assert float((ref[1][j] - out['emb'][j]).abs().max()) < TOL
+        assert float((out['emb'][j].norm(dim=-1) - 1).abs().max()) < 1e-5
+
