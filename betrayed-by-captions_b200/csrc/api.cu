@@ -30,7 +30,7 @@ struct cgg_handle {
   // from the caller's stream with events and joined back before the call's work ends on it.
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_kv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};
+  cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};   // CGG_OVERLAP: head call j done; default mode: fork of layer j's q projection
   bool overlap = false;      // CGG_OVERLAP: K/V levels 1,2 and the early mask einsums on helper streams (slower, debug)
   bool overlap_kv = false;   // K/V levels 1,2 on a helper stream on a capped number of SMs
   int kv_cta_cap = 0;
@@ -411,7 +411,8 @@ extern "C" int cgg_masked_attention(cgg_handle* h, int batch, int num_keys, cons
 
 static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
                               const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
-                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out);
+                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out,
+                              bool q_ready = false);
 
 extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
                                  const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
@@ -422,7 +423,7 @@ extern "C" int cgg_decoder_layer(cgg_handle* h, const cgg_weights* w, int batch,
 
 static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, int layer, const float* x_in,
                               const uint32_t* bitmap, const uint8_t* all_masked, float* x_out, void* workspace,
-                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out) {
+                              size_t workspace_bytes, void* stream, bool chained_in, bool chained_out, bool q_ready) {
   if (!h || !w || !x_in || !x_out) return CGG_ERR_NULL;
   cudaStream_t s = (cudaStream_t)stream;
   Workspace ws;
@@ -436,7 +437,7 @@ static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, in
     const long kvs = (long)n * 2 * C, kvb = (long)K * kvs;
     const __nv_bfloat16* kv = at<__nv_bfloat16>(workspace, ws.kv[l]);
     int st = tc_decoder_layer(h->tc, w, batch, layer, x_in, kv + (size_t)sl * C, kv + (size_t)(n + sl) * C, kvs, kvb, K,
-                              bitmap, all_masked, x_out, at<void>(workspace, ws.tcws), s, chained_in, chained_out);
+                              bitmap, all_masked, x_out, at<void>(workspace, ws.tcws), s, chained_in, chained_out, q_ready);
     if (st != CGG_OK) return fail(h, st, std::string("tc_decoder_layer: ") + tc_last_error(h->tc));
     return CGG_OK;
   }
@@ -535,8 +536,18 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
   }
   CU(launch_broadcast_rows(w->query_feat, xs, batch, Q, C, s));          // head.py:808-809
   int einsum_done = 0;   // head calls whose mask einsum has been enqueued (helper stream)
+  static const bool q_branch = getenv("CGG_Q_BRANCH") ? atoi(getenv("CGG_Q_BRANCH")) != 0 : true;
   for (int j = 0; j <= L; ++j) {
     const bool need_mask = j < L;                                           // the last mask is never used
+    // layer j's query projection needs the decoder state only: it runs on a helper stream underneath head call j
+    const bool q_par = q_branch && ovl_kv && tcm && j > 0 && j < L;
+    if (q_par) {
+      CU(cudaEventRecord(h->ev_me[j], s));
+      CU(cudaStreamWaitEvent(h->side[1], h->ev_me[j], 0));
+      int st = tc_layer_qproj(h->tc, w, batch, j, tws, h->side[1]);
+      if (st != CGG_OK) return fail(h, st, std::string("tc_layer_qproj: ") + tc_last_error(h->tc));
+      CU(cudaEventRecord(h->ev_join[1], h->side[1]));
+    }
     uint32_t* bm = need_mask ? ((bitmaps && bitmaps[j]) ? bitmaps[j] : at<uint32_t>(workspace, ws.bitmap)) : nullptr;
     uint8_t* am = need_mask ? (all_masked ? all_masked + (size_t)j * batch * Q : at<uint8_t>(workspace, ws.allm))
                             : nullptr;
@@ -558,8 +569,9 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     if (j < L) {
       const int lvl = j % CGG_NUM_LEVELS;
       if ((ovl || ovl_kv) && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
+      if (q_par) CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
       ST(decoder_layer_impl(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream,
-                            /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm));
+                            /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm, /*q_ready=*/q_par));
     }
   }
   if (tcm && h->final_mask_only) {

@@ -74,7 +74,8 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
 int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
                      const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,
                      const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s, bool chained_in = false,
-                     bool chained_out = false);
+                     bool chained_out = false, bool q_ready = false);
+int tc_layer_qproj(TcState* t, const cgg_weights* w, int batch, int layer, void* ws, cudaStream_t s);
 // me_f32 == nullptr: the mask embeddings go straight into the all-call hi/lo operand (slot call_slot)
 // from the last GEMM's epilogue; z_ready: post_norm(x) is already in the workspace.
 int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, float* cls, float* emb, float* me_f32,

@@ -252,7 +252,8 @@ int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, 
 // K5 + K6: one DetrTransformerDecoderLayer (head.py:829-840), bf16 operands on tensor cores.
 int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, const float* x_in, const void* k,
                      const void* v, long kv_stride, long kv_bstride, int num_keys, const uint32_t* bitmap,
-                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s, bool chained_in, bool chained_out) {
+                     const uint8_t* all_masked, float* x_out, void* ws, cudaStream_t s, bool chained_in, bool chained_out,
+                     bool q_ready) {
   const cgg_config& c = t->cfg;
   const int C = c.embed_dim, Q = c.num_queries, M = batch * Q, F = c.ffn_dim;
   const cgg_layer_weights& lw = w->layers[layer];
@@ -278,8 +279,10 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
     count_launch();
     TCU(cudaGetLastError());
   }
-  TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
-  TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
+  if (!q_ready) {      // (q_ready: tc_layer_qproj already ran, on a branch parallel to the head call)
+    TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
+    TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
+  }
   {
     const int level = layer % CGG_NUM_LEVELS, slot = layer / CGG_NUM_LEVELS;
     long rcols = 0;
@@ -315,6 +318,20 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   else
     TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, nullptr, nullptr, 0, nullptr, s, nullptr, nullptr,
                        kparts, pstride));
+  return CGG_OK;
+}
+
+// The cross-attention query projection of `layer` from the bf16 (x + query_embed) copy the previous layer left in
+// the workspace.  It depends on the decoder state only, not on the head call, so the whole-path entry point runs
+// it on a helper stream underneath the head call's six kernels.
+int tc_layer_qproj(TcState* t, const cgg_weights* w, int batch, int layer, void* ws, cudaStream_t s) {
+  const cgg_config& c = t->cfg;
+  const int C = c.embed_dim, M = batch * c.num_queries;
+  const float qscale = 1.0f / sqrtf((float)(C / c.num_heads));
+  TcWs o;
+  o.carve(t, batch);
+  TcSeg sq[1] = {seg(0, C, at<float>(ws, o.qf), C, false, false, qscale)};
+  TST(tc_linear(t, at<__nv_bfloat16>(ws, o.xqb), M, C, t->pl[layer].wq_c, C, w->layers[layer].cross_in_b, sq, 1, s));
   return CGG_OK;
 }
 
