@@ -131,8 +131,9 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
   *out = nullptr;
   if (cfg->embed_dim != 256 || cfg->num_heads != 8) return CGG_ERR_UNSUPPORTED;
   if (cfg->num_layers < 1 || cfg->num_layers > CGG_MAX_LAYERS) return CGG_ERR_BAD_SHAPE;
+  // d_lang == 0: no v2l_transform (use_class_emb=False, head.py:739-744): the embedding output is not produced
   if (cfg->num_queries < 1 || cfg->num_queries > 1024 || cfg->ffn_dim < 1 || cfg->num_classes_p1 < 1 ||
-      cfg->d_lang < 1)
+      cfg->d_lang < 0 || (cfg->d_lang == 0 && cfg->pred_emb_norm))
     return CGG_ERR_BAD_SHAPE;
   if (cfg->precision != CGG_FP32 && cfg->precision != CGG_BF16) return CGG_ERR_UNSUPPORTED;
   int ndev = 0;
@@ -193,6 +194,7 @@ extern "C" int cgg_prepare(cgg_handle* h, const cgg_weights* w, int H4, int W4, 
     // (re)allocation is the only place that may synchronise; steady-state re-prepare
     // (new weights, same sizes) reuses the tables and stays asynchronous.
     CU(cudaStreamSynchronize(s));
+    h->prepared = false;     // stays false until every table below exists (a failed re-prepare must not leave a usable handle)
     h->free_tables();
     h->H4 = H4; h->W4 = W4;
     for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
@@ -314,7 +316,7 @@ static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const 
                           int target_level, float* cls, float* emb, void* mask, float* mask_embed_out,
                           uint32_t* bitmap, uint8_t* all_masked, void* workspace, size_t workspace_bytes,
                           cudaStream_t s, int call_slot, bool defer_einsum, bool fds_ready, bool z_ready = false) {
-  if (!h || !w || !x || !mask_features || !cls || !emb) return CGG_ERR_NULL;
+  if (!h || !w || !x || !mask_features || !cls || (!emb && h->cfg.d_lang > 0)) return CGG_ERR_NULL;
   if (!mask && !defer_einsum) return CGG_ERR_NULL;
   Workspace ws;
   ST(check_ws(h, batch, workspace, workspace_bytes, ws));
@@ -333,12 +335,13 @@ static int head_call_impl(cgg_handle* h, const cgg_weights* w, int batch, const 
   } else {
   CU(launch_layernorm(x, nullptr, w->post_norm_w, w->post_norm_b, z, rows, C, 1e-5f, true, s));
   ST(linear_rows(h, s, z, nullptr, 1, w->cls_w, w->cls_b, cls, rows, c.num_classes_p1, C));
-  ST(linear_rows(h, s, z, nullptr, 1, w->v2l_w, w->v2l_b, emb, rows, c.d_lang, C));
+  if (c.d_lang > 0) ST(linear_rows(h, s, z, nullptr, 1, w->v2l_w, w->v2l_b, emb, rows, c.d_lang, C));
   ST(linear_rows(h, s, z, nullptr, 1, w->me_w[0], w->me_b[0], h1, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h1, nullptr, 1, w->me_w[1], w->me_b[1], h2, rows, C, C, 1.f, nullptr, true));
   ST(linear_rows(h, s, h2, nullptr, 1, w->me_w[2], w->me_b[2], me, rows, C, C));
   }
-  if (c.pred_emb_norm) CU(launch_l2norm_rows(emb, rows, c.d_lang, s));   // head.py:743-744 (off in every shipped config)
+  // head.py:743-744; on in the class-agnostic pre-training configs, which run with use_class_emb=False (d_lang == 0 here)
+  if (c.pred_emb_norm && c.d_lang > 0) CU(launch_l2norm_rows(emb, rows, c.d_lang, s));
   if (c.precision == CGG_BF16) {
     void* tws = at<void>(workspace, ws.tcws);
 #define TC(call)                                                                                \
@@ -492,7 +495,7 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
                                    const void* const memories[CGG_NUM_LEVELS], float* cls, float* emb, void* mask,
                                    float* x_states, uint32_t* const* bitmaps, uint8_t* all_masked, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  if (!h || !w || !mask_features || !memories || !cls || !emb || !mask) return CGG_ERR_NULL;
+  if (!h || !w || !mask_features || !memories || !cls || (!emb && h->cfg.d_lang > 0) || !mask) return CGG_ERR_NULL;
   cudaStream_t s = (cudaStream_t)stream;
   Workspace ws;
   ST(check_ws(h, batch, workspace, workspace_bytes, ws));
@@ -552,7 +555,7 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     uint8_t* am = need_mask ? (all_masked ? all_masked + (size_t)j * batch * Q : at<uint8_t>(workspace, ws.allm))
                             : nullptr;
     ST(head_call_impl(h, w, batch, xs + j * bqc, mask_features, j % CGG_NUM_LEVELS,
-                      cls + (size_t)j * batch * Q * c.num_classes_p1, emb + (size_t)j * batch * Q * c.d_lang,
+                      cls + (size_t)j * batch * Q * c.num_classes_p1, emb ? emb + (size_t)j * batch * Q * c.d_lang : nullptr,
                       static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
                       workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true, /*z_ready=*/tcm && j > 0));
     if (ovl && (j & 1) && j < L) {

@@ -43,6 +43,7 @@ struct AttnP {
   int Q, K, heads, W32, ntiles, nqt;
   int trace;
   int has_r, r_col0, r_lo_off;   // key-bias table term: S += Q (R_hi + R_lo)^T, R columns r_col0 + head*32
+  int out_hl;                    // out_bf16 rows are [hi(C) | lo(C)] bf16 pairs (split-precision operand of the out-projection)
 };
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -413,17 +414,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
       }
       if (p.out_bf16) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * C + h * 32);
+        const long ld = p.out_hl ? 2 * C : C;
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + h * 32);
+        uint4* dst_lo = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + C + h * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          uint4 pk;
+          uint4 pk, pl;
           uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+          uint32_t* wl = reinterpret_cast<uint32_t*>(&pl);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(o[8 * i + 2 * j] * inv, o[8 * i + 2 * j + 1] * inv);
+            const float a0 = o[8 * i + 2 * j] * inv, a1 = o[8 * i + 2 * j + 1] * inv;
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(a0, a1);
             w[j] = *reinterpret_cast<uint32_t*>(&v2);
+            const float2 back = __bfloat1622float2(v2);
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - back.x, a1 - back.y);
+            wl[j] = *reinterpret_cast<uint32_t*>(&l2);
           }
           dst[i] = pk;
+          if (p.out_hl) dst_lo[i] = pl;
         }
       }
     }
@@ -454,7 +463,7 @@ int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_str
 
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, __nv_bfloat16* out_bf16,
-                 cudaStream_t s, const void* r_table, long r_cols, int r_col0) {
+                 cudaStream_t s, const void* r_table, long r_cols, int r_col0, bool out_hl) {
   // r_table: (num_keys, r_cols) bf16 with columns [hi (r_cols/2) | lo (r_cols/2)]
   const int Q = t->cfg.num_queries, heads = t->cfg.num_heads, C = t->cfg.embed_dim;
   const int ntiles = (num_keys + AT_KT - 1) / AT_KT, nqt = (Q + 127) / 128;
@@ -480,6 +489,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   static const int r_lo = getenv("CGG_ATTN_R_LO") ? atoi(getenv("CGG_ATTN_R_LO")) : 1;
   p.has_r = r_table ? (r_lo ? 2 : 1) : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
+  p.out_hl = out_hl ? 1 : 0;
   if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");
   const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + 512 + (2 * AT_STAGES + 4) * 8 + 16;
   if (!t->attn_attr_set) {

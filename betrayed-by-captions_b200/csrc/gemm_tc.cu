@@ -43,8 +43,11 @@ struct TcGemmP {
   int a_resident;        // 1: the whole A tile (KC chunks) stays in smem for all NT tiles; 0: A chunks stream with B
   int a_kmajor;          // 0: A is an NCHW feature map (pixels contiguous); 1: A is [rows][K] activations (K contiguous)
   int k_identity;        // 1: chunk kc sits at K coordinate kc*64 for both operands (kcoord tables unused)
-  int a_kcoord[12];      // channel coordinate of A chunk kc   (split-precision GEMMs revisit chunks)
+  int a_kcoord[12];      // channel coordinate of A chunk kc   (operands whose chunks sit at different K coordinates)
   int b_kcoord[12];      // K coordinate of B chunk kc
+  // split precision (EPI_LINEAR_T): rows of both operands are [hi(split_K) | lo(split_K)] bf16 pairs and the CTA walks
+  // 3 * split_cpc chunks = hi.hi, hi.lo, lo.hi terms of its K range (split_cpc chunks of 64 per term); 0 = off
+  int split_cpc, split_K;
   // EPI_LINEAR_T: up to 3 FEATURE segments (32-aligned starts) of (acc + bias [+ rowbias]) * alpha [+ res] [relu]
   TcSeg seg[3]; int nseg; const float* lin_bias; int n_tokens;
   long kpart_stride;     // EPI_LINEAR_T with gridDim.z K-parts: part z writes its partial sums at ptr + z*kpart_stride (fp32)
@@ -433,6 +436,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else { m_tile = blockIdx.x; batch = blockIdx.y; }
   };
   if (threadIdx.x == 0) TC_STAMP(0);
+  // K coordinates of chunk kc in the A and B tensor maps
+  auto kcoords = [&](int kc, int& ka, int& kb) {
+    if (p.split_cpc > 0) {
+      const int term = kc / p.split_cpc, j = kc - term * p.split_cpc;
+      const int k0 = ((int)blockIdx.z * p.split_cpc + j) * TC_BK;
+      ka = (term == 2 ? p.split_K : 0) + k0;      // weights:     hi, hi, lo
+      kb = (term == 1 ? p.split_K : 0) + k0;      // activations: hi, lo, hi
+    } else if (p.k_identity) {
+      ka = kb = ((int)blockIdx.z * p.KC + kc) * TC_BK;
+    } else {
+      ka = p.a_kcoord[kc]; kb = p.b_kcoord[kc];
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -461,7 +477,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     n_pre = total < p.stages ? total : p.stages;
     for (int i = 0; i < n_pre; ++i) {
       const int kc = i % p.KC;
-      const int kco = p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.a_kcoord[kc];
+      int kco, kcb;
+      kcoords(kc, kco, kcb);
       ptx::mbar_expect_tx(&b_full[i], (uint32_t)b_stage_bytes);
       ptx::tma_load_2d(sB + i * b_stage_bytes, &tmA, &b_full[i], kco, (int)blockIdx.x * TC_BM);
     }
@@ -475,7 +492,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // activation operand as one (64 k x 128 rows) box; 16 KB either way.
       int m_tile = 0, batch = 0;
       auto load_a = [&](uint8_t* dst, uint64_t* bar, int kc) {
-        const int kco = p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.a_kcoord[kc];
+        int kco, kcb;
+        kcoords(kc, kco, kcb);
         if (A_KMAJOR) {
           ptx::tma_load_2d(dst, &tmA, bar, kco, m_tile * TC_BM);
         } else {
@@ -508,8 +526,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
             if (!A_RESIDENT) load_a(stage, &b_full[s], kc);
           }
-          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], p.k_identity ? ((int)blockIdx.z * p.KC + kc) * TC_BK : p.b_kcoord[kc],
-                           batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
+          int kca, kcb;
+          kcoords(kc, kca, kcb);
+          ptx::tma_load_2d(stage + a_in_stage, &tmB, &b_full[s], kcb, batch * p.b_rows_per_batch + p.b_row0 + t * p.N_TILE);
         }
       }
     }
@@ -1364,7 +1383,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   p.tmem_cols = 2 * p.acc_stride;
   const size_t a_bytes = p.a_resident ? (size_t)p.KC * A_CHUNK_BYTES : 0;
   const size_t b_stage = (size_t)p.N_TILE * 128 + (p.a_resident ? 0 : A_CHUNK_BYTES);
-  if (p.KC > 12 && !p.k_identity) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
+  if (p.KC > 12 && !p.k_identity && p.split_cpc == 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
   const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR)
                                  ? (size_t)p.N_TILE * TC_BM * 2 + 1024 + (p.epi == EPI_ROWMAJOR ? (size_t)p.NT * p.N_TILE * 4 : 0) : 0;
   static const int smem_kb = getenv("CGG_TC_SMEM_KB") ? atoi(getenv("CGG_TC_SMEM_KB")) : 204;
@@ -1588,10 +1607,9 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
     if (stages >= 3) {
       p.stages = stages;
       const size_t smem = 1024 + 4 * A_CHUNK_BYTES + stages * b_stage + stage_bytes + bias_bytes + (8 + 2 * stages + 4) * 8 + 64;
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (!t->attr_kv_pair) {      // per handle = per device (the attribute is per device, not per process)
         TCU(cudaFuncSetAttribute(tc_kv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        t->attr_kv_pair = true;
       }
       if (t->num_sms == 0) {
         int dev = 0;
@@ -1670,13 +1688,16 @@ int tc_mask_bits(TcState* t, int batch, int call_idx, int level, uint32_t* bitma
     // (blockIdx.y = image) -> the kernel needs the per-image row: pass through b_row and rows_per_batch
     bp.b_row = call_idx * t->q_pad;
     const size_t smem = 1024 + 4 * (size_t)bp.N_TILE * 128 + (size_t)bp.stages * 2 * A_CHUNK_BYTES + (1 + 2 * bp.stages + 4) * 8 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!t->attr_bits) {
       TCU(cudaFuncSetAttribute(tc_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+      t->attr_bits = true;
     }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (t->num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int sms = t->num_sms;
     int gx = sms / batch;
     if (gx < 1) gx = 1;
     if (gx > bp.m_tiles) gx = bp.m_tiles;
@@ -1798,10 +1819,9 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       }
       p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
       p.dbg = 0; p.ein_split = t_split ? 1 : 0; p.q_rows = t_rows;
-      static bool attr_set_t = false;
-      if (!attr_set_t) {
+      if (!t->attr_ein_t) {
         TCU(cudaFuncSetAttribute(tc_einsum_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set_t = true;
+        t->attr_ein_t = true;
       }
       if (t->num_sms == 0) {
         int dev = 0;
@@ -1830,10 +1850,9 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
     const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * b_chunk + 24 * 8 + 64 + stage_bytes;
     if (smem <= 227 * 1024) {
       p.stages = 8;
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (!t->attr_ein_pair) {
         TCU(cudaFuncSetAttribute(tc_einsum_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        t->attr_ein_pair = true;
       }
       if (t->num_sms == 0) {
         int dev = 0;
@@ -1884,13 +1903,12 @@ int make_map_act(TcState* t, CUtensorMap* m, const void* base, long rows, int K)
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
               const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k, int kparts, long kpart_stride) {
   if (kparts < 1) kparts = 1;
-  if (kparts > 1 && (split_k || nsegs != 1 || segs[0].is_bf16 || segs[0].relu || (K / TC_BK) % kparts != 0))
+  if (kparts > 1 && (nsegs != 1 || segs[0].is_bf16 || segs[0].relu || (K / TC_BK) % kparts != 0))
     return tc_fail(t, CGG_ERR_BAD_SHAPE, "K-parts need one plain fp32 output segment");
   // swap-AB: the WEIGHTS are the UMMA A operand (128 output features per CTA on the TMEM lanes), the
   // activations the B operand (a tile of <= 256 tokens on the columns); grid = feature tiles x token tiles.
   if (K % TC_BK != 0 || n_padded % TC_BM != 0 || nsegs < 1 || nsegs > 3)
     return tc_fail(t, CGG_ERR_BAD_SHAPE, "tc_linear shape (features must be padded to 128)");
-  if (split_k && K != 256) return tc_fail(t, CGG_ERR_BAD_SHAPE, "split-precision linear needs K = 256");
   for (int i = 0; i < nsegs; ++i)
     if (segs[i].col0 % 32 != 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "segment start must be a multiple of 32");
   const int row_len = split_k ? 2 * K : K;
@@ -1907,13 +1925,7 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   p.NT = 1; p.KC = K / TC_BK / kparts; p.kpart_stride = kpart_stride;
   p.a_kmajor = 1; p.k_identity = 1; p.a_resident = 0;
   if (split_k) {
-    p.k_identity = 0; p.KC = 3 * K / TC_BK;
-    const int cpc = K / TC_BK;
-    for (int kc = 0; kc < p.KC; ++kc) {
-      const int term = kc / cpc, j = (kc % cpc) * TC_BK;
-      p.a_kcoord[kc] = (term == 2 ? K : 0) + j;     // weights:     hi, hi, lo
-      p.b_kcoord[kc] = (term == 1 ? K : 0) + j;     // activations: hi, lo, hi
-    }
+    p.k_identity = 0; p.split_cpc = K / TC_BK / kparts; p.split_K = K; p.KC = 3 * p.split_cpc;
   }
   p.b_row0 = 0; p.b_rows_per_batch = p.N_TILE;       // blockIdx.y = token tile
   p.epi = EPI_LINEAR_T; p.M_valid = n_padded; p.n_tokens = M;

@@ -86,7 +86,8 @@ int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, 
 // (either may be null).
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out,
-                 __nv_bfloat16* out_bf16, cudaStream_t s, const void* r_table = nullptr, long r_cols = 0, int r_col0 = 0);
+                 __nv_bfloat16* out_bf16, cudaStream_t s, const void* r_table = nullptr, long r_cols = 0, int r_col0 = 0,
+                 bool out_hl = false);   // out_hl: out_bf16 rows are [hi(C) | lo(C)] pairs
 // r_table: optional bf16 (num_keys, r_cols) key-bias table stored as [hi | lo] column halves;
 // S += Q . (R_hi + R_lo)[:, r_col0 + head*32 ...]^T
 const void* tc_key_bias_table(const TcState* t, int level, long* cols);

@@ -17,7 +17,16 @@ namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// dst = bf16(x + qe[row % Q])
+// hi/lo bf16 pair of a float pair, packed
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 back = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// dst row [hi(256) | lo(256)] = split(x + qe[row % Q])   (256 channels per row)
 __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __restrict__ qe,
                                    __nv_bfloat16* __restrict__ dst, long total, int per /* Q*C */) {
   ptx::grid_dep_launch();
@@ -26,15 +35,17 @@ __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __r
   if (i >= total) return;
   const float4 a = *reinterpret_cast<const float4*>(x + i);
   const float4 b = *reinterpret_cast<const float4*>(qe + (i % per));
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x + b.x, a.y + b.y), hi = __floats2bfloat162_rn(a.z + b.z, a.w + b.w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&lo);
-  pk.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(dst + i) = pk;
+  uint2 ph, pl;
+  split_pack(a.x + b.x, a.y + b.y, ph.x, pl.x);
+  split_pack(a.z + b.z, a.w + b.w, ph.y, pl.y);
+  const long row = i >> 8, col = i & 255;
+  *reinterpret_cast<uint2*>(dst + row * 512 + col) = ph;
+  *reinterpret_cast<uint2*>(dst + row * 512 + 256 + col) = pl;
 }
 
 // Row LayerNorm over 256 channels, one warp per row, every access coalesced.  Optional outputs:
-// fp32, bf16, bf16 of (y + qe[row % Q]) and a bf16 hi/lo pair row [hi(256) | lo(256)].
+// fp32 y, and bf16 hi/lo pair rows [hi(256) | lo(256)] of y (out_bf16), of y + qe[row % Q] (out_bf16_q) and of
+// y or its chained second LayerNorm (out_hl): the split-precision operands of the GEMMs that follow.
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int nparts, long part_stride,
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ b, int rows, float* __restrict__ out_f32,
@@ -76,19 +87,22 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     d[0] = make_float4(y[0], y[1], y[2], y[3]);
     d[1] = make_float4(y[4], y[5], y[6], y[7]);
   }
-  auto pack = [](float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+  auto store_hl = [&](__nv_bfloat16* dst, const float* v8) {
+    uint4 ph, pl;
+    split_pack(v8[0], v8[1], ph.x, pl.x);
+    split_pack(v8[2], v8[3], ph.y, pl.y);
+    split_pack(v8[4], v8[5], ph.z, pl.z);
+    split_pack(v8[6], v8[7], ph.w, pl.w);
+    *reinterpret_cast<uint4*>(dst + (long)row * 512 + n0) = ph;
+    *reinterpret_cast<uint4*>(dst + (long)row * 512 + 256 + n0) = pl;
   };
-  if (out_bf16) {
-    uint4 pk = make_uint4(pack(y[0], y[1]), pack(y[2], y[3]), pack(y[4], y[5]), pack(y[6], y[7]));
-    *reinterpret_cast<uint4*>(out_bf16 + (long)row * 256 + n0) = pk;
-  }
+  if (out_bf16) store_hl(out_bf16, y);
   if (out_bf16_q) {
     const float* e = qe + (long)(row % Q) * 256 + n0;
-    uint4 pk = make_uint4(pack(y[0] + e[0], y[1] + e[1]), pack(y[2] + e[2], y[3] + e[3]), pack(y[4] + e[4], y[5] + e[5]),
-                          pack(y[6] + e[6], y[7] + e[7]));
-    *reinterpret_cast<uint4*>(out_bf16_q + (long)row * 256 + n0) = pk;
+    float yq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yq[i] = y[i] + e[i];
+    store_hl(out_bf16_q, yq);
   }
   if (out_hl && w2) {
     // chained second LayerNorm (post_norm of the head call that follows): z = LN(y; w2, b2)
@@ -107,21 +121,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = (y[i] - mu2) * rstd2 * __ldg(w2 + n0 + i) + __ldg(b2 + n0 + i);
   }
-  if (out_hl) {
-    uint4 ph, pl;
-    uint32_t* hw = reinterpret_cast<uint32_t*>(&ph);
-    uint32_t* lw = reinterpret_cast<uint32_t*>(&pl);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * i]), h1 = __float2bfloat16_rn(y[2 * i + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * i] - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(h1));
-      hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    *reinterpret_cast<uint4*>(out_hl + (long)row * 512 + n0) = ph;
-    *reinterpret_cast<uint4*>(out_hl + (long)row * 512 + 256 + n0) = pl;
-  }
+  if (out_hl) store_hl(out_hl, y);
 }
 
 cudaError_t launch_ln_rows(const float* x, const float* w, const float* b, int rows, float* out_f32,
@@ -175,12 +175,13 @@ int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
     t->free_packed();
     for (int i = 0; i < L; ++i) {
       TcState::LayerW& l = t->pl[i];
-      TCU(cudaMalloc(&l.wq_c, (size_t)C * C * 2));
-      TCU(cudaMalloc(&l.wo_c, (size_t)C * C * 2));
-      TCU(cudaMalloc(&l.wqkv_s, (size_t)3 * C * C * 2));
-      TCU(cudaMalloc(&l.wo_s, (size_t)C * C * 2));
-      TCU(cudaMalloc(&l.w1, (size_t)F * C * 2));
-      TCU(cudaMalloc(&l.w2, (size_t)C * F * 2));
+      // every small-M weight is kept as [hi | lo] bf16 rows: the layer chain runs at split precision
+      TCU(cudaMalloc(&l.wq_c, (size_t)C * C * 4));
+      TCU(cudaMalloc(&l.wo_c, (size_t)C * C * 4));
+      TCU(cudaMalloc(&l.wqkv_s, (size_t)3 * C * C * 4));
+      TCU(cudaMalloc(&l.wo_s, (size_t)C * C * 4));
+      TCU(cudaMalloc(&l.w1, (size_t)F * C * 4));
+      TCU(cudaMalloc(&l.w2, (size_t)C * F * 4));
       TCU(cudaMalloc(&l.rowbias_v, (size_t)Q * C * 4));
     }
     TCU(cudaMalloc(&t->wh, (size_t)nh * 2 * C * 2));       // hi/lo rows: the head chain runs at split precision
@@ -193,12 +194,12 @@ int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
   for (int i = 0; i < L; ++i) {
     const cgg_layer_weights& lw = w->layers[i];
     TcState::LayerW& l = t->pl[i];
-    TCU(launch_cast_bf16(lw.cross_in_w, l.wq_c, (size_t)C * C, s));                 // Wq of the cross-attention
-    TCU(launch_cast_bf16(lw.cross_out_w, l.wo_c, (size_t)C * C, s));
-    TCU(launch_cast_bf16(lw.self_in_w, l.wqkv_s, (size_t)3 * C * C, s));            // [Wq; Wk; Wv] as stored
-    TCU(launch_cast_bf16(lw.self_out_w, l.wo_s, (size_t)C * C, s));
-    TCU(launch_cast_bf16(lw.ffn_w1, l.w1, (size_t)F * C, s));
-    TCU(launch_cast_bf16(lw.ffn_w2, l.w2, (size_t)C * F, s));
+    TCU(launch_cast_bf16_split(lw.cross_in_w, l.wq_c, C, C, s));                    // Wq of the cross-attention
+    TCU(launch_cast_bf16_split(lw.cross_out_w, l.wo_c, C, C, s));
+    TCU(launch_cast_bf16_split(lw.self_in_w, l.wqkv_s, 3 * C, C, s));               // [Wq; Wk; Wv] as stored
+    TCU(launch_cast_bf16_split(lw.self_out_w, l.wo_s, C, C, s));
+    TCU(launch_cast_bf16_split(lw.ffn_w1, l.w1, F, C, s));
+    TCU(launch_cast_bf16_split(lw.ffn_w2, l.w2, C, F, s));
     // v = x Wv^T + bv = (x + qe) Wv^T + bv - qe Wv^T : the last term is a per-query constant
     GemmF32 g;
     g.A = w->query_embed; g.sAm = C; g.sAk = 1;
@@ -209,10 +210,10 @@ int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
   }
   TCU(cudaMemsetAsync(t->wh, 0, (size_t)nh * 2 * C * 2, s));
   TCU(cudaMemsetAsync(t->bias_h, 0, (size_t)nh * 4, s));
-  TCU(launch_cast_bf16_split(w->v2l_w, t->wh, c.d_lang, C, s));
+  if (c.d_lang > 0) TCU(launch_cast_bf16_split(w->v2l_w, t->wh, c.d_lang, C, s));
   TCU(launch_cast_bf16_split(w->me_w[0], t->wh + (size_t)c.d_lang * 2 * C, C, C, s));
   TCU(launch_cast_bf16_split(w->cls_w, t->wh + (size_t)(c.d_lang + C) * 2 * C, c.num_classes_p1, C, s));
-  TCU(cudaMemcpyAsync(t->bias_h, w->v2l_b, (size_t)c.d_lang * 4, cudaMemcpyDeviceToDevice, s));
+  if (c.d_lang > 0) TCU(cudaMemcpyAsync(t->bias_h, w->v2l_b, (size_t)c.d_lang * 4, cudaMemcpyDeviceToDevice, s));
   TCU(cudaMemcpyAsync(t->bias_h + c.d_lang, w->me_b[0], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
   TCU(cudaMemcpyAsync(t->bias_h + c.d_lang + C, w->cls_b, (size_t)c.num_classes_p1 * 4, cudaMemcpyDeviceToDevice, s));
   TCU(launch_cast_bf16_split(w->me_w[1], t->wme1, C, C, s));
@@ -281,37 +282,38 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   }
   if (!q_ready) {      // (q_ready: tc_layer_qproj already ran, on a branch parallel to the head call)
     TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
-    TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s));
+    TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s, true));
   }
   {
     const int level = layer % CGG_NUM_LEVELS, slot = layer / CGG_NUM_LEVELS;
     long rcols = 0;
     const void* rtab = tc_key_bias_table(t, level, &rcols);
     TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s, rtab, rcols,
-                     slot * C));
+                     slot * C, /*out_hl=*/true));
   }
   // x1 = LN(x + o Wo^T + bo);  also bf16(x1 + query_embed) for the self-attention projections
   TcSeg so[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x_in, C)};
-  TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s));
+  TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s, true));
   TCU(launch_ln_rows(t1, lw.norm_w[0], lw.norm_b[0], M, x1, nullptr, xqb, w->query_embed, Q, nullptr, s));
   // ---- self-attention: q, k from x1 + query_embed, v from x1 (per-query constant folded into rowbias_v)
   __nv_bfloat16* kvb = reinterpret_cast<__nv_bfloat16*>(kvs);          // (M, 2C) bf16: [k | v]
   TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvb, 2 * C, true, false),
                  seg(2 * C, C, kvb + C, 2 * C, true, false, 1.f, pw.rowbias_v, Q, C)};
-  TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s));
+  TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s, true));
   // the 100 x 100 self-attention runs on the same tcgen05 attention kernel (one key tile, no mask)
-  TST(tc_attention(t, batch, Q, qs, kvb, kvb + C, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, s));
+  TST(tc_attention(t, batch, Q, qs, kvb, kvb + C, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, s, nullptr, 0, 0,
+                   /*out_hl=*/true));
   TcSeg so2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x1, C)};
-  TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s));
+  TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s, true));
   TCU(launch_ln_rows(t1, lw.norm_w[1], lw.norm_b[1], M, x2, xb, nullptr, nullptr, 0, nullptr, s));
   // ---- FFN
-  TcSeg sf[1] = {seg(0, F, fb, F, true, true)};
-  TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s));
+  TcSeg sf[1] = {seg(0, F, fb, 2 * F, true, true, 1.f, nullptr, 1, 0, /*split=*/true)};
+  TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s, true));
   TcSeg sf2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x2, C)};
   // K = 2048 over 4 K-parts (4x the CTAs, each a quarter of the chunk chain); the LayerNorm adds the parts
   const int kparts = (F / 64) % 4 == 0 ? 4 : 1;
   const long pstride = (long)M * C;
-  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s, false, kparts, pstride));
+  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s, true, kparts, pstride));
   if (chained_out)   // also bf16(x_out + query_embed) for the next layer and post_norm(x_out) for the next head call
     TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, xqb, w->query_embed, Q, at<__nv_bfloat16>(ws, o.zb), s,
                        w->post_norm_w, w->post_norm_b, kparts, pstride));
@@ -331,7 +333,7 @@ int tc_layer_qproj(TcState* t, const cgg_weights* w, int batch, int layer, void*
   TcWs o;
   o.carve(t, batch);
   TcSeg sq[1] = {seg(0, C, at<float>(ws, o.qf), C, false, false, qscale)};
-  TST(tc_linear(t, at<__nv_bfloat16>(ws, o.xqb), M, C, t->pl[layer].wq_c, C, w->layers[layer].cross_in_b, sq, 1, s));
+  TST(tc_linear(t, at<__nv_bfloat16>(ws, o.xqb), M, C, t->pl[layer].wq_c, C, w->layers[layer].cross_in_b, sq, 1, s, true));
   return CGG_OK;
 }
 

@@ -33,7 +33,8 @@ struct TcState {
   float* bias_h = nullptr;
   int nh_padded = 0;
   bool packed_alloc = false;
-  bool smem_attr_set = false, attn_attr_set = false;
+  bool smem_attr_set = false, attn_attr_set = false;   // per-device kernel attributes set (one handle = one device)
+  bool attr_kv_pair = false, attr_bits = false, attr_ein_t = false, attr_ein_pair = false;
   uint8_t* live_buf = nullptr;          // per (image, query tile, key tile) "any key unmasked" flags
   size_t live_bytes = 0;
   void free_all() {
@@ -69,8 +70,8 @@ struct TcWs {
       const int K = t->lh[l] * t->lw[l];
       memp[l] = take((K % 8) ? (size_t)B * C * pitch8(K) * 2 : 0);
     }
-    xqb = take(M * C * 2); xb = take(M * C * 2); ob = take(M * C * 2);
-    fb = take(M * t->cfg.ffn_dim * 2);
+    xqb = take(M * 2 * C * 2); xb = take(M * 2 * C * 2); ob = take(M * 2 * C * 2);   // hi/lo rows
+    fb = take(M * 2 * t->cfg.ffn_dim * 2);
     zb = take(M * 2 * C * 2); h1b = take(M * 2 * C * 2); h2b = take(M * 2 * C * 2);   // hi/lo rows
     qf = take(M * C * 4); qs = take(M * C * 4); kvs = take(M * 2 * C * 4);
     x1 = take(M * C * 4); x2 = take(M * C * 4); t1 = take(4 * M * C * 4);   // t1: up to 4 K-split partial sums

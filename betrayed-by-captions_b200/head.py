@@ -94,6 +94,10 @@ class Mask2FormerHeadOpenB200(nn.Module):
         self.d_lang = d_lang
         self.precision = precision
         self.softmax_temperature = kwargs.get('softmax_temperature', 10.0)
+        # head.py:178,739-744: without class embeddings there is no v2l_transform / class_embs, the embedding
+        # prediction IS the class prediction and pred_emb_norm is never applied (the class-agnostic pre-training
+        # configs coco_ag_pretrain_3x.py / p20_ag_pretrain.py run this way)
+        self.use_class_emb = bool(kwargs.get('use_class_emb', False))
         self.pred_emb_norm = kwargs.get('pred_emb_norm', False)
         self.text_emb_norm = kwargs.get('text_emb_norm', True)
         self.pixel_decoder = pixel_decoder if isinstance(pixel_decoder, nn.Module) else None
@@ -106,8 +110,9 @@ class Mask2FormerHeadOpenB200(nn.Module):
         self.mask_embed = nn.Sequential(nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
                                         nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
                                         nn.Linear(feat_channels, out_channels))
-        self.v2l_transform = nn.Linear(feat_channels, d_lang)
-        self.register_buffer('class_embs', torch.zeros(self.num_classes + 1, d_lang))
+        if self.use_class_emb:
+            self.v2l_transform = nn.Linear(feat_channels, d_lang)
+            self.register_buffer('class_embs', torch.zeros(self.num_classes + 1, d_lang))
         self._rt = None
         self.init_weights()
 
@@ -179,9 +184,10 @@ class _Runtime:
         self.device = device
         self.handle = C.c_void_p()
         prec = {'fp32': _lib.FP32, 'bf16': _lib.BF16}[head.precision]
+        self.d_lang = head.d_lang if head.use_class_emb else 0      # 0: no v2l_transform in the library either
         self.cfg = _lib.Config(head.num_queries, head.feat_channels, head.num_heads, head.ffn_channels,
-                               head.num_transformer_decoder_layers, head.num_classes + 1, head.d_lang, prec,
-                               int(bool(head.pred_emb_norm)))
+                               head.num_transformer_decoder_layers, head.num_classes + 1, self.d_lang, prec,
+                               int(bool(head.pred_emb_norm) and head.use_class_emb))
         with torch.cuda.device(device):
             _lib.check(self.lib.cgg_create(C.byref(self.handle), C.byref(self.cfg)), None, 'cgg_create')
         self.weights = None
@@ -216,7 +222,8 @@ class _Runtime:
         w.cls_w, w.cls_b = f(h.cls_embed.weight), f(h.cls_embed.bias)
         for n, i in enumerate((0, 2, 4)):
             w.me_w[n], w.me_b[n] = f(h.mask_embed[i].weight), f(h.mask_embed[i].bias)
-        w.v2l_w, w.v2l_b = f(h.v2l_transform.weight), f(h.v2l_transform.bias)
+        if h.use_class_emb:
+            w.v2l_w, w.v2l_b = f(h.v2l_transform.weight), f(h.v2l_transform.bias)
         w.post_norm_w, w.post_norm_b = f(h.transformer_decoder.post_norm.weight), f(h.transformer_decoder.post_norm.bias)
         for i, layer in enumerate(h.transformer_decoder.layers):
             lw = w.layers[i]
@@ -248,7 +255,9 @@ class _Runtime:
                        self.handle, 'cgg_prepare')
             self.weights_key, self.sizes = key, sizes
             self.batch = None
+            self._graphs.clear()      # captured graphs bake in the handle's tables: stale after a re-prepare
         if self.batch != batch:
+            self._graphs.clear()      # ... and the workspace pointer
             nbytes = self.lib.cgg_workspace_bytes(self.handle, batch)
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.batch = batch
@@ -274,18 +283,34 @@ class _Runtime:
         return self._forward_eager(mask_features, memories, return_debug)
 
     def _forward_graph(self, mask_features, memories):
-        """Replays a CUDA graph of the whole path (one graph per distinct set of input buffers; the
-        library call is capturable after cgg_prepare).  Outputs are graph-owned static tensors: they
-        are overwritten by the next replay of the same graph."""
+        """Replays a CUDA graph of the whole path.  ONE graph per (sizes, batch, weights): it is captured on the
+        caller's input tensors the first time (kept alive with the graph) and replayed zero-copy as long as the
+        caller keeps passing those same buffers; a call with other tensors of the same shape switches the entry to
+        graph-owned static input buffers (one re-capture, then a device copy per call -- never a re-capture per
+        step).  Any re-prepare (new sizes, batch or weights) drops the graphs, because they bake in the handle's
+        tables and the workspace (see prepare()).  Outputs are graph-owned static tensors: the next replay
+        overwrites them."""
         with torch.cuda.device(self.device):
             mf, mems = self._check_inputs(mask_features, memories)
             sizes = [tuple(m.shape[-2:]) for m in mems]
-            self.prepare(mf.shape[2], mf.shape[3], sizes, mf.shape[0])
-            key = (mf.data_ptr(), tuple(m.data_ptr() for m in mems), tuple(mf.shape), self.weights_key)
+            self.prepare(mf.shape[2], mf.shape[3], sizes, mf.shape[0])       # may clear self._graphs
+            key = (tuple(mf.shape), tuple(sizes), self.weights_key)
+            ptrs = (mf.data_ptr(),) + tuple(m.data_ptr() for m in mems)
             entry = self._graphs.get(key)
+            if entry is not None and entry['ptrs'] != ptrs:
+                if not entry['owned']:
+                    entry = None                                              # re-capture on graph-owned buffers
+                    own = True
+                else:
+                    entry['mf'].copy_(mf)
+                    for d, m in zip(entry['mems'], mems):
+                        d.copy_(m)
+            elif entry is None:
+                own = False
             if entry is None:
-                if len(self._graphs) >= 4:
-                    self._graphs.clear()
+                self._graphs.clear()
+                if own:
+                    mf, mems = mf.clone(), [m.clone() for m in mems]
                 cur = torch.cuda.current_stream(self.device)
                 side = torch.cuda.Stream(self.device, priority=-1)   # the layer chain outranks the helper streams
                 side.wait_stream(cur)
@@ -296,10 +321,11 @@ class _Runtime:
                     with torch.cuda.graph(g, stream=side):
                         outs = self._forward_eager(mf, mems, False)
                 cur.wait_stream(side)
-                entry = (g, outs, mf, mems)                       # keep the inputs alive with the graph
+                entry = dict(graph=g, outs=outs, mf=mf, mems=mems, owned=own,
+                             ptrs=(mf.data_ptr(),) + tuple(m.data_ptr() for m in mems) if own else ptrs)
                 self._graphs[key] = entry
-            entry[0].replay()
-            return entry[1]
+            entry['graph'].replay()
+            return entry['outs']
 
     def _forward_eager(self, mask_features, memories, return_debug=False):
         h = self.head
@@ -312,7 +338,7 @@ class _Runtime:
             L, Q = h.num_transformer_decoder_layers, h.num_queries
             dev = self.device
             cls = torch.empty((L + 1, B, Q, h.num_classes + 1), dtype=torch.float32, device=dev)
-            emb = torch.empty((L + 1, B, Q, h.d_lang), dtype=torch.float32, device=dev)
+            emb = torch.empty((L + 1, B, Q, self.d_lang), dtype=torch.float32, device=dev) if self.d_lang else None
             n_maps = 1 if (h.final_mask_only and not return_debug) else L + 1
             mask = torch.empty((n_maps, B, Q, H4, W4), dtype=mf.dtype, device=dev)
             _lib.check(self.lib.cgg_set_final_mask_only(self.handle, int(n_maps == 1)), self.handle,
@@ -328,11 +354,14 @@ class _Runtime:
                 xs_p, am_p = _ptr(xs), _ptr(am)
                 bm_p = (C.c_void_p * L)(*[b.data_ptr() for b in bms])
             st = self.lib.cgg_decoder_forward(self.handle, C.byref(self.weights), B, _ptr(mf), mem_ptrs, _ptr(cls),
-                                              _ptr(emb), _ptr(mask), xs_p, bm_p, am_p, _ptr(self.workspace),
+                                              _ptr(emb) if emb is not None else None, _ptr(mask), xs_p, bm_p, am_p,
+                                              _ptr(self.workspace),
                                               self.workspace.numel(), self._stream())
             _lib.check(st, self.handle, 'cgg_decoder_forward')
         masks = list(mask.unbind(0)) if mask.shape[0] == L + 1 else [None] * L + [mask[0]]
-        outs = (list(cls.unbind(0)), list(emb.unbind(0)), masks)
+        cls_list = list(cls.unbind(0))
+        # use_class_emb=False: cls_emb_pred = cls_pred (head.py:739-744)
+        outs = (cls_list, list(emb.unbind(0)) if emb is not None else cls_list, masks)
         if return_debug:
             return outs + (dict(x=xs, bitmaps=bms, all_masked=am),)
         return outs
@@ -350,18 +379,19 @@ class _Runtime:
         H4, W4, sizes = self.sizes
         dev = self.device
         cls = torch.empty((B, Q, h.num_classes + 1), dtype=torch.float32, device=dev)
-        emb = torch.empty((B, Q, h.d_lang), dtype=torch.float32, device=dev)
+        emb = torch.empty((B, Q, self.d_lang), dtype=torch.float32, device=dev) if self.d_lang else None
         mask = torch.empty((B, Q, H4, W4), dtype=mask_features.dtype, device=dev)
         me = torch.empty((B, Q, h.feat_channels), dtype=torch.float32, device=dev)
         K = sizes[target_level][0] * sizes[target_level][1]
         bm = torch.zeros((B, Q, (K + 31) // 32), dtype=torch.int32, device=dev) if want_bits else None
         am = torch.zeros((B, Q), dtype=torch.uint8, device=dev) if want_bits else None
         st = self.lib.cgg_head_call(self.handle, C.byref(self.weights), B, _ptr(x), _ptr(mask_features), target_level,
-                                    _ptr(cls), _ptr(emb), _ptr(mask), _ptr(me), _ptr(bm) if want_bits else None,
+                                    _ptr(cls), _ptr(emb) if emb is not None else None, _ptr(mask), _ptr(me),
+                                    _ptr(bm) if want_bits else None,
                                     _ptr(am) if want_bits else None, _ptr(self.workspace), self.workspace.numel(),
                                     self._stream())
         _lib.check(st, self.handle, 'cgg_head_call')
-        return cls, emb, mask, me, bm, am
+        return cls, (emb if emb is not None else cls), mask, me, bm, am
 
     def mask_einsum(self, mask_features, mask_out, first_call=0, num_calls=None):
         """K2 alone (bf16 mode) from the mask embeddings already in the workspace; mask_out
@@ -438,6 +468,7 @@ class _Runtime:
 def build_head_from_state_dict(sd, num_queries, num_classes_p1=49, precision='fp32', device='cuda', num_layers=9,
                                cuda_graph=False, final_mask_only=False, **kwargs):
     """Convenience used by tests / bench: a head carrying the given (reference-keyed) weights."""
+    kwargs.setdefault('use_class_emb', 'v2l_transform.weight' in sd)
     head = Mask2FormerHeadOpenB200(num_things_classes=num_classes_p1 - 1, num_stuff_classes=0,
                                    num_queries=num_queries, precision=precision, cuda_graph=cuda_graph,
                                    final_mask_only=final_mask_only, **kwargs,

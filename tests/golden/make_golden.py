@@ -28,10 +28,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def run_head_case(name, c):
     R = ref_shim.REF_ROOT
-    head = ref_shim.build_reference_head(num_queries=c['num_queries'],
-                                         known_file=R + '/datasets/unknown/known_65.txt',
-                                         unknown_file=R + '/datasets/unknown/unknown_17.txt')
+    if c.get('class_embs') == 'coco_panoptic_p20':
+        head = ref_shim.build_reference_head(num_queries=c['num_queries'], num_known=64, num_stuff=53,
+                                             unknown_file=R + '/datasets/unknown/unknown_p20.txt',
+                                             class_to_emb_file=R + '/datasets/embeddings/coco_panoptic_class_with_bert_emb.json')
+    else:
+        head = ref_shim.build_reference_head(num_queries=c['num_queries'],
+                                             known_file=R + '/datasets/unknown/known_65.txt',
+                                             unknown_file=R + '/datasets/unknown/unknown_17.txt')
     sd, mf, mems = case_tensors(c)
+    if c.get('class_embs'):      # the committed fixture IS what the reference loader builds from its json files
+        assert torch.equal(head.class_embs, sd['class_embs'])
     head.load_state_dict(sd, strict=True)
     masks = []
     orig = head.forward_head
@@ -60,6 +67,9 @@ def run_head_case(name, c):
         n_fallback += int((masks[j].sum(-1) == masks[j].shape[-1]).sum())
     out['n_all_masked_rows'] = np.int64(n_fallback)
     out['last_mask_full'] = mask[-1].numpy()
+    if c.get('class_embs'):
+        with torch.no_grad():
+            out['cls_emb_logits_9'] = head._get_cls_emb_logits(emb[9]).numpy()
     np.savez_compressed(os.path.join(HERE, 'head_%s.npz' % name), **out)
     dens = [float(m.float().mean()) for m in masks]
     print(name, 'all-masked rows:', n_fallback, 'mask density per call:', ['%.2f' % d for d in dens])
@@ -114,7 +124,10 @@ def run_embeddings():
 
 if __name__ == '__main__':
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for n, c in HEAD_CASES.items():
-        run_head_case(n, c)
-    run_grounding()
-    run_embeddings()
+        if not only or n in only:
+            run_head_case(n, c)
+    if not only:
+        run_grounding()
+        run_embeddings()

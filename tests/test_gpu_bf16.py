@@ -64,34 +64,128 @@ def test_bf16_teacher_forced_layers(Q, B, H, W):
         assert _rel(x_out, ref['x'][i + 1]) < REL_TOL, 'decoder layer %d' % i
 
 
-def test_bf16_free_running_final_outputs():
-    Q, B, H, W = 100, 2, 256, 256
-    sd, mf, mems, head = _setup(Q, B, H, W, 33, 9)
+def _iou(got, want):
+    inter = (got & want).flatten(2).sum(-1).float()
+    union = (got | want).flatten(2).sum(-1).float().clamp(min=1)
+    return float((inter / union).mean())
+
+
+def _free_running(Q, B, H, W, pseed, iseed, ncls1=49, class_embs=None):
+    """Free-running forward, ALL 10 head calls, at the BASELINE tolerances (no loosened bars): max-abs <= 1e-2 of the
+    logit range for mask / class / embedding logits, >= 99.9 % attention-mask bits on every head call, final-mask
+    IoU >= 0.99."""
+    sd = synth.make_params(seed=pseed, num_queries=Q, perturb=True, num_classes_p1=ncls1)
+    if class_embs is not None:
+        sd['class_embs'] = class_embs
+    mf, mems = synth.make_inputs(iseed, B, H, W)
+    mf, mems = mf.bfloat16().float(), [m.bfloat16().float() for m in mems]
+    head = build_head_from_state_dict(sd, Q, ncls1, 'bf16', DEV)
     ref = O.decoder_forward(sd, mf, mems)
     cls, emb, mask, dbg = head.decoder_forward(mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems],
                                                return_debug=True)
     assert mask[0].dtype == torch.bfloat16 and len(mask) == 10
     sizes = [tuple(m.shape[-2:]) for m in mems]
-    # Free-running, the decoder state itself carries bf16 rounding from the layers before, so the
-    # 99.9% bar (asserted per layer on identical inputs in the teacher-forced test above) applies
-    # to head call 0 only; deeper calls are held to 99.5% and reported.
+    for j in range(10):
+        assert _rel(mask[j], ref['mask'][j]) <= REL_TOL, ('mask', j, _rel(mask[j], ref['mask'][j]))
+        assert _rel(emb[j], ref['emb'][j]) <= REL_TOL, ('emb', j, _rel(emb[j], ref['emb'][j]))
+        assert _rel(cls[j], ref['cls'][j]) <= REL_TOL, ('cls', j, _rel(cls[j], ref['cls'][j]))
+        if j < 9:
+            K = sizes[j % 3][0] * sizes[j % 3][1]
+            agree = float((_unpack(dbg['bitmaps'][j], K) == ref['masked'][j]).float().mean())
+            assert agree >= BIT_AGREE, (j, agree)
+    assert _iou(mask[9].float().cpu() > 0, ref['mask'][9] > 0) >= IOU_MIN
+    # grounding / class-embedding logits from the final embeddings (head.py:631-648)
+    logits = head._get_cls_emb_logits(emb[9])
+    want_l = O.cls_emb_logits(ref['emb'][9], sd['class_embs'], 10.0)
+    assert _rel(logits, want_l) <= REL_TOL
+
+
+def test_bf16_free_running_1024_all_head_calls():
+    """BASELINE configs[1] shape: 1024x1024, Q=100, B=2."""
+    _free_running(100, 2, 1024, 1024, 33, 9)
+
+
+def test_bf16_free_running_512():
+    _free_running(100, 2, 512, 512, 5, 3)
+
+
+def test_bf16_free_running_osps_q200_ncls118():
+    """BASELINE configs[3] head shape: 200 queries, 118 class rows, the reference's real class embeddings."""
+    import cases
+    _free_running(200, 2, 512, 512, 8, 5, ncls1=118, class_embs=cases.real_class_embs('coco_panoptic_p20'))
+
+
+def test_bf16_free_running_tiny_keys_reported():
+    """256x256 inputs: the 1/32 level has 64 keys, so ONE flipped attention-mask bit moves a softmax by ~1/32 and the
+    free-running max-abs error is set by such discrete events rather than by rounding (CPU study
+    tools/bf16_drift_study.py, DESIGN.md section 3: K/V stored in bf16 alone gives 1.3e-2 .. 2.1e-2 here, 6e-4 at
+    1024^2).  The stated tolerances are asserted teacher-forced on this shape (test above) and free-running at
+    512^2 / 1024^2; here the IoU and bit bars are asserted and the float errors are printed."""
+    Q, B, H, W = 100, 2, 256, 256
+    sd, mf, mems, head = _setup(Q, B, H, W, 33, 9)
+    ref = O.decoder_forward(sd, mf, mems)
+    cls, emb, mask, dbg = head.decoder_forward(mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems],
+                                               return_debug=True)
+    sizes = [tuple(m.shape[-2:]) for m in mems]
     for j in range(9):
         K = sizes[j % 3][0] * sizes[j % 3][1]
         agree = float((_unpack(dbg['bitmaps'][j], K) == ref['masked'][j]).float().mean())
-        assert agree >= (BIT_AGREE if j == 0 else 0.995), (j, agree)
-    # final masks: IoU of the thresholded (mask > 0) predictions, per query, averaged
-    got = mask[9].float().cpu() > 0
-    want = ref['mask'][9] > 0
-    inter = (got & want).flatten(2).sum(-1).float()
-    union = (got | want).flatten(2).sum(-1).float().clamp(min=1)
-    iou = float((inter / union).mean())
-    assert iou >= IOU_MIN, iou
-    assert _rel(mask[9], ref['mask'][9]) < 3 * REL_TOL      # free-running: compounding over 9 layers
-    assert _rel(emb[9], ref['emb'][9]) < 3 * REL_TOL
-    # grounding / class-embedding logits from the final embeddings
-    logits = head._get_cls_emb_logits(emb[9])
-    want_l = O.cls_emb_logits(ref['emb'][9], sd['class_embs'], 10.0)
-    assert _rel(logits, want_l) < 3 * REL_TOL
+        assert agree >= BIT_AGREE, (j, agree)
+    assert _iou(mask[9].float().cpu() > 0, ref['mask'][9] > 0) >= IOU_MIN
+    print('256x256 free-running: mask %.3g emb %.3g of range' % (_rel(mask[9], ref['mask'][9]), _rel(emb[9], ref['emb'][9])))
+    assert _rel(mask[9], ref['mask'][9]) < 3 * REL_TOL and _rel(emb[9], ref['emb'][9]) < 3 * REL_TOL
+
+
+def test_bf16_cuda_graph_matches_eager_and_survives_reprepare():
+    """cuda_graph=True (the path bench.py measures): replay == eager bit for bit; A -> B -> A shape changes and a
+    weight update between replays must re-capture instead of replaying a graph that points at freed tables."""
+    Q = 100
+    sd = synth.make_params(seed=21, num_queries=Q, perturb=True)
+    eager = build_head_from_state_dict(sd, Q, 49, 'bf16', DEV)
+    graph = build_head_from_state_dict(sd, Q, 49, 'bf16', DEV, cuda_graph=True)
+
+    def inputs(iseed, B, H, W):
+        mf, mems = synth.make_inputs(iseed, B, H, W)
+        return mf.to(DEV).bfloat16(), [m.to(DEV).bfloat16() for m in mems]
+
+    def same(a, b):
+        return all(torch.equal(x, y) for la, lb in zip(a, b) for x, y in zip(la, lb))
+
+    inA, inB = inputs(1, 2, 256, 256), inputs(2, 1, 256, 320)
+    for inp in (inA, inB, inA, inA):          # A -> B -> A -> A (replay)
+        want = eager.decoder_forward(*inp)
+        got = graph.decoder_forward(*inp)
+        torch.cuda.synchronize()
+        assert same(want, got)
+    # fresh tensors of the same shape (a real pixel decoder returns new tensors every step): no stale pointers
+    inA2 = tuple(inputs(3, 2, 256, 256))
+    assert same(eager.decoder_forward(*inA2), graph.decoder_forward(*inA2))
+    inA3 = tuple(inputs(4, 2, 256, 256))
+    assert same(eager.decoder_forward(*inA3), graph.decoder_forward(*inA3))
+    # weight update between replays
+    with torch.no_grad():
+        for h in (eager, graph):
+            h.transformer_decoder.layers[3].ffns[0].layers[1].weight.mul_(1.5)
+            h.query_feat.weight.add_(0.25)
+    assert same(eager.decoder_forward(*inA3), graph.decoder_forward(*inA3))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_use_class_emb_false_returns_cls_as_emb(precision):
+    """head.py:739-744 with use_class_emb=False (the class-agnostic pre-training configs, which also set
+    pred_emb_norm=True): cls_emb_pred IS cls_pred, no v2l_transform, no normalisation."""
+    Q, B = 32, 2
+    sd = synth.make_params(seed=14, num_queries=Q, perturb=True)
+    mf, mems = synth.make_inputs(6, B, 256, 256)
+    mf, mems = mf.bfloat16().float(), [m.bfloat16().float() for m in mems]
+    ref = O.decoder_forward(sd, mf, mems)
+    sd2 = {k: v for k, v in sd.items() if not k.startswith('v2l_transform') and k != 'class_embs'}
+    head = build_head_from_state_dict(sd2, Q, 49, precision, DEV, pred_emb_norm=True)
+    dt = torch.float32 if precision == 'fp32' else torch.bfloat16
+    cls, emb, mask = head.decoder_forward(mf.to(DEV).to(dt), [m.to(DEV).to(dt) for m in mems])
+    assert all(e is c_ for e, c_ in zip(emb, cls))
+    assert _rel(cls[0], ref['cls'][0]) < (1e-4 if precision == 'fp32' else REL_TOL)
+    assert _rel(mask[0], ref['mask'][0]) < (1e-4 if precision == 'fp32' else REL_TOL)
 
 
 def test_bf16_final_mask_only_matches_full_forward():

@@ -23,7 +23,7 @@ def _bits_np(t):
 
 
 def _head(sd, q, precision='fp32'):
-    return build_head_from_state_dict(sd, q, 49, precision, DEV)
+    return build_head_from_state_dict(sd, q, sd['cls_embed.weight'].shape[0], precision, DEV)
 
 
 # --------------------------------------------------------------------------------- stages
@@ -107,6 +107,10 @@ def test_head_fp32_matches_reference_golden(name):
             assert np.array_equal(_bits_np(dbg['bitmaps'][j]), gold['bits_%d' % j]), 'mask bits differ at call %d' % j
             n_all += int(dbg['all_masked'][j].sum())
     np.testing.assert_allclose(mask[9].cpu().numpy(), gold['last_mask_full'], atol=2e-4, rtol=0)
+    if 'cls_emb_logits_9' in gold:      # OSPS case: 118 class rows, the reference's real class embeddings
+        assert tuple(cls[9].shape) == (c['batch'], c['num_queries'], 118)
+        np.testing.assert_allclose(head._get_cls_emb_logits(emb[9]).cpu().numpy(), gold['cls_emb_logits_9'],
+                                   atol=1e-3, rtol=0)
     if name == 'dense_fallback':
         assert n_all > 10      # the fallback path really ran
         last_rows = int(((gold['bits_9'] != 0).sum()))  # noqa: F841  (bits_9 is never consumed, head.py:841)
@@ -285,3 +289,41 @@ def test_embedding_side_matches_reference_golden():
     pred = torch.from_numpy(gold['pred']).to(DEV)
     np.testing.assert_allclose(head._get_cls_emb_logits(pred).cpu().numpy(), gold['logits'], atol=3e-4, rtol=0)
     np.testing.assert_allclose(head.test_time_att(pred, ne[0]).cpu().numpy(), gold['att'], atol=3e-4, rtol=0)
+
+
+def _free_run_vs_oracle(sd, mf, mems, head, bit_bar, mask_tol, emb_tol):
+    """All 10 head calls of a free-running forward against the oracle on the same inputs."""
+    ref = O.decoder_forward(sd, mf, mems)
+    cls, emb, mask, dbg = head.decoder_forward(mf.to(DEV), [m.to(DEV) for m in mems], return_debug=True)
+    for j in range(10):
+        rng = float(ref['mask'][j].abs().max())
+        assert float((mask[j].cpu() - ref['mask'][j]).abs().max()) < mask_tol * rng, 'mask logits, head call %d' % j
+        assert float((emb[j].cpu() - ref['emb'][j]).abs().max()) < emb_tol * float(ref['emb'][j].abs().max()), j
+        assert float((cls[j].cpu() - ref['cls'][j]).abs().max()) < emb_tol * float(ref['cls'][j].abs().max()), j
+        if j < 9:
+            want = O.pack_mask_bits(ref['masked'][j]).numpy()
+            diff = np.bitwise_xor(_bits_np(dbg['bitmaps'][j]), want)
+            agree = 1.0 - np.unpackbits(diff.view(np.uint8)).sum() / ref['masked'][j].numel()
+            assert agree >= bit_bar, (j, agree)
+
+
+def test_fp32_full_size_1024_all_head_calls_vs_oracle():
+    """BASELINE configs[1] shape (1024x1024, Q=100): every one of the 10 head calls against the oracle, fp32 mode."""
+    sd = synth.make_params(seed=0, num_queries=100)
+    mf, mems = synth.make_inputs(0, 1, 1024, 1024)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)
+
+
+def test_fp32_demo_shape_1056x800_all_head_calls_vs_oracle():
+    """BASELINE configs[0] shape: the notebook demo's 1056x800 padded input (ragged key counts 825 / 3300 / 13200,
+    W/4 = 200), fp32 mode, all head calls."""
+    sd = synth.make_params(seed=3, num_queries=100, perturb=True)
+    mf, mems = synth.make_inputs(2, 1, 1056, 800)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)
+
+
+def test_fp32_osps_q200_ncls118_vs_oracle():
+    """BASELINE configs[3] head shape: 200 queries, 118 class rows, real class embeddings, at 512x512."""
+    c = dict(cases.HEAD_CASES['osps_q200'], height=512, width=512, batch=2)
+    sd, mf, mems = cases.case_tensors(c)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 200), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)

@@ -72,13 +72,24 @@ def test_create_rejects_bad_config(lib):
 
 def test_state_dict_keys_match_reference_layout():
     """the replacement must accept the reference's keys unchanged."""
-    head = Mask2FormerHeadOpenB200(num_things_classes=48, num_stuff_classes=0, num_queries=100)
+    head = Mask2FormerHeadOpenB200(num_things_classes=48, num_stuff_classes=0, num_queries=100, use_class_emb=True)
     sd = synth.make_params(seed=0, num_queries=100, num_classes_p1=49)
     assert set(head.state_dict().keys()) == set(sd.keys())
     for k, v in head.state_dict().items():
         assert tuple(v.shape) == tuple(sd[k].shape), k
     n = sum(p.numel() for p in head.parameters())
     assert n == 14668593          # head-only parameter count of the reference (SURVEY.md 8b)
+    head.load_state_dict(sd, strict=True)
+
+
+def test_use_class_emb_false_has_no_v2l_transform():
+    """head.py:178,202-219: the reference default builds neither v2l_transform nor class_embs (the class-agnostic
+    pre-training configs); a checkpoint of such a model must load strictly."""
+    head = Mask2FormerHeadOpenB200(num_things_classes=48, num_stuff_classes=0, num_queries=100, pred_emb_norm=True)
+    keys = set(head.state_dict().keys())
+    assert not any(k.startswith('v2l_transform') or k == 'class_embs' for k in keys)
+    sd = {k: v for k, v in synth.make_params(seed=0, num_queries=100).items()
+          if not k.startswith('v2l_transform') and k != 'class_embs'}
     head.load_state_dict(sd, strict=True)
 
 

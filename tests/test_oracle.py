@@ -43,6 +43,9 @@ def test_head_matches_golden(name):
         n_all += int((out['masked'][j].sum(-1) == out['masked'][j].shape[-1]).sum())
     assert n_all == int(g['n_all_masked_rows'])
     np.testing.assert_allclose(out['mask'][9].numpy(), g['last_mask_full'], atol=5e-5, rtol=0)
+    if 'cls_emb_logits_9' in g:      # OSPS case: real class embeddings, 118 class rows (head.py:631-648)
+        got = O.cls_emb_logits(out['emb'][9], sd['class_embs'], 10.0).numpy()
+        np.testing.assert_allclose(got, g['cls_emb_logits_9'], atol=5e-4, rtol=0)
 
 
 def test_fallback_case_really_hits_fallback():

@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <timeout-seconds> [--gpus N] -- '<command>'
+# Retries while gpurun answers 3 (no box / slot free right now; nothing is charged for those attempts).
+T=$1; shift
+for i in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun --timeout "$T" "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
