@@ -8,7 +8,16 @@ outputs.
                     [--batch B_per_gpu] [--precision bf16|fp32] [--queries Q]
 
 N>1 is launched by torch.distributed.run, one rank per GPU; images shard by batch, no data-path
-collective, so "scaling" is weak.  Rank 0 prints ONE JSON line.
+collective, so "scaling" is weak.  Rank 0 prints ONE JSON line.  Besides the
+contract's keys the line carries, each measured in the same run:
+  roofline          dominant kernel (mask einsum) against BOTH roofs, timed in a sustained loop
+  sustained         the device-resident leg repeated for >= 2 s (clocks sampled)
+  strong_scaling    BASELINE configs[2]: global batch 64 split 64/N per GPU
+  train             BASELINE configs[3]: OSPS head (Q=200, 118 classes) forward + backward with the grounding loss,
+                    NCCL gradient all-reduce at N GPUs, exposed communication time
+  grounding         the K7 grounding-loss stage alone (forward + backward)
+  torch_gpu_baseline  (N=1) the same path as plain torch CUDA ops (what the reference executes), fp32 and bf16 autocast
+  cpu_baseline      (N=1) the reference's CPU path on the host cores
 """
 import argparse
 import json
@@ -86,14 +95,14 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ''
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(',')]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])), mx.append(float(f[1]))
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
@@ -101,7 +110,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    samples=len(sm), reasons=sorted(reasons))
+                    power_w_max=(max(pw) if pw else None), samples=len(sm), reasons=sorted(reasons))
 
 
 def reduce_max(value, world, device):
@@ -114,8 +123,8 @@ def reduce_max(value, world, device):
 
 
 def whole_job_value(world, batch_per_gpu, steps, ms):
-    """images/s of the whole job: every rank processed batch_per_gpu images per step (weak scaling,
-    batch-sharded, no data-path collective -- SURVEY.md section 8e)."""
+    """images/s of the whole job: every rank processed batch_per_gpu images per step (batch-sharded, no
+    data-path collective -- SURVEY.md section 8e)."""
     return world * batch_per_gpu * steps / (ms * 1e-3)
 
 
@@ -123,34 +132,107 @@ def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
 
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """e2e staging: pinned host buffers are first-touch allocated, so each rank first moves itself onto the CPUs next
+    to its GPU (round-1 SCALE: all ranks on NUMA 0 capped the 8-GPU e2e leg at 120 GB/s aggregate)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 # ------------------------------------------------------------------------------ CPU legs
-def cpu_reference_step(sd, mf, mems):
-    from oracle import cgg_oracle as O
-    with torch.no_grad():
-        return O.decoder_forward(sd, mf, mems)
+def _reference_head(Q):
+    """The UNMODIFIED reference head (oracle/_ref or /root/reference through the dependency shim) with the seeded
+    weights, or None when no copy of the reference is available (then the oracle port is timed)."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            return None
+        R = ref_shim.REF_ROOT
+        head = ref_shim.build_reference_head(num_queries=Q, known_file=R + '/datasets/unknown/known_65.txt',
+                                             unknown_file=R + '/datasets/unknown/unknown_17.txt')
+        return head, ref_shim
+    except Exception as e:      # noqa: BLE001  (a broken copy must not take the bench line down)
+        sys.stderr.write('reference head unavailable (%s); timing the oracle port\n' % e)
+        return None
 
 
-def cpu_baseline(Q, threads, repeats=3):
-    """The oracle (a port of the reference's fp32 PyTorch path) timed on the host cores on a
-    bounded sample: one 1024x1024 image per pass."""
+def cpu_path(Q):
+    """Returns (kind, step(mf, mems)) for the reference's CPU path."""
     from cgg_b200 import synth
-    torch.set_num_threads(threads)
     sd = synth.make_params(seed=0, num_queries=Q)
-    mf, mems = synth.make_inputs(0, 1, H, W)
-    cpu_reference_step(sd, mf, mems)
+    ref = _reference_head(Q)
+    if ref is not None:
+        head, shim = ref
+        head.load_state_dict(sd, strict=True)
+        return 'reference', lambda mf, mems: shim.run_reference_head(head, mf, mems)
+    from oracle import cgg_oracle as O
+
+    def step(mf, mems):
+        with torch.no_grad():
+            return O.decoder_forward(sd, mf, mems)
+    return 'port', step
+
+
+def _time_cpu(step, mf, mems, repeats):
+    step(mf, mems)
     ts = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_reference_step(sd, mf, mems)
+        step(mf, mems)
         ts.append(time.perf_counter() - t0)
     ts.sort()
-    return dict(value=1.0 / ts[len(ts) // 2], unit=UNIT, cores=threads, kind='port',
-                sample='1 image 1024x1024 per pass, Q=%d, fp32, median of %d passes after 1 warm-up' % (Q, repeats))
+    return ts[len(ts) // 2]
+
+
+def cpu_baseline(Q, threads):
+    """The reference's fp32 PyTorch path on the host cores, bounded samples of the same workload: one 1024x1024 image
+    per pass on all cores (median of 3) and on one thread (1 pass), and one batch-16 pass on all cores."""
+    from cgg_b200 import synth
+    kind, step = cpu_path(Q)
+    torch.set_num_threads(threads)
+    mf, mems = synth.make_inputs(0, 1, H, W)
+    t_b1 = _time_cpu(step, mf, mems, 3)
+    mf16, mems16 = synth.make_inputs(0, 16, H, W)
+    t0 = time.perf_counter()
+    step(mf16, mems16)
+    t_b16 = time.perf_counter() - t0
+    del mf16, mems16
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    step(mf, mems)
+    t_1t = time.perf_counter() - t0
+    torch.set_num_threads(threads)
+    return dict(value=1.0 / t_b1, unit=UNIT, cores=threads, kind=kind, cpu_model=cpu_model(),
+                b16_value=16.0 / t_b16, single_thread_value=1.0 / t_1t,
+                sample='Q=%d fp32 1024x1024: value = 1 image per pass, median of 3 after 1 warm-up, %d threads; b16_value = one '
+                       'batch-16 pass; single_thread_value = 1 image, 1 thread, 1 pass' % (Q, threads))
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot
-    travel to the GPU box) with all host threads, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path (verbatim head from oracle/_ref through
+    the mmcv/mmdet shim; the oracle port only if that copy is missing) with all host threads, each step a bounded
+    sample of the workload: ONE 1024x1024 image."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -159,24 +241,149 @@ def run_reference_arm(args):
     torch.set_num_threads(threads)
     Q = args.queries
     sample_b = 1
-    sd = synth.make_params(seed=0, num_queries=Q)
+    kind, step = cpu_path(Q)
     mf, mems = synth.make_inputs(0, sample_b, H, W)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(sd, mf, mems)
+        step(mf, mems)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(sd, mf, mems)
+        step(mf, mems)
     dt = time.perf_counter() - t0
     val = sample_b * args.steps / dt
+    # one batch-16 pass as well (the GPU arm's batch), reported beside the per-image number
+    mf16, mems16 = synth.make_inputs(0, 16, H, W)
+    t0 = time.perf_counter()
+    step(mf16, mems16)
+    b16 = 16.0 / (time.perf_counter() - t0)
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload='configs[1]: COCO-OVIS instance decoder head, Q=%d, 9 layers, 256-d, 1024x1024' % Q,
                             batch_per_step=sample_b, note='CPU path, bounded sample of 1 image per step'),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind='port',
-                                  sample='%d image(s) 1024x1024 per step, fp32 oracle port of the reference path' % sample_b),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind=kind, cpu_model=cpu_model(), b16_value=b16,
+                                  sample='%d image(s) 1024x1024 per step, fp32, %s; b16_value = one batch-16 pass' %
+                                         (sample_b, 'the unmodified reference head (oracle/_ref) under the mmcv/mmdet shim'
+                                          if kind == 'reference' else 'oracle port of the reference path')),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ side legs of our arm
+def torch_gpu_baseline(Q, B, dev):
+    """The same path as plain torch CUDA ops -- the oracle moved to the GPU, i.e. cuBLAS / ATen kernels, which is
+    what the reference executes on a GPU -- in fp32 and under bf16 autocast (the >= 10x target is
+    against the faster of the two)."""
+    from oracle import cgg_oracle as O
+    from cgg_b200 import synth
+    sd = {k: v.to(dev) for k, v in synth.make_params(seed=0, num_queries=Q).items()}
+    mf, mems = synth.make_inputs(0, B, H, W)
+    mf, mems = mf.to(dev), [m.to(dev) for m in mems]
+    out = {}
+    for name, ctx in (('fp32', torch.autocast('cuda', enabled=False)), ('bf16_autocast', torch.autocast('cuda', torch.bfloat16))):
+        with torch.no_grad(), ctx:
+            for _ in range(2):
+                O.decoder_forward(sd, mf, mems)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                O.decoder_forward(sd, mf, mems)
+            e1.record()
+            torch.cuda.synchronize()
+        out[name] = B * n / (e0.elapsed_time(e1) * 1e-3)
+    out.update(unit=UNIT, batch=B, note='oracle (plain torch ops) on the same GPU, 2 warm-up + 5 timed forwards, CUDA events')
+    return out
+
+
+def grounding_leg(dev, Bg=16, Q=100, T=35, D=768):
+    """K7 alone: the caption-grounding loss of one head call for Bg images x Bg captions (reference batch 2 x 8 GPUs),
+    forward + backward; algorithmic FLOPs = the similarity contraction 2 (Bg T)(Bg Q) D, x2 for the backward."""
+    from cgg_b200.grounding import grounding_loss
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randn((Bg, Q, D), generator=g).to(dev).requires_grad_(True)
+    cap = (torch.randn((Bg, T, D), generator=g) * 0.85).to(dev)
+    m = torch.zeros((Bg, T), dtype=torch.long)
+    for b in range(Bg):
+        m[b, :(3 * b) % 11] = 1
+    m = m.to(dev)
+    for _ in range(3):
+        grounding_loss(pred, cap, m, 10.0, 2.0).backward()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        pred.grad = None
+        grounding_loss(pred, cap, m, 10.0, 2.0).backward()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    fl = 2.0 * (Bg * T) * (Bg * Q) * D * 3      # forward S, backward recompute of S, dpred contraction
+    return dict(ms_fwd_bwd=ms, Bg=Bg, Q=Q, tokens=T, tflops=fl / (ms * 1e-3) / 1e12,
+                note='cgg_grounding_loss + cgg_grounding_loss_backward, one head call, fp32')
+
+
+def train_leg(args, rank, world, dev):
+    """BASELINE configs[3]: OSPS head (200 queries, 118 class rows), forward + backward of the decoder head with the
+    caption-grounding loss on every head call (weight 2.0) + class-embedding CE + a mask surrogate, per-GPU batch 2
+    (coco_panoptic_p20.py:236), NCCL all-reduce of the 14.7 M head gradients overlapped with the backward."""
+    import torch.distributed as dist
+    from cgg_b200 import synth
+    from cgg_b200.head import build_head_from_state_dict
+    from cgg_b200.grounding import grounding_loss, gather_captions_and_preds, similarity
+    from cgg_b200.train import GradReducer
+    Q, B, ncls1 = 200, args.train_batch, 118
+    sd = synth.make_params(seed=0, num_queries=Q, num_classes_p1=ncls1)
+    head = build_head_from_state_dict(sd, Q, ncls1, 'fp32', dev).train()
+    mf, mems = synth.make_inputs(100 + rank, B, H, W)
+    mf, mems = mf.to(dev), [m.to(dev) for m in mems]
+    ids, cap_mask, table, lw, lb = synth.make_captions(rank, B)
+    cap = head.extract_word_embeddings(table.to(dev), lw.to(dev), lb.to(dev), ids.to(dev))
+    cap_mask = cap_mask.to(dev)
+    g = torch.Generator().manual_seed(rank)
+    labels = torch.randint(0, ncls1, (B, Q), generator=g).to(dev)
+    targets = (torch.rand((B, Q, H // 4, W // 4), generator=g) > 0.5).to(dev).float()
+    reducer = GradReducer(head.parameters())
+
+    def step():
+        for p in head.parameters():
+            p.grad = None
+        cls, emb, mask = head.decoder_forward_auto(mf, mems)
+        loss = 0.0
+        embs_all, mask_all, preds_all = gather_captions_and_preds(cap, cap_mask, torch.stack(emb, 0))
+        for j in range(len(cls)):
+            loss = loss + grounding_loss(preds_all[j], embs_all, mask_all, 10.0, 2.0)
+            logits = similarity(emb[j].reshape(B * Q, -1), head.class_embs, 0.1)
+            loss = loss + torch.nn.functional.cross_entropy(logits, labels.reshape(-1))
+            loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(mask[j], targets)
+        loss.backward()
+        reducer.finish()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = args.train_steps
+    exposed = 0.0
+    e0.record()
+    for _ in range(n):
+        step()
+        exposed += reducer.exposed()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = reduce_max(e0.elapsed_time(e1) / n, world, dev)
+    exposed = reduce_max(exposed / n, world, dev)
+    nparam = sum(p.numel() for p in head.parameters())
+    reducer.remove()
+    return dict(ms_per_step=ms, images_per_s=world * B / (ms * 1e-3), batch_per_gpu=B, queries=Q, classes_p1=ncls1,
+                allreduce_exposed_ms=exposed, grad_bytes=4 * nparam, precision='fp32',
+                note='forward + backward through cgg_b200.train (every node a C-ABI kernel), losses: grounding x10 + '
+                     'class-embedding CE x10 + mask BCE surrogate x10; optimizer step excluded; bucketed NCCL all-reduce '
+                     'overlapped with backward')
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -188,6 +395,7 @@ def run_b200_arm(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback')
+    numa_cpus = pin_to_gpu_numa_node(local_rank) if world > 1 else 0
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -237,6 +445,18 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fork()
+        for _ in range(n):
+            step_resident()
+        join()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     fork()
     for _ in range(max(args.warmup, 3) * n_fly):
         out = step_resident()
@@ -255,16 +475,7 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.cgg_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    fork()
-    for _ in range(args.steps):
-        out = step_resident()
-    join()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(args.steps)
     launches = lib.cgg_launch_count() - launches0
     if launches == 0:
         # CUDA-graph replay: the host-side counter does not tick; count one eager pass of the same
@@ -276,6 +487,16 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = reduce_max(ms, world, dev)
     value = whole_job_value(world, B, args.steps, ms)
+
+    # ---- sustained leg: the same loop for >= 2 s (the K-step region above lasts tens of ms at boost clocks)
+    n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms / args.steps)) + 1)
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
+    ms_sus = reduce_max(timed(n_sus), world, dev)
+    sus_clocks = sampler2.stop() if rank == 0 else None
+    sustained = dict(value=whole_job_value(world, B, n_sus, ms_sus), unit=UNIT, steps=n_sus, seconds=ms_sus * 1e-3,
+                     ms_per_step=ms_sus / n_sus, clocks=sus_clocks)
 
     # ---- e2e: public API with HOST buffers; H2D of the step's inputs and D2H of the step's
     # result (last layer's cls / cls_emb / mask logits, what simple_test consumes, head.py:943-945)
@@ -333,12 +554,36 @@ def run_b200_arm(args):
     barrier()
     e2e_val = whole_job_value(world, B, e2e_steps, 1e3 * reduce_max(time.perf_counter() - t0, world, dev))
     d2h = sum(x.numel() * x.element_size() for x in res_h)
+    del in_bufs
+
+    # ---- strong scaling, BASELINE configs[2]: global batch 64 split evenly, 64/N images per GPU per step
+    strong = None
+    if args.precision == 'bf16' and not args.no_strong and 64 % world == 0:
+        bs = 64 // world
+        chunk = min(bs, 16)                      # N=1 runs the 64 images as 4 x 16
+        hs = head if chunk == B else build_head_from_state_dict(sd, Q, NCLS1, args.precision, dev, cuda_graph=not args.no_graph)
+        mfs, memss = synth.make_inputs(1000 + rank, chunk, H, W, dtype=dt_in)
+        mfs, memss = mfs.to(dev), [m.to(dev) for m in memss]
+        for _ in range(3):
+            hs.decoder_forward(mfs, memss)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = 5
+        e0.record()
+        for _ in range(n_it * (bs // chunk)):
+            hs.decoder_forward(mfs, memss)
+        e1.record()
+        barrier()
+        ms_s = reduce_max(e0.elapsed_time(e1) / n_it, world, dev)
+        strong = dict(global_batch=64, batch_per_gpu=bs, ms_per_global_batch=ms_s, value=64.0 / (ms_s * 1e-3), unit=UNIT,
+                      scaling='strong', note='configs[2]: 64 images per step over N GPUs, one batch in flight per GPU')
+        del hs, mfs, memss
 
     # ---- roofline of the dominant kernel (the mask einsum, 55% of the path's FLOPs): CUDA events
-    # on the launching stream around that stage alone, same inputs, averaged over launches
+    # on the launching stream around that stage alone, same inputs, back-to-back for >= 1 s so the clocks are the
+    # SUSTAINED ones the sustained peak was measured at
     rt = head._runtime(dev)
     peaks = measured_peaks()
-    reps = 10
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.precision == 'bf16':
         # K2 alone: ONE launch of the tcgen05 GEMM computes the mask logits of all 10 head calls
@@ -349,16 +594,23 @@ def run_b200_arm(args):
             rt.mask_einsum(mf_d, mask_out)
         torch.cuda.synchronize()
         k0.record()
+        rt.mask_einsum(mf_d, mask_out)
+        k1.record()
+        torch.cuda.synchronize()
+        reps = max(10, int(1000.0 / max(k0.elapsed_time(k1), 1e-3)))
+        k0.record()
         for _ in range(reps):
             rt.mask_einsum(mf_d, mask_out)
         k1.record()
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / reps
         flops = einsum_flops_per_launch(Q, B) * (LAYERS + 1)
+        alg_bytes = B * C * (H // 4) * (W // 4) * 2 + (LAYERS + 1) * B * Q * (H // 4) * (W // 4) * 2
         kname = 'tc_einsum_t_kernel (cta_group::2, queries on TMEM lanes): mask einsum of all 10 head calls, one launch (cgg_mask_einsum)'
         del mask_out
     else:
         x0 = torch.randn((B, Q, C), device=dev)
+        reps = 10
         for _ in range(3):
             rt.head_call(x0, mf_d, 0, want_bits=False)
         torch.cuda.synchronize()
@@ -369,21 +621,53 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / reps
         flops = einsum_flops_per_launch(Q, B)
+        alg_bytes = B * C * (H // 4) * (W // 4) * 4 + B * Q * (H // 4) * (W // 4) * 4
         kname = 'cgg_head_call stage (fp32 SIMT heads + mask einsum of one head call)'
-    ach = flops / (kern_ms * 1e-3) / 1e12
-    traffic = None
+    ach_tf = flops / (kern_ms * 1e-3) / 1e12
+    ach_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
+    frac_t, frac_h = ach_tf / peaks['tflops'], ach_gbs / peaks['hbm_gbs']
+    # the binding roof is the one the kernel sits closer to: arithmetic intensity vs the ridge of the measured peaks
+    ai, ridge = flops / alg_bytes, peaks['tflops'] * 1e12 / (peaks['hbm_gbs'] * 1e9)
+    hbm_bound = ai < ridge
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, 'profiles', 'einsum_dram_traffic.json')
     if args.precision == 'bf16' and os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get('batch') == B and tj.get('queries') == Q:
             traffic = tj.get('dram_bytes_per_launch')
-    roofline = dict(bound='tensor', achieved=ach, peak=peaks['tflops'], unit='TFLOP/s', frac=ach / peaks['tflops'],
-                    traffic=traffic, kernel=kname, kernel_ms=kern_ms,
-                    algorithmic_bytes=(B * C * (H // 4) * (W // 4) * 2 + (LAYERS + 1) * B * Q * (H // 4) * (W // 4) * 2)
-                    if args.precision == 'bf16' else None,
-                    peak_source=peaks['source'] + ' (sustained bf16)',
-                    whole_path=dict(achieved=flops_per_image(Q) * value / 1e12, unit='TFLOP/s',
-                                    frac=flops_per_image(Q) * value / 1e12 / peaks['tflops']))
+            traffic_src = 'profiles/einsum_dram_traffic.json (ncu --set full capture %s, not re-measured in this run)' % tj.get('capture', '')
+    per_gpu_value = value / world
+    roofline = dict(bound='hbm' if hbm_bound else 'tensor',
+                    achieved=ach_gbs if hbm_bound else ach_tf, peak=peaks['hbm_gbs'] if hbm_bound else peaks['tflops'],
+                    unit='GB/s' if hbm_bound else 'TFLOP/s', frac=frac_h if hbm_bound else frac_t,
+                    traffic=traffic, traffic_source=traffic_src, kernel=kname, kernel_ms=kern_ms, launches_timed=reps,
+                    algorithmic_bytes=alg_bytes, algorithmic_flops=flops, arithmetic_intensity=ai, ridge=ridge,
+                    tensor=dict(achieved=ach_tf, peak=peaks['tflops'], frac=frac_t, unit='TFLOP/s',
+                                frac_of_burst=ach_tf / peaks['tflops_burst']),
+                    hbm=dict(achieved=ach_gbs, peak=peaks['hbm_gbs'], frac=frac_h, unit='GB/s'),
+                    peak_source=peaks['source'] + ' (sustained bf16: the kernel is timed back-to-back for >= 1 s; HBM copy bandwidth)',
+                    whole_path=dict(achieved=flops_per_image(Q) * per_gpu_value / 1e12, unit='TFLOP/s per GPU',
+                                    frac=flops_per_image(Q) * per_gpu_value / 1e12 / peaks['tflops'],
+                                    sustained_frac=flops_per_image(Q) * sustained['value'] / world / 1e12 / peaks['tflops']))
+
+    # ---- stage / config legs
+    grounding = train = None
+    if not args.no_train:
+        try:
+            grounding = grounding_leg(dev) if rank == 0 else None
+            del heads, fly_in
+            torch.cuda.empty_cache()
+            train = train_leg(args, rank, world, dev)
+        except Exception as e:      # noqa: BLE001
+            train = dict(error=repr(e)[:300])
+    tgb = None
+    if rank == 0 and world == 1 and not args.no_torch_baseline:
+        try:
+            torch.cuda.empty_cache()
+            tgb = torch_gpu_baseline(Q, B, dev)
+            tgb['speedup_vs_faster'] = value / max(tgb['fp32'], tgb['bf16_autocast'])
+        except Exception as e:      # noqa: BLE001
+            tgb = dict(error=repr(e)[:300])
 
     if rank == 0:
         cpu = cpu_baseline(Q, os.cpu_count() or 1) if (world == 1 and not args.no_cpu_baseline) else None
@@ -396,10 +680,19 @@ def run_b200_arm(args):
                                 cuda_graph=not args.no_graph, in_flight_batches=n_fly,
                                 final_mask_only=bool(args.final_mask_only),
                                 single_batch_latency_ms=latency_ms,
+                                single_batch_images_per_s=B / (latency_ms * 1e-3),
                                 l2='inputs (%.0f MB per step) larger than L2, no explicit flush' % (h2d / 1e6),
-                                flops_per_image=flops_per_image(Q)),
+                                flops_per_image=flops_per_image(Q), numa_pinned_cpus=numa_cpus),
                     e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
-                    gpu_launches=int(launches), roofline=roofline, clocks=clocks)
+                    gpu_launches=int(launches), roofline=roofline, clocks=clocks, sustained=sustained)
+        if strong is not None:
+            line['strong_scaling'] = strong
+        if train is not None:
+            line['train'] = train
+        if grounding is not None:
+            line['grounding'] = grounding
+        if tgb is not None:
+            line['torch_gpu_baseline'] = tgb
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
@@ -417,6 +710,12 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--queries', type=int, default=100)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the configs[3] training-step leg and the K7 stage leg')
+    ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling leg')
+    ap.add_argument('--train-batch', type=int, default=2, help='images per GPU in the training-step leg')
+    ap.add_argument('--train-steps', type=int, default=3)
+    ap.add_argument('--sustain-s', type=float, default=2.0, help='length of the sustained leg in seconds')
     ap.add_argument('--no-graph', action='store_true', help='launch the path eagerly instead of replaying a CUDA graph')
     ap.add_argument('--final-mask-only', action='store_true',
                     help='opt-in inference shortcut: produce the last head call mask only (NOT the headline contract)')

@@ -673,3 +673,124 @@ extern "C" int cgg_grounding_loss_backward(cgg_handle* h, const float* pred, con
   CU(launch_gemm_f32(p, s));
   return CGG_OK;
 }
+
+// ====================================================================== training-step stages
+extern "C" int cgg_gemm_f32(cgg_handle* h, const cgg_gemm_desc* d, void* stream) {
+  if (!h || !d || !d->A || !d->W || !d->C) return CGG_ERR_NULL;
+  if (d->M < 0 || d->N < 0 || d->K < 0 || d->batch < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad gemm shape");
+  if ((long)d->batch > 65535 || ((long)d->N + 63) / 64 > 65535) return fail(h, CGG_ERR_BAD_SHAPE, "gemm grid too large");
+  GemmF32 p;
+  p.A = d->A; p.sAb = d->sAb; p.sAm = d->sAm; p.sAk = d->sAk;
+  if (d->A2) { p.A2 = d->A2; p.sA2m = d->sA2m; p.sA2k = d->sA2k; p.a2_mod = d->a2_mod > 0 ? d->a2_mod : 1; }
+  p.W = d->W; p.sWb = d->sWb; p.sWn = d->sWn; p.sWk = d->sWk;
+  p.bias = d->bias;
+  if (d->R) { p.R = d->R; p.sRb = d->sRb; p.sRm = d->sRm; p.sRn = d->sRn; p.r_mod = d->r_mod > 0 ? d->r_mod : 1; p.r_ncols = d->r_ncols; }
+  p.C = d->C; p.sCb = d->sCb; p.sCm = d->sCm; p.sCn = d->sCn;
+  p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+  if (d->relu) p.relu_from = 0;
+  p.alpha = d->alpha;
+  p.a_mmajor = d->a_mmajor != 0; p.c_mmajor = d->c_mmajor != 0;
+  CU(launch_gemm_f32(p, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_layernorm(cgg_handle* h, const float* x, const float* w, const float* b, float* y, int rows, int n,
+                             float eps, void* stream) {
+  if (!h || !x || !w || !b || !y) return CGG_ERR_NULL;
+  if (rows < 0 || n <= 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_layernorm(x, nullptr, w, b, y, rows, n, eps, true, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" size_t cgg_layernorm_bwd_scratch_bytes(int rows, int n) {
+  return rows > 0 && n > 0 ? (size_t)((rows + 7) / 8) * 2 * n * sizeof(float) : 0;
+}
+
+extern "C" int cgg_layernorm_backward(cgg_handle* h, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                                      float* db, void* scratch, size_t scratch_bytes, int rows, int n, float eps,
+                                      void* stream) {
+  if (!h || !x || !w || !dy || !dx || !dw || !db || !scratch) return CGG_ERR_NULL;
+  if (rows <= 0 || n <= 0 || (size_t)8 * 2 * n * sizeof(float) > 200 * 1024) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if (scratch_bytes < cgg_layernorm_bwd_scratch_bytes(rows, n)) return fail(h, CGG_ERR_WORKSPACE, "scratch too small");
+  CU(launch_layernorm_bwd(x, w, dy, dx, dw, db, static_cast<float*>(scratch), rows, n, eps, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_relu_backward(cgg_handle* h, const float* y, const float* dy, float* dx, long n, float alpha, void* stream) {
+  if (!h || !y || !dy || !dx) return CGG_ERR_NULL;
+  CU(launch_relu_bwd(y, dy, dx, n, alpha, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_axpy(cgg_handle* h, const float* in, float* out, long n, float alpha, void* stream) {
+  if (!h || !in || !out) return CGG_ERR_NULL;
+  CU(launch_axpy(in, out, n, alpha, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_add_rows(cgg_handle* h, const float* x, const float* add, float* out, int batch, long per, void* stream) {
+  if (!h || !add || !out) return CGG_ERR_NULL;
+  if (batch < 1 || per < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_add_rows(x, add, out, batch, per, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_sum_batch(cgg_handle* h, const float* g, float* out, int batch, long per, void* stream) {
+  if (!h || !g || !out) return CGG_ERR_NULL;
+  if (batch < 1 || per < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_sum_batch(g, out, batch, per, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_colsum(cgg_handle* h, const float* g, float* out, long rows, int n, float alpha, void* stream) {
+  if (!h || !g || !out) return CGG_ERR_NULL;
+  if (rows < 0 || n < 1 || (rows + 255) / 256 > 65535) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_colsum(g, out, rows, n, alpha, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_mem_prep(cgg_handle* h, const float* mem, const float* level, const float* pos_level, float* key_in,
+                            float* val_in, int batch, int C, int K, void* stream) {
+  if (!h || !mem || !level || !pos_level || !key_in || !val_in) return CGG_ERR_NULL;
+  if (batch < 1 || batch > 65535 || C < 1 || K < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_mem_prep(mem, level, pos_level, key_in, val_in, batch, C, K, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_mem_prep_backward(cgg_handle* h, const float* dkey_in, const float* dval_in, float* dmem, int batch,
+                                     int C, int K, void* stream) {
+  if (!h || !dkey_in || !dval_in || !dmem) return CGG_ERR_NULL;
+  if (batch < 1 || batch > 65535 || C < 1 || K < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_mem_prep_bwd(dkey_in, dval_in, dmem, batch, C, K, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_sine_pos(cgg_handle* h, float* out, int hh, int ww, int C, void* stream) {
+  if (!h || !out) return CGG_ERR_NULL;
+  if (hh < 1 || ww < 1 || C < 2 || (C & 1)) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_pos_level(nullptr, out, hh, ww, C, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_attention_f32(cgg_handle* h, int batch, int num_q, int num_keys, const float* q, const float* k,
+                                 const float* v, long kv_stride, long kv_batch_stride, const uint32_t* bitmap,
+                                 const uint8_t* all_masked, float* out, void* stream) {
+  if (!h || !q || !k || !v || !out) return CGG_ERR_NULL;
+  if (batch < 1 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_attention_f32(q, k, v, false, kv_stride, kv_batch_stride, bitmap, all_masked, out, nullptr, batch, num_q,
+                          num_keys, h->cfg.num_heads, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_attention_backward(cgg_handle* h, int batch, int num_q, int num_keys, const float* q, const float* k,
+                                      const float* v, long kv_stride, long kv_batch_stride, const uint32_t* bitmap,
+                                      const uint8_t* all_masked, const float* out, const float* dout, float* dq,
+                                      float* dk, float* dv, long dkv_stride, long dkv_batch_stride, float* scratch,
+                                      void* stream) {
+  if (!h || !q || !k || !v || !out || !dout || !dq || !dk || !dv || !scratch) return CGG_ERR_NULL;
+  if (batch < 1 || batch > 65535 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  const size_t n = (size_t)batch * h->cfg.num_heads * num_q;
+  CU(launch_attention_bwd(q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, dout, scratch, scratch + n, dq, dk,
+                          dv, dkv_stride, dkv_batch_stride, batch, num_q, num_keys, h->cfg.num_heads, (cudaStream_t)stream));
+  return CGG_OK;
+}

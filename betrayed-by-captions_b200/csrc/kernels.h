@@ -67,6 +67,23 @@ cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, cons
                                        int D, float temperature, const float* dg_l2v, const float* dg_v2l,
                                        float grad_scale, float* dS, cudaStream_t s);
 
+// ---- training step (train_kernels.cu)
+cudaError_t launch_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                                 float* partial, int rows, int n, float eps, cudaStream_t s);
+cudaError_t launch_relu_bwd(const float* y, const float* dy, float* dx, long n, float alpha, cudaStream_t s);
+cudaError_t launch_axpy(const float* in, float* out, long n, float alpha, cudaStream_t s);
+cudaError_t launch_add_rows(const float* x, const float* add, float* out, int batch, long per, cudaStream_t s);
+cudaError_t launch_sum_batch(const float* g, float* out, int batch, long per, cudaStream_t s);
+cudaError_t launch_mem_prep(const float* mem, const float* level, const float* pos_level, float* key_in, float* val_in,
+                            int B, int C, int K, cudaStream_t s);
+cudaError_t launch_mem_prep_bwd(const float* dkey, const float* dval, float* dmem, int B, int C, int K, cudaStream_t s);
+cudaError_t launch_colsum(const float* g, float* out, long rows, int n, float alpha, cudaStream_t s);
+// lse, dsum: (B, heads, Q) scratch each
+cudaError_t launch_attention_bwd(const float* q, const float* k, const float* v, long kv_stride, long kv_bstride,
+                                 const uint32_t* bitmap, const uint8_t* all_masked, const float* o, const float* dout,
+                                 float* lse, float* dsum, float* dq, float* dk, float* dv, long dkv_stride,
+                                 long dkv_bstride, int B, int Q, int K, int heads, cudaStream_t s);
+
 // fp32 (rows, cols) -> bf16 (rows, 2*cols) hi/lo pairs: [hi | lo] per row
 cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s);
 // fp32 -> bf16 cast (n elements)

@@ -165,7 +165,7 @@ __global__ void pos_level_kernel(const float* __restrict__ level_embed, float* _
   const float dim_t = (float)pow(10000.0, (double)(2 * (cc / 2)) / (double)F);
   const float a = e / dim_t;
   const float v = (cc & 1) ? (float)cos((double)a) : (float)sin((double)a);
-  out[i] = v + level_embed[c];
+  out[i] = v + (level_embed ? level_embed[c] : 0.f);
 }
 cudaError_t launch_pos_level(const float* level_embed, float* out, int h, int w, int C, cudaStream_t s) {
   const long total = (long)h * w * C;

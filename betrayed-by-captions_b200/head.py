@@ -143,6 +143,14 @@ class Mask2FormerHeadOpenB200(nn.Module):
                                 'mmdet\'s MSDeformAttnPixelDecoder)')
         mask_features, multi_scale_memorys = self.pixel_decoder(feats)       # head.py:787
         assert mask_features.shape[0] == batch_size
+        return self.decoder_forward_auto(mask_features, multi_scale_memorys)
+
+    def decoder_forward_auto(self, mask_features, multi_scale_memorys):
+        """Inference kernels under no_grad, the autograd-connected training path (train.py) when gradients are
+        being recorded -- the reference's forward is one function for both (head.py:763-849)."""
+        if torch.is_grad_enabled() and (mask_features.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .train import decoder_forward_train
+            return decoder_forward_train(self, mask_features, multi_scale_memorys)
         with torch.no_grad():
             return self.decoder_forward(mask_features, multi_scale_memorys)
 
@@ -197,6 +205,7 @@ class _Runtime:
         self.batch = None
         self._keep = []
         self._graphs = {}
+        self._pos = {}
 
     def __del__(self):
         try:
@@ -365,6 +374,17 @@ class _Runtime:
         if return_debug:
             return outs + (dict(x=xs, bitmaps=bms, all_masked=am),)
         return outs
+
+    def sine_pos(self, h, w):
+        """(h*w, C) sine positional encoding (head.py:798-804), cached per size."""
+        key = (h, w)
+        if key not in self._pos:
+            out = torch.empty((h * w, self.head.feat_channels), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.cgg_sine_pos(self.handle, _ptr(out), h, w, self.head.feat_channels, self._stream()),
+                           self.handle, 'cgg_sine_pos')
+            self._pos[key] = out
+        return self._pos[key]
 
     # ---- stages (parity tests, teacher forcing)
     def kv_project(self, memories):

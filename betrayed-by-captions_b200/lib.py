@@ -15,7 +15,11 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            'cgg_decoder_forward', 'cgg_kv_project', 'cgg_head_call', 'cgg_attn_mask_from_logits',
            'cgg_decoder_layer', 'cgg_mask_einsum', 'cgg_masked_attention', 'cgg_noun_embeddings', 'cgg_similarity',
            'cgg_grounding_scratch_bytes', 'cgg_grounding_loss', 'cgg_grounding_bwd_scratch_bytes',
-           'cgg_grounding_loss_backward', 'cgg_set_final_mask_only']
+           'cgg_grounding_loss_backward', 'cgg_set_final_mask_only',
+           # training-step stages
+           'cgg_gemm_f32', 'cgg_layernorm', 'cgg_layernorm_bwd_scratch_bytes', 'cgg_layernorm_backward', 'cgg_relu_backward',
+           'cgg_axpy', 'cgg_add_rows', 'cgg_sum_batch', 'cgg_colsum', 'cgg_mem_prep', 'cgg_mem_prep_backward', 'cgg_sine_pos',
+           'cgg_attention_f32', 'cgg_attention_backward']
 
 
 class Config(C.Structure):
@@ -34,6 +38,19 @@ class Weights(C.Structure):
                [('me_w', C.c_void_p * 3), ('me_b', C.c_void_p * 3)] + \
                [(n, C.c_void_p) for n in ('v2l_w', 'v2l_b', 'post_norm_w', 'post_norm_b')] + \
                [('layers', LayerWeights * MAX_LAYERS)]
+
+
+class GemmDesc(C.Structure):
+    """cgg_gemm_desc (include/cgg_b200.h)"""
+    _fields_ = [('A', C.c_void_p), ('sAb', C.c_long), ('sAm', C.c_long), ('sAk', C.c_long),
+                ('A2', C.c_void_p), ('sA2m', C.c_long), ('sA2k', C.c_long), ('a2_mod', C.c_int),
+                ('W', C.c_void_p), ('sWb', C.c_long), ('sWn', C.c_long), ('sWk', C.c_long),
+                ('bias', C.c_void_p),
+                ('R', C.c_void_p), ('sRb', C.c_long), ('sRm', C.c_long), ('sRn', C.c_long), ('r_mod', C.c_int),
+                ('r_ncols', C.c_int),
+                ('C', C.c_void_p), ('sCb', C.c_long), ('sCm', C.c_long), ('sCn', C.c_long),
+                ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch', C.c_int),
+                ('relu', C.c_int), ('alpha', C.c_float), ('a_mmajor', C.c_int), ('c_mmajor', C.c_int)]
 
 
 class CggError(RuntimeError):
@@ -82,6 +99,22 @@ def load():
     lib.cgg_grounding_bwd_scratch_bytes.argtypes = [i, i, i]
     lib.cgg_grounding_bwd_scratch_bytes.restype = sz
     lib.cgg_grounding_loss_backward.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_float, C.c_float, C.c_float, vp, vp, sz, vp]
+    f32, lg = C.c_float, C.c_long
+    lib.cgg_gemm_f32.argtypes = [vp, C.POINTER(GemmDesc), vp]
+    lib.cgg_layernorm.argtypes = [vp, vp, vp, vp, vp, i, i, f32, vp]
+    lib.cgg_layernorm_bwd_scratch_bytes.argtypes = [i, i]
+    lib.cgg_layernorm_bwd_scratch_bytes.restype = sz
+    lib.cgg_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, f32, vp]
+    lib.cgg_relu_backward.argtypes = [vp, vp, vp, vp, lg, f32, vp]
+    lib.cgg_axpy.argtypes = [vp, vp, vp, lg, f32, vp]
+    lib.cgg_add_rows.argtypes = [vp, vp, vp, vp, i, lg, vp]
+    lib.cgg_sum_batch.argtypes = [vp, vp, vp, i, lg, vp]
+    lib.cgg_colsum.argtypes = [vp, vp, vp, lg, i, f32, vp]
+    lib.cgg_mem_prep.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.cgg_mem_prep_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    lib.cgg_sine_pos.argtypes = [vp, vp, i, i, i, vp]
+    lib.cgg_attention_f32.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp]
+    lib.cgg_attention_backward.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp, vp, vp, vp, lg, lg, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('cgg_destroy',):

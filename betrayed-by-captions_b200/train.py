@@ -1,0 +1,410 @@
+"""Training step of the decoder head: the forward of `Mask2FormerHeadOpen.forward` (mask2former_head.py:763-849) as an
+autograd graph whose every node is a kernel of the C-ABI library -- forward AND backward -- so that
+`forward_train -> loss -> backward` (mask2former_head.py:851-921, :393-462) reaches every parameter of the head, the
+pixel-decoder features and the memories exactly as the reference's autograd does (the
+attention mask is detached, nothing flows through K3).
+
+PyTorch is the tape (autograd.Function), the allocator and the stream; it computes nothing here.  All arithmetic is fp32
+(CGG_FP32 kernels): the parity mode extended with gradients.  Gradient all-reduce over NVLink for data-parallel
+training lives in `GradReducer` below (bucketed NCCL all-reduce overlapped with the backward; reference: mmcv's
+MMDistributedDataParallel built at open_set/apis/train.py:156-161).
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _K:
+    """Thin launcher over the stage entry points of include/cgg_b200.h for one runtime (handle + device)."""
+
+    def __init__(self, rt):
+        self.rt, self.lib, self.h, self.dev = rt, rt.lib, rt.handle, rt.device
+
+    def s(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def chk(self, st, what):
+        _lib.check(st, self.h, what)
+
+    def new(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def gemm(self, A, sA, W, sW, Cc, sC, M, N, K, batch=1, bias=None, R=None, sR=(0, 0, 0), r_mod=None, alpha=1.0,
+             relu=False, a_mmajor=False, c_mmajor=False):
+        """C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); element strides
+        sA = (b, m, k), sW = (b, n, k), sC = (b, m, n), sR = (b, m, n)."""
+        d = _lib.GemmDesc()
+        d.A, (d.sAb, d.sAm, d.sAk) = A.data_ptr(), sA
+        d.A2, d.a2_mod = None, 1
+        d.W, (d.sWb, d.sWn, d.sWk) = W.data_ptr(), sW
+        d.bias = bias.data_ptr() if bias is not None else None
+        if R is not None:
+            d.R, (d.sRb, d.sRm, d.sRn) = R.data_ptr(), sR
+            d.r_mod = r_mod if r_mod is not None else M
+        else:
+            d.R, d.r_mod = None, 1
+        d.r_ncols = 1 << 30
+        d.C, (d.sCb, d.sCm, d.sCn) = Cc.data_ptr(), sC
+        d.M, d.N, d.K, d.batch = M, N, K, batch
+        d.relu, d.alpha = int(relu), float(alpha)
+        d.a_mmajor, d.c_mmajor = int(a_mmajor), int(c_mmajor)
+        self.chk(self.lib.cgg_gemm_f32(self.h, C.byref(d), self.s()), 'cgg_gemm_f32')
+
+
+# ------------------------------------------------------------------------------------------- autograd nodes
+class _Linear(torch.autograd.Function):
+    """y = relu?((x W^T + b) * alpha + res).  x (rows, K) contiguous, W (N, K), res (rows, N) or None."""
+
+    @staticmethod
+    def forward(ctx, k, x, W, b, res, alpha, relu):
+        rows, Kd = x.shape
+        N = W.shape[0]
+        y = k.new(rows, N)
+        k.gemm(x, (0, Kd, 1), W, (0, Kd, 1), y, (0, N, 1), rows, N, Kd, bias=b, R=res, sR=(0, N, 1), r_mod=rows,
+               alpha=alpha, relu=relu)
+        ctx.k, ctx.alpha, ctx.relu, ctx.has_res, ctx.has_b = k, alpha, relu, res is not None, b is not None
+        ctx.save_for_backward(x, W, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = ctx.k
+        x, W, y = ctx.saved_tensors
+        rows, Kd = x.shape
+        N = W.shape[0]
+        dy = dy.contiguous()
+        g = dy
+        if ctx.relu:                                      # (never combined with a residual on this path)
+            g = k.new(rows, N)
+            k.chk(k.lib.cgg_relu_backward(k.h, _p(y), _p(dy), _p(g), rows * N, 1.0, k.s()), 'cgg_relu_backward')
+        dx = dW = db = None
+        if ctx.needs_input_grad[1]:                       # dx[m,kk] = alpha * sum_n g[m,n] W[n,kk]
+            dx = k.new(rows, Kd)
+            k.gemm(g, (0, N, 1), W, (0, 1, Kd), dx, (0, Kd, 1), rows, Kd, N, alpha=ctx.alpha)
+        if ctx.needs_input_grad[2]:                       # dW[n,kk] = alpha * sum_m g[m,n] x[m,kk]
+            dW = k.new(N, Kd)
+            k.gemm(g, (0, 1, N), x, (0, 1, Kd), dW, (0, Kd, 1), N, Kd, rows, alpha=ctx.alpha, a_mmajor=True)
+        if ctx.has_b and ctx.needs_input_grad[3]:
+            db = k.new(N)
+            k.chk(k.lib.cgg_colsum(k.h, _p(g), _p(db), rows, N, ctx.alpha, k.s()), 'cgg_colsum')
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        return None, dx, dW, db, dres, None, None
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, k, x, w, b, eps):
+        rows, n = x.shape
+        y = k.new(rows, n)
+        k.chk(k.lib.cgg_layernorm(k.h, _p(x), _p(w), _p(b), _p(y), rows, n, eps, k.s()), 'cgg_layernorm')
+        ctx.k, ctx.eps = k, eps
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k = ctx.k
+        x, w = ctx.saved_tensors
+        rows, n = x.shape
+        dy = dy.contiguous()
+        dx, dw, db = k.new(rows, n), k.new(n), k.new(n)
+        nb = k.lib.cgg_layernorm_bwd_scratch_bytes(rows, n)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=k.dev)
+        k.chk(k.lib.cgg_layernorm_backward(k.h, _p(x), _p(w), _p(dy), _p(dx), _p(dw), _p(db), _p(scratch), nb, rows, n,
+                                           ctx.eps, k.s()), 'cgg_layernorm_backward')
+        return None, dx, dw, db, None
+
+
+class _AddRows(torch.autograd.Function):
+    """out[b] = x[b] + add  (x (B, M, K) or None = zeros; add (M, K)): `x + query_embed`, the query_feat broadcast."""
+
+    @staticmethod
+    def forward(ctx, k, x, add, batch):
+        per = add.numel()
+        out = k.new(batch, *add.shape)
+        k.chk(k.lib.cgg_add_rows(k.h, _p(x), _p(add), _p(out), batch, per, k.s()), 'cgg_add_rows')
+        ctx.k, ctx.batch, ctx.has_x = k, batch, x is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k = ctx.k
+        g = g.contiguous()
+        dadd = None
+        if ctx.needs_input_grad[2]:
+            dadd = k.new(*g.shape[1:])
+            k.chk(k.lib.cgg_sum_batch(k.h, _p(g), _p(dadd), ctx.batch, dadd.numel(), k.s()), 'cgg_sum_batch')
+        return None, (g if ctx.has_x else None), dadd, None
+
+
+class _MemPrep(torch.autograd.Function):
+    """key_in = mem^T + level + pos, val_in = mem^T + level (head.py:792-804); mem (B, C, h, w) -> (B, K, C) x 2."""
+
+    @staticmethod
+    def forward(ctx, k, mem, level, pos):
+        B, Cc, h, w = mem.shape
+        K = h * w
+        pos_level = k.new(K, Cc)
+        k.chk(k.lib.cgg_add_rows(k.h, _p(pos), _p(level), _p(pos_level), K, Cc, k.s()), 'cgg_add_rows')   # pos + level
+        key_in, val_in = k.new(B, K, Cc), k.new(B, K, Cc)
+        k.chk(k.lib.cgg_mem_prep(k.h, _p(mem), _p(level), _p(pos_level), _p(key_in), _p(val_in), B, Cc, K, k.s()),
+              'cgg_mem_prep')
+        ctx.k, ctx.shape = k, (B, Cc, h, w)
+        return key_in, val_in
+
+    @staticmethod
+    def backward(ctx, dkey, dval):
+        k = ctx.k
+        B, Cc, h, w = ctx.shape
+        K = h * w
+        dkey, dval = dkey.contiguous(), dval.contiguous()
+        dmem = dlevel = None
+        if ctx.needs_input_grad[1]:
+            dmem = k.new(B, Cc, h, w)
+            k.chk(k.lib.cgg_mem_prep_backward(k.h, _p(dkey), _p(dval), _p(dmem), B, Cc, K, k.s()), 'cgg_mem_prep_backward')
+        if ctx.needs_input_grad[2]:
+            a, b2 = k.new(Cc), k.new(Cc)
+            k.chk(k.lib.cgg_colsum(k.h, _p(dkey), _p(a), B * K, Cc, 1.0, k.s()), 'cgg_colsum')
+            k.chk(k.lib.cgg_colsum(k.h, _p(dval), _p(b2), B * K, Cc, 1.0, k.s()), 'cgg_colsum')
+            k.chk(k.lib.cgg_axpy(k.h, _p(b2), _p(a), Cc, 1.0, k.s()), 'cgg_axpy')
+            dlevel = a
+        return None, dmem, dlevel, None
+
+
+class _Attention(torch.autograd.Function):
+    """softmax(q k^T + mask) v per head.  q (B, Q, C) scaled; k, v (B, K, C); bitmap / all_masked or None."""
+
+    @staticmethod
+    def forward(ctx, k_, q, kk, v, bitmap, all_masked):
+        B, Q, Cc = q.shape
+        K = kk.shape[1]
+        out = k_.new(B, Q, Cc)
+        k_.chk(k_.lib.cgg_attention_f32(k_.h, B, Q, K, _p(q), _p(kk), _p(v), Cc, K * Cc, _p(bitmap), _p(all_masked),
+                                        _p(out), k_.s()), 'cgg_attention_f32')
+        ctx.k = k_
+        ctx.save_for_backward(q, kk, v, out, bitmap, all_masked)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        k_ = ctx.k
+        q, kk, v, out, bitmap, all_masked = ctx.saved_tensors
+        B, Q, Cc = q.shape
+        K = kk.shape[1]
+        dout = dout.contiguous()
+        dq, dk, dv = k_.new(B, Q, Cc), k_.new(B, K, Cc), k_.new(B, K, Cc)
+        heads = k_.rt.head.num_heads
+        scratch = k_.new(2 * B * heads * Q)
+        k_.chk(k_.lib.cgg_attention_backward(k_.h, B, Q, K, _p(q), _p(kk), _p(v), Cc, K * Cc, _p(bitmap), _p(all_masked),
+                                             _p(out), _p(dout), _p(dq), _p(dk), _p(dv), Cc, K * Cc, _p(scratch),
+                                             k_.s()), 'cgg_attention_backward')
+        return None, dq, dk, dv, None, None
+
+
+class _MaskEinsum(torch.autograd.Function):
+    """mask_pred[b,q,p] = sum_c me[b,q,c] F[b,c,p]  (head.py:748).  me (B, Q, C), F (B, C, H4, W4)."""
+
+    @staticmethod
+    def forward(ctx, k, me, F):
+        B, Q, Cc = me.shape
+        H4, W4 = F.shape[-2:]
+        HW = H4 * W4
+        out = k.new(B, Q, H4, W4)
+        k.gemm(F, (Cc * HW, 1, HW), me, (Q * Cc, Cc, 1), out, (Q * HW, 1, HW), HW, Q, Cc, batch=B, a_mmajor=True,
+               c_mmajor=True)
+        ctx.k = k
+        ctx.save_for_backward(me, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, dmask):
+        k = ctx.k
+        me, F = ctx.saved_tensors
+        B, Q, Cc = me.shape
+        H4, W4 = F.shape[-2:]
+        HW = H4 * W4
+        dmask = dmask.contiguous()
+        dme = dF = None
+        if ctx.needs_input_grad[1]:                       # dme[b,q,c] = sum_p dmask[b,q,p] F[b,c,p]
+            dme = k.new(B, Q, Cc)
+            k.gemm(dmask, (Q * HW, HW, 1), F, (Cc * HW, HW, 1), dme, (Q * Cc, Cc, 1), Q, Cc, HW, batch=B)
+        if ctx.needs_input_grad[2]:                       # dF[b,c,p] = sum_q me[b,q,c] dmask[b,q,p]
+            dF = k.new(B, Cc, H4, W4)
+            k.gemm(dmask, (Q * HW, 1, HW), me, (Q * Cc, 1, Cc), dF, (Cc * HW, 1, HW), HW, Cc, Q, batch=B, a_mmajor=True,
+                   c_mmajor=True)
+        return None, dme, dF
+
+
+# --------------------------------------------------------------------------------------------- the forward
+def decoder_forward_train(head, mask_features, multi_scale_memorys):
+    """Autograd-connected `(cls_list, cls_emb_list, mask_list)` (10 entries each) of head.py:787-849, fp32.
+    mask_features (B, C, H4, W4) and the three memories may require grad (they come from the pixel decoder)."""
+    if not mask_features.is_cuda:
+        raise _lib.CggError('the training path runs on CUDA only (no CPU fallback)')
+    if head.pred_emb_norm and head.use_class_emb:
+        raise _lib.CggError('pred_emb_norm with use_class_emb is not built on the training path')
+    rt = head._runtime(mask_features.device)
+    k = _K(rt)
+    mf = mask_features.float().contiguous()
+    mems = [m.float().contiguous() for m in multi_scale_memorys]
+    B, Cc, H4, W4 = mf.shape
+    Q, L = head.num_queries, head.num_transformer_decoder_layers
+    sizes = [tuple(m.shape[-2:]) for m in mems]
+    scale = 1.0 / math.sqrt(Cc // head.num_heads)
+    dec = head.transformer_decoder
+    qe = head.query_embed.weight
+    with torch.no_grad():
+        pos = [rt.sine_pos(h, w) for (h, w) in sizes]                          # (K_l, C) constants
+    prep = [_MemPrep.apply(k, mems[l], head.level_embed.weight[l], pos[l]) for l in range(3)]
+
+    def lin(x, m, res=None, alpha=1.0, relu=False, rows=None):
+        W, b = (m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m
+        return _Linear.apply(k, x, W, b, res, alpha, relu)
+
+    def ln(x, m):
+        return _LayerNorm.apply(k, x, m.weight, m.bias, 1e-5)
+
+    cls_list, emb_list, mask_list = [], [], []
+
+    def head_call(x, lvl):
+        """forward_head, head.py:711-761; returns the detached attention-mask bitmap for level lvl."""
+        z = ln(x.view(B * Q, Cc), dec.post_norm)
+        cls = lin(z, head.cls_embed).view(B, Q, -1)
+        emb = lin(z, head.v2l_transform).view(B, Q, -1) if head.use_class_emb else cls
+        me = lin(lin(lin(z, head.mask_embed[0], relu=True), head.mask_embed[2], relu=True), head.mask_embed[4])
+        mask = _MaskEinsum.apply(k, me.view(B, Q, Cc), mf)
+        cls_list.append(cls), emb_list.append(emb), mask_list.append(mask)
+        if lvl is None:
+            return None, None
+        with torch.no_grad():                                                   # head.py:759: attn_mask.detach()
+            return rt.attn_mask_from_logits(mask.detach(), sizes[lvl])
+
+    x = _AddRows.apply(k, None, head.query_feat.weight, B)                       # head.py:808-809
+    bm, am = head_call(x, 0)
+    for i in range(L):
+        lvl = i % 3
+        layer = dec.layers[i]
+        ca, sa = layer.attentions[0].attn, layer.attentions[1].attn
+        key_in, val_in = prep[lvl]
+        K = key_in.shape[1]
+        x2d = x.view(B * Q, Cc)
+        # ---- masked cross-attention (mmcv MultiheadAttention wrapper: identity + attn, value gets no pos)
+        xq = _AddRows.apply(k, x, qe, B).view(B * Q, Cc)
+        q = _Linear.apply(k, xq, ca.in_proj_weight[:Cc], ca.in_proj_bias[:Cc], None, scale, False)
+        kk = _Linear.apply(k, key_in.view(B * K, Cc), ca.in_proj_weight[Cc:2 * Cc], ca.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
+        vv = _Linear.apply(k, val_in.view(B * K, Cc), ca.in_proj_weight[2 * Cc:], ca.in_proj_bias[2 * Cc:], None, 1.0, False)
+        o = _Attention.apply(k, q.view(B, Q, Cc), kk.view(B, K, Cc), vv.view(B, K, Cc), bm, am)
+        t = _Linear.apply(k, o.view(B * Q, Cc), ca.out_proj.weight, ca.out_proj.bias, x2d, 1.0, False)
+        x1 = ln(t, layer.norms[0])
+        # ---- self-attention: q = k-input = x1 + query_embed, v-input = x1
+        x1q = _AddRows.apply(k, x1.view(B, Q, Cc), qe, B).view(B * Q, Cc)
+        q2 = _Linear.apply(k, x1q, sa.in_proj_weight[:Cc], sa.in_proj_bias[:Cc], None, scale, False)
+        k2 = _Linear.apply(k, x1q, sa.in_proj_weight[Cc:2 * Cc], sa.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
+        v2 = _Linear.apply(k, x1, sa.in_proj_weight[2 * Cc:], sa.in_proj_bias[2 * Cc:], None, 1.0, False)
+        o2 = _Attention.apply(k, q2.view(B, Q, Cc), k2.view(B, Q, Cc), v2.view(B, Q, Cc), None, None)
+        t2 = _Linear.apply(k, o2.view(B * Q, Cc), sa.out_proj.weight, sa.out_proj.bias, x1, 1.0, False)
+        x2 = ln(t2, layer.norms[1])
+        # ---- FFN
+        f = lin(x2, layer.ffns[0].layers[0][0], relu=True)
+        t3 = lin(f, layer.ffns[0].layers[1], res=x2)
+        x = ln(t3, layer.norms[2]).view(B, Q, Cc)
+        bm, am = head_call(x, (i + 1) % 3 if i + 1 < L else None)
+    return cls_list, emb_list, mask_list
+
+
+# ------------------------------------------------------------------------------------ gradient all-reduce
+class GradReducer:
+    """Bucketed NCCL all-reduce of the head's gradients, overlapped with the backward (data-parallel training,
+    BASELINE.json configs[3]; reference: DDP built at open_set/apis/train.py:156-161).
+
+    Parameters are packed, in reverse registration order (the order the backward produces them), into flat fp32 buckets
+    of ~`bucket_mb`; `post_accumulate_grad` hooks copy a finished gradient into its bucket and launch the bucket's
+    all-reduce on a side stream as soon as its last gradient has arrived.  `finish()` joins the side stream, divides by
+    the world size and points every `.grad` at its bucket slice.  `exposed_ms` is the time between the end of the
+    backward on the main stream and the end of the last all-reduce -- the part of the communication that was NOT
+    hidden."""
+
+    def __init__(self, params, bucket_mb=8.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        self.cuda = dev.type == 'cuda'
+        self.stream = torch.cuda.Stream(dev) if self.cuda else None
+        self.buckets = []            # dict(flat, params[(p, off)], pending)
+        cap = int(bucket_mb * (1 << 20) / 4)
+        cur, n = [], 0
+        for p in reversed(self.params):
+            if cur and n + p.numel() > cap:
+                self._close(cur, n, dev)
+                cur, n = [], 0
+            cur.append((p, n))
+            n += p.numel()
+        if cur:
+            self._close(cur, n, dev)
+        self.index = {}
+        for bi, bk in enumerate(self.buckets):
+            for p, off in bk['params']:
+                self.index[p] = (bi, off)
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.t_bwd_end = self.t_comm_end = None
+        self.exposed_ms = 0.0
+        self.reset()
+
+    def _close(self, cur, n, dev):
+        self.buckets.append(dict(flat=torch.zeros(n, dtype=torch.float32, device=dev), params=list(cur), pending=0, work=None))
+
+    def reset(self):
+        for bk in self.buckets:
+            bk['pending'] = len(bk['params'])
+            bk['work'] = None
+
+    def _hook(self, p):
+        bi, off = self.index[p]
+        bk = self.buckets[bi]
+        bk['flat'][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        bk['pending'] -= 1
+        if bk['pending'] == 0 and self.world > 1:
+            if self.cuda:
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    bk['work'] = dist.all_reduce(bk['flat'], group=self.group, async_op=True)
+            else:
+                bk['work'] = dist.all_reduce(bk['flat'], group=self.group, async_op=True)
+
+    def finish(self):
+        """Call after loss.backward().  Returns the exposed communication time in ms (0 on one rank)."""
+        if self.cuda:
+            self.t_bwd_end = torch.cuda.Event(enable_timing=True)
+            self.t_bwd_end.record(torch.cuda.current_stream())
+        for bk in self.buckets:
+            if bk['work'] is not None:
+                bk['work'].wait()
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.t_comm_end = torch.cuda.Event(enable_timing=True)
+            self.t_comm_end.record(torch.cuda.current_stream())
+        for bk in self.buckets:
+            if self.world > 1:
+                bk['flat'].div_(self.world)
+            for p, off in bk['params']:
+                p.grad = bk['flat'][off:off + p.numel()].view_as(p)
+        self.reset()
+
+    def exposed(self):
+        if not self.cuda or self.t_bwd_end is None:
+            return 0.0
+        torch.cuda.synchronize()
+        return self.t_bwd_end.elapsed_time(self.t_comm_end)
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()

@@ -224,6 +224,63 @@ int cgg_grounding_loss_backward(cgg_handle *h, const float *pred, const float *c
                                 int Bg, int Q, int T, int D, float temperature, float loss_weight, float grad_out,
                                 float *dpred, void *scratch, size_t scratch_bytes, void *stream);
 
+/* ---- training step (BASELINE.json configs[3]): stage kernels with their backward -----------------------------
+ * The reference trains through autograd over the path (forward_train head.py:851-921 -> loss :393-462 -> backward);
+ * the replacement exposes each stage's forward and backward so that a tape (betrayed-by-captions_b200/train.py builds
+ * one with torch.autograd.Function) reaches every head parameter, the mask features and the memories.  All fp32. */
+
+/* Generic strided GEMM: C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); strides in
+ * elements.  Every linear layer's forward, dX = dY W and dW = dY^T X, the mask einsum (head.py:748) and both of its
+ * gradients are calls of this entry point.  a_mmajor / c_mmajor only say which index consecutive lanes walk. */
+typedef struct {
+  const float *A; long sAb, sAm, sAk;
+  const float *A2; long sA2m, sA2k; int a2_mod;      /* optional addend A2[m % a2_mod, k] of A (may be NULL) */
+  const float *W; long sWb, sWn, sWk;
+  const float *bias;
+  const float *R; long sRb, sRm, sRn; int r_mod; int r_ncols;
+  float *C; long sCb, sCm, sCn;
+  int M, N, K, batch;
+  int relu;
+  float alpha;
+  int a_mmajor, c_mmajor;
+} cgg_gemm_desc;
+int cgg_gemm_f32(cgg_handle *h, const cgg_gemm_desc *d, void *stream);
+
+/* torch.nn.LayerNorm forward / backward over rows of length n (post_norm, norms.{0,1,2}). */
+int cgg_layernorm(cgg_handle *h, const float *x, const float *w, const float *b, float *y, int rows, int n, float eps,
+                  void *stream);
+size_t cgg_layernorm_bwd_scratch_bytes(int rows, int n);
+int cgg_layernorm_backward(cgg_handle *h, const float *x, const float *w, const float *dy, float *dx, float *dw,
+                           float *db, void *scratch, size_t scratch_bytes, int rows, int n, float eps, void *stream);
+/* dx = dy * alpha where the ReLU output y > 0 */
+int cgg_relu_backward(cgg_handle *h, const float *y, const float *dy, float *dx, long n, float alpha, void *stream);
+/* out += alpha * in */
+int cgg_axpy(cgg_handle *h, const float *in, float *out, long n, float alpha, void *stream);
+/* out[b,i] = (x ? x[b,i] : 0) + add[i], i < per   (x + query_embed; the query_feat broadcast, head.py:808-811) */
+int cgg_add_rows(cgg_handle *h, const float *x, const float *add, float *out, int batch, long per, void *stream);
+/* out[i] = sum_b g[b,i]   (its backward) */
+int cgg_sum_batch(cgg_handle *h, const float *g, float *out, int batch, long per, void *stream);
+/* out[n] = alpha * sum_rows g[row,n]   (bias gradients) */
+int cgg_colsum(cgg_handle *h, const float *g, float *out, long rows, int n, float alpha, void *stream);
+/* head.py:792-804: key_in[b,key,:] = mem[b,:,key] + level + pos[key,:], val_in = mem[b,:,key] + level, and the backward
+ * dmem[b,c,key] = dkey_in[b,key,c] + dval_in[b,key,c].  pos_level (K,C) = pos + level. */
+int cgg_mem_prep(cgg_handle *h, const float *mem, const float *level, const float *pos_level, float *key_in,
+                 float *val_in, int batch, int C, int K, void *stream);
+int cgg_mem_prep_backward(cgg_handle *h, const float *dkey_in, const float *dval_in, float *dmem, int batch, int C,
+                          int K, void *stream);
+/* mmdet SinePositionalEncoding(normalize=True) of an (hh, ww) map -> (hh*ww, C) fp32 (head.py:798-804) */
+int cgg_sine_pos(cgg_handle *h, float *out, int hh, int ww, int C, void *stream);
+/* softmax(q k^T + mask) v for num_q queries (cross-attention: Q queries; self-attention: num_q = num_keys), fp32, and
+ * its backward (dq, dk, dv; softmax recomputed from the saved q, k; bitmap as in the forward).
+ * scratch: 2 * batch * heads * num_q floats. */
+int cgg_attention_f32(cgg_handle *h, int batch, int num_q, int num_keys, const float *q, const float *k, const float *v,
+                      long kv_stride, long kv_batch_stride, const uint32_t *bitmap, const uint8_t *all_masked,
+                      float *out, void *stream);
+int cgg_attention_backward(cgg_handle *h, int batch, int num_q, int num_keys, const float *q, const float *k,
+                           const float *v, long kv_stride, long kv_batch_stride, const uint32_t *bitmap,
+                           const uint8_t *all_masked, const float *out, const float *dout, float *dq, float *dk,
+                           float *dv, long dkv_stride, long dkv_batch_stride, float *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,19 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get('CGG_REFERENCE_ROOT', '/root/reference')
+def _find_ref_root():
+    """/root/reference in the build container; on the GPU box the verbatim copy that oracle/make_ref.py left in the
+    git-ignored oracle/_ref/ (it travels with the snapshot)."""
+    env = os.environ.get('CGG_REFERENCE_ROOT')
+    if env:
+        return env
+    for cand in ('/root/reference', os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')):
+        if os.path.isfile(os.path.join(cand, 'open_set/models/mask2former_head.py')):
+            return cand
+    return '/root/reference'
+
+
+REF_ROOT = _find_ref_root()
 
 
 def reference_available():

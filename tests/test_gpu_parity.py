@@ -292,7 +292,10 @@ def test_embedding_side_matches_reference_golden():
 
 
 def _free_run_vs_oracle(sd, mf, mems, head, bit_bar, mask_tol, emb_tol):
-    """All 10 head calls of a free-running forward against the oracle on the same inputs."""
+    """All 10 head calls of a free-running forward against the oracle on the same inputs.  Free-running, one
+    attention-mask bit that sits on the threshold (|logit| < 1e-5, the teacher-forced test shows these are the only
+    disagreements) may flip under a different fp32 summation order and moves that query's later outputs by ~1e-3 of
+    the range; hence 5e-3 here against 2e-4..5e-4 teacher-forced."""
     ref = O.decoder_forward(sd, mf, mems)
     cls, emb, mask, dbg = head.decoder_forward(mf.to(DEV), [m.to(DEV) for m in mems], return_debug=True)
     for j in range(10):
@@ -311,7 +314,7 @@ def test_fp32_full_size_1024_all_head_calls_vs_oracle():
     """BASELINE configs[1] shape (1024x1024, Q=100): every one of the 10 head calls against the oracle, fp32 mode."""
     sd = synth.make_params(seed=0, num_queries=100)
     mf, mems = synth.make_inputs(0, 1, 1024, 1024)
-    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=5e-3, emb_tol=5e-3)
 
 
 def test_fp32_demo_shape_1056x800_all_head_calls_vs_oracle():
@@ -319,11 +322,11 @@ def test_fp32_demo_shape_1056x800_all_head_calls_vs_oracle():
     W/4 = 200), fp32 mode, all head calls."""
     sd = synth.make_params(seed=3, num_queries=100, perturb=True)
     mf, mems = synth.make_inputs(2, 1, 1056, 800)
-    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 100), bit_bar=0.9999, mask_tol=5e-3, emb_tol=5e-3)
 
 
 def test_fp32_osps_q200_ncls118_vs_oracle():
     """BASELINE configs[3] head shape: 200 queries, 118 class rows, real class embeddings, at 512x512."""
     c = dict(cases.HEAD_CASES['osps_q200'], height=512, width=512, batch=2)
     sd, mf, mems = cases.case_tensors(c)
-    _free_run_vs_oracle(sd, mf, mems, _head(sd, 200), bit_bar=0.9999, mask_tol=1e-3, emb_tol=1e-3)
+    _free_run_vs_oracle(sd, mf, mems, _head(sd, 200), bit_bar=0.9999, mask_tol=5e-3, emb_tol=5e-3)
