@@ -3,6 +3,7 @@
 #include "../../include/cgg_b200.h"
 #include "kernels.h"
 #include "gemm_tc.h"
+#include "tc_state.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -35,6 +36,18 @@ struct cgg_handle {
   bool overlap_kv = false;   // K/V levels 1,2 on a helper stream on a capped number of SMs
   int kv_cta_cap = 0;
   bool final_mask_only = false;   // cgg_set_final_mask_only
+  // K7 on tensor cores: the similarity contraction of the grounding loss (and its backward contraction) as split-precision
+  // tcgen05 GEMMs.  Operand buffers live in the handle (grown on demand); tc_aux serves handles created in CGG_FP32 mode.
+  TcState* tc_aux = nullptr;
+  struct K7Buf {
+    __nv_bfloat16 *pred_hl = nullptr, *cap_hl = nullptr, *dst_hl = nullptr, *capT_hl = nullptr;
+    float* S = nullptr;
+    size_t n_pred = 0, n_cap = 0, n_dst = 0, n_capT = 0, n_S = 0;
+    void release() {
+      cudaFree(pred_hl); cudaFree(cap_hl); cudaFree(dst_hl); cudaFree(capT_hl); cudaFree(S);
+      pred_hl = cap_hl = dst_hl = capT_hl = nullptr; S = nullptr; n_pred = n_cap = n_dst = n_capT = n_S = 0;
+    }
+  } k7;
   void free_tables() {
     for (int l = 0; l < CGG_NUM_LEVELS; ++l) {
       cudaFree(pos_level[l]); cudaFree(wkv[l]); cudaFree(rk[l]); cudaFree(bkv[l]);
@@ -170,6 +183,8 @@ extern "C" void cgg_destroy(cgg_handle* h) {
   if (!h) return;
   h->free_tables();
   if (h->tc) tc_destroy(h->tc);
+  if (h->tc_aux) tc_destroy(h->tc_aux);
+  h->k7.release();
   for (int i = 0; i < 2; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -621,6 +636,54 @@ extern "C" int cgg_similarity(cgg_handle* h, const float* a, const float* b, int
   return CGG_OK;
 }
 
+namespace {
+
+inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+// CGG_K7_SIMT=1: the fp32 SIMT similarity of round 1 (one dot product per (token, query) inside the pair kernel)
+bool k7_tensor_cores() {
+  static const bool simt = getenv("CGG_K7_SIMT") != nullptr && atoi(getenv("CGG_K7_SIMT")) != 0;
+  return !simt;
+}
+
+template <typename T>
+int grow(cgg_handle* h, T** p, size_t* have, size_t want_elems, cudaStream_t s, bool zero) {
+  if (*have >= want_elems) return CGG_OK;
+  CU(cudaStreamSynchronize(s));
+  cudaFree(*p);
+  *p = nullptr; *have = 0;
+  CU(cudaMalloc(p, want_elems * sizeof(T)));
+  if (zero) CU(cudaMemsetAsync(*p, 0, want_elems * sizeof(T), s));
+  *have = want_elems;
+  return CGG_OK;
+}
+
+// S[(i,t), (j,q)] = cap_i[t] . pred_j[q] / T for ALL caption x image pairs: ONE tcgen05 GEMM (M = Bg*T tokens,
+// N = Bg*Q, K = D) at split (hi/lo bf16, 3-term) precision -- the raw similarities reach |120| (BERT rows of norm ~24),
+// so plain bf16 operands would move the softmax arguments by ~0.05.
+int k7_similarity(cgg_handle* h, const float* pred, const float* cap, int Bg, int Q, int T, int D, float temperature,
+                  cudaStream_t s) {
+  TcState* t = h->tc ? h->tc : h->tc_aux;
+  if (!t) {
+    h->tc_aux = tc_create(h->cfg);
+    if (!h->tc_aux) return fail(h, CGG_ERR_CUDA, "tc_create (grounding) failed");
+    t = h->tc_aux;
+  }
+  const int rows_p = Bg * Q, rows_c = Bg * T, np = round_up_i(rows_p, 128);
+  ST(grow(h, &h->k7.pred_hl, &h->k7.n_pred, (size_t)np * 2 * D, s, true));      // pad rows stay zero
+  ST(grow(h, &h->k7.cap_hl, &h->k7.n_cap, (size_t)rows_c * 2 * D, s, false));
+  ST(grow(h, &h->k7.S, &h->k7.n_S, (size_t)rows_c * rows_p, s, false));
+  CU(launch_cast_bf16_split(pred, h->k7.pred_hl, rows_p, D, s));
+  CU(launch_cast_bf16_split(cap, h->k7.cap_hl, rows_c, D, s));
+  TcSeg sg = {};
+  sg.col0 = 0; sg.ncols = rows_p; sg.ptr = h->k7.S; sg.ld = rows_p; sg.alpha = 1.0f / temperature; sg.rb_mod = 1;
+  int st = tc_linear(t, h->k7.cap_hl, rows_c, D, h->k7.pred_hl, np, nullptr, &sg, 1, s, /*split_k=*/true);
+  if (st != CGG_OK) return fail(h, st, std::string("tc_linear (grounding similarity): ") + tc_last_error(t));
+  return CGG_OK;
+}
+
+}  // namespace
+
 extern "C" size_t cgg_grounding_scratch_bytes(int Bg, int Q, int T) {
   (void)Q; (void)T;
   return Bg > 0 ? (size_t)2 * Bg * Bg * sizeof(float) : 0;
@@ -630,13 +693,18 @@ extern "C" int cgg_grounding_loss(cgg_handle* h, const float* pred, const float*
                                   int Q, int T, int D, float temperature, float loss_weight, float* loss,
                                   void* scratch, size_t scratch_bytes, void* stream) {
   if (!h || !pred || !cap || !cap_mask || !loss || !scratch) return CGG_ERR_NULL;
-  if (Bg <= 0 || Bg > 96 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if (Bg <= 0 || Bg > 128 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   if ((size_t)(T * Q + T + Q) * sizeof(float) > 200 * 1024) return fail(h, CGG_ERR_BAD_SHAPE, "T*Q too large");
   if (scratch_bytes < cgg_grounding_scratch_bytes(Bg, Q, T)) return fail(h, CGG_ERR_WORKSPACE, "scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
   float* g1 = static_cast<float*>(scratch);
   float* g2 = g1 + (size_t)Bg * Bg;
-  CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s));
+  const float* S_pre = nullptr;
+  if (k7_tensor_cores() && D % 64 == 0) {
+    ST(k7_similarity(h, pred, cap, Bg, Q, T, D, temperature, s));
+    S_pre = h->k7.S;
+  }
+  CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s, S_pre));
   CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s));
   return CGG_OK;
 }
@@ -651,7 +719,7 @@ extern "C" int cgg_grounding_loss_backward(cgg_handle* h, const float* pred, con
                                            float grad_out, float* dpred, void* scratch, size_t scratch_bytes,
                                            void* stream) {
   if (!h || !pred || !cap || !cap_mask || !dpred || !scratch) return CGG_ERR_NULL;
-  if (Bg <= 0 || Bg > 96 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if (Bg <= 0 || Bg > 128 || Q <= 0 || T <= 0 || D <= 0 || (D % 4) != 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   if ((size_t)(T * Q + 3 * T + 3 * Q) * sizeof(float) > 200 * 1024) return fail(h, CGG_ERR_BAD_SHAPE, "T*Q too large");
   if (scratch_bytes < cgg_grounding_bwd_scratch_bytes(Bg, Q, T)) return fail(h, CGG_ERR_WORKSPACE, "scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
@@ -661,6 +729,25 @@ extern "C" int cgg_grounding_loss_backward(cgg_handle* h, const float* pred, con
   float* d2 = d1 + (size_t)Bg * Bg;
   float* loss = d2 + (size_t)Bg * Bg;
   float* dS = loss + 1;
+  if (k7_tensor_cores() && D % 64 == 0) {
+    // tensor-core mode: S once (tcgen05), pair kernels on S, then dpred[(j,q), :] = sum_(i,t) dS[(j,q), (i,t)] cap[(i,t), :]
+    // as a second split-precision tcgen05 GEMM (M = Bg*Q tokens, N = D, K = Bg*T padded to 64)
+    ST(k7_similarity(h, pred, cap, Bg, Q, T, D, temperature, s));
+    const int rows_p = Bg * Q, rows_c = Bg * T, Kp = round_up_i(rows_c, 64), nd = round_up_i(D, 128);
+    ST(grow(h, &h->k7.dst_hl, &h->k7.n_dst, (size_t)rows_p * 2 * Kp, s, true));    // pad columns stay zero
+    ST(grow(h, &h->k7.capT_hl, &h->k7.n_capT, (size_t)nd * 2 * Kp, s, true));
+    CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s, h->k7.S));
+    CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s, d1, d2));
+    CU(launch_grounding_bwd_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, d1, d2, grad_out, nullptr, s, h->k7.S,
+                                  h->k7.dst_hl, Kp));
+    CU(launch_transpose_split(cap, h->k7.capT_hl, rows_c, D, Kp, s));
+    TcState* t = h->tc ? h->tc : h->tc_aux;
+    TcSeg sg = {};
+    sg.col0 = 0; sg.ncols = D; sg.ptr = dpred; sg.ld = D; sg.alpha = 1.0f; sg.rb_mod = 1;
+    int st = tc_linear(t, h->k7.dst_hl, rows_p, Kp, h->k7.capT_hl, nd, nullptr, &sg, 1, s, /*split_k=*/true);
+    if (st != CGG_OK) return fail(h, st, std::string("tc_linear (grounding backward): ") + tc_last_error(t));
+    return CGG_OK;
+  }
   // recompute the pair distances, then d loss / d cost, d loss / d S, and dpred_j = sum_{i,t} dS[j][i][t][:]^T cap[i][t][:]
   CU(launch_grounding_pairs(pred, cap, cap_mask, Bg, Q, T, D, temperature, g1, g2, s));
   CU(launch_grounding_finish(g1, g2, cap_mask, Bg, T, loss_weight, loss, s, d1, d2));
@@ -792,5 +879,33 @@ extern "C" int cgg_attention_backward(cgg_handle* h, int batch, int num_q, int n
   const size_t n = (size_t)batch * h->cfg.num_heads * num_q;
   CU(launch_attention_bwd(q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, dout, scratch, scratch + n, dq, dk,
                           dv, dkv_stride, dkv_batch_stride, batch, num_q, num_keys, h->cfg.num_heads, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+// ====================================================================== the step after the path (test time)
+extern "C" int cgg_upsample_masks(cgg_handle* h, const void* logits, int is_bf16, float* out, int planes, int h4, int w4,
+                                  int up_h, int up_w, void* stream) {
+  if (!h || !logits || !out) return CGG_ERR_NULL;
+  if (planes < 1 || planes > 65535 || h4 < 1 || w4 < 1 || up_h < 1 || up_w < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_upsample_masks(logits, is_bf16 != 0, out, planes, h4, w4, up_h, up_w, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_instance_mask_stats(cgg_handle* h, const void* logits, int is_bf16, const int* geom, int batch, int num_q,
+                                       int h4, int w4, int up_h, int up_w, int max_out_h, int max_out_w, uint32_t* bits,
+                                       int* count, float* sig_sum, int* bbox, void* stream) {
+  if (!h || !logits || !geom || !count || !sig_sum || !bbox) return CGG_ERR_NULL;
+  if (batch < 1 || num_q < 1 || (long)batch * num_q > 65535 || h4 < 1 || w4 < 1 || up_h < 1 || up_w < 1 || max_out_h < 1 ||
+      max_out_w < 1)
+    return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_instance_mask_stats(logits, is_bf16 != 0, geom, batch, num_q, h4, w4, up_h, up_w, max_out_h, max_out_w, bits, count,
+                                sig_sum, bbox, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_softmax_rows(cgg_handle* h, float* x, int rows, int n, void* stream) {
+  if (!h || !x) return CGG_ERR_NULL;
+  if (rows < 0 || n < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_softmax_rows(x, rows, n, (cudaStream_t)stream));
   return CGG_OK;
 }

@@ -56,7 +56,7 @@ cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, b
 // K7 grounding: per (caption i, image j) pair distances, then the contrastive reduction.
 cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const int64_t* cap_mask,
                                    int Bg, int Q, int T, int D, float temperature,
-                                   float* g_l2v, float* g_v2l, cudaStream_t s);
+                                   float* g_l2v, float* g_v2l, cudaStream_t s, const float* S_pre = nullptr);
 // in-place L2 normalisation of rows (pred_emb_norm, head.py:743-744)
 cudaError_t launch_l2norm_rows(float* x, int rows, int D, cudaStream_t s);
 cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, const int64_t* cap_mask,
@@ -65,7 +65,10 @@ cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, cons
 // backward: dS[j][i][t][q] = d loss / d (cap_i[t].pred_j[q]) (already divided by the temperature)
 cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, const int64_t* cap_mask, int Bg, int Q, int T,
                                        int D, float temperature, const float* dg_l2v, const float* dg_v2l,
-                                       float grad_scale, float* dS, cudaStream_t s);
+                                       float grad_scale, float* dS, cudaStream_t s, const float* S_pre = nullptr,
+                                       __nv_bfloat16* dS_hl = nullptr, int Kp = 0);
+// (R, D) fp32 -> (D, 2*Kp) bf16 [hi | lo] transposed, zero padded columns
+cudaError_t launch_transpose_split(const float* in, __nv_bfloat16* out, int R, int D, int Kp, cudaStream_t s);
 
 // ---- training step (train_kernels.cu)
 cudaError_t launch_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
@@ -83,6 +86,14 @@ cudaError_t launch_attention_bwd(const float* q, const float* k, const float* v,
                                  const uint32_t* bitmap, const uint8_t* all_masked, const float* o, const float* dout,
                                  float* lse, float* dsum, float* dq, float* dk, float* dv, long dkv_stride,
                                  long dkv_bstride, int B, int Q, int K, int heads, cudaStream_t s);
+
+// ---- test-time step after the path (post_kernels.cu)
+cudaError_t launch_upsample_masks(const void* logits, bool bf16, float* out, int planes, int h4, int w4, int up_h, int up_w,
+                                  cudaStream_t s);
+cudaError_t launch_instance_mask_stats(const void* logits, bool bf16, const int* geom, int B, int Q, int h4, int w4, int up_h,
+                                       int up_w, int max_out_h, int max_out_w, uint32_t* bits, int* count, float* sig_sum,
+                                       int* bbox, cudaStream_t s);
+cudaError_t launch_softmax_rows(float* x, int rows, int n, cudaStream_t s);
 
 // fp32 (rows, cols) -> bf16 (rows, 2*cols) hi/lo pairs: [hi | lo] per row
 cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s);

@@ -370,7 +370,8 @@ cudaError_t launch_attention_f32(const float* q, const void* k, const void* v, b
 // l2v softmax over queries (token-masked) and the v2l softmax over ALL max_tokens.
 __global__ void __launch_bounds__(256) grounding_pairs_kernel(
     const float* __restrict__ pred, const float* __restrict__ cap, const int64_t* __restrict__ cap_mask,
-    int Bg, int Q, int T, int D, float inv_temp, float* __restrict__ g_l2v, float* __restrict__ g_v2l) {
+    int Bg, int Q, int T, int D, float inv_temp, float* __restrict__ g_l2v, float* __restrict__ g_v2l,
+    const float* __restrict__ S_pre) {
   extern __shared__ float sm[];
   float* S = sm;                 // T*Q
   float* part_t = S + T * Q;     // T
@@ -378,6 +379,14 @@ __global__ void __launch_bounds__(256) grounding_pairs_kernel(
   const int i = blockIdx.y, j = blockIdx.x, t = threadIdx.x;
   const float* ci = cap + (long)i * T * D;
   const float* pj = pred + (long)j * Q * D;
+  // S_pre: the similarities of ALL pairs, (Bg*T, Bg*Q) row-major, already divided by the temperature -- one tcgen05
+  // GEMM (cgg_grounding_loss, tensor-core mode) instead of T*Q dot products per CTA
+  if (S_pre) {
+    for (int idx = t; idx < T * Q; idx += 256) {
+      const int tt = idx / Q, qq = idx % Q;
+      S[idx] = S_pre[((long)i * T + tt) * ((long)Bg * Q) + (long)j * Q + qq];
+    }
+  } else
   for (int idx = t; idx < T * Q; idx += 256) {
     const int tt = idx / Q, qq = idx % Q;
     const float4* a = reinterpret_cast<const float4*>(ci + (long)tt * D);
@@ -432,12 +441,12 @@ __global__ void __launch_bounds__(256) grounding_pairs_kernel(
 
 cudaError_t launch_grounding_pairs(const float* pred, const float* cap, const int64_t* cap_mask,
                                    int Bg, int Q, int T, int D, float temperature,
-                                   float* g_l2v, float* g_v2l, cudaStream_t s) {
+                                   float* g_l2v, float* g_v2l, cudaStream_t s, const float* S_pre) {
   const size_t smem = (size_t)(T * Q + T + Q) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(grounding_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   grounding_pairs_kernel<<<dim3(Bg, Bg), 256, smem, s>>>(pred, cap, cap_mask, Bg, Q, T, D,
-                                                         1.0f / temperature, g_l2v, g_v2l);
+                                                         1.0f / temperature, g_l2v, g_v2l, S_pre);
   count_launch();
   return cudaGetLastError();
 }
@@ -526,7 +535,7 @@ cudaError_t launch_grounding_finish(const float* g_l2v, const float* g_v2l, cons
 __global__ void __launch_bounds__(256) grounding_bwd_pairs_kernel(
     const float* __restrict__ pred, const float* __restrict__ cap, const int64_t* __restrict__ cap_mask,
     int Bg, int Q, int T, int D, float inv_temp, const float* __restrict__ dg_l2v, const float* __restrict__ dg_v2l,
-    float grad_scale, float* __restrict__ dS) {
+    float grad_scale, float* __restrict__ dS, const float* __restrict__ S_pre, __nv_bfloat16* __restrict__ dS_hl, int Kp) {
   extern __shared__ float sm[];
   float* S = sm;                   // T*Q
   float* st_max = S + T * Q;       // per token: max, 1/sum, f_t
@@ -538,6 +547,12 @@ __global__ void __launch_bounds__(256) grounding_bwd_pairs_kernel(
   const int i = blockIdx.y, j = blockIdx.x, t = threadIdx.x;
   const float* ci = cap + (long)i * T * D;
   const float* pj = pred + (long)j * Q * D;
+  if (S_pre) {
+    for (int idx = t; idx < T * Q; idx += 256) {
+      const int tt = idx / Q, qq = idx % Q;
+      S[idx] = S_pre[((long)i * T + tt) * ((long)Bg * Q) + (long)j * Q + qq];
+    }
+  } else
   for (int idx = t; idx < T * Q; idx += 256) {
     const int tt = idx / Q, qq = idx % Q;
     const float4* a = reinterpret_cast<const float4*>(ci + (long)tt * D);
@@ -589,19 +604,44 @@ __global__ void __launch_bounds__(256) grounding_bwd_pairs_kernel(
     const float a = expf(sv - st_max[tt]) * st_inv[tt];
     const float b = expf(sv - sq_max[qq]) * sq_inv[qq];
     const float m = (cap_mask[(long)i * T + tt] != 0) ? 1.f : 0.f;
-    const float d = gl * m * (-a) * (1.0f + sv + st_f[tt]) + gv * (-b) * (1.0f + sv + sq_g[qq]);
-    out[idx] = d * inv_temp;
+    const float d = (gl * m * (-a) * (1.0f + sv + st_f[tt]) + gv * (-b) * (1.0f + sv + sq_g[qq])) * inv_temp;
+    if (dS_hl) {
+      // tensor-core mode: row (j, q) of the K-major operand of dpred = dS . cap, column (i, t), as a bf16 hi/lo pair
+      const __nv_bfloat16 hi = __float2bfloat16_rn(d);
+      __nv_bfloat16* row = dS_hl + ((long)j * Q + qq) * 2 * Kp + (long)i * T + tt;
+      row[0] = hi;
+      row[Kp] = __float2bfloat16_rn(d - __bfloat162float(hi));
+    } else {
+      out[idx] = d;
+    }
   }
+}
+
+// cap (R rows, D) fp32 -> capT (D rows, 2*Kp) bf16 [hi | lo], column = source row (zero padded to Kp)
+__global__ void transpose_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int D, int Kp) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * Kp) return;
+  const int r = (int)(idx % Kp), d = (int)(idx / Kp);
+  const float x = r < R ? in[(long)r * D + d] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  out[(long)d * 2 * Kp + r] = hi;
+  out[(long)d * 2 * Kp + Kp + r] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+cudaError_t launch_transpose_split(const float* in, __nv_bfloat16* out, int R, int D, int Kp, cudaStream_t s) {
+  const long n = (long)D * Kp;
+  transpose_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, R, D, Kp);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_grounding_bwd_pairs(const float* pred, const float* cap, const int64_t* cap_mask, int Bg, int Q, int T,
                                        int D, float temperature, const float* dg_l2v, const float* dg_v2l,
-                                       float grad_scale, float* dS, cudaStream_t s) {
+                                       float grad_scale, float* dS, cudaStream_t s, const float* S_pre, __nv_bfloat16* dS_hl, int Kp) {
   const size_t smem = (size_t)(T * Q + 3 * T + 3 * Q) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(grounding_bwd_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   grounding_bwd_pairs_kernel<<<dim3(Bg, Bg), 256, smem, s>>>(pred, cap, cap_mask, Bg, Q, T, D, 1.0f / temperature, dg_l2v,
-                                                             dg_v2l, grad_scale, dS);
+                                                             dg_v2l, grad_scale, dS, S_pre, dS_hl, Kp);
   count_launch();
   return cudaGetLastError();
 }

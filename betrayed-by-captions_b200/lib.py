@@ -19,7 +19,9 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            # training-step stages
            'cgg_gemm_f32', 'cgg_layernorm', 'cgg_layernorm_bwd_scratch_bytes', 'cgg_layernorm_backward', 'cgg_relu_backward',
            'cgg_axpy', 'cgg_add_rows', 'cgg_sum_batch', 'cgg_colsum', 'cgg_mem_prep', 'cgg_mem_prep_backward', 'cgg_sine_pos',
-           'cgg_attention_f32', 'cgg_attention_backward']
+           'cgg_attention_f32', 'cgg_attention_backward',
+           # test-time step after the path
+           'cgg_upsample_masks', 'cgg_instance_mask_stats', 'cgg_softmax_rows']
 
 
 class Config(C.Structure):
@@ -115,6 +117,9 @@ def load():
     lib.cgg_sine_pos.argtypes = [vp, vp, i, i, i, vp]
     lib.cgg_attention_f32.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp]
     lib.cgg_attention_backward.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp, vp, vp, vp, lg, lg, vp, vp]
+    lib.cgg_upsample_masks.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
+    lib.cgg_instance_mask_stats.argtypes = [vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.cgg_softmax_rows.argtypes = [vp, vp, i, i, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('cgg_destroy',):

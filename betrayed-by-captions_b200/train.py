@@ -244,9 +244,11 @@ class _MaskEinsum(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------- the forward
-def decoder_forward_train(head, mask_features, multi_scale_memorys):
+def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_masks=None):
     """Autograd-connected `(cls_list, cls_emb_list, mask_list)` (10 entries each) of head.py:787-849, fp32.
-    mask_features (B, C, H4, W4) and the three memories may require grad (they come from the pixel decoder)."""
+    mask_features (B, C, H4, W4) and the three memories may require grad (they come from the pixel decoder).
+    forced_attn_masks (tests only): 9 (bitmap, all_masked) pairs used INSTEAD of the masks derived from this forward's
+    own logits, so that a gradient comparison cannot be derailed by one threshold-band bit of a tiny key set."""
     if not mask_features.is_cuda:
         raise _lib.CggError('the training path runs on CUDA only (no CPU fallback)')
     if head.pred_emb_norm and head.use_class_emb:
@@ -284,6 +286,8 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys):
         cls_list.append(cls), emb_list.append(emb), mask_list.append(mask)
         if lvl is None:
             return None, None
+        if forced_attn_masks is not None:
+            return forced_attn_masks[len(mask_list) - 1]
         with torch.no_grad():                                                   # head.py:759: attn_mask.detach()
             return rt.attn_mask_from_logits(mask.detach(), sizes[lvl])
 

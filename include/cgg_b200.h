@@ -281,6 +281,24 @@ int cgg_attention_backward(cgg_handle *h, int batch, int num_q, int num_keys, co
                            const uint8_t *all_masked, const float *out, const float *dout, float *dq, float *dk,
                            float *dv, long dkv_stride, long dkv_batch_stride, float *scratch, void *stream);
 
+/* ---- the step after the path at test time ---------------------------------------------------
+ * logits: the LAST head call's mask logits (B, Q, h4, w4), fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1).
+ * cgg_upsample_masks: F.interpolate(logits, (up_h, up_w), bilinear, align_corners=False) materialised in fp32, the
+ *   tensor simple_test returns (head.py:957-964).
+ * cgg_instance_mask_stats: the same upsample FUSED with what MaskFormerFusionHeadOpen does next -- crop to img_shape,
+ *   optional second bilinear resample to ori_shape (maskformer_fusion_head.py:412-425), `> 0`, sum of sigmoid over the
+ *   positive pixels, pixel count and bounding box (instance_postprocess_emb :352-362, mmdet mask2bbox) -- without ever
+ *   writing full-resolution logits.  geom (DEVICE, B x 4 int32) = {crop_h, crop_w, out_h, out_w} per image (out = crop
+ *   when not rescaling).  Outputs: bits (B, Q, max_out_h, ceil(max_out_w/32)) u32 packed binary masks (may be NULL),
+ *   count (B,Q) int32, sig_sum (B,Q) fp32, bbox (B,Q,4) int32 = x0, y0, x1+1, y1+1 (zeros for an empty mask).
+ * cgg_softmax_rows: in-place row softmax (get_cls_emb_scores, maskformer_fusion_head.py:312-313). */
+int cgg_upsample_masks(cgg_handle *h, const void *logits, int is_bf16, float *out, int planes, int h4, int w4, int up_h,
+                       int up_w, void *stream);
+int cgg_instance_mask_stats(cgg_handle *h, const void *logits, int is_bf16, const int *geom, int batch, int num_q, int h4,
+                            int w4, int up_h, int up_w, int max_out_h, int max_out_w, uint32_t *bits, int *count,
+                            float *sig_sum, int *bbox, void *stream);
+int cgg_softmax_rows(cgg_handle *h, float *x, int rows, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,130 @@
+"""2-rank NCCL tests (need >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py`; skipped on a
+single-GPU box): the two real exchange steps of the training config --
+  * the batched caption / prediction all-gather before the grounding loss (mask2former_head.py:650-684) on the CUDA
+    `all_gather_into_tensor` branch, with OUR grounding-loss kernels on the gathered operands, against the single-process
+    oracle loss and its gradient;
+  * the bucketed gradient all-reduce of a data-parallel training step (open_set/apis/train.py:156-161): the reduced
+    gradients must equal the gradient of the loss averaged over the global batch, computed by the oracle's autograd."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+need2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+
+
+def _init(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+
+
+def _gather_data(world, L=3, B=2, Q=20, T=35, D=768):
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn((L, world * B, Q, D), generator=g)
+    cap = torch.randn((world * B, T, D), generator=g) * 0.85
+    mask = torch.zeros((world * B, T), dtype=torch.long)
+    for b, n in enumerate([3, 35, 0, 7][:world * B]):
+        mask[b, :n] = 1
+    return pred, cap, mask
+
+
+def _gather_worker(rank, world, port, q):
+    _init(rank, world, port)
+    from cgg_b200.grounding import gather_captions_and_preds, grounding_loss
+    dev = torch.device('cuda', rank)
+    pred_all, cap_all, mask_all = _gather_data(world)
+    B = 2
+    sl = slice(rank * B, (rank + 1) * B)
+    pred = pred_all[:, sl].clone().to(dev).requires_grad_(True)
+    embs, mask, preds = gather_captions_and_preds(list(cap_all[sl].to(dev)), list(mask_all[sl].to(dev)), pred)
+    loss = sum(grounding_loss(preds[l], embs, mask, 10.0, 2.0) for l in range(preds.shape[0]))
+    loss.backward()
+    q.put((rank, embs.cpu(), mask.cpu(), preds.detach().cpu(), float(loss), pred.grad.cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@need2
+def test_nccl_caption_gather_and_grounding_loss():
+    sys.path.insert(0, ROOT)
+    from oracle import cgg_oracle as O
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 32500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    pred_all, cap_all, mask_all = _gather_data(2)
+    full = pred_all.clone().requires_grad_(True)
+    want = sum(O.grounding_loss(full[l], cap_all, mask_all, 10.0, 2.0) for l in range(full.shape[0]))
+    want.backward()
+    for rank, embs, mask, preds, loss, grad in res:
+        assert torch.equal(embs, cap_all) and torch.equal(mask, mask_all)
+        assert torch.equal(preds, pred_all)
+        assert abs(loss - float(want)) < 2e-5 * max(1.0, abs(float(want)))
+        torch.testing.assert_close(grad, full.grad[:, rank * 2:(rank + 1) * 2], rtol=2e-4, atol=1e-7)
+
+
+def _train_worker(rank, world, port, q):
+    _init(rank, world, port)
+    from cgg_b200 import synth
+    from cgg_b200.head import build_head_from_state_dict
+    from cgg_b200.train import GradReducer
+    dev = torch.device('cuda', rank)
+    Q, B = 16, 1
+    sd = synth.make_params(seed=51, num_queries=Q, perturb=True)
+    head = build_head_from_state_dict(sd, Q, 49, 'fp32', dev).train()
+    mf, mems = synth.make_inputs(60 + rank, B, 96, 128)
+    red = GradReducer(head.parameters(), bucket_mb=4.0)
+    assert len(red.buckets) > 1
+    cls, emb, mask = head.decoder_forward_auto(mf.to(dev), [m.to(dev) for m in mems])
+    loss = sum((c ** 2).mean() + (e ** 2).mean() + (m ** 2).mean() for c, e, m in zip(cls, emb, mask))
+    loss.backward()
+    red.finish()
+    torch.cuda.synchronize()
+    q.put((rank, {k: p.grad.cpu() for k, p in head.named_parameters()}, red.exposed()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@need2
+def test_nccl_gradient_allreduce_matches_global_batch_gradient():
+    sys.path.insert(0, ROOT)
+    from oracle import cgg_oracle as O
+    from cgg_b200 import synth
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 34500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    sd = synth.make_params(seed=51, num_queries=16, perturb=True)
+    sd_o = {k: v.clone().requires_grad_(k != 'class_embs') for k, v in sd.items()}
+    total = 0.0
+    for rank in range(2):
+        mf, mems = synth.make_inputs(60 + rank, 1, 96, 128)
+        ref = O.decoder_forward(sd_o, mf, mems)
+        total = total + sum((c ** 2).mean() + (e ** 2).mean() + (m ** 2).mean()
+                            for c, e, m in zip(ref['cls'], ref['emb'], ref['mask']))
+    (total / 2).backward()
+    for rank, grads, exposed in res:
+        for k, g in grads.items():
+            want = sd_o[k].grad
+            err = float((g - want).abs().max()) / (float(want.abs().max()) + 1e-12)
+            assert err < 2e-3, (rank, k, err)
+    assert torch.equal(res[0][1]['query_feat.weight'], res[1][1]['query_feat.weight'])

@@ -99,6 +99,51 @@ def test_batched_caption_gather_matches_single_process():
         torch.testing.assert_close(grad, full.grad[:, rank * 2:(rank + 1) * 2], rtol=1e-5, atol=1e-7)
 
 
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from cgg_b200.train import GradReducer
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 2048), torch.nn.ReLU(), torch.nn.Linear(2048, 512), torch.nn.Linear(512, 4))
+    red = GradReducer(net.parameters(), bucket_mb=1.0)
+    x = torch.randn((8, 16), generator=torch.Generator().manual_seed(10 + rank))
+    for _ in range(2):                      # two steps: buckets are reusable
+        for p in net.parameters():
+            p.grad = None
+        net(x).pow(2).mean().backward()
+        red.finish()
+    q.put((rank, len(red.buckets), [p.grad.clone() for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_grad_reducer_two_ranks_gloo():
+    """Host logic of the gradient all-reduce (train.py GradReducer): buckets in reverse parameter order, hooks fire the
+    collective when a bucket is complete, the result is the mean over ranks and lands in .grad."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 2048), torch.nn.ReLU(), torch.nn.Linear(2048, 512), torch.nn.Linear(512, 4))
+    total = 0.0
+    for rank in range(2):
+        x = torch.randn((8, 16), generator=torch.Generator().manual_seed(10 + rank))
+        total = total + net(x).pow(2).mean()
+    (total / 2).backward()
+    assert res[0][1] > 1
+    for rank, nb, grads in res:
+        for g, p in zip(grads, net.parameters()):
+            torch.testing.assert_close(g, p.grad, rtol=1e-5, atol=1e-7)
+
+
 def test_reference_arm_runs_on_rank0_only():
     env = dict(os.environ, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
