@@ -20,6 +20,7 @@
 //   mbarrier phase means "O(j) ready" and "S(j+2) ready" (a tcgen05.commit costs the issuing thread
 //   several hundred cycles); a softmax thread that has seen O(j) hands tile j's K/V stage back to the producer.
 #include <cstdio>
+#include <cuda_fp16.h>
 #include "kernels.h"
 #include "tc_ptx.cuh"
 #include "tc_state.h"
@@ -43,9 +44,47 @@ struct AttnP {
   int Q, K, heads, W32, ntiles, nqt;
   int trace;
   int has_r, r_col0, r_lo_off;   // key-bias table term: S += Q (R_hi + R_lo)^T, R columns r_col0 + head*32
-  int out_hl;                    // out_bf16 rows are [hi(C) | lo(C)] bf16 pairs (split-precision operand of the out-projection)
+  int out_hl;                    // out_bf16: 0 = bf16 rows of C, 1 = [hi(C) | lo(C)] bf16 pairs, 2 = IEEE half rows of C
   int dbg;                       // CGG_AT_DBG experiments (timing only, results wrong): 1 no key-bias MMAs, 2 no P.V MMAs, 4 no exp2
 };
+
+
+// row (b, qi), head h of the attention output: o[32] * inv as fp32 and / or as a 16-bit GEMM operand (AttnP::out_hl)
+__device__ __forceinline__ void store_attn_out(const AttnP& p, int b, int qi, int h, int C, const float* o, float inv) {
+  if (p.out) {
+    float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+  }
+  if (p.out_bf16) {
+    const long ld = p.out_hl == 1 ? 2 * C : C;
+    uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + h * 32);
+    uint4* dst_lo = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + C + h * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 pk, pl;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+      uint32_t* wl = reinterpret_cast<uint32_t*>(&pl);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = o[8 * i + 2 * j] * inv, a1 = o[8 * i + 2 * j + 1] * inv;
+        if (p.out_hl == 2) {
+          const __half2 h2 = __floats2half2_rn(a0, a1);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        } else {
+          __nv_bfloat162 v2 = __floats2bfloat162_rn(a0, a1);
+          w[j] = *reinterpret_cast<uint32_t*>(&v2);
+          const float2 back = __bfloat1622float2(v2);
+          __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - back.x, a1 - back.y);
+          wl[j] = *reinterpret_cast<uint32_t*>(&l2);
+        }
+      }
+      dst[i] = pk;
+      if (p.out_hl == 1) dst_lo[i] = pl;
+    }
+  }
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -406,37 +445,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         for (int i = 0; i < 32; ++i) o[i] += src[2 + i] * a1;
       }
     }
-    if (row_ok && hf == 0) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      if (p.out) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
-      }
-      if (p.out_bf16) {
-        const long ld = p.out_hl ? 2 * C : C;
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + h * 32);
-        uint4* dst_lo = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + C + h * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 pk, pl;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
-          uint32_t* wl = reinterpret_cast<uint32_t*>(&pl);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a0 = o[8 * i + 2 * j] * inv, a1 = o[8 * i + 2 * j + 1] * inv;
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(a0, a1);
-            w[j] = *reinterpret_cast<uint32_t*>(&v2);
-            const float2 back = __bfloat1622float2(v2);
-            __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - back.x, a1 - back.y);
-            wl[j] = *reinterpret_cast<uint32_t*>(&l2);
-          }
-          dst[i] = pk;
-          if (p.out_hl) dst_lo[i] = pl;
-        }
-      }
-    }
+    if (row_ok && hf == 0) store_attn_out(p, b, qi, h, C, o, l_run > 0.f ? 1.0f / l_run : 0.f);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -793,37 +802,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           for (int i = 0; i < 32; ++i) o[i] += src[2 + i] * a1;
         }
       }
-      if (row_ok) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        if (p.out) {
-          float4* dst = reinterpret_cast<float4*>(p.out + ((long)b * p.Q + qi) * C + h * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
-        }
-        if (p.out_bf16) {
-          const long ld = p.out_hl ? 2 * C : C;
-          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + h * 32);
-          uint4* dst_lo = reinterpret_cast<uint4*>(p.out_bf16 + ((long)b * p.Q + qi) * ld + C + h * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 pkk, pl;
-            uint32_t* w = reinterpret_cast<uint32_t*>(&pkk);
-            uint32_t* wl = reinterpret_cast<uint32_t*>(&pl);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a0v = o[8 * i + 2 * j] * inv, a1v = o[8 * i + 2 * j + 1] * inv;
-              __nv_bfloat162 v2 = __floats2bfloat162_rn(a0v, a1v);
-              w[j] = *reinterpret_cast<uint32_t*>(&v2);
-              const float2 back = __bfloat1622float2(v2);
-              __nv_bfloat162 l2 = __floats2bfloat162_rn(a0v - back.x, a1v - back.y);
-              wl[j] = *reinterpret_cast<uint32_t*>(&l2);
-            }
-            dst[i] = pkk;
-            if (p.out_hl) dst_lo[i] = pl;
-          }
-        }
-      }
+      if (row_ok) store_attn_out(p, b, qi, h, C, o, l_run > 0.f ? 1.0f / l_run : 0.f);
     }
   }
   ptx::tc_fence_before();
@@ -852,7 +831,7 @@ int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_str
 
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out, __nv_bfloat16* out_bf16,
-                 cudaStream_t s, const void* r_table, long r_cols, int r_col0, bool out_hl) {
+                 cudaStream_t s, const void* r_table, long r_cols, int r_col0, int out_mode) {
   // r_table: (num_keys, r_cols) bf16 with columns [hi (r_cols/2) | lo (r_cols/2)]
   const int Q = t->cfg.num_queries, heads = t->cfg.num_heads, C = t->cfg.embed_dim;
   const int ntiles = (num_keys + AT_KT - 1) / AT_KT, nqt = (Q + 127) / 128;
@@ -878,7 +857,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
   static const int r_lo = getenv("CGG_ATTN_R_LO") ? atoi(getenv("CGG_ATTN_R_LO")) : 1;
   p.has_r = r_table ? (r_lo ? 2 : 1) : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
-  p.out_hl = out_hl ? 1 : 0;
+  p.out_hl = out_mode;
   static const int at_dbg = getenv("CGG_AT_DBG") ? atoi(getenv("CGG_AT_DBG")) : 0;
   p.dbg = at_dbg;
   if (at_dbg & 1) p.has_r = 0;

@@ -268,7 +268,7 @@ struct LinCtx {
       if (sgi < p.nseg && m >= p.seg[sgi].col0 && m < p.seg[sgi].col0 + p.seg[sgi].ncols) {
         on = true;
         f = m - p.seg[sgi].col0;
-        mode = p.seg[sgi].is_bf16 ? (p.seg[sgi].split ? 2 : 1) : 0;
+        mode = p.seg[sgi].is_bf16 == 3 ? 3 : (p.seg[sgi].is_bf16 ? (p.seg[sgi].split ? 2 : 1) : 0);   // 3 = IEEE half
         floor = p.seg[sgi].relu ? 0.f : -INFINITY;
         ptr = p.seg[sgi].ptr; ld = p.seg[sgi].ld; alpha = p.seg[sgi].alpha;
         rowbias = p.seg[sgi].rowbias; rb_mod = p.seg[sgi].rb_mod; rb_ld = p.seg[sgi].rb_ld;
@@ -363,6 +363,8 @@ __device__ __forceinline__ void epi_linear_t(const TcGemmP& p, const EpiCtx& c, 
           static_cast<float*>(L.ptr)[off] = x;
         } else if (MODE == 1) {
           static_cast<__nv_bfloat16*>(L.ptr)[off] = __float2bfloat16_rn(x);
+        } else if (MODE == 3) {
+          static_cast<__half*>(L.ptr)[off] = __float2half_rn(x);
         } else {
           __nv_bfloat16 hi, lo;
           split_bf16(x, hi, lo);
@@ -384,6 +386,8 @@ __device__ __forceinline__ void epi_linear_dispatch(const TcGemmP& p, const EpiC
   } else if (L.mode == 1) {
     if (rb) epi_linear_t<1, true, false>(p, c, L, pre);
     else epi_linear_t<1, false, false>(p, c, L, pre);
+  } else if (L.mode == 3) {
+    epi_linear_t<3, false, false>(p, c, L, pre);
   } else {
     epi_linear_t<2, false, false>(p, c, L, pre);
   }
@@ -1901,7 +1905,7 @@ int make_map_act(TcState* t, CUtensorMap* m, const void* base, long rows, int K)
 }  // namespace
 
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
-              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k, int kparts, long kpart_stride) {
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k, int kparts, long kpart_stride, bool f16) {
   if (kparts < 1) kparts = 1;
   if (kparts > 1 && (nsegs != 1 || segs[0].is_bf16 || segs[0].relu || (K / TC_BK) % kparts != 0))
     return tc_fail(t, CGG_ERR_BAD_SHAPE, "K-parts need one plain fp32 output segment");
@@ -1929,6 +1933,7 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   }
   p.b_row0 = 0; p.b_rows_per_batch = p.N_TILE;       // blockIdx.y = token tile
   p.epi = EPI_LINEAR_T; p.M_valid = n_padded; p.n_tokens = M;
+  p.f16 = f16 ? 1 : 0;
   p.nseg = nsegs; p.lin_bias = bias;
   for (int i = 0; i < nsegs; ++i) p.seg[i] = segs[i];
   return launch_tc_gemm(t, mW, mX, p, n_padded / TC_BM, n_tok_tiles, s, nullptr, kparts);

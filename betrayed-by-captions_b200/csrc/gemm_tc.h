@@ -15,7 +15,7 @@ struct TcState;
 struct TcSeg {
   int col0, ncols;
   void* ptr; long ld;
-  int is_bf16, relu;
+  int is_bf16, relu;   // is_bf16: 0 = fp32 output, 1 = bf16, 3 = IEEE half
   int split;      // bf16 only: write x as a hi/lo pair, hi at column n, lo at column ncols+n of the row
   float alpha;
   const float* rowbias; int rb_mod; long rb_ld;
@@ -64,7 +64,8 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
 // split_k: A and W rows are [hi(256) | lo(256)] bf16 pairs and the contraction is evaluated as
 // hi.hi + lo.hi + hi.lo (fp32 accumulate), i.e. with ~16 mantissa bits per operand (K must be 256).
 int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int n_padded, const float* bias,
-              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false, int kparts = 1, long kpart_stride = 0);
+              const TcSeg* segs, int nsegs, cudaStream_t s, bool split_k = false, int kparts = 1, long kpart_stride = 0,
+              bool f16 = false);   // f16: both operands are IEEE half (11 significand bits) instead of bf16
 // kparts > 1: the K range is split over gridDim.z CTAs; part z writes fp32 partial sums at ptr + z*kpart_stride
 // (bias / residual added by part 0); the consumer (LayerNorm) adds the parts.
 // The bf16-mode decoder layer (K5 + K6) and the query heads (K1) built from the pieces above.
@@ -87,7 +88,7 @@ int tc_query_heads(TcState* t, const cgg_weights* w, int batch, const float* x, 
 int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void* k, const void* v, long kv_stride,
                  long kv_bstride, const uint32_t* bitmap, const uint8_t* all_masked, float* out,
                  __nv_bfloat16* out_bf16, cudaStream_t s, const void* r_table = nullptr, long r_cols = 0, int r_col0 = 0,
-                 bool out_hl = false);   // out_hl: out_bf16 rows are [hi(C) | lo(C)] pairs
+                 int out_mode = 0);   // out_bf16 format: 0 = bf16 rows, 1 = [hi(C) | lo(C)] bf16 pairs, 2 = IEEE half rows
 // r_table: optional bf16 (num_keys, r_cols) key-bias table stored as [hi | lo] column halves;
 // S += Q . (R_hi + R_lo)[:, r_col0 + head*32 ...]^T
 const void* tc_key_bias_table(const TcState* t, int level, long* cols);

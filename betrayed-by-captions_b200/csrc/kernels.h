@@ -97,6 +97,8 @@ cudaError_t launch_softmax_rows(float* x, int rows, int n, cudaStream_t s);
 
 // fp32 (rows, cols) -> bf16 (rows, 2*cols) hi/lo pairs: [hi | lo] per row
 cudaError_t launch_cast_bf16_split(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t s);
+// fp32 -> IEEE half cast (n elements)
+cudaError_t launch_cast_f16(const float* in, void* out, size_t n, cudaStream_t s);
 // fp32 -> bf16 cast (n elements)
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s);
 

@@ -3,6 +3,7 @@
 // work.  No fast-math: the sigmoid threshold and the softmax follow IEEE expf / division so the
 // attention-mask bits match the PyTorch CUDA reference (hard part 2).
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include <math.h>
 #include <atomic>
 
@@ -672,6 +673,17 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+cudaError_t launch_cast_f16(const float* in, void* out, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  cast_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, static_cast<__half*>(out), n);
   count_launch();
   return cudaGetLastError();
 }

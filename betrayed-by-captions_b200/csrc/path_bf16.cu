@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "tc_ptx.cuh"
 #include "tc_state.h"
+#include <cuda_fp16.h>
 
 #include <math.h>
 #include <stdlib.h>
@@ -26,7 +27,7 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// dst row [hi(256) | lo(256)] = split(x + qe[row % Q])   (256 channels per row)
+// dst = half(x + qe[row % Q]): the IEEE-half operand of the layer's q / k projections
 __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __restrict__ qe,
                                    __nv_bfloat16* __restrict__ dst, long total, int per /* Q*C */) {
   ptx::grid_dep_launch();
@@ -35,17 +36,19 @@ __global__ void add_qe_cast_kernel(const float* __restrict__ x, const float* __r
   if (i >= total) return;
   const float4 a = *reinterpret_cast<const float4*>(x + i);
   const float4 b = *reinterpret_cast<const float4*>(qe + (i % per));
-  uint2 ph, pl;
-  split_pack(a.x + b.x, a.y + b.y, ph.x, pl.x);
-  split_pack(a.z + b.z, a.w + b.w, ph.y, pl.y);
-  const long row = i >> 8, col = i & 255;
-  *reinterpret_cast<uint2*>(dst + row * 512 + col) = ph;
-  *reinterpret_cast<uint2*>(dst + row * 512 + 256 + col) = pl;
+  const __half2 lo = __floats2half2_rn(a.x + b.x, a.y + b.y), hi = __floats2half2_rn(a.z + b.z, a.w + b.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst + i) = pk;
 }
 
-// Row LayerNorm over 256 channels, one warp per row, every access coalesced.  Optional outputs:
-// fp32 y, and bf16 hi/lo pair rows [hi(256) | lo(256)] of y (out_bf16), of y + qe[row % Q] (out_bf16_q) and of
-// y or its chained second LayerNorm (out_hl): the split-precision operands of the GEMMs that follow.
+// Row LayerNorm over 256 channels, one warp per row, every access coalesced.  Optional outputs: fp32 y; IEEE-half rows
+// of y (out_bf16) and of y + qe[row % Q] (out_bf16_q) -- the operands of the layer's linear layers, which run on
+// kind::f16 MMAs with HALF operands (11 significand bits: the residual stream is LayerNorm-scaled, so the range is no
+// issue, and a CPU study shows bf16 operands here cost the attention masks ~0.1 % of their bits after 9 layers, half
+// operands 0.01 %) -- and a bf16 hi/lo pair row [hi(256) | lo(256)] of y or of its chained second
+// LayerNorm (out_hl), the split-precision operand of the query heads.
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int nparts, long part_stride,
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ b, int rows, float* __restrict__ out_f32,
@@ -96,13 +99,23 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     *reinterpret_cast<uint4*>(dst + (long)row * 512 + n0) = ph;
     *reinterpret_cast<uint4*>(dst + (long)row * 512 + 256 + n0) = pl;
   };
-  if (out_bf16) store_hl(out_bf16, y);
+  auto store_h = [&](__nv_bfloat16* dst, const float* v8) {
+    uint4 pk;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h2 = __floats2half2_rn(v8[2 * i], v8[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dst + (long)row * 256 + n0) = pk;
+  };
+  if (out_bf16) store_h(out_bf16, y);
   if (out_bf16_q) {
     const float* e = qe + (long)(row % Q) * 256 + n0;
     float yq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) yq[i] = y[i] + e[i];
-    store_hl(out_bf16_q, yq);
+    store_h(out_bf16_q, yq);
   }
   if (out_hl && w2) {
     // chained second LayerNorm (post_norm of the head call that follows): z = LN(y; w2, b2)
@@ -175,13 +188,13 @@ int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
     t->free_packed();
     for (int i = 0; i < L; ++i) {
       TcState::LayerW& l = t->pl[i];
-      // every small-M weight is kept as [hi | lo] bf16 rows: the layer chain runs at split precision
-      TCU(cudaMalloc(&l.wq_c, (size_t)C * C * 4));
-      TCU(cudaMalloc(&l.wo_c, (size_t)C * C * 4));
-      TCU(cudaMalloc(&l.wqkv_s, (size_t)3 * C * C * 4));
-      TCU(cudaMalloc(&l.wo_s, (size_t)C * C * 4));
-      TCU(cudaMalloc(&l.w1, (size_t)F * C * 4));
-      TCU(cudaMalloc(&l.w2, (size_t)C * F * 4));
+      // the layer chain's weights are kept in IEEE half
+      TCU(cudaMalloc(&l.wq_c, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.wo_c, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.wqkv_s, (size_t)3 * C * C * 2));
+      TCU(cudaMalloc(&l.wo_s, (size_t)C * C * 2));
+      TCU(cudaMalloc(&l.w1, (size_t)F * C * 2));
+      TCU(cudaMalloc(&l.w2, (size_t)C * F * 2));
       TCU(cudaMalloc(&l.rowbias_v, (size_t)Q * C * 4));
     }
     TCU(cudaMalloc(&t->wh, (size_t)nh * 2 * C * 2));       // hi/lo rows: the head chain runs at split precision
@@ -194,12 +207,12 @@ int tc_pack_weights(TcState* t, const cgg_weights* w, cudaStream_t s) {
   for (int i = 0; i < L; ++i) {
     const cgg_layer_weights& lw = w->layers[i];
     TcState::LayerW& l = t->pl[i];
-    TCU(launch_cast_bf16_split(lw.cross_in_w, l.wq_c, C, C, s));                    // Wq of the cross-attention
-    TCU(launch_cast_bf16_split(lw.cross_out_w, l.wo_c, C, C, s));
-    TCU(launch_cast_bf16_split(lw.self_in_w, l.wqkv_s, 3 * C, C, s));               // [Wq; Wk; Wv] as stored
-    TCU(launch_cast_bf16_split(lw.self_out_w, l.wo_s, C, C, s));
-    TCU(launch_cast_bf16_split(lw.ffn_w1, l.w1, F, C, s));
-    TCU(launch_cast_bf16_split(lw.ffn_w2, l.w2, C, F, s));
+    TCU(launch_cast_f16(lw.cross_in_w, l.wq_c, (size_t)C * C, s));                  // Wq of the cross-attention
+    TCU(launch_cast_f16(lw.cross_out_w, l.wo_c, (size_t)C * C, s));
+    TCU(launch_cast_f16(lw.self_in_w, l.wqkv_s, (size_t)3 * C * C, s));             // [Wq; Wk; Wv] as stored
+    TCU(launch_cast_f16(lw.self_out_w, l.wo_s, (size_t)C * C, s));
+    TCU(launch_cast_f16(lw.ffn_w1, l.w1, (size_t)F * C, s));
+    TCU(launch_cast_f16(lw.ffn_w2, l.w2, (size_t)C * F, s));
     // v = x Wv^T + bv = (x + qe) Wv^T + bv - qe Wv^T : the last term is a per-query constant
     GemmF32 g;
     g.A = w->query_embed; g.sAm = C; g.sAk = 1;
@@ -282,38 +295,39 @@ int tc_decoder_layer(TcState* t, const cgg_weights* w, int batch, int layer, con
   }
   if (!q_ready) {      // (q_ready: tc_layer_qproj already ran, on a branch parallel to the head call)
     TcSeg sq[1] = {seg(0, C, qf, C, false, false, qscale)};
-    TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s, true));
+    TST(tc_linear(t, xqb, M, C, pw.wq_c, C, lw.cross_in_b, sq, 1, s, false, 1, 0, /*f16=*/true));
   }
   {
     const int level = layer % CGG_NUM_LEVELS, slot = layer / CGG_NUM_LEVELS;
     long rcols = 0;
     const void* rtab = tc_key_bias_table(t, level, &rcols);
     TST(tc_attention(t, batch, num_keys, qf, k, v, kv_stride, kv_bstride, bitmap, all_masked, nullptr, ob, s, rtab, rcols,
-                     slot * C, /*out_hl=*/true));
+                     slot * C, /*out_mode: IEEE half*/ 2));
   }
   // x1 = LN(x + o Wo^T + bo);  also bf16(x1 + query_embed) for the self-attention projections
   TcSeg so[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x_in, C)};
-  TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s, true));
+  TST(tc_linear(t, ob, M, C, pw.wo_c, C, lw.cross_out_b, so, 1, s, false, 1, 0, true));
   TCU(launch_ln_rows(t1, lw.norm_w[0], lw.norm_b[0], M, x1, nullptr, xqb, w->query_embed, Q, nullptr, s));
   // ---- self-attention: q, k from x1 + query_embed, v from x1 (per-query constant folded into rowbias_v)
   __nv_bfloat16* kvb = reinterpret_cast<__nv_bfloat16*>(kvs);          // (M, 2C) bf16: [k | v]
   TcSeg sk[3] = {seg(0, C, qs, C, false, false, qscale), seg(C, C, kvb, 2 * C, true, false),
                  seg(2 * C, C, kvb + C, 2 * C, true, false, 1.f, pw.rowbias_v, Q, C)};
-  TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s, true));
+  TST(tc_linear(t, xqb, M, C, pw.wqkv_s, 3 * C, lw.self_in_b, sk, 3, s, false, 1, 0, true));
   // the 100 x 100 self-attention runs on the same tcgen05 attention kernel (one key tile, no mask)
   TST(tc_attention(t, batch, Q, qs, kvb, kvb + C, 2 * C, (long)Q * 2 * C, nullptr, nullptr, nullptr, ob, s, nullptr, 0, 0,
-                   /*out_hl=*/true));
+                   /*out_mode: IEEE half*/ 2));
   TcSeg so2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x1, C)};
-  TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s, true));
+  TST(tc_linear(t, ob, M, C, pw.wo_s, C, lw.self_out_b, so2, 1, s, false, 1, 0, true));
   TCU(launch_ln_rows(t1, lw.norm_w[1], lw.norm_b[1], M, x2, xb, nullptr, nullptr, 0, nullptr, s));
   // ---- FFN
-  TcSeg sf[1] = {seg(0, F, fb, 2 * F, true, true, 1.f, nullptr, 1, 0, /*split=*/true)};
-  TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s, true));
+  TcSeg sf[1] = {seg(0, F, fb, F, true, true)};
+  sf[0].is_bf16 = 3;                                   // IEEE half: the operand of FFN2
+  TST(tc_linear(t, xb, M, C, pw.w1, F, lw.ffn_b1, sf, 1, s, false, 1, 0, true));
   TcSeg sf2[1] = {seg(0, C, t1, C, false, false, 1.f, nullptr, 1, 0, false, x2, C)};
   // K = 2048 over 4 K-parts (4x the CTAs, each a quarter of the chunk chain); the LayerNorm adds the parts
   const int kparts = (F / 64) % 4 == 0 ? 4 : 1;
   const long pstride = (long)M * C;
-  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s, true, kparts, pstride));
+  TST(tc_linear(t, fb, M, F, pw.w2, C, lw.ffn_b2, sf2, 1, s, false, kparts, pstride, true));
   if (chained_out)   // also bf16(x_out + query_embed) for the next layer and post_norm(x_out) for the next head call
     TCU(launch_ln_rows(t1, lw.norm_w[2], lw.norm_b[2], M, x_out, nullptr, xqb, w->query_embed, Q, at<__nv_bfloat16>(ws, o.zb), s,
                        w->post_norm_w, w->post_norm_b, kparts, pstride));
@@ -333,7 +347,8 @@ int tc_layer_qproj(TcState* t, const cgg_weights* w, int batch, int layer, void*
   TcWs o;
   o.carve(t, batch);
   TcSeg sq[1] = {seg(0, C, at<float>(ws, o.qf), C, false, false, qscale)};
-  TST(tc_linear(t, at<__nv_bfloat16>(ws, o.xqb), M, C, t->pl[layer].wq_c, C, w->layers[layer].cross_in_b, sq, 1, s, true));
+  TST(tc_linear(t, at<__nv_bfloat16>(ws, o.xqb), M, C, t->pl[layer].wq_c, C, w->layers[layer].cross_in_b, sq, 1, s, false, 1, 0,
+                true));
   return CGG_OK;
 }
 

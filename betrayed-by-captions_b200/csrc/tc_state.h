@@ -70,8 +70,8 @@ struct TcWs {
       const int K = t->lh[l] * t->lw[l];
       memp[l] = take((K % 8) ? (size_t)B * C * pitch8(K) * 2 : 0);
     }
-    xqb = take(M * 2 * C * 2); xb = take(M * 2 * C * 2); ob = take(M * 2 * C * 2);   // hi/lo rows
-    fb = take(M * 2 * t->cfg.ffn_dim * 2);
+    xqb = take(M * C * 2); xb = take(M * C * 2); ob = take(M * C * 2);   // IEEE-half rows
+    fb = take(M * t->cfg.ffn_dim * 2);
     zb = take(M * 2 * C * 2); h1b = take(M * 2 * C * 2); h2b = take(M * 2 * C * 2);   // hi/lo rows
     qf = take(M * C * 4); qs = take(M * C * 4); kvs = take(M * 2 * C * 4);
     x1 = take(M * C * 4); x2 = take(M * C * 4); t1 = take(4 * M * C * 4);   // t1: up to 4 K-split partial sums
