@@ -59,6 +59,18 @@ def _get(cfg, *path, default=None):
     return default if cfg is None else cfg
 
 
+class _BertEmbeddings(nn.Module):
+    """open_set/models/utils/bert_embeddings.py:4-13: only the word-embedding table and the embedding LayerNorm of
+    bert-base-uncased (state_dict keys bert_embeddings.word_embeddings.weight, bert_embeddings.LayerNorm.*); frozen."""
+
+    def __init__(self, vocab=30522, d=768, eps=1e-12):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, d, padding_idx=0)
+        self.LayerNorm = nn.LayerNorm(d, eps=eps)
+        for p_ in self.parameters():
+            p_.requires_grad = False
+
+
 class Mask2FormerHeadOpenB200(nn.Module):
     """Drop-in for ``Mask2FormerHeadOpen`` on the decoder hot path.
 
@@ -113,6 +125,18 @@ class Mask2FormerHeadOpenB200(nn.Module):
         if self.use_class_emb:
             self.v2l_transform = nn.Linear(feat_channels, d_lang)
             self.register_buffer('class_embs', torch.zeros(self.num_classes + 1, d_lang))
+        # caption side (head.py:249-254, :171): frozen BERT word embeddings for the noun tokens, grounding-loss weight
+        self.use_caption = bool(kwargs.get('use_caption', False))
+        self.caption_emb_type = kwargs.get('caption_emb_type', 'bert')
+        self.loss_only_last = bool(kwargs.get('loss_only_last', False))
+        self.loss_aux_weight = float(kwargs.get('loss_aux_weight', 1.0))
+        self.loss_grounding_weight = float(_get(kwargs.get('loss_grounding'), 'loss_weight', default=1.0))
+        self.test_cfg = kwargs.get('test_cfg') or {}
+        self.bert_embeddings = None
+        if self.use_caption:
+            if self.caption_emb_type != 'bert':
+                raise ValueError('only caption_emb_type="bert" is built (the shipped configs use it)')
+            self.bert_embeddings = _BertEmbeddings(kwargs.get('bert_vocab_size', 30522), d_lang)
         self._rt = None
         self.init_weights()
 
@@ -171,6 +195,83 @@ class Mask2FormerHeadOpenB200(nn.Module):
         """head.py:686-698 (bert branch) for a stacked (B, max_tokens) id tensor."""
         rt = self._runtime(ids.device)
         return rt.noun_embeddings(table, ln_weight, ln_bias, ids, eps, self.text_emb_norm)
+
+    def extract_caption_embeddings(self, ids_list, mask_list):
+        """The reference's `extract_word_embeddings(ids_list, mask_list, 'bert')` (head.py:686-709): per image, the BERT
+        word-embedding rows of the caption's noun ids, LayerNorm'ed when text_emb_norm.  Returns (embs_list, mask_list)."""
+        if self.bert_embeddings is None:
+            raise _lib.CggError('the head was built without use_caption=True: no BERT embedding table')
+        be = self.bert_embeddings
+        ids = torch.stack(list(ids_list), 0)
+        embs = self.extract_word_embeddings(be.word_embeddings.weight, be.LayerNorm.weight, be.LayerNorm.bias, ids,
+                                            eps=be.LayerNorm.eps)
+        return list(embs.unbind(0)), list(mask_list)
+
+    # ------------------------------------------------------------------- the reference's callers
+    def loss(self, all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list, gt_caption_ids_list,
+             gt_caption_embs_list, gt_caption_mask_list, gt_caption_nouns_ids_list, gt_caption_nouns_embs_list,
+             gt_caption_nouns_mask_list, img_metas):
+        """head.py:393-462 for the term that is on the path: the caption-grounding loss of every head call
+        (loss_single :540-548), computed on the CUDA kernels with the batched cross-rank gather.  The matching-based
+        terms (loss_cls / loss_cls_emb / loss_mask / loss_dice: Hungarian assignment on point-sampled masks, :320-390,
+        :591-627) are the step AFTER the path and stay with mmdet: attach them through
+        `self.matching_losses(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list,
+        img_metas) -> dict` and they are merged into the result."""
+        from .grounding import gather_captions_and_preds, grounding_loss
+        losses = {}
+        if self.use_caption:
+            preds = torch.stack(list(all_cls_emb_preds), 0)                       # (L+1, B, Q, d_l)
+            embs, mask, preds_all = gather_captions_and_preds(gt_caption_nouns_embs_list, gt_caption_nouns_mask_list, preds)
+            n = preds_all.shape[0]
+            for j in range(n):
+                if self.loss_only_last and j != n - 1:
+                    continue
+                lg = grounding_loss(preds_all[j], embs, mask, float(self.softmax_temperature), self.loss_grounding_weight)
+                if j == n - 1:
+                    losses['loss_grounding'] = lg
+                else:
+                    losses['d%d.loss_grounding' % j] = lg * self.loss_aux_weight
+        hook = getattr(self, 'matching_losses', None)
+        if hook is not None:
+            losses.update(hook(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list, img_metas))
+        return losses
+
+    def forward_train(self, feats, img_metas, gt_bboxes, gt_labels, gt_masks, gt_semantic_seg, gt_caption_ids,
+                      gt_caption_mask, gt_caption_nouns_ids, gt_caption_nouns_mask, gt_bboxes_ignore=None, **kwargs):
+        """head.py:851-921 (same signature): forward on the autograd-connected path, noun embeddings, losses.
+        `preprocess_gt` (mmdet, :903) only feeds the matching-based losses and is left to the `matching_losses` hook."""
+        assert gt_bboxes_ignore is None
+        all_cls_scores, all_cls_emb_preds, all_mask_preds = self(feats, img_metas)
+        nouns_embs = nouns_mask = None
+        if self.use_caption:
+            nouns_embs, nouns_mask = self.extract_caption_embeddings(gt_caption_nouns_ids, gt_caption_nouns_mask)
+        return self.loss(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels, gt_masks, gt_caption_ids, None,
+                         gt_caption_mask, gt_caption_nouns_ids, nouns_embs, nouns_mask, img_metas)
+
+    def simple_test(self, feats, img_metas, **kwargs):
+        """head.py:923-980 (same signature and return tuple): last head call's outputs, masks upsampled to the padded
+        input size, optional query x noun attention `att`.  Two branches need components outside the path and raise:
+        test-time label assignment (`gt_labels`, the Hungarian assigner) and caption generation (`with_caption`)."""
+        from .postprocess import upsample_masks
+        all_cls_scores, all_cls_emb_preds, all_mask_preds = self(feats, img_metas)
+        mask_cls_results, mask_cls_emb_results, mask_pred_results = all_cls_scores[-1], all_cls_emb_preds[-1], all_mask_preds[-1]
+        assigned_labels = mask_cls_results
+        if kwargs.get('gt_labels', None) is not None:
+            raise _lib.CggError('simple_test(gt_labels=...) needs the mask Hungarian assigner (outside the path)')
+        img_shape = kwargs.get('img_shape') or img_metas[0]['batch_input_shape']
+        mask_pred_results = upsample_masks(self, mask_pred_results, (img_shape[0], img_shape[1]))      # :957-964
+        if kwargs.get('with_caption', False) or 'cap_results' in self.test_cfg.get('eval_types', []):
+            raise _lib.CggError('caption generation (beam search) is outside the path')
+        att = None
+        if kwargs.get('with_att', False):                                                               # :973-978
+            ids = kwargs['nouns_ids']
+            be = self.bert_embeddings
+            if be is None:
+                raise _lib.CggError('with_att needs use_caption=True (BERT embedding table)')
+            nouns_embs = self.extract_word_embeddings(be.word_embeddings.weight, be.LayerNorm.weight, be.LayerNorm.bias,
+                                                      ids.reshape(-1), eps=be.LayerNorm.eps)
+            att = self.test_time_att(mask_cls_emb_results, nouns_embs)
+        return assigned_labels, mask_cls_emb_results, mask_pred_results, None, att
 
     def grounding_loss(self, cls_emb_pred, gt_caption_embs, gt_caption_mask, loss_weight=1.0):
         """losses/grounding_loss.py:9-77; differentiable w.r.t. cls_emb_pred (grounding.py)."""

@@ -86,3 +86,74 @@ def test_upsample_masks_matches_interpolate():
         want = F.interpolate(x.float(), size=(264, 200), mode='bilinear', align_corners=False)
         got = P.upsample_masks(head, x, (264, 200))
         assert float((got - want).abs().max()) < 1e-5
+
+
+class _StubPixelDecoder(torch.nn.Module):
+    """Stands in for mmdet's MSDeformAttnPixelDecoder (the step BEFORE the path): passes precomputed features through."""
+
+    def forward(self, feats):
+        return feats[0], list(feats[1:])
+
+
+def _caption_head(Q, precision='fp32'):
+    from cgg_b200.head import Mask2FormerHeadOpenB200
+    sd = synth.make_params(seed=6, num_queries=Q, perturb=True)
+    head = Mask2FormerHeadOpenB200(num_things_classes=48, num_stuff_classes=0, num_queries=Q, precision=precision,
+                                   use_class_emb=True, use_caption=True, bert_vocab_size=1500,
+                                   loss_grounding=dict(type='GroundingLoss', loss_weight=2.0),
+                                   pixel_decoder=_StubPixelDecoder())
+    ids, cap_mask, table, lw, lb = synth.make_captions(6, 2, vocab=1500)
+    sd = dict(sd)
+    sd['bert_embeddings.word_embeddings.weight'] = table
+    sd['bert_embeddings.LayerNorm.weight'] = lw + 0.1
+    sd['bert_embeddings.LayerNorm.bias'] = lb - 0.05
+    head.load_state_dict(sd, strict=True)
+    return head.to(DEV), sd, ids, cap_mask
+
+
+def test_simple_test_contract_and_att():
+    """mask2former_head.py:923-980: (assigned_labels, cls_emb[-1], upsampled mask[-1], None, att)."""
+    from oracle import cgg_oracle as O
+    Q, B = 24, 2
+    head, sd, ids, cap_mask = _caption_head(Q)
+    head.eval()
+    mf, mems = synth.make_inputs(8, B, 128, 160)
+    feats = [mf.to(DEV)] + [m.to(DEV) for m in mems]
+    metas = [dict(batch_input_shape=(128, 160), img_shape=(128, 160, 3), ori_shape=(128, 160, 3)) for _ in range(B)]
+    noun_ids = ids[0, :5].to(DEV)
+    with torch.no_grad():
+        labels, emb, masks, cap, att = head.simple_test(feats, metas, with_att=True, nouns_ids=noun_ids)
+    ref = O.decoder_forward({k: v for k, v in sd.items() if not k.startswith('bert')}, mf, mems)
+    want_mask = F.interpolate(ref['mask'][9], size=(128, 160), mode='bilinear', align_corners=False)
+    assert cap is None and tuple(masks.shape) == (B, Q, 128, 160)
+    assert float((masks.cpu() - want_mask).abs().max()) < 2e-3 * float(want_mask.abs().max())
+    assert float((labels.cpu() - ref['cls'][9]).abs().max()) < 2e-3 * float(ref['cls'][9].abs().max())
+    nouns = O.noun_embeddings(sd['bert_embeddings.word_embeddings.weight'], sd['bert_embeddings.LayerNorm.weight'],
+                              sd['bert_embeddings.LayerNorm.bias'], ids[0, :5])
+    want_att = ref['emb'][9][0] @ nouns.t()
+    assert float((att.cpu() - want_att).abs().max()) < 2e-3 * float(want_att.abs().max())
+
+
+def test_forward_train_grounding_losses_and_gradients():
+    """mask2former_head.py:851-921 -> loss :393-462 for the on-path term: 10 grounding losses under the reference's
+    key names, weight 2.0, autograd-connected to the head's parameters."""
+    from oracle import cgg_oracle as O
+    Q, B = 24, 2
+    head, sd, ids, cap_mask = _caption_head(Q)
+    head.train()
+    mf, mems = synth.make_inputs(8, B, 128, 160)
+    feats = [mf.to(DEV)] + [m.to(DEV) for m in mems]
+    metas = [dict() for _ in range(B)]
+    losses = head.forward_train(feats, metas, None, None, None, None, None, None, list(ids.to(DEV)), list(cap_mask.to(DEV)))
+    assert set(losses) == {'loss_grounding'} | {'d%d.loss_grounding' % j for j in range(9)}
+    sd_o = {k: v for k, v in sd.items() if not k.startswith('bert')}
+    ref = O.decoder_forward(sd_o, mf, mems)
+    nouns = O.noun_embeddings(sd['bert_embeddings.word_embeddings.weight'], sd['bert_embeddings.LayerNorm.weight'],
+                              sd['bert_embeddings.LayerNorm.bias'], ids)
+    for j in range(10):
+        want = float(O.grounding_loss(ref['emb'][j], nouns, cap_mask, 10.0, 2.0))
+        got = float(losses['loss_grounding' if j == 9 else 'd%d.loss_grounding' % j])
+        assert abs(got - want) < 2e-3 * max(1.0, abs(want)), (j, got, want)
+    sum(losses.values()).backward()
+    assert head.v2l_transform.weight.grad is not None and float(head.v2l_transform.weight.grad.abs().max()) > 0
+    assert head.query_feat.weight.grad is not None and head.bert_embeddings.word_embeddings.weight.grad is None
