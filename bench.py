@@ -719,7 +719,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch the path eagerly instead of replaying a CUDA graph')
     ap.add_argument('--final-mask-only', action='store_true',
                     help='opt-in inference shortcut: produce the last head call mask only (NOT the headline contract)')
-    ap.add_argument('--in-flight', type=int, default=2,
+    ap.add_argument('--in-flight', type=int, default=4,
                     help='batches in flight in the device-resident throughput leg (one head + stream each)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -103,6 +103,10 @@ def _caption_head(Q, precision='fp32'):
                                    loss_grounding=dict(type='GroundingLoss', loss_weight=2.0),
                                    pixel_decoder=_StubPixelDecoder())
     ids, cap_mask, table, lw, lb = synth.make_captions(6, 2, vocab=1500)
+    ids[0, :4] = torch.tensor([1001, 1100, 1250, 1499])          # image 0: four nouns; image 1: an empty caption
+    cap_mask[0, :4] = 1
+    ids[0, 4:] = 0
+    cap_mask[0, 4:] = 0
     sd = dict(sd)
     sd['bert_embeddings.word_embeddings.weight'] = table
     sd['bert_embeddings.LayerNorm.weight'] = lw + 0.1

@@ -10,13 +10,13 @@ CS=/usr/local/cuda/bin/compute-sanitizer
 PYT="python -m pytest -q -x -p no:cacheprovider"
 run() {  # name, tool, pytest selection
   echo "== $1 ($2)"
-  timeout 600 $CS --tool $2 --error-exitcode 99 --launch-timeout 0 $PYT $3 > $OUT/sanitize_$1.log 2>&1
+  eval "timeout 900 $CS --tool $2 --error-exitcode 99 --launch-timeout 0 $PYT $3" > $OUT/sanitize_$1.log 2>&1
   echo "exit $?" >> $OUT/sanitize_$1.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|exit" $OUT/sanitize_$1.log | tail -4
 }
 run memcheck_attention memcheck "tests/test_gpu_bf16.py -k attention_stage"
 run memcheck_einsum memcheck "tests/test_gpu_bf16.py -k batched_einsum"
-run memcheck_fp32 memcheck "tests/test_gpu_parity.py -k 'mask_bits_stage or masked_attention_stage or tiny'"
+run memcheck_fp32 memcheck "tests/test_gpu_parity.py -k \"mask_bits_stage or masked_attention_stage or tiny\""
 run memcheck_train memcheck "tests/test_gpu_train.py -k dispatch"
-run racecheck_attention racecheck "tests/test_gpu_bf16.py -k 'attention_stage and 64-0.5'"
+run racecheck_attention racecheck "tests/test_gpu_bf16.py -k \"attention_stage and 64-0.5\""
 run racecheck_einsum racecheck "tests/test_gpu_bf16.py -k batched_einsum"
