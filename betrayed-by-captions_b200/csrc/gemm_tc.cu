@@ -934,17 +934,15 @@ tc_kv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   signals "accumulator ready" + "ring slots free".  Both accumulators (2 x 256 columns) fill the TMEM.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmE,
-                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
-                   const __grid_constant__ TcGemmP p) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcGemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int KC = 4;
   const int e_chunk_bytes = p.q_rows * 128;               // this CTA's query rows x 64 k
+  const int sub_bytes = p.q_rows * 128;                   // staging sub-tile: query rows x 64 px
   uint8_t* sF = smem;                                     // features of this CTA's 128 pixels: 4 chunks of 16 KB
   uint8_t* sE = sF + KC * A_CHUNK_BYTES;                  // [2 step slots][KC chunks]
-  const int sub_bytes = p.q_rows * 128;                   // staging sub-tile: this CTA's query rows x 64 px
-  uint8_t* sStage = sE + 2 * KC * e_chunk_bytes;          // 4 sub-tiles (q_rows * 128 is a multiple of 1024); every epilogue
-                                                          // warp owns the 32-row slice of one sub-tile
+  uint8_t* sStage = sE + 2 * KC * e_chunk_bytes;          // 4 sub-tiles (q_pad * 128 is a multiple of 1024)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * sub_bytes);
   uint64_t* f_full = bars;
   uint64_t* f_empty = bars + 4;
@@ -1042,37 +1040,30 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         }
     }
   } else {
-    // ---------------- epilogue (both CTAs): lane = query row of this CTA's head call, 256 pixel columns.
-    // Every warp is its own pipeline: warp (quarter, part) owns rows [32 quarter, 32 quarter + 32) x the 64 pixels of
-    // sub-tile `part`, stages them in its PRIVATE 4 KB tile (128-byte rows, 16-byte chunks swizzled with the row: the
-    // TMA 128B-swizzle layout) and issues its own TMA store -- no CTA-wide barrier anywhere in the epilogue (the first
-    // version synchronised all 16 warps twice per step around one leader's stores: ncu showed 9.4 barrier-stall cycles
-    // per issued instruction).  Rows past the call's last query fall outside the tensor and are clipped by the TMA unit;
-    // in the split form (one call over the CTA pair) a warp whose rows reach into the peer's half stores through a
-    // second map with a shorter box.
+    // ---------------- epilogue (both CTAs): lane = query row of this CTA's head call, 256 pixel columns
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2;                       // 64-pixel sub-tile of the 256-pixel step
+    const int part = (warp - 2) >> 2;                       // 16-pixel chunk `part` of every 64-pixel sub-tile
     const int row = quarter * 32 + lane;
-    const int rows_here = min(32, p.q_rows - quarter * 32);  // rows of this warp that belong to this CTA (<= 0: none)
+    const bool row_ok = row < p.q_rows;
+    const bool leader = warp == 2 && lane == 0;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    uint8_t* myStage = sStage + part * sub_bytes + quarter * 4096;
-    const CUtensorMap* myMap = (rows_here >= 32) ? &tmC : &tmC2;
     int g = 0;
     for (int w = pair; w < n_work; w += n_pairs) {
       const int batch = w / mt2, px_pair = (w - batch * mt2) * 2 * TC_BM;
+      const bool last_work = w + n_pairs >= n_work;
       for (int t = 0; t < NS; ++t, ++g) {
         const int buf = g & 1;
         const uint32_t use = (uint32_t)(g >> 1);
         const int call = p.ein_split ? t : 2 * t + (int)rank;
         ptx::mbar_wait(&acc_full[buf], use & 1u);
         ptx::tc_fence_after();
-        // 1. accumulator -> registers: the 64 columns of this warp's sub-tile
-        const uint32_t ta = tmem_base + (uint32_t)(buf * 256 + part * 64) + lane_off;
+        // 1. accumulator -> registers: sub-tile j, pixels 64 j + 16 part .. + 15
+        const uint32_t ta = tmem_base + (uint32_t)(buf * 256 + part * 16) + lane_off;
         uint32_t r0[16], r1[16], r2[16], r3[16];
         ptx::tmem_ld16_issue(ta, r0);
-        ptx::tmem_ld16_issue(ta + 16, r1);
-        ptx::tmem_ld16_issue(ta + 32, r2);
-        ptx::tmem_ld16_issue(ta + 48, r3);
+        ptx::tmem_ld16_issue(ta + 64, r1);
+        ptx::tmem_ld16_issue(ta + 128, r2);
+        ptx::tmem_ld16_issue(ta + 192, r3);
         ptx::tmem_ld_wait16(r0);
         ptx::tmem_ld_wait16(r1);
         ptx::tmem_ld_wait16(r2);
@@ -1081,33 +1072,35 @@ tc_einsum_t_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
-        // 3. this warp's previous store must have finished READING its staging tile
-        if (lane == 0) ptx::tma_store_wait_read();
-        __syncwarp();
-        auto stage16 = [&](const uint32_t (&r)[16], int c) {      // 16 pixels = chunks 2c, 2c+1 of the 128-byte row
+        // 3. the previous step's stores must have finished READING the staging tiles
+        if (leader) ptx::tma_store_wait_read();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        auto stage16 = [&](const uint32_t (&r)[16], int j) {
           uint4 o[2];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
           for (int i = 0; i < 8; ++i) ow[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          uint8_t* base = myStage + lane * 128;
-          *reinterpret_cast<uint4*>(base + (((2 * c) ^ (lane & 7)) << 4)) = o[0];
-          *reinterpret_cast<uint4*>(base + (((2 * c + 1) ^ (lane & 7)) << 4)) = o[1];
+          uint8_t* base = sStage + j * sub_bytes + row * 128;
+          *reinterpret_cast<uint4*>(base + (((2 * part) ^ (row & 7)) << 4)) = o[0];
+          *reinterpret_cast<uint4*>(base + (((2 * part + 1) ^ (row & 7)) << 4)) = o[1];
         };
-        stage16(r0, 0);
-        stage16(r1, 1);
-        stage16(r2, 2);
-        stage16(r3, 3);
+        if (row_ok) {
+          stage16(r0, 0);
+          stage16(r1, 1);
+          stage16(r2, 2);
+          stage16(r3, 3);
+        }
         ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (call < p.n_calls && rows_here > 0)
-            ptx::tma_store_3d(myMap, myStage, px_pair + part * 64, q0 + quarter * 32, call * p.n_batch + batch);
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (leader) {
+          if (call < p.n_calls)
+            for (int j = 0; j < 4; ++j)
+              ptx::tma_store_3d(&tmC, sStage + j * sub_bytes, px_pair + j * 64, q0, call * p.n_batch + batch);
           ptx::tma_store_commit();
+          if (last_work && t == NS - 1) ptx::tma_store_wait_read();
         }
       }
     }
-    if (lane == 0) ptx::tma_store_wait_read();     // the staging tile must stay valid until the last store has read it
-    (void)row;
   }
   __syncwarp();
   ptx::tc_fence_before();
@@ -1819,18 +1812,15 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
     const size_t e_chunk = (size_t)t_rows * 128;
     const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * e_chunk + 4 * e_chunk + 24 * 8 + 64;
     if (smem <= 227 * 1024) {
-      CUtensorMap mE, mCt, mCt2;
+      CUtensorMap mE, mCt;
       st = make_map_B(t, &mE, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, t_rows);
       if (st != CGG_OK) return st;
-      // output maps: one (64 px x 32 rows) box per epilogue warp; the warp whose rows straddle the end of this CTA's
-      // row range (t_rows % 32 rows) stores through a second map with the shorter box
-      for (int which = 0; which < 2; ++which) {
-        const int box_rows = which == 0 ? 32 : (t_rows % 32 ? t_rows % 32 : 32);
+      {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)Q, (cuuint64_t)num_calls * batch};
         cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)Q * HW * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)t_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = t->encode(which == 0 ? &mCt : &mCt2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
+        CUresult r = t->encode(&mCt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, mask_bf16, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out, swizzled) failed: " + std::to_string((int)r));
@@ -1848,7 +1838,7 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       }
       int pairs = t->num_sms / 2;
       if (pairs > p.n_work / 2) pairs = p.n_work / 2;
-      TCU(launch_pdl_cluster(2, tc_einsum_t_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem, s, mA, mE, mCt, mCt2, p));
+      TCU(launch_pdl_cluster(2, tc_einsum_t_kernel, dim3(2 * pairs), dim3(TC_THREADS), smem, s, mA, mE, mCt, p));
       count_launch();
       TCU(cudaGetLastError());
       return CGG_OK;
