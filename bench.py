@@ -593,11 +593,16 @@ def run_b200_arm(args):
         for _ in range(3):
             rt.mask_einsum(mf_d, mask_out)
         torch.cuda.synchronize()
+        # (a) 10 launches back to back (~6 ms, boost clocks): the regime MEASURED_PEAKS.json's HBM copy peak and burst
+        #     tensor peak were taken in ("best of 10")
         k0.record()
-        rt.mask_einsum(mf_d, mask_out)
+        for _ in range(10):
+            rt.mask_einsum(mf_d, mask_out)
         k1.record()
         torch.cuda.synchronize()
-        reps = max(10, int(1000.0 / max(k0.elapsed_time(k1), 1e-3)))
+        kern_ms_burst = k0.elapsed_time(k1) / 10
+        # (b) back to back for >= 1 s (power-capped clocks): the regime of the sustained tensor peak
+        reps = max(10, int(1000.0 / max(kern_ms_burst, 1e-3)))
         k0.record()
         for _ in range(reps):
             rt.mask_einsum(mf_d, mask_out)
@@ -619,33 +624,45 @@ def run_b200_arm(args):
             rt.head_call(x0, mf_d, 0, want_bits=False)
         k1.record()
         torch.cuda.synchronize()
-        kern_ms = k0.elapsed_time(k1) / reps
+        kern_ms = kern_ms_burst = k0.elapsed_time(k1) / reps
         flops = einsum_flops_per_launch(Q, B)
         alg_bytes = B * C * (H // 4) * (W // 4) * 4 + B * Q * (H // 4) * (W // 4) * 4
         kname = 'cgg_head_call stage (fp32 SIMT heads + mask einsum of one head call)'
+    # tensor roof: sustained loop against the sustained peak; HBM roof: the 10-launch timing against the copy peak (both
+    # are burst measurements; MEASURED_PEAKS.json has no sustained HBM figure) -- the sustained-loop HBM fraction is
+    # reported beside it
     ach_tf = flops / (kern_ms * 1e-3) / 1e12
-    ach_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
+    ach_gbs = alg_bytes / (kern_ms_burst * 1e-3) / 1e9
+    ach_gbs_sus = alg_bytes / (kern_ms * 1e-3) / 1e9
     frac_t, frac_h = ach_tf / peaks['tflops'], ach_gbs / peaks['hbm_gbs']
-    # the binding roof is the one the kernel sits closer to: arithmetic intensity vs the ridge of the measured peaks
+    # the binding roof: arithmetic intensity against the ridge of the measured peaks
     ai, ridge = flops / alg_bytes, peaks['tflops'] * 1e12 / (peaks['hbm_gbs'] * 1e9)
     hbm_bound = ai < ridge
-    traffic, traffic_src = None, None
+    traffic, traffic_src, write_only = None, None, None
     tpath = os.path.join(ROOT, 'profiles', 'einsum_dram_traffic.json')
     if args.precision == 'bf16' and os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get('batch') == B and tj.get('queries') == Q:
             traffic = tj.get('dram_bytes_per_launch')
-            traffic_src = 'profiles/einsum_dram_traffic.json (ncu --set full capture %s, not re-measured in this run)' % tj.get('capture', '')
+            traffic_src = 'ncu --set full capture committed under profiles/ (%s); not re-measured in this run' % tj.get('source', '')
+    wpath = os.path.join(ROOT, 'profiles', 'r02_hbm_write_ceiling.json')
+    if os.path.exists(wpath):
+        write_only = json.load(open(wpath))
     per_gpu_value = value / world
     roofline = dict(bound='hbm' if hbm_bound else 'tensor',
                     achieved=ach_gbs if hbm_bound else ach_tf, peak=peaks['hbm_gbs'] if hbm_bound else peaks['tflops'],
                     unit='GB/s' if hbm_bound else 'TFLOP/s', frac=frac_h if hbm_bound else frac_t,
-                    traffic=traffic, traffic_source=traffic_src, kernel=kname, kernel_ms=kern_ms, launches_timed=reps,
+                    traffic=traffic, traffic_source=traffic_src, kernel=kname, kernel_ms=kern_ms_burst,
+                    kernel_ms_sustained=kern_ms, launches_timed=[10, reps],
                     algorithmic_bytes=alg_bytes, algorithmic_flops=flops, arithmetic_intensity=ai, ridge=ridge,
                     tensor=dict(achieved=ach_tf, peak=peaks['tflops'], frac=frac_t, unit='TFLOP/s',
-                                frac_of_burst=ach_tf / peaks['tflops_burst']),
-                    hbm=dict(achieved=ach_gbs, peak=peaks['hbm_gbs'], frac=frac_h, unit='GB/s'),
-                    peak_source=peaks['source'] + ' (sustained bf16: the kernel is timed back-to-back for >= 1 s; HBM copy bandwidth)',
+                                timing='>= 1 s back to back (sustained clocks) against the sustained bf16 peak',
+                                frac_of_burst=flops / (kern_ms_burst * 1e-3) / 1e12 / peaks['tflops_burst']),
+                    hbm=dict(achieved=ach_gbs, peak=peaks['hbm_gbs'], frac=frac_h, unit='GB/s',
+                             timing='10 launches back to back against the copy peak (both burst-clock measurements)',
+                             frac_sustained_clocks=ach_gbs_sus / peaks['hbm_gbs'],
+                             write_only_ceiling=write_only),
+                    peak_source=peaks['source'],
                     whole_path=dict(achieved=flops_per_image(Q) * per_gpu_value / 1e12, unit='TFLOP/s per GPU',
                                     frac=flops_per_image(Q) * per_gpu_value / 1e12 / peaks['tflops'],
                                     sustained_frac=flops_per_image(Q) * sustained['value'] / world / 1e12 / peaks['tflops']))

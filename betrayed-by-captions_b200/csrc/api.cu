@@ -31,10 +31,8 @@ struct cgg_handle {
   // from the caller's stream with events and joined back before the call's work ends on it.
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_kv[CGG_NUM_LEVELS] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};   // CGG_OVERLAP: head call j done; default mode: fork of layer j's q projection
-  bool overlap = false;      // CGG_OVERLAP: K/V levels 1,2 and the early mask einsums on helper streams (slower, debug)
-  bool overlap_kv = false;   // K/V levels 1,2 on a helper stream on a capped number of SMs
-  int kv_cta_cap = 0;
+  cudaEvent_t ev_me[CGG_MAX_LAYERS + 1] = {};   // fork of layer j's q projection
+  bool overlap_kv = false;   // K/V levels 1,2 and the layers' q projections on helper streams (set when the streams exist)
   bool final_mask_only = false;   // cgg_set_final_mask_only
   // K7 on tensor cores: the similarity contraction of the grounding loss (and its backward contraction) as split-precision
   // tcgen05 GEMMs.  Operand buffers live in the handle (grown on demand); tc_aux serves handles created in CGG_FP32 mode.
@@ -157,12 +155,10 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
   if (cfg->precision == CGG_BF16) {
     h->tc = tc_create(*cfg);
     if (!h->tc) { delete h; return CGG_ERR_CUDA; }
-    // CGG_KV_OVERLAP=0 disables the helper-stream K/V projection, =N>1 caps it at N CTAs (measured on B200 at
-    // B=16, 1024^2: off 3.536 ms/step, cap 64 3.516, cap 96 3.479, cap 120 3.470, no cap 3.468)
-    const char* kvo = getenv("CGG_KV_OVERLAP");
-    const bool want_kvo = kvo ? atoi(kvo) > 0 : true;
-    h->kv_cta_cap = kvo && atoi(kvo) > 1 ? atoi(kvo) : 0;
-    if (getenv("CGG_OVERLAP") || want_kvo) {   // CGG_OVERLAP: measured slower on B200 (5.33 vs 4.69 ms/step) -- the helper kernels starve the layer chain of SMs
+    // helper streams: the K/V projection of levels 1 and 2 (5/6 of that work, first needed by layers 1 and 2) and each
+    // layer's query projection run underneath the latency-bound head-call / layer chain (measured on B200 at B=16,
+    // 1024^2: 3.536 ms/step without, 3.468 with; putting the mask einsums there as well was slower and is gone)
+    {
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
       bool ok = true;
@@ -171,8 +167,7 @@ extern "C" int cgg_create(cgg_handle** out, const cgg_config* cfg) {
       for (int i = 0; i < 2; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < CGG_NUM_LEVELS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_kv[i], cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i <= CGG_MAX_LAYERS; ++i) ok = ok && cudaEventCreateWithFlags(&h->ev_me[i], cudaEventDisableTiming) == cudaSuccess;
-      h->overlap = ok && getenv("CGG_OVERLAP") != nullptr;
-      h->overlap_kv = ok && !h->overlap && want_kvo;
+      h->overlap_kv = ok;
     }
   }
   *out = h;
@@ -500,7 +495,6 @@ static int decoder_layer_impl(cgg_handle* h, const cgg_weights* w, int batch, in
 extern "C" int cgg_set_final_mask_only(cgg_handle* h, int on) {
   if (!h) return CGG_ERR_NULL;
   if (on && h->cfg.precision != CGG_BF16) return fail(h, CGG_ERR_UNSUPPORTED, "final-mask-only is a CGG_BF16 option");
-  if (on && h->overlap) return fail(h, CGG_ERR_UNSUPPORTED, "final-mask-only excludes CGG_OVERLAP");
   h->final_mask_only = on != 0;
   return CGG_OK;
 }
@@ -521,7 +515,6 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
   const size_t mask_elt = (c.precision == CGG_BF16) ? 2 : 4;
   float* xs = x_states ? x_states : at<float>(workspace, ws.xs);
   const bool tcm = c.precision == CGG_BF16;
-  const bool ovl = tcm && h->overlap && L + 1 <= CGG_MAX_LAYERS + 1;
   const bool ovl_kv = tcm && h->overlap_kv && L >= CGG_NUM_LEVELS;
   void* tws = at<void>(workspace, ws.tcws);
   if (ovl_kv) {
@@ -530,16 +523,6 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     // underneath head call 0 / layer 0 / head call 1 / layer 1, which are latency-bound and leave most SMs idle.
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
-    ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, s, 0, 1));
-    for (int l = 1; l < CGG_NUM_LEVELS; ++l) {
-      ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, h->side[0], l, l + 1, h->kv_cta_cap));
-      CU(cudaEventRecord(h->ev_kv[l], h->side[0]));
-    }
-  } else if (ovl) {
-    // fork: level 0 K/V on the caller's stream (layer 0 needs it first), levels 1 and 2 on a helper stream
-    CU(cudaEventRecord(h->ev_fork, s));
-    CU(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
-    CU(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
     ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, s, 0, 1));
     for (int l = 1; l < CGG_NUM_LEVELS; ++l) {
       ST(kv_project_levels(h, w, batch, memories, workspace, workspace_bytes, h->side[0], l, l + 1));
@@ -553,12 +536,10 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     if (st != CGG_OK) return fail(h, st, std::string("tc_downsample: ") + tc_last_error(h->tc));
   }
   CU(launch_broadcast_rows(w->query_feat, xs, batch, Q, C, s));          // head.py:808-809
-  int einsum_done = 0;   // head calls whose mask einsum has been enqueued (helper stream)
-  static const bool q_branch = getenv("CGG_Q_BRANCH") ? atoi(getenv("CGG_Q_BRANCH")) != 0 : true;
   for (int j = 0; j <= L; ++j) {
     const bool need_mask = j < L;                                           // the last mask is never used
     // layer j's query projection needs the decoder state only: it runs on a helper stream underneath head call j
-    const bool q_par = q_branch && ovl_kv && tcm && j > 0 && j < L;
+    const bool q_par = ovl_kv && j > 0 && j < L;
     if (q_par) {
       CU(cudaEventRecord(h->ev_me[j], s));
       CU(cudaStreamWaitEvent(h->side[1], h->ev_me[j], 0));
@@ -573,20 +554,9 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
                       cls + (size_t)j * batch * Q * c.num_classes_p1, emb ? emb + (size_t)j * batch * Q * c.d_lang : nullptr,
                       static_cast<char*>(mask) + (size_t)j * batch * Q * HW * mask_elt, nullptr, bm, am, workspace,
                       workspace_bytes, s, j, /*defer_einsum=*/tcm, /*fds_ready=*/true, /*z_ready=*/tcm && j > 0));
-    if (ovl && (j & 1) && j < L) {
-      // K2 of head calls j-1 and j (one 2-call N tile) runs on a helper stream underneath the
-      // latency-bound layer chain; only the last pair stays on the critical path
-      CU(cudaEventRecord(h->ev_me[j], s));
-      CU(cudaStreamWaitEvent(h->side[1], h->ev_me[j], 0));
-      int st = tc_mask_einsum(h->tc, batch, j - 1, 2, mask_features,
-                              static_cast<char*>(mask) + (size_t)(j - 1) * batch * Q * HW * mask_elt,
-                              (long)batch * Q * HW, tws, h->side[1]);
-      if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
-      einsum_done = j + 1;
-    }
     if (j < L) {
       const int lvl = j % CGG_NUM_LEVELS;
-      if ((ovl || ovl_kv) && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
+      if (ovl_kv && j == lvl && lvl > 0) CU(cudaStreamWaitEvent(s, h->ev_kv[lvl], 0));   // first use of this level's K/V
       if (q_par) CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
       ST(decoder_layer_impl(h, w, batch, j, xs + j * bqc, bm, am, xs + (j + 1) * bqc, workspace, workspace_bytes, stream,
                             /*chained_in=*/tcm && j > 0, /*chained_out=*/tcm, /*q_ready=*/q_par));
@@ -597,17 +567,9 @@ extern "C" int cgg_decoder_forward(cgg_handle* h, const cgg_weights* w, int batc
     int st = tc_mask_einsum(h->tc, batch, L, 1, mask_features, mask, (long)batch * Q * HW, tws, s);
     if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
   } else if (tcm) {
-    // K2 of the remaining head calls (all L+1 in one pass over mask_features when nothing was overlapped)
-    int st = tc_mask_einsum(h->tc, batch, einsum_done, L + 1 - einsum_done, mask_features,
-                            static_cast<char*>(mask) + (size_t)einsum_done * batch * Q * HW * mask_elt,
-                            (long)batch * Q * HW, tws, s);
+    // K2 of all L+1 head calls in one pass over mask_features
+    int st = tc_mask_einsum(h->tc, batch, 0, L + 1, mask_features, mask, (long)batch * Q * HW, tws, s);
     if (st != CGG_OK) return fail(h, st, std::string("tc_mask_einsum: ") + tc_last_error(h->tc));
-  }
-  if (ovl) {
-    for (int i = 0; i < 2; ++i) {   // join
-      CU(cudaEventRecord(h->ev_join[i], h->side[i]));
-      CU(cudaStreamWaitEvent(s, h->ev_join[i], 0));
-    }
   }
   return CGG_OK;
 }

@@ -855,12 +855,15 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   AttnP p;
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = nullptr;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
-  static const int r_lo = getenv("CGG_ATTN_R_LO") ? atoi(getenv("CGG_ATTN_R_LO")) : 1;
-  p.has_r = r_table ? (r_lo ? 2 : 1) : 0; p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
+  p.has_r = r_table ? 2 : 0;      // hi + lo halves of the key-bias table p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   p.out_hl = out_mode;
-  static const int at_dbg = getenv("CGG_AT_DBG") ? atoi(getenv("CGG_AT_DBG")) : 0;
+#ifdef CGG_AT_TRACING
+  static const int at_dbg = getenv("CGG_AT_DBG") ? atoi(getenv("CGG_AT_DBG")) : 0;   // timing experiments of the trace build
   p.dbg = at_dbg;
   if (at_dbg & 1) p.has_r = 0;
+#else
+  p.dbg = 0;
+#endif
   if (ntiles > 512) return tc_fail(t, CGG_ERR_BAD_SHAPE, "more than 512 key tiles");
   const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_STAGES * AT_STAGE_BYTES + 512 + (2 * AT_STAGES + 4) * 8 + 16;
   if (!t->attn_attr_set) {

@@ -144,16 +144,14 @@ __device__ __forceinline__ void epi_mask_t(const TcGemmP& p, const EpiCtx& c, ui
 #pragma unroll
     for (int i = 0; i < 16; ++i) dst[i * TC_BM] = __float2bfloat16_rn(__uint_as_float(r[i]));
   };
-  if (!(p.dbg & 256)) {
-    if (on0) stage16(r0, ch0);
-    if (on1) stage16(r1, ch1);
-    if (on2) stage16(r2, ch2);
-    if (on3) stage16(r3, ch3);
-  }
+  if (on0) stage16(r0, ch0);
+  if (on1) stage16(r1, ch1);
+  if (on2) stage16(r2, ch2);
+  if (on3) stage16(r3, ch3);
   if (leader) TC_TRACE(c.g, 7);
   ptx::fence_proxy_async_smem();
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  if (leader && !(p.dbg & (256 | 1024))) {
+  if (leader) {
     const int r0 = c.col0;                       // first (call, q) row of this tile
     const int N_TILE = c.chunks * 16, q_pad = p.q_pad;
     if (N_TILE >= q_pad) {
@@ -568,7 +566,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bd = bd0 + (uint64_t)((uint32_t)s * stage16);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
-              if (!(p.dbg & 512)) ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * a_step), bd + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+              ptx::mma_bf16_ss(d_tmem, ad + (uint64_t)(k * a_step), bd + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
             ptx::mma_commit(&b_empty[s]);      // frees the B stage when these MMAs retire
             if (A_RESIDENT && t == p.NT - 1) ptx::mma_commit(&a_empty[kc]);
             if (kc == p.KC - 1) ptx::mma_commit(&acc_full[buf]);     // accumulator tile complete
@@ -1394,8 +1392,7 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
   if (p.KC > 12 && !p.k_identity && p.split_cpc == 0) return tc_fail(t, CGG_ERR_BAD_SHAPE, "too many K chunks");
   const size_t stage_bytes = (p.epi == EPI_MASK_T || p.epi == EPI_ROWMAJOR)
                                  ? (size_t)p.N_TILE * TC_BM * 2 + 1024 + (p.epi == EPI_ROWMAJOR ? (size_t)p.NT * p.N_TILE * 4 : 0) : 0;
-  static const int smem_kb = getenv("CGG_TC_SMEM_KB") ? atoi(getenv("CGG_TC_SMEM_KB")) : 204;
-  const size_t budget = (size_t)smem_kb * 1024 - stage_bytes;
+  const size_t budget = (size_t)204 * 1024 - stage_bytes;
   int stages = (int)((budget - a_bytes) / b_stage);
   if (stages > 8) stages = 8;
   if (stages > p.NT * p.KC) stages = p.NT * p.KC;
@@ -1416,15 +1413,13 @@ int launch_tc_gemm(TcState* t, const CUtensorMap& mA, const CUtensorMap& mB, TcG
     return tc_fail(t, CGG_ERR_BAD_SHAPE, "operand layout does not match the kernel specialisation");
   static const bool timing = getenv("CGG_TC_TIMING") != nullptr;
   p.dbg = timing ? 1 : 0;
-  static const int dbgmode = getenv("CGG_TC_DBGMODE") ? atoi(getenv("CGG_TC_DBGMODE")) : 0;
-  p.dbg |= dbgmode;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(s); cudaEventRecord(e0, s); }
   dim3 grid(m_tiles, batch, kparts);
   const dim3 block(TC_THREADS);
   p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
   if (want_res) {
-    static const int persist = getenv("CGG_TC_PERSIST") ? atoi(getenv("CGG_TC_PERSIST")) : 1;
+    const int persist = 1;
     if (t->num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -1601,8 +1596,7 @@ int tc_kv_project(TcState* t, int level, int batch, const void* mem_bf16, void* 
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(kv out) failed: " + std::to_string((int)r));
   }
   const int m_tiles = (K + TC_BM - 1) / TC_BM;
-  static const int kv_pair = getenv("CGG_KV_PAIR") ? atoi(getenv("CGG_KV_PAIR")) : 1;
-  if (kv_pair && m_tiles % 2 == 0 && K % TC_BM == 0 && p.KC == 4) {
+  if (m_tiles % 2 == 0 && K % TC_BM == 0 && p.KC == 4) {
     CUtensorMap mBh;
     st = make_map_B(t, &mBh, t->wkv[level], N, C, p.N_TILE / 2);
     if (st != CGG_OK) return st;
@@ -1804,10 +1798,9 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
     if (r != CUDA_SUCCESS) return tc_fail(t, CGG_ERR_CUDA, "cuTensorMapEncodeTiled(mask out) failed: " + std::to_string((int)r));
   }
   const int m_tiles = (int)((HW + TC_BM - 1) / TC_BM);
-  static const int use_t = getenv("CGG_EIN_T") ? atoi(getenv("CGG_EIN_T")) : 1;
   const bool t_split = t->q_pad > 128;      // one head call per step, its rows split over the CTA pair (Q up to 256)
   const int t_rows = t_split ? t->q_pad / 2 : t->q_pad;
-  if (use_t && m_tiles % 2 == 0 && HW % (2 * TC_BM) == 0 && t->q_pad <= 256 && t_rows % 8 == 0 && t_rows <= 128 && p.KC == 4 && C == 256) {
+  if (m_tiles % 2 == 0 && HW % (2 * TC_BM) == 0 && t->q_pad <= 256 && t_rows % 8 == 0 && t_rows <= 128 && p.KC == 4 && C == 256) {
     // transposed CTA-pair kernel: queries on the TMEM lanes, pixels on the columns
     const size_t e_chunk = (size_t)t_rows * 128;
     const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * e_chunk + 4 * e_chunk + 24 * 8 + 64;
@@ -1844,15 +1837,14 @@ int tc_mask_einsum(TcState* t, int batch, int first_call, int num_calls, const v
       return CGG_OK;
     }
   }
-  static const int use_pair = getenv("CGG_EIN_PAIR") ? atoi(getenv("CGG_EIN_PAIR")) : 1;
-  if (use_pair && m_tiles % 2 == 0 && HW % TC_BM == 0 && p.N_TILE % 16 == 0 && p.KC == 4) {
+  if (m_tiles % 2 == 0 && HW % TC_BM == 0 && p.N_TILE % 16 == 0 && p.KC == 4) {
     // CTA-pair kernel: each CTA loads N_TILE/2 rows of every B chunk
     st = make_map_B(t, &mB, base + w.me_all, (long)batch * t->rows_per_batch + 128, 2 * C, p.N_TILE / 2);
     if (st != CGG_OK) return st;
     p.acc_stride = p.N_TILE <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     p.m_tiles = m_tiles; p.n_batch = batch; p.n_work = m_tiles * batch;
-    p.dbg = getenv("CGG_TC_DBGMODE") ? atoi(getenv("CGG_TC_DBGMODE")) : 0;
+    p.dbg = 0;
     const size_t stage_bytes = (size_t)p.N_TILE * TC_BM * 2 + 1024;
     const size_t b_chunk = (size_t)(p.N_TILE / 2) * 128;
     const size_t smem = 1024 + 4 * A_CHUNK_BYTES + 8 * b_chunk + 24 * 8 + 64 + stage_bytes;
@@ -1922,7 +1914,7 @@ int tc_linear(TcState* t, const __nv_bfloat16* A, int M, int K, const __nv_bfloa
   const int row_len = split_k ? 2 * K : K;
   TcGemmP p = {};
   // token tile: as few CTAs-worth of padding as possible with N <= 256 (multiple of 16)
-  static const int tok_cap = getenv("CGG_TOK_TILE") ? atoi(getenv("CGG_TOK_TILE")) : 128;   // 128: measured best (3.93 vs 4.29 ms/step at 256)
+  const int tok_cap = 128;   // tokens per tile; measured best (3.93 vs 4.29 ms/step at 256)
   const int n_tok_tiles = (M + tok_cap - 1) / tok_cap;
   p.N_TILE = ((M + n_tok_tiles - 1) / n_tok_tiles + 15) / 16 * 16;
   CUtensorMap mW, mX;

@@ -72,7 +72,7 @@ def test_nccl_caption_gather_and_grounding_loss():
     for rank, embs, mask, preds, loss, grad in res:
         assert torch.equal(embs, cap_all) and torch.equal(mask, mask_all)
         assert torch.equal(preds, pred_all)
-        assert abs(loss - float(want)) < 2e-5 * max(1.0, abs(float(want)))
+        assert abs(loss - float(want)) < 2e-4 * max(1.0, abs(float(want))), (loss, float(want))
         torch.testing.assert_close(grad, full.grad[:, rank * 2:(rank + 1) * 2], rtol=2e-4, atol=1e-7)
 
 
