@@ -813,6 +813,322 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Version 3 (CGG_ATTN_V3=1): version 2 with THREE S accumulators.  P(j) is written over the scores it was computed from
+// (each thread overwrites the first 16 columns of its own 32-column quarter of S(j)), which frees the 128 TMEM columns of
+// the separate P tiles for a third S buffer: Q K^T of tile j+3 is issued with P.V of tile j, so the softmax warps always
+// find the next two score tiles ready instead of waiting one MMA round trip per tile.  Six K/V stages.
+constexpr int AT3_STAGES = 6;
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ AttnP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                   // 8 KB
+  uint8_t* sKV = sQ + AT_Q_BYTES;                       // AT3_STAGES x (K, V, R_hi, R_lo tiles)
+  uint8_t* sX = sKV;                                    // exchange area of the final merge (the ring is idle by then)
+  uint8_t* sLive = sKV + AT3_STAGES * AT_STAGE_BYTES;   // this CTA's live-tile flags (<= 512 key tiles)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLive + 512);
+  uint64_t* kv_full = bars;
+  uint64_t* kv_empty = kv_full + AT3_STAGES;
+  uint64_t* step = kv_empty + AT3_STAGES;   // [3] commit n of step[b]: S(3n+b) ready and (n > 0) P.V(3(n-1)+b) done
+  uint64_t* p_full = step + 3;              // [3] P tile written (512 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.heads, qt = blockIdx.x / p.heads, b = blockIdx.y;
+  const uint8_t* live = sLive;
+  const int C = p.heads * 32;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    if (p.has_r) ptx::prefetch_tmap(&tmR);
+    for (int i = 0; i < AT3_STAGES; ++i) { ptx::mbar_init(&kv_full[i], 1); ptx::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&step[i], 1); ptx::mbar_init(&p_full[i], 512); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  // live-tile flags, as in version 1
+  {
+    const int q0 = qt * 128, nrows = min(128, p.Q - q0);
+    bool all_live = p.bitmap == nullptr;
+    if (!all_live && p.all_masked)
+      for (int r = lane; r < nrows; r += 32) all_live = all_live || p.all_masked[(long)b * p.Q + q0 + r] != 0;
+    all_live = __any_sync(0xffffffffu, all_live);
+    for (int t = warp; t < p.ntiles; t += AT_THREADS / 32) {
+      bool any = all_live;
+      if (!all_live) {
+        for (int r = lane; r < nrows; r += 32) {
+          const uint32_t* brow = p.bitmap + ((long)b * p.Q + q0 + r) * p.W32;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int widx = t * 4 + w, k0 = t * AT_KT + w * 32;
+            if (widx < p.W32 && k0 < p.K) {
+              const uint32_t valid = (k0 + 32 > p.K) ? ((1u << (p.K - k0)) - 1u) : 0xffffffffu;
+              any = any || ((~__ldg(brow + widx)) & valid) != 0u;
+            }
+          }
+        }
+      }
+      any = __any_sync(0xffffffffu, any);
+      if (lane == 0) sLive[t] = any ? 1 : 0;
+    }
+  }
+  if (warp >= 2 && warp < 6) {
+    // Q tile -> bf16, core-matrix (no-swizzle) K-major layout (version 1)
+    const int row = (warp & 3) * 32 + lane, qi = qt * 128 + row;
+    float qv[32];
+    if (qi < p.Q) {
+      const float4* src = reinterpret_cast<const float4*>(p.q + ((long)b * p.Q + qi) * C + h * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = __ldg(src + i);
+        qv[4 * i] = x.x; qv[4 * i + 1] = x.y; qv[4 * i + 2] = x.z; qv[4 * i + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) qv[i] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 pk;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 v2 = __floats2bfloat162_rn(qv[8 * c + 2 * j], qv[8 * c + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&v2);
+      }
+      *reinterpret_cast<uint4*>(sQ + (row >> 3) * 512 + c * 128 + (row & 7) * 16) = pk;
+    }
+    fence_async_smem();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;          // 3 x 128 columns (fp32 scores); P(j) overwrites the first 16 columns of each
+                                              // key quarter of S(j) (a thread only overwrites scores it has already read)
+  const uint32_t tmem_O = tmem_base + 384;    // 4 key quarters x 32 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------- TMA producer (version 1)
+      int it = 0;
+      for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; t = next_live(live, t + 1, p.ntiles), ++it) {
+        const int s = it % AT3_STAGES;
+        ptx::mbar_wait(&kv_empty[s], ((uint32_t)(it / AT3_STAGES) & 1u) ^ 1u);
+        ptx::mbar_expect_tx(&kv_full[s], (p.has_r ? (p.has_r > 1 ? 4 : 3) : 2) * AT_KV_TILE_BYTES);
+        uint8_t* st = sKV + s * AT_STAGE_BYTES;
+        if (p.has_r) {
+          ptx::tma_load_2d(st + 2 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_col0 + h * 32, t * AT_KT);
+          if (p.has_r > 1) ptx::tma_load_2d(st + 3 * AT_KV_TILE_BYTES, &tmR, &kv_full[s], p.r_lo_off + p.r_col0 + h * 32, t * AT_KT);
+        }
+        ptx::tma_load_3d(st, &tmK, &kv_full[s], h * 32, t * AT_KT, b);
+        ptx::tma_load_3d(st + AT_KV_TILE_BYTES, &tmV, &kv_full[s], h * 32, t * AT_KT, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------- MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues
+    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, AT_KT, false, false);   // S = Q K^T
+    const uint32_t idesc_o = ptx::umma_idesc_bf16(128, 32, false, true);       // O = P V (A from TMEM, N-major B)
+    int n_live = 0;
+    for (int t = 0; t < p.ntiles; ++t) n_live += live[t] ? 1 : 0;
+    const uint64_t qd0 = umma_desc(ptx::smem_u32(sQ), 128, 512, 0);
+    const uint64_t kd0 = umma_desc(ptx::smem_u32(sKV), 16, 512, 4);
+    const uint64_t vd0 = umma_desc(ptx::smem_u32(sKV + AT_KV_TILE_BYTES), 1024, 512, 4);
+    auto wait_kv = [&](int j) {
+      ptx::mbar_wait(&kv_full[j % AT3_STAGES], (uint32_t)(j / AT3_STAGES) & 1u);
+      ptx::tc_fence_after();
+    };
+    auto issue_qk = [&](int j) {                // elected lane only
+      const uint64_t kd = kd0 + (uint64_t)((j % AT3_STAGES) * (AT_STAGE_BYTES >> 4));
+      const uint32_t d = tmem_S + (uint32_t)((j % 3) * 128);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) ptx::mma_bf16_ss(d, qd0 + (uint64_t)(k * 16), kd + (uint64_t)(k * 2), idesc_s, k);
+      if (p.has_r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < 2 || p.has_r > 1)
+            ptx::mma_bf16_ss(d, qd0 + (uint64_t)((k & 1) * 16),
+                             kd + (uint64_t)((((2 + (k >> 1)) * AT_KV_TILE_BYTES) >> 4) + (k & 1) * 2), idesc_s, 1u);
+      }
+    };
+    for (int j = 0; j < 3 && j < n_live; ++j) {
+      wait_kv(j);
+      if (ptx::elect_one()) { issue_qk(j); ptx::mma_commit(&step[j]); }
+      __syncwarp();
+    }
+    for (int j = 0; j < n_live; ++j) {
+      const int s = j % AT3_STAGES;
+      ptx::mbar_wait(&p_full[j % 3], (uint32_t)(j / 3) & 1u);
+      if (lane == 0) AT_TRACE(j, 0);
+      if (j + 3 < n_live) wait_kv(j + 3);
+      ptx::tc_fence_after();
+      if (lane == 0) AT_TRACE(j, 1);
+      if (ptx::elect_one()) {
+        const uint64_t vd = vd0 + (uint64_t)(s * (AT_STAGE_BYTES >> 4));
+        const uint32_t pa = tmem_S + (uint32_t)((j % 3) * 128);
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+          // O_quarter += P[:, 32 keys of this quarter] . V[those keys, :]   (two K-steps of 16 keys = 8 TMEM columns)
+          if (p.dbg & 2) break;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            mma_bf16_ts(tmem_O + (uint32_t)(cq * 32), pa + (uint32_t)(cq * 32 + k * 8),
+                        vd + (uint64_t)((cq * 2048 + k * 1024) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        // S(j) has been consumed and P(j) is read by the P.V MMAs just issued (same thread: executed in order), so
+        // the buffer takes Q K^T of tile j+3 right behind them
+        if (j + 3 < n_live) issue_qk(j + 3);
+        ptx::mma_commit(&step[j % 3]);
+      }
+      __syncwarp();
+      if (lane == 0) AT_TRACE(j, 2);
+    }
+  } else {
+    // ------------- softmax: thread = query row x key quarter cq of every tile
+    const int quarter = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane, qi = qt * 128 + row;
+    const bool row_ok = qi < p.Q;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const bool ignore_mask = !row_ok || p.bitmap == nullptr || (p.all_masked && p.all_masked[(long)b * p.Q + qi]);
+    const uint32_t* brow = p.bitmap ? p.bitmap + ((long)b * p.Q + (row_ok ? qi : 0)) * p.W32 : nullptr;
+    const uint32_t taddr_o = tmem_O + (uint32_t)(cq * 32) + lane_off;
+    float m_ref = -INFINITY, l_run = 0.f;       // m_ref in log2 units (score * LOG2E)
+    auto load_mask = [&](int t) -> uint32_t {
+      const int widx = t * 4 + cq;
+      uint32_t word = 0u;
+      if (!ignore_mask && widx < p.W32) word = __ldg(brow + widx);
+      const int k0 = t * AT_KT + cq * 32;
+      if (k0 + 32 > p.K) word |= (k0 >= p.K) ? 0xffffffffu : ~((1u << (p.K - k0)) - 1u);
+      return word;
+    };
+    int it = 0;
+    uint32_t mw_next = 0u;
+    {
+      const int t0 = next_live(live, 0, p.ntiles);
+      if (t0 < p.ntiles) mw_next = load_mask(t0);
+    }
+    for (int t = next_live(live, 0, p.ntiles); t < p.ntiles; ++it) {
+      const int buf = it % 3;
+      const int t_next = next_live(live, t + 1, p.ntiles);
+      const uint32_t mw = mw_next;
+      if (t_next < p.ntiles) mw_next = load_mask(t_next);
+      ptx::mbar_wait(&step[buf], (uint32_t)(it / 3) & 1u);           // S(it) ready (and P.V(it-3) done)
+      ptx::tc_fence_after();
+      AT_TRACE_W(it, 3);
+      float v[32];
+      tmem_ld32(tmem_S + (uint32_t)(buf * 128 + cq * 32) + lane_off, v);
+      AT_TRACE_W(it, 4);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if ((mw >> i) & 1u) v[i] = -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      mx *= LOG2E;
+      // lazy rescale: move the reference only when the tile maximum exceeds it by more than 2^TAU
+      const bool move = mx > m_ref + AT2_TAU;     // (false for mx = -inf; true for m_ref = -inf and finite mx)
+      const bool fix = move && m_ref != -INFINITY;                  // something has been accumulated at the old reference
+      if (__any_sync(0xffffffffu, fix)) {
+        // P.V(it-1) accumulates into the same O tile: it must have completed before the row is rescaled in place
+        ptx::mbar_wait(&step[(it - 1) % 3], (uint32_t)(((it - 1) / 3) + 1) & 1u);
+        ptx::tc_fence_after();
+        const float sc = fix ? fast_exp2(m_ref - mx) : 1.f;
+        float ov[32];
+        tmem_ld32(taddr_o, ov);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] *= sc;
+        tmem_st32(taddr_o, ov);
+        l_run *= sc;
+      }
+      if (move) m_ref = mx;
+      AT_TRACE_W(it, 5);
+      const float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      // p = exp2(s * log2e - m_ref) as bf16 pairs straight into the TMEM P tile of this buffer
+      uint32_t pk[16];
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float e0, e1;
+        if (p.dbg & 4) { e0 = fmaf(v[2 * j], LOG2E, mneg); e1 = fmaf(v[2 * j + 1], LOG2E, mneg); }
+        else { e0 = fast_exp2(fmaf(v[2 * j], LOG2E, mneg)); e1 = fast_exp2(fmaf(v[2 * j + 1], LOG2E, mneg)); }
+        __nv_bfloat162 v2 = __floats2bfloat162_rn(e0, e1);
+        pk[j] = *reinterpret_cast<uint32_t*>(&v2);
+        psum += e0 + e1;
+      }
+      l_run += psum;
+      AT_TRACE_W(it, 6);
+      tmem_st16(tmem_S + (uint32_t)(buf * 128 + cq * 32) + lane_off, pk);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[buf]);
+      AT_TRACE_W(it, 7);
+      // hand the previous tile's K/V stage back once its P.V has completed (long done by now)
+      if (it > 0 && warp == 2) {
+        ptx::mbar_wait(&step[(it - 1) % 3], (uint32_t)(((it - 1) / 3) + 1) & 1u);
+        if (lane == 0) ptx::mbar_arrive(&kv_empty[(it - 1) % AT3_STAGES]);
+      }
+      t = t_next;
+    }
+    float o[32];
+    if (it > 0) {
+      ptx::mbar_wait(&step[(it - 1) % 3], (uint32_t)(((it - 1) / 3) + 1) & 1u);      // the last P.V
+      ptx::tc_fence_after();
+      tmem_ld32(taddr_o, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    }
+    // merge the four key quarters of the row: quarters 1..3 publish (m, l, o) through shared memory (the K/V ring:
+    // every tile has been consumed once all 512 threads have seen the last commit)
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    float* xch = reinterpret_cast<float*>(sX);
+    if (cq > 0) {
+      float* dst = xch + ((cq - 1) * 128 + row) * 35;
+      dst[0] = m_ref;
+      dst[1] = l_run;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[2 + i] = o[i];
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (cq == 0) {
+      float m = m_ref;
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) m = fmaxf(m, xch[(c2 * 128 + row) * 35]);
+      const float a0 = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m);
+      l_run *= a0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = (m_ref == -INFINITY) ? 0.f : o[i] * a0;
+#pragma unroll
+      for (int c2 = 0; c2 < 3; ++c2) {
+        const float* src = xch + (c2 * 128 + row) * 35;
+        const float m1 = src[0];
+        if (m1 != -INFINITY) {           // (a quarter that never saw an unmasked key holds zeros / nothing useful)
+          const float a1 = fast_exp2(m1 - m);
+          l_run += src[1] * a1;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] += src[2 + i] * a1;
+        }
+      }
+      if (row_ok) store_attn_out(p, b, qi, h, C, o, l_run > 0.f ? 1.0f / l_run : 0.f);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int make_map_kv(TcState* t, CUtensorMap* m, const void* base, int K, long kv_stride, long kv_bstride, int B, int C) {
   if ((kv_stride * 2) % 16 != 0 || (kv_bstride * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15))
     return tc_fail(t, CGG_ERR_UNSUPPORTED, "K/V rows must be 16-byte aligned");
@@ -855,7 +1171,8 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   AttnP p;
   p.q = q; p.out = out; p.out_bf16 = out_bf16; p.bitmap = bitmap; p.all_masked = all_masked; p.live = nullptr;
   p.Q = Q; p.K = num_keys; p.heads = heads; p.W32 = W32; p.ntiles = ntiles; p.nqt = nqt;
-  p.has_r = r_table ? 2 : 0;      // hi + lo halves of the key-bias table p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
+  p.has_r = r_table ? 2 : 0;      // hi + lo halves of the key-bias table
+  p.r_col0 = r_col0; p.r_lo_off = (int)(r_cols / 2);
   p.out_hl = out_mode;
 #ifdef CGG_AT_TRACING
   static const int at_dbg = getenv("CGG_AT_DBG") ? atoi(getenv("CGG_AT_DBG")) : 0;   // timing experiments of the trace build
@@ -869,12 +1186,16 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   if (!t->attn_attr_set) {
     TCU(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TCU(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCU(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     t->attn_attr_set = true;
   }
   static const bool trace = getenv("CGG_AT_TRACE") != nullptr;
   p.trace = trace ? atoi(getenv("CGG_AT_TRACE")) : 0;
   static const int use_v1 = getenv("CGG_ATTN_V1") ? atoi(getenv("CGG_ATTN_V1")) : 0;   // A/B switch: the first version
+  static const int use_v3 = getenv("CGG_ATTN_V3") ? atoi(getenv("CGG_ATTN_V3")) : 0;   // A/B switch: three S buffers
+  const size_t smem3 = 1024 + AT_Q_BYTES + AT3_STAGES * AT_STAGE_BYTES + 512 + (2 * AT3_STAGES + 6) * 8 + 16;
   if (use_v1) TCU(launch_pdl(attention_tc_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem, s, mK, mV, mR, p));
+  else if (use_v3) TCU(launch_pdl(attention_tc3_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem3, s, mK, mV, mR, p));
   else TCU(launch_pdl(attention_tc2_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem, s, mK, mV, mR, p));
   count_launch();
   TCU(cudaGetLastError());
