@@ -457,7 +457,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Version 2 of the kernel (default).  A clock-stamp trace of the first version (profiles/r02_attention_trace.txt)
+// Version 2 of the kernel.  A clock-stamp trace of the first version (profiles/r02_attention_trace.txt)
 // showed where its 2800 cycles per 128-key tile go: the softmax warps compute for ~1100 cycles and then WAIT ~1200 for
 // the tensor side, whose 14 MMAs per tile take ~1400 cycles although their math is ~500 -- every MMA fetched both
 // operands from shared memory (88 KB per tile) while the softmax warps wrote the 32 KB P tile and TMA another 32 KB into
@@ -814,7 +814,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Version 3 (CGG_ATTN_V3=1): version 2 with THREE S accumulators.  P(j) is written over the scores it was computed from
+// Version 3 (default; CGG_ATTN_V3=0 selects version 2): version 2 with THREE S accumulators.  P(j) is written over the scores it was computed from
 // (each thread overwrites the first 16 columns of its own 32-column quarter of S(j)), which frees the 128 TMEM columns of
 // the separate P tiles for a third S buffer: Q K^T of tile j+3 is issued with P.V of tile j, so the softmax warps always
 // find the next two score tiles ready instead of waiting one MMA round trip per tile.  Six K/V stages.
@@ -1192,7 +1192,7 @@ int tc_attention(TcState* t, int batch, int num_keys, const float* q, const void
   static const bool trace = getenv("CGG_AT_TRACE") != nullptr;
   p.trace = trace ? atoi(getenv("CGG_AT_TRACE")) : 0;
   static const int use_v1 = getenv("CGG_ATTN_V1") ? atoi(getenv("CGG_ATTN_V1")) : 0;   // A/B switch: the first version
-  static const int use_v3 = getenv("CGG_ATTN_V3") ? atoi(getenv("CGG_ATTN_V3")) : 0;   // A/B switch: three S buffers
+  static const int use_v3 = getenv("CGG_ATTN_V3") ? atoi(getenv("CGG_ATTN_V3")) : 1;   // A/B switch: 0 = version 2 (two S buffers)
   const size_t smem3 = 1024 + AT_Q_BYTES + AT3_STAGES * AT_STAGE_BYTES + 512 + (2 * AT3_STAGES + 6) * 8 + 16;
   if (use_v1) TCU(launch_pdl(attention_tc_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem, s, mK, mV, mR, p));
   else if (use_v3) TCU(launch_pdl(attention_tc3_kernel, dim3(heads * nqt, batch), dim3(AT_THREADS), smem3, s, mK, mV, mR, p));
