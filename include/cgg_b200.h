@@ -72,9 +72,10 @@ typedef struct {
   int ffn_dim;       /* 2048                                                :90  */
   int num_layers;    /* 9                                                   :77  */
   int num_classes_p1;/* ncls+1: 49 (instance) / 118 (OSPS)                       */
-  int d_lang;        /* 768 (BERT width of v2l_transform, head.py:219)           */
+  int d_lang;        /* 768 (BERT width of v2l_transform, head.py:219); 0 = no
+                        v2l_transform: use_class_emb=False, emb output = cls (:739-744) */
   int precision;     /* cgg_precision                                            */
-  int pred_emb_norm; /* head.py:743-744                                          */
+  int pred_emb_norm; /* head.py:743-744 (only with d_lang > 0)                   */
 } cgg_config;
 
 /* Per-layer weights: state_dict keys transformer_decoder.layers.<i>.* (SURVEY.md 8b). */
