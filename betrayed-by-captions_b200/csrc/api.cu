@@ -3,6 +3,7 @@
 #include "../../include/cgg_b200.h"
 #include "kernels.h"
 #include "gemm_tc.h"
+#include "gemm_tf32.h"
 #include "tc_state.h"
 
 #include <math.h>
@@ -37,6 +38,7 @@ struct cgg_handle {
   // K7 on tensor cores: the similarity contraction of the grounding loss (and its backward contraction) as split-precision
   // tcgen05 GEMMs.  Operand buffers live in the handle (grown on demand); tc_aux serves handles created in CGG_FP32 mode.
   TcState* tc_aux = nullptr;
+  Tf32Ctx* tf32 = nullptr;   // training-step contractions on tcgen05 (gemm_tf32.cu), created on first use
   struct K7Buf {
     __nv_bfloat16 *pred_hl = nullptr, *cap_hl = nullptr, *dst_hl = nullptr, *capT_hl = nullptr;
     float* S = nullptr;
@@ -179,6 +181,7 @@ extern "C" void cgg_destroy(cgg_handle* h) {
   h->free_tables();
   if (h->tc) tc_destroy(h->tc);
   if (h->tc_aux) tc_destroy(h->tc_aux);
+  if (h->tf32) tf32_destroy(h->tf32);
   h->k7.release();
   for (int i = 0; i < 2; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -739,6 +742,16 @@ extern "C" int cgg_gemm_f32(cgg_handle* h, const cgg_gemm_desc* d, void* stream)
   if (d->relu) p.relu_from = 0;
   p.alpha = d->alpha;
   p.a_mmajor = d->a_mmajor != 0; p.c_mmajor = d->c_mmajor != 0;
+  if (d->batch_inner > 1) {
+    if (d->batch % d->batch_inner) return fail(h, CGG_ERR_BAD_SHAPE, "batch must be a multiple of batch_inner");
+    p.batch_inner = d->batch_inner; p.sAb2 = d->sAb2; p.sWb2 = d->sWb2; p.sCb2 = d->sCb2;
+  }
+  if (d->tf32) {
+    if (!h->tf32 && !(h->tf32 = tf32_create())) return fail(h, CGG_ERR_CUDA, "tf32_create failed");
+    const int r = launch_gemm_tf32(h->tf32, p, (cudaStream_t)stream);
+    if (r == 0) return CGG_OK;
+    if (r < 0) return fail(h, CGG_ERR_CUDA, tf32_last_error(h->tf32));
+  }
   CU(launch_gemm_f32(p, (cudaStream_t)stream));
   return CGG_OK;
 }
@@ -841,6 +854,22 @@ extern "C" int cgg_attention_backward(cgg_handle* h, int batch, int num_q, int n
   const size_t n = (size_t)batch * h->cfg.num_heads * num_q;
   CU(launch_attention_bwd(q, k, v, kv_stride, kv_batch_stride, bitmap, all_masked, out, dout, scratch, scratch + n, dq, dk,
                           dv, dkv_stride, dkv_batch_stride, batch, num_q, num_keys, h->cfg.num_heads, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_attn_softmax_rows(cgg_handle* h, float* scores, const uint32_t* bitmap, const uint8_t* all_masked,
+                                     int batch, int num_q, int num_keys, void* stream) {
+  if (!h || !scores) return CGG_ERR_NULL;
+  if (batch < 1 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_attn_softmax_rows(scores, bitmap, all_masked, batch, h->cfg.num_heads, num_q, num_keys, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_attn_dscore(cgg_handle* h, const float* probs, float* dprobs, const float* out, const float* dout,
+                               int batch, int num_q, int num_keys, void* stream) {
+  if (!h || !probs || !dprobs || !out || !dout) return CGG_ERR_NULL;
+  if (batch < 1 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_attn_dscore(probs, dprobs, out, dout, batch, h->cfg.num_heads, num_q, num_keys, (cudaStream_t)stream));
   return CGG_OK;
 }
 

@@ -25,6 +25,8 @@ struct GemmF32 {
   const float* R = nullptr; long sRb = 0, sRm = 0, sRn = 0; int r_mod = 1; int r_ncols = 1 << 30;
   float* C = nullptr; long sCb = 0, sCm = 0, sCn = 0;
   int M = 0, N = 0, K = 0, batch = 1;
+  // two-level batch: z in [0, batch) -> (z / batch_inner) * sXb + (z % batch_inner) * sXb2 for A, W and C (R: z * sRb)
+  int batch_inner = 1; long sAb2 = 0, sWb2 = 0, sCb2 = 0;
   int relu_from = 1 << 30;   // relu applied to columns n >= relu_from
   float alpha = 1.f;
   bool a_mmajor = false, c_mmajor = false;
@@ -86,6 +88,12 @@ cudaError_t launch_attention_bwd(const float* q, const float* k, const float* v,
                                  const uint32_t* bitmap, const uint8_t* all_masked, const float* o, const float* dout,
                                  float* lse, float* dsum, float* dq, float* dk, float* dv, long dkv_stride,
                                  long dkv_bstride, int B, int Q, int K, int heads, cudaStream_t s);
+
+// attention as tensor-core products (tf32 training mode): row softmax with the bitmap / dS = P o (dP - D), in place
+cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uint8_t* all_masked, int B, int heads, int Q,
+                                     int K, cudaStream_t s);
+cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int Q, int K,
+                               cudaStream_t s);
 
 // ---- test-time step after the path (post_kernels.cu)
 cudaError_t launch_upsample_masks(const void* logits, bool bf16, float* out, int planes, int h4, int w4, int up_h, int up_w,

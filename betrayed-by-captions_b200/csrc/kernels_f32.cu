@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const float* __restrict__ A = p.A + (long)b * p.sAb;
-  const float* __restrict__ W = p.W + (long)b * p.sWb;
+  const long bo = b / p.batch_inner, bi = b % p.batch_inner;
+  const float* __restrict__ A = p.A + bo * p.sAb + bi * p.sAb2;
+  const float* __restrict__ W = p.W + bo * p.sWb + bi * p.sWb2;
   for (int k0 = 0; k0 < p.K; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
     }
     __syncthreads();
   }
-  float* __restrict__ C = p.C + (long)b * p.sCb;
+  float* __restrict__ C = p.C + bo * p.sCb + bi * p.sCb2;
   const float* __restrict__ R = p.R ? p.R + (long)b * p.sRb : nullptr;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

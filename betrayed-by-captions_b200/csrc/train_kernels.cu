@@ -223,6 +223,79 @@ __global__ void __launch_bounds__(256) attn_rowstats_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------ attention as tensor-core products: the two row-wise stages
+// Training step with tf32 contractions: S = q k^T, O = P v, dP = dO v^T, dQ = dS k, dK = dS^T q, dV = P^T dO are calls
+// of the tcgen05 GEMM over (image, head) batches; what is left is row-wise work on the (B, heads, Q, K) score tensor.
+//
+// P = softmax over the unmasked keys of a row, in place (bit = 1 in the bitmap excludes the key, unless the row's
+// all_masked flag is set: mask2former_head.py:825-826).  One CTA per row; the row (<= 144 KB) is re-read from L1/L2.
+__global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restrict__ S, const uint32_t* __restrict__ bitmap,
+                                                                const uint8_t* __restrict__ all_masked, int heads, int Q,
+                                                                int K) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const long r = blockIdx.x;                            // (b, h, q)
+  const int qi = (int)(r % Q);
+  const long b = r / ((long)Q * heads);
+  float* row = S + r * K;
+  const int W32 = (K + 31) / 32;
+  const bool use_mask = bitmap != nullptr && !(all_masked && all_masked[b * Q + qi]);
+  const uint32_t* brow = use_mask ? bitmap + (b * Q + qi) * W32 : nullptr;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  auto masked = [&](int k) { return brow && ((brow[k >> 5] >> (k & 31)) & 1u); };
+  float m = -INFINITY;
+  for (int k = t; k < K; k += 256)
+    if (!masked(k)) m = fmaxf(m, row[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (t == 0) {
+    float mm = red[0];
+    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, red[i]);
+    bcast = mm;
+  }
+  __syncthreads();
+  m = bcast;
+  float l = 0.f;
+  if (m != -INFINITY)
+    for (int k = t; k < K; k += 256)
+      if (!masked(k)) l += expf(row[k] - m);
+  l = warp_sum(l);
+  __syncthreads();
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  if (t == 0) {
+    float ll = 0.f;
+    for (int i = 0; i < 8; ++i) ll += red[i];
+    bcast = ll;
+  }
+  __syncthreads();
+  l = bcast;
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  for (int k = t; k < K; k += 256) row[k] = (m != -INFINITY && !masked(k)) ? expf(row[k] - m) * inv : 0.f;
+}
+
+// dS = P o (dP - D), D[b,h,q] = dO[b,q,h,:] . O[b,q,h,:]; written over dP.
+__global__ void __launch_bounds__(256) attn_dscore_kernel(const float* __restrict__ P, float* __restrict__ dP,
+                                                          const float* __restrict__ O, const float* __restrict__ dO,
+                                                          int heads, int Q, int K) {
+  __shared__ float Dsh;
+  const long r = blockIdx.x;
+  const int qi = (int)(r % Q), h = (int)((r / Q) % heads);
+  const long b = r / ((long)Q * heads);
+  if (threadIdx.x < 32) {
+    const long off = (b * Q + qi) * (long)(heads * HD) + h * HD + threadIdx.x;
+    const float d = warp_sum(O[off] * dO[off]);
+    if (threadIdx.x == 0) Dsh = d;
+  }
+  __syncthreads();
+  const float D = Dsh;
+  const float* prow = P + r * K;
+  float* drow = dP + r * K;
+  for (int k = threadIdx.x; k < K; k += 256) drow[k] = prow[k] * (drow[k] - D);
+}
+
 // ----------------------------------------------------------------------------- attention backward (fp32 SIMT)
 // One CTA per (key tile of 64 keys, head, image): it owns dK, dV of its keys (no atomics) and adds its share of dQ
 // with atomicAdd.  p = exp(s - lse); dP = dO . v; dS = p (dP - D); dQ += dS k; dK += dS^T q; dV += p^T dO.
@@ -339,6 +412,24 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__
 }
 
 }  // namespace
+
+cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uint8_t* all_masked, int B, int heads, int Q,
+                                     int K, cudaStream_t s) {
+  const long rows = (long)B * heads * Q;
+  if (rows <= 0 || K <= 0) return cudaSuccess;
+  attn_softmax_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(S, bitmap, all_masked, heads, Q, K);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int Q, int K,
+                               cudaStream_t s) {
+  const long rows = (long)B * heads * Q;
+  if (rows <= 0 || K <= 0) return cudaSuccess;
+  attn_dscore_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, O, dO, heads, Q, K);
+  count_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
                                  float* partial, int rows, int n, float eps, cudaStream_t s) {

@@ -76,7 +76,8 @@ class Mask2FormerHeadOpenB200(nn.Module):
 
     Constructor kwargs follow the reference (head.py:76-100 and init_kwargs :175-195); the ones
     that only matter to losses / caption generation are accepted and ignored.  New kwargs:
-    ``precision`` ('fp32' parity mode | 'bf16' throughput mode), ``cuda_graph`` (replay the whole path
+    ``precision`` ('fp32' parity mode | 'bf16' throughput mode), ``train_precision`` ('fp32' | 'tf32', the arithmetic
+    of the training step's contractions; default follows ``precision``), ``cuda_graph`` (replay the whole path
     as one CUDA graph per set of input buffers) and ``pixel_decoder`` may be an
     ``nn.Module`` instance (mmdet builds it from the config dict in the real stack, see
     INTEGRATION.md)."""
@@ -111,6 +112,11 @@ class Mask2FormerHeadOpenB200(nn.Module):
         # configs coco_ag_pretrain_3x.py / p20_ag_pretrain.py run this way)
         self.use_class_emb = bool(kwargs.get('use_class_emb', False))
         self.pred_emb_norm = kwargs.get('pred_emb_norm', False)
+        # training-step arithmetic: 'fp32' (FMA, the parity mode with gradients) or 'tf32' (every contraction on tcgen05
+        # kind::tf32 MMAs straight from the fp32 tensors; softmax, LayerNorm and all accumulation stay fp32)
+        self.train_precision = kwargs.get('train_precision', 'tf32' if precision == 'bf16' else 'fp32')
+        if self.train_precision not in ('fp32', 'tf32'):
+            raise ValueError("train_precision must be 'fp32' or 'tf32'")
         self.text_emb_norm = kwargs.get('text_emb_norm', True)
         self.pixel_decoder = pixel_decoder if isinstance(pixel_decoder, nn.Module) else None
         # ---- parameters under the reference's names

@@ -19,7 +19,7 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            # training-step stages
            'cgg_gemm_f32', 'cgg_layernorm', 'cgg_layernorm_bwd_scratch_bytes', 'cgg_layernorm_backward', 'cgg_relu_backward',
            'cgg_axpy', 'cgg_add_rows', 'cgg_sum_batch', 'cgg_colsum', 'cgg_mem_prep', 'cgg_mem_prep_backward', 'cgg_sine_pos',
-           'cgg_attention_f32', 'cgg_attention_backward',
+           'cgg_attention_f32', 'cgg_attention_backward', 'cgg_attn_softmax_rows', 'cgg_attn_dscore',
            # test-time step after the path
            'cgg_upsample_masks', 'cgg_instance_mask_stats', 'cgg_softmax_rows']
 
@@ -52,7 +52,8 @@ class GemmDesc(C.Structure):
                 ('r_ncols', C.c_int),
                 ('C', C.c_void_p), ('sCb', C.c_long), ('sCm', C.c_long), ('sCn', C.c_long),
                 ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch', C.c_int),
-                ('relu', C.c_int), ('alpha', C.c_float), ('a_mmajor', C.c_int), ('c_mmajor', C.c_int)]
+                ('relu', C.c_int), ('alpha', C.c_float), ('a_mmajor', C.c_int), ('c_mmajor', C.c_int), ('tf32', C.c_int),
+                ('batch_inner', C.c_int), ('sAb2', C.c_long), ('sWb2', C.c_long), ('sCb2', C.c_long)]
 
 
 class CggError(RuntimeError):
@@ -117,6 +118,8 @@ def load():
     lib.cgg_sine_pos.argtypes = [vp, vp, i, i, i, vp]
     lib.cgg_attention_f32.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp]
     lib.cgg_attention_backward.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp, vp, vp, vp, lg, lg, vp, vp]
+    lib.cgg_attn_softmax_rows.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    lib.cgg_attn_dscore.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cgg_upsample_masks.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
     lib.cgg_instance_mask_stats.argtypes = [vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     lib.cgg_softmax_rows.argtypes = [vp, vp, i, i, vp]

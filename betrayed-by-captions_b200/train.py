@@ -4,8 +4,10 @@ autograd graph whose every node is a kernel of the C-ABI library -- forward AND 
 pixel-decoder features and the memories exactly as the reference's autograd does (the
 attention mask is detached, nothing flows through K3).
 
-PyTorch is the tape (autograd.Function), the allocator and the stream; it computes nothing here.  All arithmetic is fp32
-(CGG_FP32 kernels): the parity mode extended with gradients.  Gradient all-reduce over NVLink for data-parallel
+PyTorch is the tape (autograd.Function), the allocator and the stream; it computes nothing here.  With
+`train_precision='fp32'` all arithmetic is fp32 FMA (the parity mode extended with gradients); with 'tf32' every
+contraction -- each linear layer, the mask einsum and all of their dX / dW products -- runs on tcgen05 kind::tf32 MMAs
+fed by TMA from the same fp32 tensors (csrc/gemm_tf32.cu), everything else stays fp32.  Gradient all-reduce over NVLink for data-parallel
 training lives in `GradReducer` below (bucketed NCCL all-reduce overlapped with the backward; reference: mmcv's
 MMDistributedDataParallel built at open_set/apis/train.py:156-161).
 """
@@ -25,8 +27,9 @@ def _p(t):
 class _K:
     """Thin launcher over the stage entry points of include/cgg_b200.h for one runtime (handle + device)."""
 
-    def __init__(self, rt):
+    def __init__(self, rt, tf32=False):
         self.rt, self.lib, self.h, self.dev = rt, rt.lib, rt.handle, rt.device
+        self.tf32 = int(bool(tf32))      # contractions on tcgen05 kind::tf32 MMAs instead of fp32 FMAs
 
     def s(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -38,7 +41,7 @@ class _K:
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
     def gemm(self, A, sA, W, sW, Cc, sC, M, N, K, batch=1, bias=None, R=None, sR=(0, 0, 0), r_mod=None, alpha=1.0,
-             relu=False, a_mmajor=False, c_mmajor=False):
+             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0)):
         """C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); element strides
         sA = (b, m, k), sW = (b, n, k), sC = (b, m, n), sR = (b, m, n)."""
         d = _lib.GemmDesc()
@@ -56,6 +59,8 @@ class _K:
         d.M, d.N, d.K, d.batch = M, N, K, batch
         d.relu, d.alpha = int(relu), float(alpha)
         d.a_mmajor, d.c_mmajor = int(a_mmajor), int(c_mmajor)
+        d.tf32 = self.tf32
+        d.batch_inner, (d.sAb2, d.sWb2, d.sCb2) = batch_inner, s2     # (image, head) batches: inner strides of A, W, C
         self.chk(self.lib.cgg_gemm_f32(self.h, C.byref(d), self.s()), 'cgg_gemm_f32')
 
 
@@ -209,6 +214,51 @@ class _Attention(torch.autograd.Function):
         return None, dq, dk, dv, None, None
 
 
+class _AttentionGemm(torch.autograd.Function):
+    """The same attention written as tensor-core products (tf32 training mode): S = q k^T, P = softmax(S | bitmap),
+    O = P v and the four gradient products are calls of the tcgen05 GEMM over (image, head) batches; P is kept for the
+    backward (B * heads * Q * K floats)."""
+
+    @staticmethod
+    def forward(ctx, k_, q, kk, v, bitmap, all_masked):
+        B, Q, Cc = q.shape
+        K = kk.shape[1]
+        H = k_.rt.head.num_heads
+        d = Cc // H
+        P = k_.new(B, H, Q, K)
+        bh = dict(batch=B * H, batch_inner=H)
+        # S[b,h,q,key] = q[b,q,h,:] . k[b,key,h,:]
+        k_.gemm(q, (Q * Cc, Cc, 1), kk, (K * Cc, Cc, 1), P, (H * Q * K, K, 1), Q, K, d, s2=(d, d, Q * K), **bh)
+        k_.chk(k_.lib.cgg_attn_softmax_rows(k_.h, _p(P), _p(bitmap), _p(all_masked), B, Q, K, k_.s()), 'cgg_attn_softmax_rows')
+        out = k_.new(B, Q, Cc)
+        # O[b,q,h,:] = sum_key P[b,h,q,key] v[b,key,h,:]
+        k_.gemm(P, (H * Q * K, K, 1), v, (K * Cc, 1, Cc), out, (Q * Cc, Cc, 1), Q, d, K, s2=(Q * K, d, d), **bh)
+        ctx.k = k_
+        ctx.save_for_backward(q, kk, v, P, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        k_ = ctx.k
+        q, kk, v, P, out = ctx.saved_tensors
+        B, Q, Cc = q.shape
+        K = kk.shape[1]
+        H = k_.rt.head.num_heads
+        d = Cc // H
+        dout = dout.contiguous()
+        bh = dict(batch=B * H, batch_inner=H)
+        dS = k_.new(B, H, Q, K)
+        # dP[b,h,q,key] = dO[b,q,h,:] . v[b,key,h,:]
+        k_.gemm(dout, (Q * Cc, Cc, 1), v, (K * Cc, Cc, 1), dS, (H * Q * K, K, 1), Q, K, d, s2=(d, d, Q * K), **bh)
+        k_.chk(k_.lib.cgg_attn_dscore(k_.h, _p(P), _p(dS), _p(out), _p(dout), B, Q, K, k_.s()), 'cgg_attn_dscore')
+        dq, dk, dv = k_.new(B, Q, Cc), k_.new(B, K, Cc), k_.new(B, K, Cc)
+        # dq[b,q,h,:] = sum_key dS k ;  dk[b,key,h,:] = sum_q dS q ;  dv[b,key,h,:] = sum_q P dO
+        k_.gemm(dS, (H * Q * K, K, 1), kk, (K * Cc, 1, Cc), dq, (Q * Cc, Cc, 1), Q, d, K, s2=(Q * K, d, d), **bh)
+        k_.gemm(dS, (H * Q * K, 1, K), q, (Q * Cc, 1, Cc), dk, (K * Cc, Cc, 1), K, d, Q, s2=(Q * K, d, d), a_mmajor=True, **bh)
+        k_.gemm(P, (H * Q * K, 1, K), dout, (Q * Cc, 1, Cc), dv, (K * Cc, Cc, 1), K, d, Q, s2=(Q * K, d, d), a_mmajor=True, **bh)
+        return None, dq, dk, dv, None, None
+
+
 class _MaskEinsum(torch.autograd.Function):
     """mask_pred[b,q,p] = sum_c me[b,q,c] F[b,c,p]  (head.py:748).  me (B, Q, C), F (B, C, H4, W4)."""
 
@@ -254,7 +304,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
     if head.pred_emb_norm and head.use_class_emb:
         raise _lib.CggError('pred_emb_norm with use_class_emb is not built on the training path')
     rt = head._runtime(mask_features.device)
-    k = _K(rt)
+    k = _K(rt, tf32=(head.train_precision == 'tf32'))
     mf = mask_features.float().contiguous()
     mems = [m.float().contiguous() for m in multi_scale_memorys]
     B, Cc, H4, W4 = mf.shape
@@ -274,6 +324,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
     def ln(x, m):
         return _LayerNorm.apply(k, x, m.weight, m.bias, 1e-5)
 
+    attention = _AttentionGemm if k.tf32 else _Attention          # fp32: the flash-style FMA kernels (exact mode)
     cls_list, emb_list, mask_list = [], [], []
 
     def head_call(x, lvl):
@@ -305,7 +356,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
         q = _Linear.apply(k, xq, ca.in_proj_weight[:Cc], ca.in_proj_bias[:Cc], None, scale, False)
         kk = _Linear.apply(k, key_in.view(B * K, Cc), ca.in_proj_weight[Cc:2 * Cc], ca.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
         vv = _Linear.apply(k, val_in.view(B * K, Cc), ca.in_proj_weight[2 * Cc:], ca.in_proj_bias[2 * Cc:], None, 1.0, False)
-        o = _Attention.apply(k, q.view(B, Q, Cc), kk.view(B, K, Cc), vv.view(B, K, Cc), bm, am)
+        o = attention.apply(k, q.view(B, Q, Cc), kk.view(B, K, Cc), vv.view(B, K, Cc), bm, am)
         t = _Linear.apply(k, o.view(B * Q, Cc), ca.out_proj.weight, ca.out_proj.bias, x2d, 1.0, False)
         x1 = ln(t, layer.norms[0])
         # ---- self-attention: q = k-input = x1 + query_embed, v-input = x1
@@ -313,7 +364,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
         q2 = _Linear.apply(k, x1q, sa.in_proj_weight[:Cc], sa.in_proj_bias[:Cc], None, scale, False)
         k2 = _Linear.apply(k, x1q, sa.in_proj_weight[Cc:2 * Cc], sa.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
         v2 = _Linear.apply(k, x1, sa.in_proj_weight[2 * Cc:], sa.in_proj_bias[2 * Cc:], None, 1.0, False)
-        o2 = _Attention.apply(k, q2.view(B, Q, Cc), k2.view(B, Q, Cc), v2.view(B, Q, Cc), None, None)
+        o2 = attention.apply(k, q2.view(B, Q, Cc), k2.view(B, Q, Cc), v2.view(B, Q, Cc), None, None)
         t2 = _Linear.apply(k, o2.view(B * Q, Cc), sa.out_proj.weight, sa.out_proj.bias, x1, 1.0, False)
         x2 = ln(t2, layer.norms[1])
         # ---- FFN

@@ -244,6 +244,12 @@ typedef struct {
   int relu;
   float alpha;
   int a_mmajor, c_mmajor;
+  int tf32;      /* 0: fp32 FMA (parity mode, exact); 1: tcgen05 kind::tf32 MMAs fed by TMA from the same fp32 tensors
+                  * (10-bit operand mantissas, fp32 accumulate, split-K summed in a fixed order).  Products whose strides
+                  * TMA cannot describe (a row pitch that is not a multiple of 16 bytes) run on the FMA kernel. */
+  int batch_inner;            /* two-level batch (0 or 1 = off): item z of A / W / C sits at (z / batch_inner) * sXb +
+                               * (z % batch_inner) * sXb2 -- (image, head) batches of the attention products */
+  long sAb2, sWb2, sCb2;
 } cgg_gemm_desc;
 int cgg_gemm_f32(cgg_handle *h, const cgg_gemm_desc *d, void *stream);
 
@@ -281,6 +287,15 @@ int cgg_attention_backward(cgg_handle *h, int batch, int num_q, int num_keys, co
                            const float *v, long kv_stride, long kv_batch_stride, const uint32_t *bitmap,
                            const uint8_t *all_masked, const float *out, const float *dout, float *dq, float *dk,
                            float *dv, long dkv_stride, long dkv_batch_stride, float *scratch, void *stream);
+/* The same attention as tensor-core products (training step with tf32 contractions): S = q k^T, O = P v and the four
+ * gradient products are cgg_gemm_f32 calls over (image, head) batches (batch_inner = heads); these two entry points are
+ * the row-wise stages in between, in place on the (batch, heads, num_q, num_keys) fp32 score tensor:
+ *   cgg_attn_softmax_rows: scores -> softmax over the keys the bitmap leaves (all keys for all_masked rows);
+ *   cgg_attn_dscore:       dprobs -> probs * (dprobs - D),  D[b,h,q] = dout[b,q,h,:] . out[b,q,h,:]. */
+int cgg_attn_softmax_rows(cgg_handle *h, float *scores, const uint32_t *bitmap, const uint8_t *all_masked, int batch,
+                          int num_q, int num_keys, void *stream);
+int cgg_attn_dscore(cgg_handle *h, const float *probs, float *dprobs, const float *out, const float *dout, int batch,
+                    int num_q, int num_keys, void *stream);
 
 /* ---- the step after the path at test time ---------------------------------------------------
  * logits: the LAST head call's mask logits (B, Q, h4, w4), fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1).

@@ -160,12 +160,15 @@ def decoder_layer(sd, i, x, qe, key_in, val_in, masked):
 
 
 def decoder_forward(sd, mask_features, memories, num_layers=9, pred_emb_norm=False,
-                    teacher_x=None):
+                    teacher_x=None, forced_masked=None):
     """Mask2FormerHeadOpen.forward after the pixel decoder, mask2former_head.py:787-849.
 
     sd: state_dict (reference key names).  memories: [mem32, mem16, mem8] each (B,C,h,w).
     teacher_x: optional list of (B,Q,C) states; when given, layer i consumes teacher_x[i]
     instead of its own running state (teacher-forced comparison).
+    forced_masked: optional list of boolean attention masks (before the fallback) used INSTEAD of the ones derived from
+    this run's own logits (they are detached constants of the graph, :759) -- lets a reduced-precision run of this same
+    function be compared with the fp32 one on identical masks.
 
     Returns dict with lists of length num_layers+1: cls, emb, mask; plus x (decoder state fed
     to each head call), masked (bool mask produced by each head call, BEFORE fallback),
@@ -189,6 +192,8 @@ def decoder_forward(sd, mask_features, memories, num_layers=9, pred_emb_norm=Fal
         cls, emb, mp, masked, me = head_call(sd, x, mask_features, sizes[lvl], pred_emb_norm)
         out['cls'].append(cls), out['emb'].append(emb), out['mask'].append(mp)
         out['x'].append(x), out['masked'].append(masked), out['mask_embed'].append(me)
+        if forced_masked is not None:
+            return forced_masked[len(out['masked']) - 1]
         return masked
 
     masked = call_head(x, 0)                                                # :816-820
