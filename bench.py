@@ -327,15 +327,17 @@ def grounding_leg(dev, Bg=16, Q=100, T=35, D=768):
 def train_leg(args, rank, world, dev):
     """BASELINE configs[3]: OSPS head (200 queries, 118 class rows), forward + backward of the decoder head with the
     caption-grounding loss on every head call (weight 2.0) + class-embedding CE + a mask surrogate, per-GPU batch 2
-    (coco_panoptic_p20.py:236), NCCL all-reduce of the 14.7 M head gradients overlapped with the backward."""
+    (coco_panoptic_p20.py:236), bucketed NCCL all-reduce of the 14.7 M head gradients overlapped with the backward.
+    Contractions on tcgen05 (kind::tf32), the whole step replayed as one CUDA graph; the same step issued eagerly and
+    the same step as plain torch CUDA ops (the oracle on the GPU, TF32 matmuls: what the reference executes) beside it."""
     import torch.distributed as dist
     from cgg_b200 import synth
     from cgg_b200.head import build_head_from_state_dict
     from cgg_b200.grounding import grounding_loss, gather_captions_and_preds, similarity
-    from cgg_b200.train import GradReducer
+    from cgg_b200.train import GradReducer, GraphedStep
     Q, B, ncls1 = 200, args.train_batch, 118
     sd = synth.make_params(seed=0, num_queries=Q, num_classes_p1=ncls1)
-    head = build_head_from_state_dict(sd, Q, ncls1, 'fp32', dev).train()
+    head = build_head_from_state_dict(sd, Q, ncls1, 'fp32', dev, train_precision=args.train_precision).train()
     mf, mems = synth.make_inputs(100 + rank, B, H, W)
     mf, mems = mf.to(dev), [m.to(dev) for m in mems]
     ids, cap_mask, table, lw, lb = synth.make_captions(rank, B)
@@ -345,45 +347,100 @@ def train_leg(args, rank, world, dev):
     labels = torch.randint(0, ncls1, (B, Q), generator=g).to(dev)
     targets = (torch.rand((B, Q, H // 4, W // 4), generator=g) > 0.5).to(dev).float()
     reducer = GradReducer(head.parameters())
+    ce, bce = torch.nn.functional.cross_entropy, torch.nn.functional.binary_cross_entropy_with_logits
 
-    def step():
-        for p in head.parameters():
-            p.grad = None
+    def loss_fn():
         cls, emb, mask = head.decoder_forward_auto(mf, mems)
         loss = 0.0
         embs_all, mask_all, preds_all = gather_captions_and_preds(cap, cap_mask, torch.stack(emb, 0))
         for j in range(len(cls)):
             loss = loss + grounding_loss(preds_all[j], embs_all, mask_all, 10.0, 2.0)
-            logits = similarity(emb[j].reshape(B * Q, -1), head.class_embs, 0.1)
-            loss = loss + torch.nn.functional.cross_entropy(logits, labels.reshape(-1))
-            loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(mask[j], targets)
-        loss.backward()
-        reducer.finish()
+            loss = loss + ce(similarity(emb[j].reshape(B * Q, -1), head.class_embs, 0.1), labels.reshape(-1))
+            loss = loss + bce(mask[j], targets)
         return loss
 
+    def eager_step():
+        reducer.zero()
+        loss_fn().backward()
+        reducer.finish()
+
+    def timed(fn, n, after=None):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        extra = 0.0
+        e0.record()
+        for _ in range(n):
+            fn()
+            if after:
+                extra += after()
+        e1.record()
+        torch.cuda.synchronize()
+        return reduce_max(e0.elapsed_time(e1) / n, world, dev), extra / n
+
+    n = args.train_steps
     for _ in range(2):
-        step()
-    torch.cuda.synchronize()
+        eager_step()
+    eager_ms, exposed = timed(eager_step, n, after=reducer.exposed)
+    exposed = reduce_max(exposed, world, dev)
+    out = dict(batch_per_gpu=B, queries=Q, classes_p1=ncls1, precision=args.train_precision,
+               grad_bytes=4 * sum(p.numel() for p in head.parameters()),
+               eager=dict(ms_per_step=eager_ms, allreduce_exposed_ms=exposed,
+                          note='issued launch by launch; exposed = end of backward -> end of the last bucket all-reduce'))
+    ms = eager_ms
+    if not args.no_train_graph:
+        reducer.timing = False
+        gs = GraphedStep(loss_fn, head.parameters(), reducer=reducer)
+        for _ in range(2):
+            gs.replay()
+        ms, _ = timed(gs.replay, max(n, 10))
+        out['cuda_graph'] = True
+    out.update(ms_per_step=ms, images_per_s=world * B / (ms * 1e-3),
+               note='forward + backward through cgg_b200.train (every node a C-ABI kernel; contractions on tcgen05 '
+                    'kind::tf32), losses: grounding x10 + class-embedding CE x10 + mask BCE surrogate x10; optimizer step '
+                    'excluded; bucketed NCCL all-reduce overlapped with the backward%s'
+                    % (', the whole step one CUDA graph' if out.get('cuda_graph') else ''))
+    reducer.remove()
+    if rank == 0 and not args.no_torch_baseline:
+        # the same step as plain torch CUDA ops: the oracle on this GPU (single process, no all-reduce)
+        from oracle import cgg_oracle as O
+        sd_t = {k: v.to(dev).requires_grad_(k != 'class_embs') for k, v in sd.items()}
+
+        def torch_step():
+            for v in sd_t.values():
+                v.grad = None
+            ref = O.decoder_forward(sd_t, mf, mems)
+            loss = 0.0
+            for j in range(10):
+                loss = loss + O.grounding_loss(ref['emb'][j], cap, cap_mask, 10.0, 2.0)
+                loss = loss + ce(O.cls_emb_logits(ref['emb'][j].reshape(B * Q, -1), sd_t['class_embs'], 10.0), labels.reshape(-1))
+                loss = loss + bce(ref['mask'][j], targets)
+            loss.backward()
+
+        res = {}
+        old = torch.backends.cuda.matmul.allow_tf32
+        try:
+            for name, flag in (('fp32', False), ('tf32', True)):
+                torch.backends.cuda.matmul.allow_tf32 = flag
+                for _ in range(2):
+                    torch_step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    torch_step()
+                e1.record()
+                torch.cuda.synchronize()
+                res[name + '_ms_per_step'] = e0.elapsed_time(e1) / 3
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        res['note'] = 'oracle (plain torch ops + autograd) on the same GPU, same losses, one process'
+        res['speedup_vs_faster'] = min(res['fp32_ms_per_step'], res['tf32_ms_per_step']) / ms
+        out['torch_gpu_baseline'] = res
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = args.train_steps
-    exposed = 0.0
-    e0.record()
-    for _ in range(n):
-        step()
-        exposed += reducer.exposed()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = reduce_max(e0.elapsed_time(e1) / n, world, dev)
-    exposed = reduce_max(exposed / n, world, dev)
-    nparam = sum(p.numel() for p in head.parameters())
-    reducer.remove()
-    return dict(ms_per_step=ms, images_per_s=world * B / (ms * 1e-3), batch_per_gpu=B, queries=Q, classes_p1=ncls1,
-                allreduce_exposed_ms=exposed, grad_bytes=4 * nparam, precision='fp32',
-                note='forward + backward through cgg_b200.train (every node a C-ABI kernel), losses: grounding x10 + '
-                     'class-embedding CE x10 + mask BCE surrogate x10; optimizer step excluded; bucketed NCCL all-reduce '
-                     'overlapped with backward')
+    return out
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -731,7 +788,10 @@ def main():
     ap.add_argument('--no-train', action='store_true', help='skip the configs[3] training-step leg and the K7 stage leg')
     ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling leg')
     ap.add_argument('--train-batch', type=int, default=2, help='images per GPU in the training-step leg')
-    ap.add_argument('--train-steps', type=int, default=3)
+    ap.add_argument('--train-steps', type=int, default=5)
+    ap.add_argument('--train-precision', choices=['fp32', 'tf32'], default='tf32',
+                    help="arithmetic of the training step's contractions: tcgen05 kind::tf32 or fp32 FMA (parity mode)")
+    ap.add_argument('--no-train-graph', action='store_true', help='time the training step eagerly only')
     ap.add_argument('--sustain-s', type=float, default=2.0, help='length of the sustained leg in seconds')
     ap.add_argument('--no-graph', action='store_true', help='launch the path eagerly instead of replaying a CUDA graph')
     ap.add_argument('--final-mask-only', action='store_true',

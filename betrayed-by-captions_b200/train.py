@@ -381,11 +381,13 @@ class GradReducer:
     BASELINE.json configs[3]; reference: DDP built at open_set/apis/train.py:156-161).
 
     Parameters are packed, in reverse registration order (the order the backward produces them), into flat fp32 buckets
-    of ~`bucket_mb`; `post_accumulate_grad` hooks copy a finished gradient into its bucket and launch the bucket's
-    all-reduce on a side stream as soon as its last gradient has arrived.  `finish()` joins the side stream, divides by
-    the world size and points every `.grad` at its bucket slice.  `exposed_ms` is the time between the end of the
-    backward on the main stream and the end of the last all-reduce -- the part of the communication that was NOT
-    hidden."""
+    of ~`bucket_mb`, and every `.grad` IS a view of its bucket slice: the backward accumulates straight into the
+    buckets, no copy.  A `post_accumulate_grad` hook launches a bucket's all-reduce on a side stream as soon as its
+    last gradient has arrived; `finish()` joins the side stream and divides by the world size.  `zero()` clears the
+    buckets at the start of a step.  Everything is stream work, so the whole step -- forward, backward, the overlapped
+    collectives -- can be captured in one CUDA graph (`GraphedStep`).  `exposed()` is the time between the end of the
+    backward on the main stream and the end of the last all-reduce: the part of the communication that was NOT hidden
+    (eager steps only; events cannot be timed inside a graph)."""
 
     def __init__(self, params, bucket_mb=8.0, group=None):
         self.group = group
@@ -409,9 +411,10 @@ class GradReducer:
         for bi, bk in enumerate(self.buckets):
             for p, off in bk['params']:
                 self.index[p] = (bi, off)
+                p.grad = bk['flat'][off:off + p.numel()].view_as(p)
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.t_bwd_end = self.t_comm_end = None
-        self.exposed_ms = 0.0
+        self.timing = True
         self.reset()
 
     def _close(self, cur, n, dev):
@@ -422,10 +425,22 @@ class GradReducer:
             bk['pending'] = len(bk['params'])
             bk['work'] = None
 
+    def zero(self):
+        """Start of a step: clear the buckets (the backward accumulates into them) and re-attach any .grad that was
+        replaced (`p.grad = None`, an optimizer's set_to_none)."""
+        for bk in self.buckets:
+            bk['flat'].zero_()
+            for p, off in bk['params']:
+                view = bk['flat'][off:off + p.numel()].view_as(p)
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    p.grad = view
+
     def _hook(self, p):
         bi, off = self.index[p]
         bk = self.buckets[bi]
-        bk['flat'][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        if p.grad.data_ptr() != bk['flat'].data_ptr() + 4 * off:       # the caller replaced .grad: fold it back in
+            bk['flat'][off:off + p.numel()].copy_(p.grad.reshape(-1))
+            p.grad = bk['flat'][off:off + p.numel()].view_as(p)
         bk['pending'] -= 1
         if bk['pending'] == 0 and self.world > 1:
             if self.cuda:
@@ -436,22 +451,25 @@ class GradReducer:
                 bk['work'] = dist.all_reduce(bk['flat'], group=self.group, async_op=True)
 
     def finish(self):
-        """Call after loss.backward().  Returns the exposed communication time in ms (0 on one rank)."""
-        if self.cuda:
+        """Call after loss.backward(): joins the collectives and averages."""
+        capturing = self.cuda and torch.cuda.is_current_stream_capturing()
+        if self.cuda and self.timing and not capturing:
             self.t_bwd_end = torch.cuda.Event(enable_timing=True)
             self.t_bwd_end.record(torch.cuda.current_stream())
+        launched = False
         for bk in self.buckets:
             if bk['work'] is not None:
                 bk['work'].wait()
+                launched = True
         if self.cuda:
-            torch.cuda.current_stream().wait_stream(self.stream)
-            self.t_comm_end = torch.cuda.Event(enable_timing=True)
-            self.t_comm_end.record(torch.cuda.current_stream())
-        for bk in self.buckets:
-            if self.world > 1:
+            if launched:                       # (the side stream is part of the step only when a collective ran on it)
+                torch.cuda.current_stream().wait_stream(self.stream)
+            if self.timing and not capturing:
+                self.t_comm_end = torch.cuda.Event(enable_timing=True)
+                self.t_comm_end.record(torch.cuda.current_stream())
+        if self.world > 1:
+            for bk in self.buckets:
                 bk['flat'].div_(self.world)
-            for p, off in bk['params']:
-                p.grad = bk['flat'][off:off + p.numel()].view_as(p)
         self.reset()
 
     def exposed(self):
@@ -463,3 +481,50 @@ class GradReducer:
     def remove(self):
         for h in self.handles:
             h.remove()
+
+
+class GraphedStep:
+    """One training step -- forward, loss, backward and (with a GradReducer) the overlapped gradient all-reduce --
+    captured once as a CUDA graph and replayed: the step is ~2000 small launches, and at 2 images per GPU the host
+    cannot issue them as fast as the device retires them.
+
+    `step_fn()` computes the loss from tensors the caller keeps alive and overwrites in place between steps (the static
+    inputs) and returns it; it must not synchronise.  Gradients land in the parameters' `.grad` (the reducer's buckets
+    when one is given) after every `replay()`; `self.loss` is the static loss tensor.  No autograd graph over these
+    parameters that was built on another stream may still be alive at construction (drop old loss tensors first): its
+    AccumulateGrad nodes are bound to that stream and cannot join the capture."""
+
+    def __init__(self, step_fn, params, reducer=None, warmup=3):
+        self.params = [p for p in params if p.requires_grad]
+        self.reducer = reducer
+        self.step_fn = step_fn
+        dev = self.params[0].device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up off the default stream: sizes every lazily grown buffer
+            for _ in range(warmup):
+                self._one()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if reducer is None:
+            for p in self.params:
+                p.grad = None                     # the captured backward allocates .grad from the graph's pool
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._one()
+
+    def _one(self):
+        if self.reducer is not None:
+            self.reducer.zero()
+        elif not torch.cuda.is_current_stream_capturing():
+            for p in self.params:
+                p.grad = None
+        loss = self.step_fn()
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        return loss.detach()
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

@@ -98,6 +98,57 @@ def _train_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _graph_worker(rank, world, port, q):
+    _init(rank, world, port)
+    from cgg_b200 import synth
+    from cgg_b200.head import build_head_from_state_dict
+    from cgg_b200.train import GradReducer, GraphedStep
+    dev = torch.device('cuda', rank)
+    torch.cuda.set_device(dev)
+    Q, B = 16, 1
+    sd = synth.make_params(seed=51, num_queries=Q, perturb=True)
+    head = build_head_from_state_dict(sd, Q, 49, 'fp32', dev, train_precision='tf32').train()
+    mf, mems = synth.make_inputs(60 + rank, B, 96, 128)
+    s_mf, s_mems = mf.to(dev), [m.to(dev) for m in mems]
+
+    def step_fn():
+        cls, emb, mask = head.decoder_forward_auto(s_mf, s_mems)
+        return sum((c ** 2).mean() + (e ** 2).mean() + (m ** 2).mean() for c, e, m in zip(cls, emb, mask))
+
+    red = GradReducer(head.parameters(), bucket_mb=4.0)
+    gs = GraphedStep(step_fn, head.parameters(), reducer=red)         # the bucketed all-reduces are part of the graph
+    gs.replay()
+    gs.replay()
+    torch.cuda.synchronize()
+    graphed = {k: p.grad.clone() for k, p in head.named_parameters()}
+    red.zero()                                                         # the same step eagerly, same reducer
+    step_fn().backward()
+    red.finish()
+    torch.cuda.synchronize()
+    q.put((rank, {k: (graphed[k].cpu(), p.grad.cpu()) for k, p in head.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@need2
+def test_graphed_training_step_with_nccl_allreduce_inside_the_graph():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_graph_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for k in res[0][1]:
+        g0, e0 = res[0][1][k]
+        g1, e1 = res[1][1][k]
+        assert torch.equal(g0, g1), k                                   # both ranks hold the averaged gradient
+        assert float((g0 - e0).abs().max()) <= 1e-6 * float(e0.abs().max()) + 1e-12, k     # graph replay == eager step
+
+
 @need2
 def test_nccl_gradient_allreduce_matches_global_batch_gradient():
     sys.path.insert(0, ROOT)

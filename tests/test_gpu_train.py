@@ -39,9 +39,23 @@ def _setup(Q, B, H, W, ncls1=49, seed=41):
     return sd, mf, mems, probes, cap, cap_mask
 
 
-# tolerances (relative to each tensor's own max-abs): fp32 FMA mode is the parity mode; in tf32 mode every contraction
-# rounds its operands to 10-bit mantissas (what torch.backends.cuda.matmul.allow_tf32 does to the reference's own step)
-TOL = {'fp32': dict(fwd=5e-4, loss=1e-4, grad=2e-3), 'tf32': dict(fwd=5e-3, loss=2e-3, grad=5e-2)}
+# fp32 (FMA) mode is the parity mode: tolerances relative to each tensor's own max-abs.  In tf32 mode every contraction
+# rounds its operands to 10-bit mantissas -- what torch.backends.cuda.matmul.allow_tf32 does to the reference's own step --
+# and the gradients of a randomly initialised 9-layer ReLU network are sensitive to that (a pre-activation near zero
+# changes its gate): the forward outputs are held to BASELINE.json's 1e-2-of-range bar, the gradients are calibrated
+# against the same step run through plain torch CUDA ops with TF32 matmuls (same oracle code, same masks).
+TOL = {'fp32': dict(fwd=5e-4, loss=1e-4, grad=2e-3), 'tf32': dict(fwd=1e-2, loss=None, grad=None)}
+TF32_VS_TORCH_TF32 = 4.0        # tf32 mode may be at most this many times further from fp32 than torch's TF32 step
+                                # (tcgen05 truncates the operands to tf32, cuBLAS rounds them to nearest; the attention
+                                # products are tf32 too, torch's fused attention stays fp32)
+
+
+def _rel(a, b):
+    return float((a.detach().cpu() - b.detach().cpu()).abs().max()) / (float(b.detach().abs().max()) + 1e-12)
+
+
+def _l2(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).norm() / (b.detach().double().norm() + 1e-30))
 
 
 @pytest.mark.parametrize('train_precision', ['fp32', 'tf32'])
@@ -82,42 +96,47 @@ def test_training_step_gradients_match_oracle_autograd(Q, B, H, W, ncls1, train_
     torch.cuda.synchronize()
     # forward values
     for j in range(10):
-        assert float((mask[j].detach().cpu() - ref['mask'][j].detach()).abs().max()) < tol['fwd'] * float(ref['mask'][j].abs().max())
-        assert float((emb[j].detach().cpu() - ref['emb'][j].detach()).abs().max()) < tol['fwd'] * float(ref['emb'][j].abs().max())
-    assert abs(float(loss) - float(loss_o)) < tol['loss'] * abs(float(loss_o))
-    # gradient of every parameter (state_dict key), relative to the gradient's own scale
-    worst = ('', 0.0)
+        assert _rel(mask[j], ref['mask'][j]) < tol['fwd']
+        assert _rel(emb[j], ref['emb'][j]) < tol['fwd']
+        assert _rel(cls[j], ref['cls'][j]) < tol['fwd']
     named = dict(head.named_parameters())
     assert set(named) == {k for k in sd if k != 'class_embs'}
     for k, p in named.items():
         assert p.grad is not None, 'no gradient reached %s' % k
-        want = sd_o[k].grad
-        err = float((p.grad.cpu() - want).abs().max()) / (float(want.abs().max()) + 1e-12)
-        if err > worst[1]:
-            worst = (k, err)
-        assert err < tol['grad'], (k, err)
-    # gradients of the path's inputs (they flow on into the pixel decoder in the real model)
-    for got, want in [(mf_d.grad, mf_o.grad)] + [(a.grad, b_.grad) for a, b_ in zip(mems_d, mems_o)]:
-        err = float((got.cpu() - want).abs().max()) / float(want.abs().max())
-        assert err < tol['grad'], err
-    print('[%s] worst parameter gradient error: %s %.2e' % ((train_precision,) + worst))
-    if train_precision == 'tf32':
-        # calibration: the same step through plain torch CUDA ops with TF32 matmuls (what the reference runs with
-        # allow_tf32) against the same fp32 oracle -- the tf32 mode must not be further from fp32 than that by much
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            sd_t = {k: v.clone().to(DEV).requires_grad_(k != 'class_embs') for k, v in sd.items()}
-            ref_t = O.decoder_forward(sd_t, mf.to(DEV), [m.to(DEV) for m in mems],
-                                      forced_masked=[r.detach().to(DEV) for r in ref['masked']])
-            loss_t = _loss_from_outputs(ref_t['cls'], ref_t['emb'], ref_t['mask'], probes_d, cap.to(DEV), cap_mask.to(DEV),
-                                        lambda e, c, m: O.grounding_loss(e, c, m, 10.0, 2.0))
-            loss_t.backward()
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
-        worst_t = max(float((sd_t[k].grad.cpu() - sd_o[k].grad).abs().max()) / (float(sd_o[k].grad.abs().max()) + 1e-12)
-                      for k in named)
-        print('[torch TF32 matmuls] worst parameter gradient error: %.2e' % worst_t)
+    inputs = [(mf_d.grad, mf_o.grad)] + [(a.grad, b_.grad) for a, b_ in zip(mems_d, mems_o)]
+    worst = max((_rel(p.grad, sd_o[k].grad), k) for k, p in named.items())
+    worst_l2 = max((_l2(p.grad, sd_o[k].grad), k) for k, p in named.items())
+    worst_in = max(_rel(g, w) for g, w in inputs)
+    print('[%s] worst parameter gradient error: max-abs %.2e (%s), L2 %.2e (%s); inputs %.2e'
+          % (train_precision, worst[0], worst[1], worst_l2[0], worst_l2[1], worst_in))
+    if train_precision == 'fp32':
+        assert abs(float(loss) - float(loss_o)) < tol['loss'] * abs(float(loss_o))
+        assert worst[0] < tol['grad'], worst          # gradient of every parameter (state_dict key)
+        assert worst_in < tol['grad'], worst_in       # and of the path's inputs (they flow on into the pixel decoder)
+        return
+    # ---- tf32: calibrate on the same step through plain torch CUDA ops with TF32 matmuls
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        sd_t = {k: v.clone().to(DEV).requires_grad_(k != 'class_embs') for k, v in sd.items()}
+        mf_t = mf.to(DEV).requires_grad_(True)
+        mems_t = [m.to(DEV).requires_grad_(True) for m in mems]
+        ref_t = O.decoder_forward(sd_t, mf_t, mems_t, forced_masked=[r.detach().to(DEV) for r in ref['masked']])
+        loss_t = _loss_from_outputs(ref_t['cls'], ref_t['emb'], ref_t['mask'], probes_d, cap.to(DEV), cap_mask.to(DEV),
+                                    lambda e, c, m: O.grounding_loss(e, c, m, 10.0, 2.0))
+        loss_t.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    t_worst = max(_rel(sd_t[k].grad, sd_o[k].grad) for k in named)
+    t_l2 = max(_l2(sd_t[k].grad, sd_o[k].grad) for k in named)
+    t_in = max(_rel(g, w) for g, w in [(mf_t.grad, mf_o.grad)] + [(a.grad, b_.grad) for a, b_ in zip(mems_t, mems_o)])
+    t_loss = abs(float(loss_t) - float(loss_o))
+    print('[torch TF32 matmuls] worst parameter gradient error: max-abs %.2e, L2 %.2e; inputs %.2e; loss %.2e (ours %.2e)'
+          % (t_worst, t_l2, t_in, t_loss, abs(float(loss) - float(loss_o))))
+    assert worst[0] < TF32_VS_TORCH_TF32 * t_worst, (worst, t_worst)
+    assert worst_l2[0] < TF32_VS_TORCH_TF32 * t_l2, (worst_l2, t_l2)
+    assert worst_in < TF32_VS_TORCH_TF32 * t_in, (worst_in, t_in)
+    assert abs(float(loss) - float(loss_o)) < 2 * TF32_VS_TORCH_TF32 * t_loss + 1e-3 * abs(float(loss_o))
 
 
 def test_forward_dispatch_inference_vs_training():
@@ -134,3 +153,45 @@ def test_forward_dispatch_inference_vs_training():
     for j in range(10):
         assert float((a[2][j] - b[2][j].detach()).abs().max()) < 2e-4
         assert float((a[1][j] - b[1][j].detach()).abs().max()) < 2e-4
+
+
+def test_graphed_step_replays_the_eager_gradients():
+    """GraphedStep: forward + loss + backward captured once as a CUDA graph; a replay on new input values gives the
+    gradients of an eager step on those values (up to the summation order of the bias-gradient atomics)."""
+    from cgg_b200.train import GraphedStep, GradReducer
+    Q, B, ncls1 = 24, 2, 49
+    sd, mf, mems, probes, cap, cap_mask = _setup(Q, B, 128, 160, ncls1)
+    head = build_head_from_state_dict(sd, Q, ncls1, 'fp32', DEV, train_precision='tf32').train()
+    probes_d = {k: [t.to(DEV) for t in v] for k, v in probes.items()}
+    cap_d, cm_d = cap.to(DEV), cap_mask.to(DEV)
+    s_mf, s_mems = mf.to(DEV).clone(), [m.to(DEV).clone() for m in mems]
+
+    def step_fn():
+        cls, emb, mask = head.decoder_forward_auto(s_mf, s_mems)
+        return _loss_from_outputs(cls, emb, mask, probes_d, cap_d, cm_d, lambda e, c, m: grounding_loss(e, c, m, 10.0, 2.0))
+
+    for use_reducer in (False, True):
+        red = GradReducer(head.parameters(), bucket_mb=4.0) if use_reducer else None
+        gs = GraphedStep(step_fn, head.parameters(), reducer=red)
+        # new input values, written into the static tensors
+        mf2, mems2 = synth.make_inputs(77, B, 128, 160)
+        s_mf.copy_(mf2.to(DEV))
+        for a, b_ in zip(s_mems, mems2):
+            a.copy_(b_.to(DEV))
+        loss_g = float(gs.replay())
+        torch.cuda.synchronize()
+        got = {k: p.grad.clone() for k, p in head.named_parameters()}
+        if red is not None:
+            red.remove()
+        for p in head.parameters():
+            p.grad = None
+        loss_e = step_fn()
+        loss_e.backward()
+        torch.cuda.synchronize()
+        assert abs(loss_g - float(loss_e)) <= 1e-6 * abs(float(loss_e))
+        for k, p in head.named_parameters():
+            assert float((got[k] - p.grad).abs().max()) <= 1e-5 * float(p.grad.abs().max()) + 1e-12, (use_reducer, k)
+        for p in head.parameters():
+            p.grad = None
+        del loss_e, gs        # (an autograd graph built on the default stream must not outlive into the next capture:
+        #                        its AccumulateGrad nodes are bound to that stream)

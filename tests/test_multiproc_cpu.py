@@ -113,6 +113,10 @@ def _reducer_worker(rank, world, port, q):
             p.grad = None
         net(x).pow(2).mean().backward()
         red.finish()
+    red.zero()                              # third step: gradients accumulate straight into the bucket views
+    assert all(p.grad.data_ptr() == red.buckets[red.index[p][0]]['flat'].data_ptr() + 4 * red.index[p][1] for p in net.parameters())
+    net(x).pow(2).mean().backward()
+    red.finish()
     q.put((rank, len(red.buckets), [p.grad.clone() for p in net.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
