@@ -25,6 +25,43 @@ def _init(rank, world, port):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
 
 
+def _np(x):
+    """Results cross the queue BY VALUE (numpy): a torch tensor would be handed over through the sender's fd-sharing
+    socket, which is gone if the worker exits before the parent unpickles."""
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy()
+    if isinstance(x, dict):
+        return {k: _np(v) for k, v in x.items()}
+    if isinstance(x, (tuple, list)):
+        return tuple(_np(v) for v in x)
+    return x
+
+
+def _pt(x):
+    import numpy as np
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(x)
+    if isinstance(x, dict):
+        return {k: _pt(v) for k, v in x.items()}
+    if isinstance(x, tuple):
+        return tuple(_pt(v) for v in x)
+    return x
+
+
+def _join(procs, timeout=90):
+    """Waits for the workers; a worker that is still alive is killed (never left behind on the box) and reported."""
+    codes = []
+    for p in procs:
+        p.join(timeout=timeout)
+        if p.is_alive():
+            p.kill()
+            p.join(timeout=10)
+            codes.append('hung')
+        else:
+            codes.append(p.exitcode)
+    assert codes == [0] * len(procs), codes
+
+
 def _gather_data(world, L=3, B=2, Q=20, T=35, D=768):
     g = torch.Generator().manual_seed(5)
     pred = torch.randn((L, world * B, Q, D), generator=g)
@@ -46,7 +83,7 @@ def _gather_worker(rank, world, port, q):
     embs, mask, preds = gather_captions_and_preds(list(cap_all[sl].to(dev)), list(mask_all[sl].to(dev)), pred)
     loss = sum(grounding_loss(preds[l], embs, mask, 10.0, 2.0) for l in range(preds.shape[0]))
     loss.backward()
-    q.put((rank, embs.cpu(), mask.cpu(), preds.detach().cpu(), float(loss), pred.grad.cpu()))
+    q.put(_np((rank, embs, mask, preds, float(loss), pred.grad)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,10 +98,10 @@ def test_nccl_caption_gather_and_grounding_loss():
     procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = sorted((_pt(q.get(timeout=150)) for _ in range(2)), key=lambda r: r[0])
+    finally:
+        _join(procs)
     pred_all, cap_all, mask_all = _gather_data(2)
     full = pred_all.clone().requires_grad_(True)
     want = sum(O.grounding_loss(full[l], cap_all, mask_all, 10.0, 2.0) for l in range(full.shape[0]))
@@ -73,7 +110,8 @@ def test_nccl_caption_gather_and_grounding_loss():
         assert torch.equal(embs, cap_all) and torch.equal(mask, mask_all)
         assert torch.equal(preds, pred_all)
         assert abs(loss - float(want)) < 2e-4 * max(1.0, abs(float(want))), (loss, float(want))
-        torch.testing.assert_close(grad, full.grad[:, rank * 2:(rank + 1) * 2], rtol=2e-4, atol=1e-7)
+        want_g = full.grad[:, rank * 2:(rank + 1) * 2]      # the similarity GEMMs run at split-bf16 precision (~1e-5 of max)
+        assert float((grad - want_g).abs().max()) < 2e-4 * float(want_g.abs().max())
 
 
 def _train_worker(rank, world, port, q):
@@ -93,7 +131,7 @@ def _train_worker(rank, world, port, q):
     loss.backward()
     red.finish()
     torch.cuda.synchronize()
-    q.put((rank, {k: p.grad.cpu() for k, p in head.named_parameters()}, red.exposed()))
+    q.put(_np((rank, {k: p.grad for k, p in head.named_parameters()}, red.exposed())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -125,7 +163,10 @@ def _graph_worker(rank, world, port, q):
     step_fn().backward()
     red.finish()
     torch.cuda.synchronize()
-    q.put((rank, {k: (graphed[k].cpu(), p.grad.cpu()) for k, p in head.named_parameters()}))
+    q.put(_np((rank, {k: (graphed[k], p.grad) for k, p in head.named_parameters()})))
+    red.remove()
+    del gs, red                                                        # the graph holds captured NCCL work: drop it first
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -138,10 +179,10 @@ def test_graphed_training_step_with_nccl_allreduce_inside_the_graph():
     procs = [ctx.Process(target=_graph_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = sorted((_pt(q.get(timeout=150)) for _ in range(2)), key=lambda r: r[0])
+    finally:
+        _join(procs)
     for k in res[0][1]:
         g0, e0 = res[0][1][k]
         g1, e1 = res[1][1][k]
@@ -160,10 +201,10 @@ def test_nccl_gradient_allreduce_matches_global_batch_gradient():
     procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = sorted((_pt(q.get(timeout=150)) for _ in range(2)), key=lambda r: r[0])
+    finally:
+        _join(procs)
     sd = synth.make_params(seed=51, num_queries=16, perturb=True)
     sd_o = {k: v.clone().requires_grad_(k != 'class_embs') for k, v in sd.items()}
     total = 0.0
