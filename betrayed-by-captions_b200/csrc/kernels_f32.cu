@@ -198,41 +198,53 @@ __device__ __forceinline__ bool masked_from_logit(float d) {
   return sg < 0.5f;
 }
 
-__global__ void __launch_bounds__(256) mask_bits_kernel(const float* __restrict__ mask_pred, int rows,
+// one warp per (row, 32-key word): 400 rows alone would leave most of the machine idle
+__global__ void __launch_bounds__(256) mask_bits_kernel(const float* __restrict__ mask_pred, long words, int W32,
                                                         int H4, int W4, int th, int tw,
-                                                        uint32_t* __restrict__ bitmap,
-                                                        uint8_t* __restrict__ all_masked) {
+                                                        uint32_t* __restrict__ bitmap) {
+  const long wid = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= words) return;
+  const long row = wid / W32;
+  const int wi = (int)(wid % W32);
+  const float* mp = mask_pred + row * H4 * W4;
+  const int K = th * tw;
+  const float sh = (float)H4 / (float)th, sw = (float)W4 / (float)tw;
+  const int key = wi * 32 + lane;
+  bool m = false;
+  if (key < K) {
+    const int r = key / tw, c = key % tw;
+    int r0, r1, c0, c1;
+    float h0, h1, w0, w1;
+    src_index(sh, r, H4, r0, r1, h0, h1);
+    src_index(sw, c, W4, c0, c1, w0, w1);
+    const float a = mp[(long)r0 * W4 + c0], bq = mp[(long)r0 * W4 + c1];
+    const float cq = mp[(long)r1 * W4 + c0], dq = mp[(long)r1 * W4 + c1];
+    const float d = h0 * (w0 * a + w1 * bq) + h1 * (w0 * cq + w1 * dq);
+    m = masked_from_logit(d);
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, m);
+  if (lane == 0) bitmap[wid] = word;
+}
+// all_masked[row] = every key of the row is masked (mask2former_head.py:825-826 fallback)
+__global__ void __launch_bounds__(256) mask_rows_full_kernel(const uint32_t* __restrict__ bitmap, int rows, int W32, int K,
+                                                             uint8_t* __restrict__ all_masked) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* mp = mask_pred + (long)row * H4 * W4;
-  const int K = th * tw, W32 = (K + 31) / 32;
-  const float sh = (float)H4 / (float)th, sw = (float)W4 / (float)tw;
-  int count = 0;
-  for (int wi = 0; wi < W32; ++wi) {
-    const int key = wi * 32 + lane;
-    bool m = false;
-    if (key < K) {
-      const int r = key / tw, c = key % tw;
-      int r0, r1, c0, c1;
-      float h0, h1, w0, w1;
-      src_index(sh, r, H4, r0, r1, h0, h1);
-      src_index(sw, c, W4, c0, c1, w0, w1);
-      const float a = mp[(long)r0 * W4 + c0], bq = mp[(long)r0 * W4 + c1];
-      const float cq = mp[(long)r1 * W4 + c0], dq = mp[(long)r1 * W4 + c1];
-      const float d = h0 * (w0 * a + w1 * bq) + h1 * (w0 * cq + w1 * dq);
-      m = masked_from_logit(d);
-    }
-    const uint32_t word = __ballot_sync(0xffffffffu, m);
-    count += __popc(word);
-    if (lane == 0) bitmap[(long)row * W32 + wi] = word;
-  }
-  if (lane == 0) all_masked[row] = (count == K) ? 1 : 0;
+  int cnt = 0;
+  for (int i = lane; i < W32; i += 32) cnt += __popc(bitmap[(long)row * W32 + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) all_masked[row] = (cnt == K) ? 1 : 0;
 }
 cudaError_t launch_mask_bits(const float* mask_pred, int rows, int H4, int W4, int th, int tw,
                              uint32_t* bitmap, uint8_t* all_masked, cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
-  mask_bits_kernel<<<(rows + 7) / 8, 256, 0, s>>>(mask_pred, rows, H4, W4, th, tw, bitmap, all_masked);
-  count_launch();
+  const int K = th * tw, W32 = (K + 31) / 32;
+  const long words = (long)rows * W32;
+  mask_bits_kernel<<<(unsigned)((words + 7) / 8), 256, 0, s>>>(mask_pred, words, W32, H4, W4, th, tw, bitmap);
+  mask_rows_full_kernel<<<(rows + 7) / 8, 256, 0, s>>>(bitmap, rows, W32, K, all_masked);
+  count_launch(2);
   return cudaGetLastError();
 }
 
