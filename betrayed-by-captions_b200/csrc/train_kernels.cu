@@ -153,8 +153,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
   const long r0 = (long)blockIdx.y * 256;
   __shared__ float red[8][33];
   float a = 0.f;
-  if (col < n)
-    for (long r = r0 + ty; r < r0 + 256 && r < rows; r += 8) a += g[r * n + col];
+  if (col < n) {
+    const long rend = (r0 + 256 < rows) ? r0 + 256 : rows;
+    long r = r0 + ty;
+    for (; r + 56 < rend; r += 64) {                     // 8 independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = g[(r + 8 * u) * n + col];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; r < rend; r += 8) a += g[r * n + col];
+  }
   red[ty][threadIdx.x & 31] = a;
   __syncthreads();
   if (ty == 0 && col < n) {
