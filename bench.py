@@ -69,48 +69,52 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock, power and throttle reasons sampled DURING the timed region: an NVML polling thread (a query is ~0.1 ms,
+    so even the 50 ms K-step region of 8 concurrent ranks gets samples; `nvidia-smi -lms` cannot promise one)."""
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while True:
+                self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx,
+                                     pynvml.nvmlDeviceGetPowerUsage(h) / 1e3, int(get_reasons(h))))
+                if self.stop_flag:          # (checked after sampling: a region shorter than one period still gets one)
+                    break
+                time.sleep(0.002)
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)[:120]
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        import threading
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ''
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    power_w_max=(max(pw) if pw else None), samples=len(sm), reasons=sorted(reasons))
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, power_w_max=None, samples=0, reasons=['nvml unavailable: %s' % self.err])
+        sm = sorted(x[0] for x in self.samples)
+        bits = 0
+        for x in self.samples:
+            bits |= x[3]
+        return dict(sm_mhz=float(sm[len(sm) // 2]), sm_max_mhz=float(self.samples[0][1]),
+                    power_w_max=max(x[2] for x in self.samples), samples=len(sm),
+                    reasons=sorted(n for m, n in self.REASONS if bits & m))
 
 
 def reduce_max(value, world, device):

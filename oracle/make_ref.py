@@ -1,5 +1,5 @@
-"""Recipe for `oracle/_ref/`: a travelling copy of the FOUR reference source files the hot path consists of plus the
-two data files its constructor reads, taken unmodified from /root/reference at build time (this container only).
+"""Recipe for `oracle/_ref/`: a travelling copy of the reference source files the hot path and its losses consist of plus the
+data files its constructor reads, taken unmodified from /root/reference at build time (this container only).
 
 `oracle/_ref/` is git-ignored -- the reference's sources never enter this repository's history -- but it is not
 gpurun-ignored, so the copy rides to the GPU box, where `bench.py --impl reference` and the `cpu_baseline` leg time the
@@ -20,6 +20,8 @@ FILES = [
     'open_set/models/losses/grounding_loss.py',       # grounding_loss (:9-77)
     'open_set/models/utils/bert_embeddings.py',       # BertEmbeddings (:4-13)
     'open_set/utils/eval/inference.py',               # imported by the head file (:27)
+    'open_set/models/losses/cross_entropy_loss.py',   # loss_cls / loss_cls_emb / loss_mask of loss_single (:62-199)
+    'open_set/assigners/mask_hungarian_assigner.py',  # the Hungarian assignment of _get_target_single (:47-146)
     'datasets/embeddings/coco_class_with_bert_emb.json',      # class_embs of the instance config
     'datasets/unknown/known_65.txt',
     'datasets/unknown/unknown_17.txt',

@@ -289,6 +289,71 @@ def _install():
     class MaskFormerHead(AnchorFreeHead):
         pass
 
+    # ---- the training-time bricks of loss_single (row f2): mmcv / mmdet entry points restated in matching_oracle.py
+    from . import matching_oracle as MO
+    BBOX_ASSIGNERS = _Registry()
+
+    class _Cost:
+        def __init__(self, weight=1.0, **kw):
+            self.weight, self.kw = weight, kw
+
+    class ClassificationCost(_Cost):
+        def __call__(self, cls_pred, gt_labels):
+            return MO.classification_cost(cls_pred, gt_labels, self.weight)
+
+    class CrossEntropyLossCost(_Cost):
+        def __call__(self, pred, gt):
+            assert self.kw.get('use_sigmoid', True)
+            return MO.cross_entropy_loss_cost(pred, gt, self.weight)
+
+    class DiceCost(_Cost):
+        def __call__(self, pred, gt):
+            return MO.dice_cost(pred, gt, self.weight, pred_act=self.kw.get('pred_act', False), eps=self.kw.get('eps', 1e-3),
+                                naive_dice=self.kw.get('naive_dice', True))
+
+    COSTS = dict(ClassificationCost=ClassificationCost, CrossEntropyLossCost=CrossEntropyLossCost, DiceCost=DiceCost)
+
+    def build_match_cost(cfg):
+        cfg = dict(cfg)
+        return COSTS[cfg.pop('type').replace('ClassficationCost', 'ClassificationCost')](**cfg)
+
+    class AssignResult:
+        def __init__(self, num_gts, gt_inds, max_overlaps, labels=None):
+            self.num_gts, self.gt_inds, self.max_overlaps, self.labels = num_gts, gt_inds, max_overlaps, labels
+
+    class _Sampled:
+        pass
+
+    class MaskPseudoSampler:
+        """mmdet/core/bbox/samplers/mask_pseudo_sampler.py"""
+        def sample(self, assign_result, masks, gt_masks, **kw):
+            r = _Sampled()
+            r.pos_inds = torch.nonzero(assign_result.gt_inds > 0, as_tuple=False).squeeze(-1).unique()
+            r.neg_inds = torch.nonzero(assign_result.gt_inds == 0, as_tuple=False).squeeze(-1).unique()
+            r.pos_assigned_gt_inds = assign_result.gt_inds[r.pos_inds] - 1
+            return r
+
+    def build_assigner(cfg):
+        importlib.import_module('open_set.assigners.mask_hungarian_assigner')     # registers the reference's own class
+        cfg = dict(cfg)
+        return BBOX_ASSIGNERS.d[cfg.pop('type')](**cfg)
+
+    def build_sampler(cfg, **kw):
+        assert cfg['type'] == 'MaskPseudoSampler'
+        return MaskPseudoSampler()
+
+    class DiceLoss(nn.Module):
+        """mmdet/models/losses/dice_loss.py (use_sigmoid + activate, naive_dice)"""
+        def __init__(self, use_sigmoid=True, activate=True, reduction='mean', naive_dice=False, loss_weight=1.0, eps=1e-3):
+            super().__init__()
+            assert use_sigmoid and activate and naive_dice and reduction == 'mean'
+            self.loss_weight, self.eps = loss_weight, eps
+
+        def forward(self, pred, target, weight=None, reduction_override=None, avg_factor=None):
+            return MO.dice_loss(pred, target, avg_factor, self.loss_weight, self.eps)
+
+    LOSSES.d['DiceLoss'] = DiceLoss
+
     m = mod('mmcv', FileClient=FileClient, load=load, _cgg_shim=True)
     m.__path__ = []
     mod('mmcv.cnn', Conv2d=nn.Conv2d,
@@ -298,17 +363,27 @@ def _install():
     mod('mmcv.cnn.bricks.transformer',
         build_positional_encoding=lambda cfg: _SinePE(**{k: v for k, v in cfg.items() if k != 'type'}),
         build_transformer_layer_sequence=lambda cfg: _Decoder(**{k: v for k, v in cfg.items() if k != 'type'}))
-    mod('mmcv.ops', point_sample=None, RoIPool=None)
+    mod('mmcv.ops', point_sample=MO.point_sample, RoIPool=None)
     mod('mmcv.runner', ModuleList=nn.ModuleList, force_fp32=force_fp32, get_dist_info=get_dist_info)
     mod('mmcv.parallel', collate=None, scatter=None)
     mod('mmdet').__path__ = []
-    mod('mmdet.core', build_assigner=None, build_sampler=None, multi_apply=multi_apply,
-        reduce_mean=reduce_mean)
+    mod('mmdet.core', build_assigner=build_assigner, build_sampler=build_sampler, multi_apply=multi_apply,
+        reduce_mean=reduce_mean).__path__ = []
+    mod('mmdet.core.bbox').__path__ = []
+    mod('mmdet.core.bbox.builder', BBOX_ASSIGNERS=BBOX_ASSIGNERS)
+    mod('mmdet.core.bbox.match_costs').__path__ = []
+    mod('mmdet.core.bbox.match_costs.builder', build_match_cost=build_match_cost)
+    mod('mmdet.core.bbox.assigners').__path__ = []
+    mod('mmdet.core.bbox.assigners.assign_result', AssignResult=AssignResult)
+    mod('mmdet.core.bbox.assigners.base_assigner', BaseAssigner=object)
+    mod('mmdet.models.losses').__path__ = []
+    mod('mmdet.models.losses.utils', weight_reduce_loss=MO.weight_reduce_loss)
     mod('mmdet.datasets', replace_ImageToTensor=None).__path__ = []
     mod('mmdet.datasets.pipelines', Compose=None)
     mod('mmdet.models').__path__ = []
     mod('mmdet.models.utils', preprocess_panoptic_gt=None,
-        get_uncertain_point_coords_with_randomness=None)
+        get_uncertain_point_coords_with_randomness=lambda mask_pred, labels, n, o, i:
+        MO.get_uncertain_point_coords_with_randomness(mask_pred, n, o, i))
     mod('mmdet.models.builder', HEADS=HEADS, LOSSES=LOSSES, build_loss=build_loss, build_head=build_head)
     mod('mmdet.models.dense_heads').__path__ = []
     mod('mmdet.models.dense_heads.anchor_free_head', AnchorFreeHead=AnchorFreeHead)
@@ -318,6 +393,7 @@ def _install():
     for name, path in [('open_set', R + '/open_set'), ('open_set.models', R + '/open_set/models'),
                        ('open_set.models.utils', R + '/open_set/models/utils'),
                        ('open_set.models.losses', R + '/open_set/models/losses'),
+                       ('open_set.assigners', R + '/open_set/assigners'),
                        ('open_set.utils', R + '/open_set/utils'),
                        ('open_set.utils.eval', R + '/open_set/utils/eval')]:
         pm = types.ModuleType(name)
@@ -331,6 +407,11 @@ def load_reference_modules():
         raise RuntimeError('reference tree not present at ' + REF_ROOT)
     _install()
     gl = importlib.import_module('open_set.models.losses.grounding_loss')
+    # the config's 'CrossEntropyLoss' is mmdet's; the reference carries its own copy of that code (CrossEntropyLossOpen,
+    # open_set/models/losses/cross_entropy_loss.py:257-): that copy computes loss_cls / loss_cls_emb / loss_mask here
+    if os.path.isfile(os.path.join(REF_ROOT, 'open_set/models/losses/cross_entropy_loss.py')):
+        ce = importlib.import_module('open_set.models.losses.cross_entropy_loss')
+        sys.modules['mmdet.models.builder'].LOSSES.d['CrossEntropyLoss'] = ce.CrossEntropyLossOpen
     head = importlib.import_module('open_set.models.mask2former_head')
     return head, gl
 
@@ -363,9 +444,30 @@ def head_cfg(num_queries=100, num_layers=9, num_known=48, num_stuff=0, embed=256
     return AttrDict.wrap(cfg)
 
 
-def build_reference_head(**kw):
+def train_cfg(num_points=12544):
+    """configs/openset_panoptic/coco_panoptic_p20.py:163-175"""
+    return AttrDict.wrap(dict(
+        num_points=num_points, oversample_ratio=3.0, importance_sample_ratio=0.75,
+        assigner=dict(type='MaskHungarianAssignerOpen', cls_cost=dict(type='ClassificationCost', weight=0.0),
+                      cls_emb_cost=dict(type='ClassificationCost', weight=2.0),
+                      mask_cost=dict(type='CrossEntropyLossCost', weight=5.0, use_sigmoid=True),
+                      dice_cost=dict(type='DiceCost', weight=5.0, pred_act=True, eps=1.0)),
+        sampler=dict(type='MaskPseudoSampler')))
+
+
+def build_reference_head(with_losses=False, num_points=12544, **kw):
     head_mod, _ = load_reference_modules()
     cfg = head_cfg(**kw)
+    if with_losses:         # the loss / assignment configuration of coco_panoptic_p20.py:111-139, :163-175
+        ncls = kw.get('num_known', 48) + kw.get('num_stuff', 0)
+        cw = [1.0] * ncls + [0.1]
+        cfg.update(AttrDict.wrap(dict(
+            loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.0, reduction='mean', class_weight=cw),
+            loss_cls_emb=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=2.0, reduction='mean', class_weight=cw),
+            loss_mask=dict(type='CrossEntropyLoss', use_sigmoid=True, reduction='mean', loss_weight=5.0),
+            loss_dice=dict(type='DiceLoss', use_sigmoid=True, activate=True, reduction='mean', naive_dice=True, eps=1.0,
+                           loss_weight=5.0),
+            train_cfg=train_cfg(num_points))))
     head = head_mod.Mask2FormerHeadOpen(**cfg)
     head.init_weights()
     return head.eval()
