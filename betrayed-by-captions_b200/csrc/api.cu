@@ -873,6 +873,70 @@ extern "C" int cgg_attn_dscore(cgg_handle* h, const float* probs, float* dprobs,
   return CGG_OK;
 }
 
+// ====================================================================== the step after the path (training time, f2)
+extern "C" int cgg_point_sample(cgg_handle* h, const float* in, const float* coords, float* out, int planes, int hh, int ww,
+                                int num_points, int coords_shared, void* stream) {
+  if (!h || !in || !coords || !out) return CGG_ERR_NULL;
+  if (planes < 0 || hh < 1 || ww < 1 || num_points < 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_point_sample(in, coords, out, planes, hh, ww, num_points, coords_shared != 0, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_point_sample_backward(cgg_handle* h, const float* dout, const float* coords, float* din, int planes, int hh,
+                                         int ww, int num_points, int coords_shared, void* stream) {
+  if (!h || !dout || !coords || !din) return CGG_ERR_NULL;
+  if (planes < 0 || hh < 1 || ww < 1 || num_points < 0) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_point_sample_bwd(dout, coords, din, planes, hh, ww, num_points, coords_shared != 0, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_matching_cost(cgg_handle* h, const float* mask_points, const float* gt_points, const float* cls_scores,
+                                 const float* cls_emb_logits, const int64_t* gt_labels, int num_q, int num_gt, int classes_p1,
+                                 int num_points, float w_cls, float w_cls_emb, float w_mask, float w_dice, float dice_eps,
+                                 float* scratch, float* cost, void* stream) {
+  if (!h || !mask_points || !gt_points || !gt_labels || !scratch || !cost) return CGG_ERR_NULL;
+  if (num_q < 0 || num_gt < 0 || num_points < 1 || classes_p1 < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  if ((w_cls != 0.f && !cls_scores) || (w_cls_emb != 0.f && !cls_emb_logits)) return CGG_ERR_NULL;
+  CU(launch_matching_cost(mask_points, gt_points, cls_scores, cls_emb_logits, gt_labels, num_q, num_gt, classes_p1, num_points,
+                          w_cls, w_cls_emb, w_mask, w_dice, dice_eps, scratch, cost, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_point_losses(cgg_handle* h, const float* pred_points, const float* target_points, int rows, int num_points,
+                                float dice_eps, float* abc, float* dice_rows, float* bce_rows, void* stream) {
+  if (!h || !pred_points || !target_points || !abc || !dice_rows || !bce_rows) return CGG_ERR_NULL;
+  if (rows < 0 || rows > 65535 || num_points < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_point_losses(pred_points, target_points, rows, num_points, dice_eps, abc, dice_rows, bce_rows, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_point_losses_backward(cgg_handle* h, const float* pred_points, const float* target_points, const float* abc,
+                                         int rows, int num_points, float dice_eps, const float* g_dice_rows,
+                                         const float* g_bce_rows, float* dpred, void* stream) {
+  if (!h || !pred_points || !target_points || !abc || !g_dice_rows || !g_bce_rows || !dpred) return CGG_ERR_NULL;
+  if (rows < 0 || rows > 65535 || num_points < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_point_losses_bwd(pred_points, target_points, abc, rows, num_points, dice_eps, g_dice_rows, g_bce_rows, dpred,
+                             (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_weighted_ce(cgg_handle* h, const float* logits, const int64_t* labels, const float* class_weight, int rows,
+                               int classes_p1, float* row_loss, float* row_weight, float* lse, void* stream) {
+  if (!h || !logits || !labels || !class_weight || !row_loss || !row_weight || !lse) return CGG_ERR_NULL;
+  if (rows < 0 || classes_p1 < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_weighted_ce(logits, labels, class_weight, rows, classes_p1, row_loss, row_weight, lse, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_weighted_ce_backward(cgg_handle* h, const float* logits, const int64_t* labels, const float* class_weight,
+                                        const float* lse, int rows, int classes_p1, const float* g_rows, float* dlogits,
+                                        void* stream) {
+  if (!h || !logits || !labels || !class_weight || !lse || !g_rows || !dlogits) return CGG_ERR_NULL;
+  if (rows < 0 || classes_p1 < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_weighted_ce_bwd(logits, labels, class_weight, lse, rows, classes_p1, g_rows, dlogits, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
 // ====================================================================== the step after the path (test time)
 extern "C" int cgg_upsample_masks(cgg_handle* h, const void* logits, int is_bf16, float* out, int planes, int h4, int w4,
                                   int up_h, int up_w, void* stream) {

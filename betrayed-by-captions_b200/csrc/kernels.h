@@ -95,6 +95,26 @@ cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uin
 cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int Q, int K,
                                cudaStream_t s);
 
+// ---- the matching-based losses after the path at training time (match_kernels.cu)
+// mmcv point_sample: in (N, H, W), coords (N or 1, P, 2) as (x, y) in [0, 1] -> out (N, P); backward scatters into din
+cudaError_t launch_point_sample(const float* in, const float* coords, float* out, int N, int H, int W, int P,
+                                bool coords_shared, cudaStream_t s);
+cudaError_t launch_point_sample_bwd(const float* dout, const float* coords, float* din, int N, int H, int W, int P,
+                                    bool coords_shared, cudaStream_t s);
+// Hungarian cost matrix (Q, G) from sampled mask logits x (Q, P), sampled ground truth g (G, P), class rows (Q, C1);
+// stats: 4*Q + G floats of scratch
+cudaError_t launch_matching_cost(const float* x, const float* g, const float* cls, const float* emb, const int64_t* labels,
+                                 int Q, int G, int C1, int P, float w_cls, float w_emb, float w_mask, float w_dice, float eps,
+                                 float* stats, float* cost, cudaStream_t s);
+cudaError_t launch_point_losses(const float* x, const float* t, int N, int P, float eps, float* abc, float* dice_rows,
+                                float* bce_rows, cudaStream_t s);
+cudaError_t launch_point_losses_bwd(const float* x, const float* t, const float* abc, int N, int P, float eps,
+                                    const float* g_dice, const float* g_bce, float* dx, cudaStream_t s);
+cudaError_t launch_weighted_ce(const float* logits, const int64_t* labels, const float* cw, int R, int C1, float* row_loss,
+                               float* row_w, float* lse, cudaStream_t s);
+cudaError_t launch_weighted_ce_bwd(const float* logits, const int64_t* labels, const float* cw, const float* lse, int R, int C1,
+                                   const float* grow, float* dlogits, cudaStream_t s);
+
 // ---- test-time step after the path (post_kernels.cu)
 cudaError_t launch_upsample_masks(const void* logits, bool bf16, float* out, int planes, int h4, int w4, int up_h, int up_w,
                                   cudaStream_t s);

@@ -143,6 +143,14 @@ class Mask2FormerHeadOpenB200(nn.Module):
             if self.caption_emb_type != 'bert':
                 raise ValueError('only caption_emb_type="bert" is built (the shipped configs use it)')
             self.bert_embeddings = _BertEmbeddings(kwargs.get('bert_vocab_size', 30522), d_lang)
+        # head.py:151-158: with a train_cfg the reference builds its assigner / sampler / point-sampling parameters; here
+        # that is the MatchingLosses object behind `loss()` (row f2: Hungarian targets, class and point-sampled mask losses)
+        self.train_cfg = kwargs.get('train_cfg') or None
+        if self.train_cfg:
+            from .matching import MatchingLosses
+            self.matching_losses = MatchingLosses(self, train_cfg=self.train_cfg, loss_cls=kwargs.get('loss_cls'),
+                                                  loss_cls_emb=kwargs.get('loss_cls_emb'), loss_mask=kwargs.get('loss_mask'),
+                                                  loss_dice=kwargs.get('loss_dice'))
         self._rt = None
         self.init_weights()
 
@@ -218,11 +226,11 @@ class Mask2FormerHeadOpenB200(nn.Module):
              gt_caption_embs_list, gt_caption_mask_list, gt_caption_nouns_ids_list, gt_caption_nouns_embs_list,
              gt_caption_nouns_mask_list, img_metas):
         """head.py:393-462 for the term that is on the path: the caption-grounding loss of every head call
-        (loss_single :540-548), computed on the CUDA kernels with the batched cross-rank gather.  The matching-based
-        terms (loss_cls / loss_cls_emb / loss_mask / loss_dice: Hungarian assignment on point-sampled masks, :320-390,
-        :591-627) are the step AFTER the path and stay with mmdet: attach them through
-        `self.matching_losses(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list,
-        img_metas) -> dict` and they are merged into the result."""
+        (loss_single :540-548), computed on the CUDA kernels with the batched cross-rank gather, merged with the
+        matching-based terms (loss_cls / loss_cls_emb / loss_mask / loss_dice: Hungarian assignment on point-sampled masks,
+        :320-390, :591-627 -- the step AFTER the path) from `self.matching_losses`
+        (cgg_b200/matching.py `MatchingLosses`, built by the constructor when a train_cfg is given; any callable
+        `(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list, img_metas) -> dict` works)."""
         from .grounding import gather_captions_and_preds, grounding_loss
         losses = {}
         if self.use_caption:

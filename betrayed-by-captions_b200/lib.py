@@ -19,7 +19,8 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            # training-step stages
            'cgg_gemm_f32', 'cgg_layernorm', 'cgg_layernorm_bwd_scratch_bytes', 'cgg_layernorm_backward', 'cgg_relu_backward',
            'cgg_axpy', 'cgg_add_rows', 'cgg_sum_batch', 'cgg_colsum', 'cgg_mem_prep', 'cgg_mem_prep_backward', 'cgg_sine_pos',
-           'cgg_attention_f32', 'cgg_attention_backward', 'cgg_attn_softmax_rows', 'cgg_attn_dscore',
+           'cgg_attention_f32', 'cgg_attention_backward', 'cgg_attn_softmax_rows', 'cgg_attn_dscore', 'cgg_point_sample', 'cgg_point_sample_backward',
+           'cgg_matching_cost', 'cgg_point_losses', 'cgg_point_losses_backward', 'cgg_weighted_ce', 'cgg_weighted_ce_backward',
            # test-time step after the path
            'cgg_upsample_masks', 'cgg_instance_mask_stats', 'cgg_softmax_rows']
 
@@ -120,6 +121,14 @@ def load():
     lib.cgg_attention_backward.argtypes = [vp, i, i, i, vp, vp, vp, lg, lg, vp, vp, vp, vp, vp, vp, vp, lg, lg, vp, vp]
     lib.cgg_attn_softmax_rows.argtypes = [vp, vp, vp, vp, i, i, i, vp]
     lib.cgg_attn_dscore.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
+    f = C.c_float
+    lib.cgg_point_sample.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.cgg_point_sample_backward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.cgg_matching_cost.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, f, f, f, f, f, vp, vp, vp]
+    lib.cgg_point_losses.argtypes = [vp, vp, vp, i, i, f, vp, vp, vp, vp]
+    lib.cgg_point_losses_backward.argtypes = [vp, vp, vp, vp, i, i, f, vp, vp, vp, vp]
+    lib.cgg_weighted_ce.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, vp]
+    lib.cgg_weighted_ce_backward.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp]
     lib.cgg_upsample_masks.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
     lib.cgg_instance_mask_stats.argtypes = [vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     lib.cgg_softmax_rows.argtypes = [vp, vp, i, i, vp]

@@ -297,6 +297,43 @@ int cgg_attn_softmax_rows(cgg_handle *h, float *scores, const uint32_t *bitmap, 
 int cgg_attn_dscore(cgg_handle *h, const float *probs, float *dprobs, const float *out, const float *dout, int batch,
                     int num_q, int num_keys, void *stream);
 
+/* ---- the matching-based losses after the path at training time -------------------
+ * loss_single (open_set/models/mask2former_head.py:464-629) and its target assignment (:320-390; assigner
+ * open_set/assigners/mask_hungarian_assigner.py:98-125).  The reference reaches into mmcv / mmdet for these steps
+ * (mmcv.ops.point_sample, mmdet match costs, DiceLoss, CrossEntropyLoss); each entry names what it replaces.  fp32. */
+
+/* mmcv.ops.point_sample (F.grid_sample on 2p-1, bilinear, zeros padding, align_corners=False) of `planes` maps (hh, ww)
+ * at num_points points (x, y) in [0,1]^2; coords (planes, P, 2), or (1, P, 2) when coords_shared (the matching step
+ * samples every query and every ground-truth mask of an image at the same points, head.py:352-363).  -> out (planes, P).
+ * The backward scatters dout into din (planes, hh, ww) (zeroed here). */
+int cgg_point_sample(cgg_handle *h, const float *in, const float *coords, float *out, int planes, int hh, int ww,
+                     int num_points, int coords_shared, void *stream);
+int cgg_point_sample_backward(cgg_handle *h, const float *dout, const float *coords, float *din, int planes, int hh, int ww,
+                              int num_points, int coords_shared, void *stream);
+/* cost (num_q, num_gt) = w_cls * ClassificationCost(cls_scores) + w_cls_emb * ClassificationCost(cls_emb_logits)
+ *                      + w_mask * CrossEntropyLossCost(use_sigmoid) + w_dice * DiceCost(pred_act, eps)   (assigner :98-125)
+ * on the sampled mask logits (num_q, P) and sampled ground-truth masks (num_gt, P).  A class term with weight 0 may pass
+ * NULL.  scratch: 4 * num_q + num_gt floats.  The Hungarian solve itself stays on the host, as in the reference (:127-134). */
+int cgg_matching_cost(cgg_handle *h, const float *mask_points, const float *gt_points, const float *cls_scores,
+                      const float *cls_emb_logits, const int64_t *gt_labels, int num_q, int num_gt, int classes_p1,
+                      int num_points, float w_cls, float w_cls_emb, float w_mask, float w_dice, float dice_eps,
+                      float *scratch, float *cost, void *stream);
+/* Per matched mask row: dice_rows = 1 - (2 s.t + eps) / (sum s + sum t + eps), s = sigmoid(pred)  (DiceLoss naive_dice,
+ * head.py:614-616) and bce_rows = sum_p BCE-with-logits(pred, t)  (loss_mask, :618-627); abc (rows, 3) is kept for the
+ * backward, which takes per-row upstream gradients (device resident). */
+int cgg_point_losses(cgg_handle *h, const float *pred_points, const float *target_points, int rows, int num_points,
+                     float dice_eps, float *abc, float *dice_rows, float *bce_rows, void *stream);
+int cgg_point_losses_backward(cgg_handle *h, const float *pred_points, const float *target_points, const float *abc,
+                              int rows, int num_points, float dice_eps, const float *g_dice_rows, const float *g_bce_rows,
+                              float *dpred, void *stream);
+/* F.cross_entropy(logits, labels, weight=class_weight, reduction='none') (loss_cls / loss_cls_emb, head.py:520-538):
+ * row_loss = w[label] (lse - x[label]), row_weight = w[label] (the avg_factor is their sum), lse kept for the backward
+ * dlogits[r, c] = g_rows[r] w[label_r] (softmax_c - [c == label_r]). */
+int cgg_weighted_ce(cgg_handle *h, const float *logits, const int64_t *labels, const float *class_weight, int rows,
+                    int classes_p1, float *row_loss, float *row_weight, float *lse, void *stream);
+int cgg_weighted_ce_backward(cgg_handle *h, const float *logits, const int64_t *labels, const float *class_weight,
+                             const float *lse, int rows, int classes_p1, const float *g_rows, float *dlogits, void *stream);
+
 /* ---- the step after the path at test time ---------------------------------------------------
  * logits: the LAST head call's mask logits (B, Q, h4, w4), fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1).
  * cgg_upsample_masks: F.interpolate(logits, (up_h, up_w), bilinear, align_corners=False) materialised in fp32, the

@@ -346,10 +346,11 @@ def _install():
         """mmdet/models/losses/dice_loss.py (use_sigmoid + activate, naive_dice)"""
         def __init__(self, use_sigmoid=True, activate=True, reduction='mean', naive_dice=False, loss_weight=1.0, eps=1e-3):
             super().__init__()
-            assert use_sigmoid and activate and naive_dice and reduction == 'mean'
+            self.ok = use_sigmoid and activate and naive_dice and reduction == 'mean'      # the form the configs use
             self.loss_weight, self.eps = loss_weight, eps
 
         def forward(self, pred, target, weight=None, reduction_override=None, avg_factor=None):
+            assert self.ok, 'only DiceLoss(use_sigmoid, activate, naive_dice, reduction=mean) is restated'
             return MO.dice_loss(pred, target, avg_factor, self.loss_weight, self.eps)
 
     LOSSES.d['DiceLoss'] = DiceLoss
