@@ -264,14 +264,28 @@ class Mask2FormerHeadOpenB200(nn.Module):
 
     def simple_test(self, feats, img_metas, **kwargs):
         """head.py:923-980 (same signature and return tuple): last head call's outputs, masks upsampled to the padded
-        input size, optional query x noun attention `att`.  Two branches need components outside the path and raise:
-        test-time label assignment (`gt_labels`, the Hungarian assigner) and caption generation (`with_caption`)."""
+        input size, optional query x noun attention `att`, optional test-time label assignment (`gt_labels` / `gt_masks`:
+        the Hungarian assignment of `_get_target_single`, cgg_b200/matching.py).  Caption generation (`with_caption`, the
+        beam search) needs a component outside the path and raises."""
         from .postprocess import upsample_masks
         all_cls_scores, all_cls_emb_preds, all_mask_preds = self(feats, img_metas)
         mask_cls_results, mask_cls_emb_results, mask_pred_results = all_cls_scores[-1], all_cls_emb_preds[-1], all_mask_preds[-1]
         assigned_labels = mask_cls_results
-        if kwargs.get('gt_labels', None) is not None:
-            raise _lib.CggError('simple_test(gt_labels=...) needs the mask Hungarian assigner (outside the path)')
+        if kwargs.get('gt_labels', None) is not None:                                                  # :947-953
+            from .grounding import similarity
+            from .matching import MatchingLosses
+            ml = getattr(self, 'matching_losses', None)
+            if not isinstance(ml, MatchingLosses):
+                ml = MatchingLosses(self, train_cfg=self.train_cfg)
+            gm = kwargs['gt_masks'][0][0]
+            if not torch.is_tensor(gm):              # mmdet BitmapMasks
+                gm = gm.pad(img_metas[0]['pad_shape'][:2], pad_val=0).to_tensor(dtype=torch.long, device=mask_cls_results.device)
+            logits = None
+            if self.use_class_emb:
+                logits = similarity(mask_cls_emb_results[0].float(), self.class_embs, 1.0 / float(self.softmax_temperature))
+            assigned_labels = ml.get_target_single(mask_cls_results[0].float(), logits, mask_pred_results[0],
+                                                   kwargs['gt_labels'][0][0].to(mask_cls_results.device),
+                                                   gm.to(mask_cls_results.device))[0]
         img_shape = kwargs.get('img_shape') or img_metas[0]['batch_input_shape']
         mask_pred_results = upsample_masks(self, mask_pred_results, (img_shape[0], img_shape[1]))      # :957-964
         if kwargs.get('with_caption', False) or 'cap_results' in self.test_cfg.get('eval_types', []):

@@ -124,3 +124,28 @@ def test_forward_train_returns_the_reference_loss_dict():
     missing = [k for k, p in head.named_parameters() if p.requires_grad and p.grad is None]
     assert missing == ['cls_embed.weight', 'cls_embed.bias'] or missing == [], missing     # loss_cls has weight 0 in this config
     assert all(torch.isfinite(v) for v in losses.values())
+
+
+def test_simple_test_assigns_labels_like_get_target_single():
+    """simple_test(gt_labels=, gt_masks=) (head.py:947-953): assigned_labels = the Hungarian assignment of image 0."""
+    from test_gpu_post import _caption_head
+    from oracle import cgg_oracle as O
+    Q, B = 24, 1
+    head, sd, _, _ = _caption_head(Q)
+    head.eval()
+    head.matching_losses = _ml(head, 300)
+    mf, mems = synth.make_inputs(12, B, 128, 160)
+    feats = [mf.to(DEV)] + [m.to(DEV) for m in mems]
+    g = torch.Generator().manual_seed(3)
+    gt_labels = torch.randint(0, 48, (4,), generator=g)
+    gt_masks = (torch.rand((4, 128, 160), generator=g) > 0.6).long()            # full resolution, the logits are 1/4 scale
+    metas = [dict(batch_input_shape=(128, 160), pad_shape=(128, 160, 3))]
+    torch.manual_seed(77)
+    with torch.no_grad():
+        got = head.simple_test(feats, metas, gt_labels=[[gt_labels]], gt_masks=[[gt_masks]])[0]
+    ref = O.decoder_forward({k: v for k, v in sd.items() if not k.startswith('bert')}, mf, mems)
+    logits = O.cls_emb_logits(ref['emb'][9][0], sd['class_embs'], 10.0)
+    torch.manual_seed(77)
+    want = MO.get_target_single(ref['cls'][9][0], logits, ref['mask'][9][0], gt_labels, gt_masks, 48,
+                                dict(MO.DEFAULT_CFG, num_points=300))[0]
+    assert torch.equal(got.cpu(), want)
