@@ -328,6 +328,56 @@ def grounding_leg(dev, Bg=16, Q=100, T=35, D=768):
                 note='cgg_grounding_loss + cgg_grounding_loss_backward, one head call, fp32')
 
 
+def matching_leg(dev, B=2, Q=200, ncls1=118, G=20, h=256, w=256, P=12544):
+    """Row f2 alone: the matching-based terms of loss_single for ONE head call at the configs[3] shapes (B images, Q
+    queries, G ground-truth masks per image, 12 544 points): point sampling, cost matrix, Hungarian solve (host),
+    class-weighted CEs, importance-sampled dice + BCE, forward + backward; the same function as plain torch CUDA ops
+    (the oracle moved to the GPU, its Hungarian solve on the host too) beside it."""
+    import time
+    from cgg_b200 import synth, matching
+    from cgg_b200.head import build_head_from_state_dict
+    from oracle import matching_oracle as MO
+    head = build_head_from_state_dict(synth.make_params(seed=0, num_queries=Q, num_classes_p1=ncls1), Q, ncls1, 'fp32', dev)
+    ml = matching.MatchingLosses(head, train_cfg=dict(num_points=P))
+    g = torch.Generator().manual_seed(4)
+    mask = (torch.randn((B, Q, h, w), generator=g) * 2).to(dev).requires_grad_(True)
+    cls = torch.randn((B, Q, ncls1), generator=g).to(dev).requires_grad_(True)
+    emb = (torch.randn((B, Q, ncls1), generator=g) * 2).to(dev).requires_grad_(True)
+    gt_labels = [torch.randint(0, ncls1 - 1, (G,), generator=g).to(dev) for _ in range(B)]
+    gt_masks = []
+    for _ in range(B):
+        m = torch.zeros((G, h, w))
+        for k in range(G):
+            y0, x0 = int(torch.randint(0, h // 2, (1,), generator=g)), int(torch.randint(0, w // 2, (1,), generator=g))
+            m[k, y0:y0 + h // 4, x0:x0 + w // 4] = 1.0
+        gt_masks.append(m.to(dev))
+
+    def ours():
+        out, _, _ = ml.loss_single(cls, emb, mask, gt_labels, gt_masks)
+        (out['loss_cls_emb'] + out['loss_mask'] + out['loss_dice']).backward()
+
+    def plain():
+        out = MO.loss_single_matching(cls, emb, mask, gt_labels, gt_masks, ncls1 - 1, dict(num_points=P))
+        (out['loss_cls_emb'] + out['loss_mask'] + out['loss_dice']).backward()
+
+    res = {}
+    for name, fn in (('ms_fwd_bwd', ours), ('torch_gpu_ms_fwd_bwd', plain)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 5
+        for _ in range(n):
+            mask.grad = cls.grad = emb.grad = None
+            fn()
+        torch.cuda.synchronize()
+        res[name] = (time.perf_counter() - t0) / n * 1e3
+    res.update(images=B, queries=Q, gts_per_image=G, points=P,
+               note='wall clock per call (the Hungarian solve and the positives gather synchronise with the host, as in '
+                    'the reference); one head call, fp32')
+    return res
+
+
 def train_leg(args, rank, world, dev):
     """BASELINE configs[3]: OSPS head (200 queries, 118 class rows), forward + backward of the decoder head with the
     caption-grounding loss on every head call (weight 2.0) + class-embedding CE + a mask surrogate, per-GPU batch 2
@@ -383,7 +433,33 @@ def train_leg(args, rank, world, dev):
         torch.cuda.synchronize()
         return reduce_max(e0.elapsed_time(e1) / n, world, dev), extra / n
 
+    # the reference's full loss dict (grounding + Hungarian-matched class / mask / dice terms, row f2): the assignment
+    # synchronises with the host (scipy, as in the reference), so this form of the step cannot be one CUDA graph
+    from cgg_b200.matching import MatchingLosses
+    ml = MatchingLosses(head, train_cfg=dict(num_points=12544))
+    G = 20
+    gt_labels = [torch.randint(0, ncls1 - 1, (G,), generator=g).to(dev) for _ in range(B)]
+    gt_masks = []
+    for _ in range(B):
+        m = torch.zeros((G, H // 4, W // 4))
+        for k in range(G):
+            y0, x0 = int(torch.randint(0, H // 8, (1,), generator=g)), int(torch.randint(0, W // 8, (1,), generator=g))
+            m[k, y0:y0 + H // 16, x0:x0 + W // 16] = 1.0
+        gt_masks.append(m.to(dev))
+
+    def full_loss_step():
+        reducer.zero()
+        cls, emb, mask = head.decoder_forward_auto(mf, mems)
+        embs_all, mask_all, preds_all = gather_captions_and_preds(cap, cap_mask, torch.stack(emb, 0))
+        loss = sum(grounding_loss(preds_all[j], embs_all, mask_all, 10.0, 2.0) for j in range(len(cls)))
+        loss = loss + sum(ml(cls, emb, mask, gt_labels, gt_masks).values())
+        loss.backward()
+        reducer.finish()
+
     n = args.train_steps
+    for _ in range(2):
+        full_loss_step()
+    full_ms, _ = timed(full_loss_step, n)
     for _ in range(2):
         eager_step()
     eager_ms, exposed = timed(eager_step, n, after=reducer.exposed)
@@ -391,7 +467,11 @@ def train_leg(args, rank, world, dev):
     out = dict(batch_per_gpu=B, queries=Q, classes_p1=ncls1, precision=args.train_precision,
                grad_bytes=4 * sum(p.numel() for p in head.parameters()),
                eager=dict(ms_per_step=eager_ms, allreduce_exposed_ms=exposed,
-                          note='issued launch by launch; exposed = end of backward -> end of the last bucket all-reduce'))
+                          note='issued launch by launch; exposed = end of backward -> end of the last bucket all-reduce'),
+               full_loss_eager=dict(ms_per_step=full_ms, gts_per_image=G, points=12544,
+                                    note='grounding x10 + Hungarian-matched loss_cls / loss_cls_emb / loss_mask / loss_dice '
+                                         'x10 (cgg_b200.matching: the reference\'s full loss dict less caption generation), '
+                                         'issued eagerly: the assignment synchronises with the host as in the reference'))
     ms = eager_ms
     if not args.no_train_graph:
         reducer.timing = False
@@ -729,10 +809,11 @@ def run_b200_arm(args):
                                     sustained_frac=flops_per_image(Q) * sustained['value'] / world / 1e12 / peaks['tflops']))
 
     # ---- stage / config legs
-    grounding = train = None
+    grounding = train = matching_rec = None
     if not args.no_train:
         try:
             grounding = grounding_leg(dev) if rank == 0 else None
+            matching_rec = matching_leg(dev) if rank == 0 else None
             del heads, fly_in
             torch.cuda.empty_cache()
             train = train_leg(args, rank, world, dev)
@@ -769,6 +850,8 @@ def run_b200_arm(args):
             line['train'] = train
         if grounding is not None:
             line['grounding'] = grounding
+        if matching_rec is not None:
+            line['matching_losses'] = matching_rec
         if tgb is not None:
             line['torch_gpu_baseline'] = tgb
         if cpu is not None:
