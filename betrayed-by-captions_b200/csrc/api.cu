@@ -858,18 +858,20 @@ extern "C" int cgg_attention_backward(cgg_handle* h, int batch, int num_q, int n
 }
 
 extern "C" int cgg_attn_softmax_rows(cgg_handle* h, float* scores, const uint32_t* bitmap, const uint8_t* all_masked,
-                                     int batch, int num_q, int num_keys, void* stream) {
+                                     int batch, int heads, int num_q, int num_keys, void* stream) {
   if (!h || !scores) return CGG_ERR_NULL;
+  if (heads <= 0) heads = h->cfg.num_heads;
   if (batch < 1 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
-  CU(launch_attn_softmax_rows(scores, bitmap, all_masked, batch, h->cfg.num_heads, num_q, num_keys, (cudaStream_t)stream));
+  CU(launch_attn_softmax_rows(scores, bitmap, all_masked, batch, heads, num_q, num_keys, (cudaStream_t)stream));
   return CGG_OK;
 }
 
 extern "C" int cgg_attn_dscore(cgg_handle* h, const float* probs, float* dprobs, const float* out, const float* dout,
-                               int batch, int num_q, int num_keys, void* stream) {
+                               int batch, int heads, int head_dim, int num_q, int num_keys, void* stream) {
   if (!h || !probs || !dprobs || !out || !dout) return CGG_ERR_NULL;
-  if (batch < 1 || num_q < 1 || num_keys < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
-  CU(launch_attn_dscore(probs, dprobs, out, dout, batch, h->cfg.num_heads, num_q, num_keys, (cudaStream_t)stream));
+  if (heads <= 0) { heads = h->cfg.num_heads; head_dim = h->cfg.embed_dim / h->cfg.num_heads; }
+  if (batch < 1 || num_q < 1 || num_keys < 1 || head_dim < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_attn_dscore(probs, dprobs, out, dout, batch, heads, head_dim, num_q, num_keys, (cudaStream_t)stream));
   return CGG_OK;
 }
 

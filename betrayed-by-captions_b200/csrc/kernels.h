@@ -92,8 +92,8 @@ cudaError_t launch_attention_bwd(const float* q, const float* k, const float* v,
 // attention as tensor-core products (tf32 training mode): row softmax with the bitmap / dS = P o (dP - D), in place
 cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uint8_t* all_masked, int B, int heads, int Q,
                                      int K, cudaStream_t s);
-cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int Q, int K,
-                               cudaStream_t s);
+cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int head_dim,
+                               int Q, int K, cudaStream_t s);
 
 // ---- the matching-based losses after the path at training time (match_kernels.cu)
 // mmcv point_sample: in (N, H, W), coords (N or 1, P, 2) as (x, y) in [0, 1] -> out (N, P); backward scatters into din

@@ -289,14 +289,16 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restric
 // dS = P o (dP - D), D[b,h,q] = dO[b,q,h,:] . O[b,q,h,:]; written over dP.
 __global__ void __launch_bounds__(256) attn_dscore_kernel(const float* __restrict__ P, float* __restrict__ dP,
                                                           const float* __restrict__ O, const float* __restrict__ dO,
-                                                          int heads, int Q, int K) {
+                                                          int heads, int hd, int Q, int K) {
   __shared__ float Dsh;
   const long r = blockIdx.x;
   const int qi = (int)(r % Q), h = (int)((r / Q) % heads);
   const long b = r / ((long)Q * heads);
   if (threadIdx.x < 32) {
-    const long off = (b * Q + qi) * (long)(heads * HD) + h * HD + threadIdx.x;
-    const float d = warp_sum(O[off] * dO[off]);
+    const long off = (b * Q + qi) * (long)(heads * hd) + (long)h * hd;
+    float d = 0.f;
+    for (int i = threadIdx.x; i < hd; i += 32) d = fmaf(O[off + i], dO[off + i], d);
+    d = warp_sum(d);
     if (threadIdx.x == 0) Dsh = d;
   }
   __syncthreads();
@@ -432,11 +434,11 @@ cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uin
   return cudaGetLastError();
 }
 
-cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int Q, int K,
-                               cudaStream_t s) {
+cudaError_t launch_attn_dscore(const float* P, float* dP, const float* O, const float* dO, int B, int heads, int head_dim,
+                               int Q, int K, cudaStream_t s) {
   const long rows = (long)B * heads * Q;
   if (rows <= 0 || K <= 0) return cudaSuccess;
-  attn_dscore_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, O, dO, heads, Q, K);
+  attn_dscore_kernel<<<(unsigned)rows, 256, 0, s>>>(P, dP, O, dO, heads, head_dim, Q, K);
   count_launch();
   return cudaGetLastError();
 }

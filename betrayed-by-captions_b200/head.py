@@ -143,6 +143,23 @@ class Mask2FormerHeadOpenB200(nn.Module):
             if self.caption_emb_type != 'bert':
                 raise ValueError('only caption_emb_type="bert" is built (the shipped configs use it)')
             self.bert_embeddings = _BertEmbeddings(kwargs.get('bert_vocab_size', 30522), d_lang)
+        # caption generator (head.py:246-248, configs .../coco_panoptic_p20.py:100-110): CaptionTransformer over the query
+        # embeddings, its loss and the test-time beam search (row f4, cgg_b200/caption.py)
+        self.use_caption_generation = bool(kwargs.get('use_caption_generation', False))
+        self.gen_only_obj_nouns = bool(kwargs.get('gen_only_obj_nouns', False))
+        self.gen_mask_obj_nouns = bool(kwargs.get('gen_mask_obj_nouns', False))
+        self.gen_replace_obj_nouns = bool(kwargs.get('gen_replace_obj_nouns', False))
+        self.loss_caption_generation_weight = float(_get(kwargs.get('loss_caption_generation'), 'loss_weight', default=1.0))
+        self.caption_generator = None
+        self.tokenizer = None          # optional bert-base-uncased tokenizer: simple_test(with_caption) then returns text
+        cg = kwargs.get('caption_generator')
+        if cg:
+            from .caption import CaptionTransformerB200
+            cg = {k_: v for k_, v in dict(cg).items() if k_ != 'type'}
+            self.caption_generator = CaptionTransformerB200(**cg)
+            self.caption_generator.bind(self)
+            if self.bert_embeddings is None:        # the generator reads token embeddings (caption_gen_emb_type 'bert')
+                self.bert_embeddings = _BertEmbeddings(kwargs.get('bert_vocab_size', 30522), d_lang)
         # head.py:151-158: with a train_cfg the reference builds its assigner / sampler / point-sampling parameters; here
         # that is the MatchingLosses object behind `loss()` (row f2: Hungarian targets, class and point-sampled mask losses)
         self.train_cfg = kwargs.get('train_cfg') or None
@@ -245,6 +262,19 @@ class Mask2FormerHeadOpenB200(nn.Module):
                     losses['loss_grounding'] = lg
                 else:
                     losses['d%d.loss_grounding' % j] = lg * self.loss_aux_weight
+        if self.use_caption_generation:                                           # loss_single :550-583
+            from .caption import caption_generation_loss
+            n = len(all_cls_emb_preds)
+            for j in range(n):
+                if self.loss_only_last and j != n - 1:
+                    continue
+                lc = caption_generation_loss(self, all_cls_emb_preds[j], gt_caption_ids_list, gt_caption_embs_list,
+                                             gt_caption_mask_list, gt_caption_nouns_ids_list,
+                                             self.loss_caption_generation_weight)
+                if j == n - 1:
+                    losses['loss_caption_generation'] = lc
+                else:
+                    losses['d%d.loss_caption_generation' % j] = lc * self.loss_aux_weight
         hook = getattr(self, 'matching_losses', None)
         if hook is not None:
             losses.update(hook(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels_list, gt_masks_list, img_metas))
@@ -256,17 +286,20 @@ class Mask2FormerHeadOpenB200(nn.Module):
         `preprocess_gt` (mmdet, :903) only feeds the matching-based losses and is left to the `matching_losses` hook."""
         assert gt_bboxes_ignore is None
         all_cls_scores, all_cls_emb_preds, all_mask_preds = self(feats, img_metas)
-        nouns_embs = nouns_mask = None
+        nouns_embs = nouns_mask = cap_embs = None
+        if self.use_caption_generation:                                                                 # :905-908
+            cap_embs, gt_caption_mask = self.extract_caption_embeddings(gt_caption_ids, gt_caption_mask)
         if self.use_caption:
             nouns_embs, nouns_mask = self.extract_caption_embeddings(gt_caption_nouns_ids, gt_caption_nouns_mask)
-        return self.loss(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels, gt_masks, gt_caption_ids, None,
+        return self.loss(all_cls_scores, all_cls_emb_preds, all_mask_preds, gt_labels, gt_masks, gt_caption_ids, cap_embs,
                          gt_caption_mask, gt_caption_nouns_ids, nouns_embs, nouns_mask, img_metas)
 
     def simple_test(self, feats, img_metas, **kwargs):
         """head.py:923-980 (same signature and return tuple): last head call's outputs, masks upsampled to the padded
         input size, optional query x noun attention `att`, optional test-time label assignment (`gt_labels` / `gt_masks`:
-        the Hungarian assignment of `_get_target_single`, cgg_b200/matching.py).  Caption generation (`with_caption`, the
-        beam search) needs a component outside the path and raises."""
+        the Hungarian assignment of `_get_target_single`, cgg_b200/matching.py) and caption generation (`with_caption` /
+        'cap_results': the beam search of cgg_b200/caption.py; the sentence text when `self.tokenizer` is set -- the
+        reference downloads bert-base-uncased's tokenizer for that -- otherwise its token ids)."""
         from .postprocess import upsample_masks
         all_cls_scores, all_cls_emb_preds, all_mask_preds = self(feats, img_metas)
         mask_cls_results, mask_cls_emb_results, mask_pred_results = all_cls_scores[-1], all_cls_emb_preds[-1], all_mask_preds[-1]
@@ -288,8 +321,13 @@ class Mask2FormerHeadOpenB200(nn.Module):
                                                    gm.to(mask_cls_results.device))[0]
         img_shape = kwargs.get('img_shape') or img_metas[0]['batch_input_shape']
         mask_pred_results = upsample_masks(self, mask_pred_results, (img_shape[0], img_shape[1]))      # :957-964
-        if kwargs.get('with_caption', False) or 'cap_results' in self.test_cfg.get('eval_types', []):
-            raise _lib.CggError('caption generation (beam search) is outside the path')
+        caption_generation_results = None
+        if kwargs.get('with_caption', False) or 'cap_results' in self.test_cfg.get('eval_types', []):     # :966-970
+            if self.caption_generator is None:
+                raise _lib.CggError('with_caption needs a head built with caption_generator=dict(...)')
+            from .caption import beam_search
+            res = beam_search(self, mask_cls_emb_results.float(), max_len=35, beam_width=7, tokenizer=self.tokenizer)
+            caption_generation_results = res['text'] if self.tokenizer is not None else res['ids']
         att = None
         if kwargs.get('with_att', False):                                                               # :973-978
             ids = kwargs['nouns_ids']
@@ -299,7 +337,7 @@ class Mask2FormerHeadOpenB200(nn.Module):
             nouns_embs = self.extract_word_embeddings(be.word_embeddings.weight, be.LayerNorm.weight, be.LayerNorm.bias,
                                                       ids.reshape(-1), eps=be.LayerNorm.eps)
             att = self.test_time_att(mask_cls_emb_results, nouns_embs)
-        return assigned_labels, mask_cls_emb_results, mask_pred_results, None, att
+        return assigned_labels, mask_cls_emb_results, mask_pred_results, caption_generation_results, att
 
     def grounding_loss(self, cls_emb_pred, gt_caption_embs, gt_caption_mask, loss_weight=1.0):
         """losses/grounding_loss.py:9-77; differentiable w.r.t. cls_emb_pred (grounding.py)."""

@@ -110,3 +110,41 @@ def make_captions(seed, batch, max_tokens=35, vocab=30522, d_l=768, force_empty=
         mask[b, :n] = 1
     table = torch.randn((vocab, d_l), generator=g) * 0.02
     return ids, mask, table, torch.ones(d_l), torch.zeros(d_l)
+
+
+CAPTION_CFG_SMALL = dict(nb_layers=2, input_dim=768, hidden_dim=768, ff_dim=512, nb_heads=8, drop_val=0.0, pre_norm=False,
+                         seq_length=35, nb_tokens=1500)
+
+
+def make_caption_params(seed=0, cfg=None, vocab=None, scale=2.0, eos_bias=2.0):
+    """Seeded weights of the caption generator under the reference's state_dict keys (`caption_generator.*`,
+    open_set/models/transformers/*.py) plus a small BERT embedding table (`bert_embeddings.*`).  `scale` widens the
+    projections beyond torch's default init so that the attention and the beam search have something to decide; `eos_bias`
+    lifts the [SEP] logit so that beams of different lengths finish."""
+    cfg = dict(cfg or CAPTION_CFG_SMALL)
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    C, F_, V = cfg['hidden_dim'], cfg['ff_dim'], vocab or cfg['nb_tokens']
+    pre = 'caption_generator.'
+    if cfg['input_dim'] != C:
+        _linear(g, sd, pre + 'adapter', C, cfg['input_dim'])
+    for i in range(cfg['nb_layers']):
+        p = pre + 'transformer_decoder.decoders.%d.' % i
+        _linear(g, sd, p + 'mha_layer.qkv_layer', 3 * C, C)
+        _linear(g, sd, p + 'mha_layer.out_layer', C, C)
+        for n in ('to_qry', 'to_key', 'to_val', 'to_out'):
+            _linear(g, sd, p + 'crx_layer.' + n, C, C)
+        _linear(g, sd, p + 'ffn_layer.linears.0.0', F_, C)
+        _linear(g, sd, p + 'ffn_layer.linears.1.0', C, F_)
+        for n in ('mha', 'crx', 'ffn'):
+            sd[p + 'layer_normalz.%s.1.weight' % n] = 1.0 + 0.2 * torch.randn((C,), generator=g)
+            sd[p + 'layer_normalz.%s.1.bias' % n] = 0.1 * torch.randn((C,), generator=g)
+    _linear(g, sd, pre + 'generator', cfg['nb_tokens'], C)
+    sd[pre + 'generator.bias'][102] += eos_bias
+    for k in list(sd):
+        if k.endswith('.weight') and 'layer_normalz' not in k:
+            sd[k] = sd[k] * scale
+    sd['bert_embeddings.word_embeddings.weight'] = torch.randn((V, 768), generator=g) * 0.05
+    sd['bert_embeddings.LayerNorm.weight'] = 1.0 + 0.1 * torch.randn((768,), generator=g)
+    sd['bert_embeddings.LayerNorm.bias'] = 0.05 * torch.randn((768,), generator=g)
+    return sd

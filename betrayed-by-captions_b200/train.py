@@ -229,7 +229,7 @@ class _AttentionGemm(torch.autograd.Function):
         bh = dict(batch=B * H, batch_inner=H)
         # S[b,h,q,key] = q[b,q,h,:] . k[b,key,h,:]
         k_.gemm(q, (Q * Cc, Cc, 1), kk, (K * Cc, Cc, 1), P, (H * Q * K, K, 1), Q, K, d, s2=(d, d, Q * K), **bh)
-        k_.chk(k_.lib.cgg_attn_softmax_rows(k_.h, _p(P), _p(bitmap), _p(all_masked), B, Q, K, k_.s()), 'cgg_attn_softmax_rows')
+        k_.chk(k_.lib.cgg_attn_softmax_rows(k_.h, _p(P), _p(bitmap), _p(all_masked), B, H, Q, K, k_.s()), 'cgg_attn_softmax_rows')
         out = k_.new(B, Q, Cc)
         # O[b,q,h,:] = sum_key P[b,h,q,key] v[b,key,h,:]
         k_.gemm(P, (H * Q * K, K, 1), v, (K * Cc, 1, Cc), out, (Q * Cc, Cc, 1), Q, d, K, s2=(Q * K, d, d), **bh)
@@ -250,12 +250,59 @@ class _AttentionGemm(torch.autograd.Function):
         dS = k_.new(B, H, Q, K)
         # dP[b,h,q,key] = dO[b,q,h,:] . v[b,key,h,:]
         k_.gemm(dout, (Q * Cc, Cc, 1), v, (K * Cc, Cc, 1), dS, (H * Q * K, K, 1), Q, K, d, s2=(d, d, Q * K), **bh)
-        k_.chk(k_.lib.cgg_attn_dscore(k_.h, _p(P), _p(dS), _p(out), _p(dout), B, Q, K, k_.s()), 'cgg_attn_dscore')
+        k_.chk(k_.lib.cgg_attn_dscore(k_.h, _p(P), _p(dS), _p(out), _p(dout), B, H, d, Q, K, k_.s()), 'cgg_attn_dscore')
         dq, dk, dv = k_.new(B, Q, Cc), k_.new(B, K, Cc), k_.new(B, K, Cc)
         # dq[b,q,h,:] = sum_key dS k ;  dk[b,key,h,:] = sum_q dS q ;  dv[b,key,h,:] = sum_q P dO
         k_.gemm(dS, (H * Q * K, K, 1), kk, (K * Cc, 1, Cc), dq, (Q * Cc, Cc, 1), Q, d, K, s2=(Q * K, d, d), **bh)
         k_.gemm(dS, (H * Q * K, 1, K), q, (Q * Cc, 1, Cc), dk, (K * Cc, Cc, 1), K, d, Q, s2=(Q * K, d, d), a_mmajor=True, **bh)
         k_.gemm(P, (H * Q * K, 1, K), dout, (Q * Cc, 1, Cc), dv, (K * Cc, Cc, 1), K, d, Q, s2=(Q * K, d, d), a_mmajor=True, **bh)
+        return None, dq, dk, dv, None, None
+
+
+class _AttentionViews(torch.autograd.Function):
+    """softmax(scale * q k^T | bitmap) v for (B, L, H, d) VIEWS q4, k4, v4 (last stride 1, any row / head / batch strides:
+    e.g. the three slices of a fused qkv projection) -> (B, Lq, H*d) contiguous.  Same products as _AttentionGemm, any
+    head count / head dim; a bit set in bitmap (B, Lq, ceil(Lk/32)) excludes the key, a row with no key left gives zeros.
+    Used by the caption transformer (row f4: 8 heads x 96)."""
+
+    @staticmethod
+    def forward(ctx, k_, q4, k4, v4, bitmap, scale):
+        B, Lq, H, d = q4.shape
+        Lk = k4.shape[1]
+        for t in (q4, k4, v4):
+            assert t.stride(3) == 1 and t.dtype == torch.float32
+        P = k_.new(B, H, Lq, Lk)
+        bh = dict(batch=B * H, batch_inner=H)
+        sq, sk, sv = q4.stride(), k4.stride(), v4.stride()
+        k_.gemm(q4, (sq[0], sq[1], 1), k4, (sk[0], sk[1], 1), P, (H * Lq * Lk, Lk, 1), Lq, Lk, d, s2=(sq[2], sk[2], Lq * Lk),
+                alpha=scale, **bh)
+        k_.chk(k_.lib.cgg_attn_softmax_rows(k_.h, _p(P), _p(bitmap), None, B, H, Lq, Lk, k_.s()), 'cgg_attn_softmax_rows')
+        out = k_.new(B, Lq, H * d)
+        k_.gemm(P, (H * Lq * Lk, Lk, 1), v4, (sv[0], 1, sv[1]), out, (Lq * H * d, H * d, 1), Lq, d, Lk, s2=(Lq * Lk, sv[2], d), **bh)
+        ctx.k, ctx.scale = k_, scale
+        ctx.save_for_backward(q4, k4, v4, P, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        k_, scale = ctx.k, ctx.scale
+        q4, k4, v4, P, out = ctx.saved_tensors
+        B, Lq, H, d = q4.shape
+        Lk = k4.shape[1]
+        Cc = H * d
+        dout = dout.contiguous()
+        bh = dict(batch=B * H, batch_inner=H)
+        sq, sk, sv = q4.stride(), k4.stride(), v4.stride()
+        dS = k_.new(B, H, Lq, Lk)
+        k_.gemm(dout, (Lq * Cc, Cc, 1), v4, (sv[0], sv[1], 1), dS, (H * Lq * Lk, Lk, 1), Lq, Lk, d, s2=(d, sv[2], Lq * Lk), **bh)
+        k_.chk(k_.lib.cgg_attn_dscore(k_.h, _p(P), _p(dS), _p(out), _p(dout), B, H, d, Lq, Lk, k_.s()), 'cgg_attn_dscore')
+        dq, dk, dv = k_.new(B, Lq, H, d), k_.new(B, Lk, H, d), k_.new(B, Lk, H, d)
+        k_.gemm(dS, (H * Lq * Lk, Lk, 1), k4, (sk[0], 1, sk[1]), dq, (Lq * Cc, Cc, 1), Lq, d, Lk, s2=(Lq * Lk, sk[2], d),
+                alpha=scale, **bh)
+        k_.gemm(dS, (H * Lq * Lk, 1, Lk), q4, (sq[0], 1, sq[1]), dk, (Lk * Cc, Cc, 1), Lk, d, Lq, s2=(Lq * Lk, sq[2], d),
+                alpha=scale, a_mmajor=True, **bh)
+        k_.gemm(P, (H * Lq * Lk, 1, Lk), dout, (Lq * Cc, 1, Cc), dv, (Lk * Cc, Cc, 1), Lk, d, Lq, s2=(Lq * Lk, d, d),
+                a_mmajor=True, **bh)
         return None, dq, dk, dv, None, None
 
 

@@ -290,12 +290,14 @@ int cgg_attention_backward(cgg_handle *h, int batch, int num_q, int num_keys, co
 /* The same attention as tensor-core products (training step with tf32 contractions): S = q k^T, O = P v and the four
  * gradient products are cgg_gemm_f32 calls over (image, head) batches (batch_inner = heads); these two entry points are
  * the row-wise stages in between, in place on the (batch, heads, num_q, num_keys) fp32 score tensor:
- *   cgg_attn_softmax_rows: scores -> softmax over the keys the bitmap leaves (all keys for all_masked rows);
- *   cgg_attn_dscore:       dprobs -> probs * (dprobs - D),  D[b,h,q] = dout[b,q,h,:] . out[b,q,h,:]. */
+ *   cgg_attn_softmax_rows: scores -> softmax over the keys the bitmap leaves (all keys for all_masked rows; a row with
+ *                          no key left becomes zeros);
+ *   cgg_attn_dscore:       dprobs -> probs * (dprobs - D),  D[b,h,q] = dout[b,q,h,:] . out[b,q,h,:].
+ * heads / head_dim: 0 = the handle's (8 x 32); the caption transformer (row f4) passes its own (8 x 96). */
 int cgg_attn_softmax_rows(cgg_handle *h, float *scores, const uint32_t *bitmap, const uint8_t *all_masked, int batch,
-                          int num_q, int num_keys, void *stream);
+                          int heads, int num_q, int num_keys, void *stream);
 int cgg_attn_dscore(cgg_handle *h, const float *probs, float *dprobs, const float *out, const float *dout, int batch,
-                    int num_q, int num_keys, void *stream);
+                    int heads, int head_dim, int num_q, int num_keys, void *stream);
 
 /* ---- the matching-based losses after the path at training time -------------------
  * loss_single (open_set/models/mask2former_head.py:464-629) and its target assignment (:320-390; assigner

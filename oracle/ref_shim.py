@@ -395,6 +395,7 @@ def _install():
                        ('open_set.models.utils', R + '/open_set/models/utils'),
                        ('open_set.models.losses', R + '/open_set/models/losses'),
                        ('open_set.assigners', R + '/open_set/assigners'),
+                       ('open_set.models.transformers', R + '/open_set/models/transformers'),
                        ('open_set.utils', R + '/open_set/utils'),
                        ('open_set.utils.eval', R + '/open_set/utils/eval')]:
         pm = types.ModuleType(name)
@@ -443,6 +444,14 @@ def head_cfg(num_queries=100, num_layers=9, num_known=48, num_stuff=0, embed=256
         known_file=known_file, unknown_file=unknown_file,
         softmax_temperature=10, pred_emb_norm=False, text_emb_norm=True)
     return AttrDict.wrap(cfg)
+
+
+def load_caption_modules():
+    """(caption_tranformer module, inference module) of the unmodified reference: CaptionTransformer and beam_search."""
+    load_reference_modules()
+    ct = importlib.import_module('open_set.models.transformers.caption_tranformer')
+    inf = importlib.import_module('open_set.utils.eval.inference')
+    return ct, inf
 
 
 def train_cfg(num_points=12544):
