@@ -1,6 +1,7 @@
 """BASELINE.json configs[4]: masked cross-attention + mask-einsum microbenchmark sweep (GPU box).
 
 queries 100-300, images 512^2-1536^2, key counts per level 256-36,864, attention-mask density 5-100 %.
+Attention masks: one contiguous window per query AND i.i.d. per key.
 Prints one JSON object per line and writes gpurun_out/sweep.jsonl.  bf16 mode, B=16 (B=8 at 1536^2 x Q=300)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -69,20 +70,29 @@ for Q in (100, 200, 300):
             q = (torch.randn((B, Q, C), generator=g) * 0.4).to(dev)
             k = torch.randn((B, K, C), generator=g).bfloat16().to(dev)
             v = torch.randn((B, K, C), generator=g).bfloat16().to(dev)
-            for density in (0.05, 0.5, 0.9, 1.0):
-                # density = fraction of keys MASKED for a query; masked-out keys form everything outside one window
-                width = max(1, int(round(K * (1.0 - density))))
-                masked = torch.ones((B, Q, K), dtype=torch.bool, device=dev)
-                if density < 1.0:
-                    start = torch.randint(0, K - width + 1, (B, Q), generator=g).to(dev)
-                    idx = torch.arange(K, device=dev)[None, None]
-                    masked = ~((idx >= start[..., None]) & (idx < start[..., None] + width))
-                am = masked.all(-1).to(torch.uint8).contiguous()
-                bits = packbits(masked)
-                ms = timeit(lambda: rt.masked_attention(q, k, v, bits, am))
-                eff = float((~masked).float().mean()) if density < 1.0 else 1.0     # fallback rows attend everywhere
-                emit(bench='masked_attention', Q=Q, size=size, batch=B, level=lvl, keys=K, masked_fraction=density,
-                     ms=ms, dense_tflops=4.0 * B * HEADS * Q * K * 32 / ms / 1e9, attended_fraction=eff)
+            for kind in ('window', 'iid'):
+                for density in (0.05, 0.5, 0.9, 1.0):
+                    if kind == 'iid' and density == 1.0:
+                        continue
+                    # density = fraction of keys MASKED for a query.  'window': the unmasked keys are one contiguous window
+                    # per query (blob-shaped, what a mask prediction looks like); 'iid': every key masked independently
+                    # (no dead tiles at all -- the worst case for tile skipping)
+                    if kind == 'window':
+                        width = max(1, int(round(K * (1.0 - density))))
+                        masked = torch.ones((B, Q, K), dtype=torch.bool, device=dev)
+                        if density < 1.0:
+                            start = torch.randint(0, K - width + 1, (B, Q), generator=g).to(dev)
+                            idx = torch.arange(K, device=dev)[None, None]
+                            masked = ~((idx >= start[..., None]) & (idx < start[..., None] + width))
+                    else:
+                        masked = (torch.rand((B, Q, K), generator=g) < density).to(dev)
+                    am = masked.all(-1).to(torch.uint8).contiguous()
+                    bits = packbits(masked)
+                    ms = timeit(lambda: rt.masked_attention(q, k, v, bits, am), reps=10)
+                    eff = float((~masked).float().mean()) if density < 1.0 else 1.0     # fallback rows attend everywhere
+                    emit(bench='masked_attention', Q=Q, size=size, batch=B, level=lvl, keys=K, mask_kind=kind,
+                         masked_fraction=density, ms=ms, dense_tflops=4.0 * B * HEADS * Q * K * 32 / ms / 1e9,
+                         attended_fraction=eff)
         del head, rt, mfd, memd
         torch.cuda.empty_cache()
 fout.close()
