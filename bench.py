@@ -380,7 +380,7 @@ def matching_leg(dev, B=2, Q=200, ncls1=118, G=20, h=256, w=256, P=12544):
 
 def train_leg(args, rank, world, dev):
     """BASELINE configs[3]: OSPS head (200 queries, 118 class rows), forward + backward of the decoder head with the
-    caption-grounding loss on every head call (weight 2.0) + class-embedding CE + a mask surrogate, per-GPU batch 2
+    caption-grounding loss on every head call (weight 2.0) + class-embedding CE + a point-sampled mask BCE, per-GPU batch 2
     (coco_panoptic_p20.py:236), bucketed NCCL all-reduce of the 14.7 M head gradients overlapped with the backward.
     Contractions on tcgen05 (kind::tf32), the whole step replayed as one CUDA graph; the same step issued eagerly and
     the same step as plain torch CUDA ops (the oracle on the GPU, TF32 matmuls: what the reference executes) beside it."""
@@ -399,7 +399,11 @@ def train_leg(args, rank, world, dev):
     cap_mask = cap_mask.to(dev)
     g = torch.Generator().manual_seed(rank)
     labels = torch.randint(0, ncls1, (B, Q), generator=g).to(dev)
-    targets = (torch.rand((B, Q, H // 4, W // 4), generator=g) > 0.5).to(dev).float()
+    # mask surrogate: BCE on 12 544 points sampled from every query's mask logits (the reference's mask losses are
+    # point-sampled too, head.py:600-627; its Hungarian matching needs the host and is timed separately below)
+    from cgg_b200.matching import point_sample
+    coords = torch.rand((1, 12544, 2), generator=g).to(dev)
+    targets = (torch.rand((B * Q, 12544), generator=g) > 0.5).to(dev).float()
     reducer = GradReducer(head.parameters())
     ce, bce = torch.nn.functional.cross_entropy, torch.nn.functional.binary_cross_entropy_with_logits
 
@@ -410,7 +414,7 @@ def train_leg(args, rank, world, dev):
         for j in range(len(cls)):
             loss = loss + grounding_loss(preds_all[j], embs_all, mask_all, 10.0, 2.0)
             loss = loss + ce(similarity(emb[j].reshape(B * Q, -1), head.class_embs, 0.1), labels.reshape(-1))
-            loss = loss + bce(mask[j], targets)
+            loss = loss + bce(point_sample(mask[j].view(B * Q, H // 4, W // 4), coords), targets)
         return loss
 
     def eager_step():
@@ -482,13 +486,14 @@ def train_leg(args, rank, world, dev):
         out['cuda_graph'] = True
     out.update(ms_per_step=ms, images_per_s=world * B / (ms * 1e-3),
                note='forward + backward through cgg_b200.train (every node a C-ABI kernel; contractions on tcgen05 '
-                    'kind::tf32), losses: grounding x10 + class-embedding CE x10 + mask BCE surrogate x10; optimizer step '
+                    'kind::tf32), losses: grounding x10 + class-embedding CE x10 + point-sampled mask BCE x10; optimizer step '
                     'excluded; bucketed NCCL all-reduce overlapped with the backward%s'
                     % (', the whole step one CUDA graph' if out.get('cuda_graph') else ''))
     reducer.remove()
     if rank == 0 and not args.no_torch_baseline:
         # the same step as plain torch CUDA ops: the oracle on this GPU (single process, no all-reduce)
         from oracle import cgg_oracle as O
+        from oracle import matching_oracle as MO
         sd_t = {k: v.to(dev).requires_grad_(k != 'class_embs') for k, v in sd.items()}
 
         def torch_step():
@@ -499,7 +504,8 @@ def train_leg(args, rank, world, dev):
             for j in range(10):
                 loss = loss + O.grounding_loss(ref['emb'][j], cap, cap_mask, 10.0, 2.0)
                 loss = loss + ce(O.cls_emb_logits(ref['emb'][j].reshape(B * Q, -1), sd_t['class_embs'], 10.0), labels.reshape(-1))
-                loss = loss + bce(ref['mask'][j], targets)
+                loss = loss + bce(MO.point_sample(ref['mask'][j].flatten(0, 1).unsqueeze(1), coords.expand(B * Q, -1, -1)).squeeze(1),
+                                  targets)
             loss.backward()
 
         res = {}

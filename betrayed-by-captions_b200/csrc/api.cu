@@ -746,6 +746,7 @@ extern "C" int cgg_gemm_f32(cgg_handle* h, const cgg_gemm_desc* d, void* stream)
     if (d->batch % d->batch_inner) return fail(h, CGG_ERR_BAD_SHAPE, "batch must be a multiple of batch_inner");
     p.batch_inner = d->batch_inner; p.sAb2 = d->sAb2; p.sWb2 = d->sWb2; p.sCb2 = d->sCb2;
   }
+  p.accumulate = d->accumulate != 0;
   if (d->tf32) {
     if (!h->tf32 && !(h->tf32 = tf32_create())) return fail(h, CGG_ERR_CUDA, "tf32_create failed");
     const int r = launch_gemm_tf32(h->tf32, p, (cudaStream_t)stream);

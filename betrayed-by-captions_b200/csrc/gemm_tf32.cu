@@ -44,6 +44,7 @@ struct Tf32P {
   int relu_from;
   float* partial;              // != nullptr: raw accumulators to partial[((split*batch + b)*M + m)*N + n]
   int epi_mode;                // 1: float4 rows, 2: m-contiguous C, 0: scalar
+  int accumulate;              // C += result
 };
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -175,7 +176,8 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
     const int quarter = warp & 3;
     const float* __restrict__ bias = p.bias;
     const float* __restrict__ R = p.R;
-    const bool plain = !p.partial && !bias && !R && p.alpha == 1.0f && p.relu_from >= p.N;
+    const bool plain = !p.partial && !bias && !R && p.alpha == 1.0f && p.relu_from >= p.N && !p.accumulate;
+    const bool plain_acc = !p.partial && !bias && !R && p.alpha == 1.0f && p.relu_from >= p.N && p.accumulate;
     uint32_t lt = 0;
     for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
       int m0, n0, b, split;
@@ -188,61 +190,95 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       float* crow = p.partial ? p.partial + (((long)split * p.batch + b) * p.M + gm) * p.N
                               : p.C + (long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2 + (long)gm * p.sCm;
       const float* rrow = (R && !p.partial) ? R + (long)b * p.sRb + (long)(p.r_mod >= p.M ? gm : gm % p.r_mod) * p.sRm : nullptr;
-      for (int j = 0; j < p.n_tile; j += 32) {
-        if (n0 + j >= p.N) break;
-        float v[32];
-        const uint32_t taddr = tmem + buf * (uint32_t)acc_cols + ((uint32_t)(quarter * 32) << 16) + (uint32_t)j;
-        ptx::tmem_ld16(taddr, v);
-        if (j + 16 < p.n_tile) ptx::tmem_ld16(taddr + 16, v + 16);
+      // The accumulator is read 32 columns at a time; the tcgen05.ld of the next chunk is in flight while the current
+      // chunk's stores are issued (two register sets, loop unrolled by two so that both stay in registers).
+      const uint32_t tbase = tmem + buf * (uint32_t)acc_cols + ((uint32_t)(quarter * 32) << 16);
+      auto issue = [&](uint32_t* r, int j) {
+        ptx::tmem_ld16_issue(tbase + (uint32_t)j, r);
+        if (j + 16 < p.n_tile) ptx::tmem_ld16_issue(tbase + (uint32_t)j + 16, r + 16);
         else
 #pragma unroll
-          for (int i = 16; i < 32; ++i) v[i] = 0.f;
-        if (!rowok) continue;
-        if (p.epi_mode == 1) {
-          const int nq = min(8, (p.N - (n0 + j)) >> 2);          // float4 groups of this chunk inside N
-          float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
-          if (p.partial || plain) {
+          for (int i = 16; i < 32; ++i) r[i] = 0u;
+      };
+      auto waitr = [&](uint32_t* r) { ptx::tmem_ld_wait16(r); ptx::tmem_ld_wait16(r + 16); };
+      auto process = [&](const uint32_t* r, int j) {
+        if (!rowok) return;
+        float v[32];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4)
-              if (c4 < nq) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.epi_mode == 1) {
+            const int nq = min(8, (p.N - (n0 + j)) >> 2);          // float4 groups of this chunk inside N
+            float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+            if (p.partial || plain) {
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                if (c4 < nq) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            } else {
+              // all loads of the chunk are issued before the first store (the stores could alias them for all the compiler knows)
+              float4 bv[8], rv[8];
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                bv[c4] = (bias && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rv[c4] = (rrow && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              const bool relu = n0 + j >= p.relu_from;             // relu_from is a multiple of 32 here (0 or "never")
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                float4 o;
+                o.x = (v[4 * c4] + bv[c4].x) * p.alpha + rv[c4].x;
+                o.y = (v[4 * c4 + 1] + bv[c4].y) * p.alpha + rv[c4].y;
+                o.z = (v[4 * c4 + 2] + bv[c4].z) * p.alpha + rv[c4].z;
+                o.w = (v[4 * c4 + 3] + bv[c4].w) * p.alpha + rv[c4].w;
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (c4 < nq) dst[c4] = o;
+              }
+            }
+          } else if (p.epi_mode == 2 && plain) {
+            float* cp = crow + (long)(n0 + j) * p.sCn;
+            const int nc = min(32, p.N - (n0 + j));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nc) *cp = v[i];
+              cp += p.sCn;
+            }
+          } else if (p.epi_mode == 2 && plain_acc) {       // C += acc: the chunk's 32 old values are read before any store
+            float* cp = crow + (long)(n0 + j) * p.sCn;
+            const int nc = min(32, p.N - (n0 + j));
+            float old[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) old[i] = (i < nc) ? cp[(long)i * p.sCn] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nc) cp[(long)i * p.sCn] = old[i] + v[i];
           } else {
-            // all loads of the chunk are issued before the first store (the stores could alias them for all the compiler knows)
-            float4 bv[8], rv[8];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              bv[c4] = (bias && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-              rv[c4] = (rrow && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const bool relu = n0 + j >= p.relu_from;             // relu_from is a multiple of 32 here (0 or "never")
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              float4 o;
-              o.x = (v[4 * c4] + bv[c4].x) * p.alpha + rv[c4].x;
-              o.y = (v[4 * c4 + 1] + bv[c4].y) * p.alpha + rv[c4].y;
-              o.z = (v[4 * c4 + 2] + bv[c4].z) * p.alpha + rv[c4].z;
-              o.w = (v[4 * c4 + 3] + bv[c4].w) * p.alpha + rv[c4].w;
-              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (c4 < nq) dst[c4] = o;
+            for (int i = 0; i < 32; ++i) {
+              const int gn = n0 + j + i;
+              if (gn < p.N) {
+                if (p.partial) crow[gn] = v[i];
+                else crow[(long)gn * p.sCn] = epi_value(p, v[i], b, gm, gn) + (p.accumulate ? crow[(long)gn * p.sCn] : 0.f);
+              }
             }
           }
-        } else if (p.epi_mode == 2 && plain) {
-          float* cp = crow + (long)(n0 + j) * p.sCn;
-          const int nc = min(32, p.N - (n0 + j));
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < nc) *cp = v[i];
-            cp += p.sCn;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int gn = n0 + j + i;
-            if (gn < p.N) {
-              if (p.partial) crow[gn] = v[i];
-              else crow[(long)gn * p.sCn] = epi_value(p, v[i], b, gm, gn);
-            }
-          }
-        }
+      };
+      auto more_after = [&](int j) { return j + 32 < p.n_tile && n0 + j + 32 < p.N; };
+      uint32_t ra[32], rb[32];
+      int j = 0;
+      issue(ra, 0);
+      waitr(ra);
+      while (true) {
+        bool more = more_after(j);
+        if (more) issue(rb, j + 32);
+        process(ra, j);
+        if (!more) break;
+        waitr(rb);
+        j += 32;
+        more = more_after(j);
+        if (more) issue(ra, j + 32);
+        process(rb, j);
+        if (!more) break;
+        waitr(ra);
+        j += 32;
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -263,8 +299,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const Tf32P p) {
   const long bm = i / p.N;
   const int gm = (int)(bm % p.M);
   const int b = (int)(bm / p.M);
-  p.C[(long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2 + (long)gm * p.sCm + (long)gn * p.sCn] =
-      epi_value(p, acc, b, gm, gn);
+  float* c = p.C + (long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2 + (long)gm * p.sCm + (long)gn * p.sCn;
+  *c = epi_value(p, acc, b, gm, gn) + (p.accumulate ? *c : 0.f);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -381,6 +417,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   p.bias = g.bias; p.alpha = g.alpha;
   p.R = g.R; p.sRb = g.sRb; p.sRm = g.sRm; p.sRn = g.sRn; p.r_mod = g.r_mod > 0 ? g.r_mod : 1; p.r_ncols = g.r_ncols;
   p.relu_from = g.relu_from;
+  p.accumulate = g.accumulate ? 1 : 0;
   if (p.splits > 1) {
     const size_t need = (size_t)p.splits * g.batch * g.M * g.N * sizeof(float);
     if (need > t->partial_bytes) {
@@ -399,7 +436,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.partial) p.epi_mode = (g.N % 4 == 0) ? 1 : 0;
-  else if (g.sCn == 1 && g.sCm % 4 == 0 && g.sCb % 4 == 0 && g.sCb2 % 4 == 0 && g.N % 4 == 0 && al16(g.C) && (!g.bias || al16(g.bias)) &&
+  else if (!g.accumulate && g.sCn == 1 && g.sCm % 4 == 0 && g.sCb % 4 == 0 && g.sCb2 % 4 == 0 && g.N % 4 == 0 && al16(g.C) && (!g.bias || al16(g.bias)) &&
            (!g.R || (g.sRn == 1 && g.sRm % 4 == 0 && g.sRb % 4 == 0 && al16(g.R) && g.r_ncols >= g.N)) &&
            (g.relu_from % 32 == 0))
     p.epi_mode = 1;

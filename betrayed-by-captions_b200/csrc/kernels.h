@@ -27,6 +27,7 @@ struct GemmF32 {
   int M = 0, N = 0, K = 0, batch = 1;
   // two-level batch: z in [0, batch) -> (z / batch_inner) * sXb + (z % batch_inner) * sXb2 for A, W and C (R: z * sRb)
   int batch_inner = 1; long sAb2 = 0, sWb2 = 0, sCb2 = 0;
+  bool accumulate = false;   // C = epi(...) + C  (gradient accumulation in place)
   int relu_from = 1 << 30;   // relu applied to columns n >= relu_from
   float alpha = 1.f;
   bool a_mmajor = false, c_mmajor = false;

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
       v *= p.alpha;
       if (R && gn < p.r_ncols) v += R[(long)(gm % p.r_mod) * p.sRm + (long)gn * p.sRn];
       if (gn >= p.relu_from) v = fmaxf(v, 0.f);
+      if (p.accumulate) v += C[(long)gm * p.sCm + (long)gn * p.sCn];
       C[(long)gm * p.sCm + (long)gn * p.sCn] = v;
     }
   }

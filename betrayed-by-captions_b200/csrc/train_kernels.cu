@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(256) attn_rowstats_kernel(const float* __restr
 //
 // P = softmax over the unmasked keys of a row, in place (bit = 1 in the bitmap excludes the key, unless the row's
 // all_masked flag is set: mask2former_head.py:825-826).  One CTA per row; the row (<= 144 KB) is re-read from L1/L2.
+template <bool CACHED>
 __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restrict__ S, const uint32_t* __restrict__ bitmap,
                                                                 const uint8_t* __restrict__ all_masked, int heads, int Q,
                                                                 int K) {
+  extern __shared__ float srow[];                       // CACHED: the row (K floats), read from HBM once
   __shared__ float red[8];
   __shared__ float bcast;
   const long r = blockIdx.x;                            // (b, h, q)
@@ -254,8 +256,11 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restric
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   auto masked = [&](int k) { return brow && ((brow[k >> 5] >> (k & 31)) & 1u); };
   float m = -INFINITY;
-  for (int k = t; k < K; k += 256)
-    if (!masked(k)) m = fmaxf(m, row[k]);
+  for (int k = t; k < K; k += 256) {
+    const float v = masked(k) ? -INFINITY : row[k];
+    if (CACHED) srow[k] = v;
+    m = fmaxf(m, v);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) red[warp] = m;
@@ -269,8 +274,12 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restric
   m = bcast;
   float l = 0.f;
   if (m != -INFINITY)
-    for (int k = t; k < K; k += 256)
-      if (!masked(k)) l += expf(row[k] - m);
+    for (int k = t; k < K; k += 256) {
+      const float v = CACHED ? srow[k] : (masked(k) ? -INFINITY : row[k]);
+      const float e = expf(v - m);                      // exp(-inf) = 0 for the masked keys
+      if (CACHED) srow[k] = e;
+      l += e;
+    }
   l = warp_sum(l);
   __syncthreads();
   if (lane == 0) red[warp] = l;
@@ -283,7 +292,12 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(float* __restric
   __syncthreads();
   l = bcast;
   const float inv = l > 0.f ? 1.f / l : 0.f;
-  for (int k = t; k < K; k += 256) row[k] = (m != -INFINITY && !masked(k)) ? expf(row[k] - m) * inv : 0.f;
+  for (int k = t; k < K; k += 256) {
+    float e;
+    if (CACHED) e = (m != -INFINITY) ? srow[k] : 0.f;
+    else e = (m != -INFINITY && !masked(k)) ? expf(row[k] - m) : 0.f;
+    row[k] = e * inv;
+  }
 }
 
 // dS = P o (dP - D), D[b,h,q] = dO[b,q,h,:] . O[b,q,h,:]; written over dP.
@@ -429,7 +443,18 @@ cudaError_t launch_attn_softmax_rows(float* S, const uint32_t* bitmap, const uin
                                      int K, cudaStream_t s) {
   const long rows = (long)B * heads * Q;
   if (rows <= 0 || K <= 0) return cudaSuccess;
-  attn_softmax_rows_kernel<<<(unsigned)rows, 256, 0, s>>>(S, bitmap, all_masked, heads, Q, K);
+  const size_t smem = (size_t)K * sizeof(float);
+  if (smem <= 96 * 1024) {                              // row cached in shared memory: one HBM read, one write
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(attn_softmax_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return e;
+      attr = true;
+    }
+    attn_softmax_rows_kernel<true><<<(unsigned)rows, 256, smem, s>>>(S, bitmap, all_masked, heads, Q, K);
+  } else {
+    attn_softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, s>>>(S, bitmap, all_masked, heads, Q, K);
+  }
   count_launch();
   return cudaGetLastError();
 }

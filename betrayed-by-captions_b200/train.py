@@ -41,7 +41,7 @@ class _K:
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
     def gemm(self, A, sA, W, sW, Cc, sC, M, N, K, batch=1, bias=None, R=None, sR=(0, 0, 0), r_mod=None, alpha=1.0,
-             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0)):
+             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0), accumulate=False):
         """C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); element strides
         sA = (b, m, k), sW = (b, n, k), sC = (b, m, n), sR = (b, m, n)."""
         d = _lib.GemmDesc()
@@ -61,6 +61,7 @@ class _K:
         d.a_mmajor, d.c_mmajor = int(a_mmajor), int(c_mmajor)
         d.tf32 = self.tf32
         d.batch_inner, (d.sAb2, d.sWb2, d.sCb2) = batch_inner, s2     # (image, head) batches: inner strides of A, W, C
+        d.accumulate = int(accumulate)                                # C += result (in-place gradient accumulation)
         self.chk(self.lib.cgg_gemm_f32(self.h, C.byref(d), self.s()), 'cgg_gemm_f32')
 
 
@@ -306,24 +307,33 @@ class _AttentionViews(torch.autograd.Function):
         return None, dq, dk, dv, None, None
 
 
+class _GradSink:
+    """One gradient buffer shared by the nodes of a step that all contribute to the same input (the mask features feed the
+    einsum of all 10 head calls): the first backward to run creates it and hands it to autograd, the later ones add into
+    it in place (GEMM epilogue `accumulate`) and return nothing -- instead of 10 full-size gradients summed pairwise."""
+
+    def __init__(self):
+        self.buf = None
+
+
 class _MaskEinsum(torch.autograd.Function):
     """mask_pred[b,q,p] = sum_c me[b,q,c] F[b,c,p]  (head.py:748).  me (B, Q, C), F (B, C, H4, W4)."""
 
     @staticmethod
-    def forward(ctx, k, me, F):
+    def forward(ctx, k, me, F, sink=None):
         B, Q, Cc = me.shape
         H4, W4 = F.shape[-2:]
         HW = H4 * W4
         out = k.new(B, Q, H4, W4)
         k.gemm(F, (Cc * HW, 1, HW), me, (Q * Cc, Cc, 1), out, (Q * HW, 1, HW), HW, Q, Cc, batch=B, a_mmajor=True,
                c_mmajor=True)
-        ctx.k = k
+        ctx.k, ctx.sink = k, sink
         ctx.save_for_backward(me, F)
         return out
 
     @staticmethod
     def backward(ctx, dmask):
-        k = ctx.k
+        k, sink = ctx.k, ctx.sink
         me, F = ctx.saved_tensors
         B, Q, Cc = me.shape
         H4, W4 = F.shape[-2:]
@@ -334,10 +344,15 @@ class _MaskEinsum(torch.autograd.Function):
             dme = k.new(B, Q, Cc)
             k.gemm(dmask, (Q * HW, HW, 1), F, (Cc * HW, HW, 1), dme, (Q * Cc, Cc, 1), Q, Cc, HW, batch=B)
         if ctx.needs_input_grad[2]:                       # dF[b,c,p] = sum_q me[b,q,c] dmask[b,q,p]
-            dF = k.new(B, Cc, H4, W4)
-            k.gemm(dmask, (Q * HW, 1, HW), me, (Q * Cc, 1, Cc), dF, (Cc * HW, 1, HW), HW, Cc, Q, batch=B, a_mmajor=True,
-                   c_mmajor=True)
-        return None, dme, dF
+            first = sink is None or sink.buf is None
+            dst = k.new(B, Cc, H4, W4) if first else sink.buf
+            k.gemm(dmask, (Q * HW, 1, HW), me, (Q * Cc, 1, Cc), dst, (Cc * HW, 1, HW), HW, Cc, Q, batch=B, a_mmajor=True,
+                   c_mmajor=True, accumulate=not first)
+            if first:
+                dF = dst
+                if sink is not None:
+                    sink.buf = dst
+        return None, dme, dF, None
 
 
 # --------------------------------------------------------------------------------------------- the forward
@@ -373,6 +388,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
 
     attention = _AttentionGemm if k.tf32 else _Attention          # fp32: the flash-style FMA kernels (exact mode)
     cls_list, emb_list, mask_list = [], [], []
+    mf_sink = _GradSink()
 
     def head_call(x, lvl):
         """forward_head, head.py:711-761; returns the detached attention-mask bitmap for level lvl."""
@@ -380,7 +396,7 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
         cls = lin(z, head.cls_embed).view(B, Q, -1)
         emb = lin(z, head.v2l_transform).view(B, Q, -1) if head.use_class_emb else cls
         me = lin(lin(lin(z, head.mask_embed[0], relu=True), head.mask_embed[2], relu=True), head.mask_embed[4])
-        mask = _MaskEinsum.apply(k, me.view(B, Q, Cc), mf)
+        mask = _MaskEinsum.apply(k, me.view(B, Q, Cc), mf, mf_sink)
         cls_list.append(cls), emb_list.append(emb), mask_list.append(mask)
         if lvl is None:
             return None, None

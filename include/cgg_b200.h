@@ -250,6 +250,7 @@ typedef struct {
   int batch_inner;            /* two-level batch (0 or 1 = off): item z of A / W / C sits at (z / batch_inner) * sXb +
                                * (z % batch_inner) * sXb2 -- (image, head) batches of the attention products */
   long sAb2, sWb2, sCb2;
+  int accumulate;             /* 1: C = (the above) + C, in place (a gradient that several products contribute to) */
 } cgg_gemm_desc;
 int cgg_gemm_f32(cgg_handle *h, const cgg_gemm_desc *d, void *stream);
 
