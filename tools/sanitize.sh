@@ -20,3 +20,9 @@ run memcheck_fp32 memcheck "tests/test_gpu_parity.py -k \"mask_bits_stage or mas
 run memcheck_train memcheck "tests/test_gpu_train.py -k dispatch"
 run racecheck_attention racecheck "tests/test_gpu_bf16.py -k \"attention_stage and 64-0.5\""
 run racecheck_einsum racecheck "tests/test_gpu_bf16.py -k batched_einsum"
+# round 2c: the tf32 GEMM (all operand-major pairs, split-K, two-level batches), the attention row kernels, the matching
+# and caption kernels
+run memcheck_tf32 memcheck "tests/test_gpu_tf32.py -k \"True or two_level or 24-20\""
+run memcheck_matching memcheck "tests/test_gpu_matching.py -k \"point_sample or cost or 1-gts0 or fixture\""
+run memcheck_caption memcheck "tests/test_gpu_caption.py -k \"fp32\""
+run racecheck_tf32 racecheck "tests/test_gpu_tf32.py -k \"case0 and True\""
