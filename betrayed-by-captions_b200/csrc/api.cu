@@ -747,6 +747,7 @@ extern "C" int cgg_gemm_f32(cgg_handle* h, const cgg_gemm_desc* d, void* stream)
     p.batch_inner = d->batch_inner; p.sAb2 = d->sAb2; p.sWb2 = d->sWb2; p.sCb2 = d->sCb2;
   }
   p.accumulate = d->accumulate != 0;
+  p.slot = d->slot;
   if (d->tf32) {
     if (!h->tf32 && !(h->tf32 = tf32_create())) return fail(h, CGG_ERR_CUDA, "tf32_create failed");
     const int r = launch_gemm_tf32(h->tf32, p, (cudaStream_t)stream);
@@ -805,10 +806,11 @@ extern "C" int cgg_sum_batch(cgg_handle* h, const float* g, float* out, int batc
   return CGG_OK;
 }
 
-extern "C" int cgg_colsum(cgg_handle* h, const float* g, float* out, long rows, int n, float alpha, void* stream) {
+extern "C" int cgg_colsum(cgg_handle* h, const float* g, float* out, long rows, int n, float alpha, int accumulate,
+                          void* stream) {
   if (!h || !g || !out) return CGG_ERR_NULL;
   if (rows < 0 || n < 1 || (rows + 255) / 256 > 65535) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
-  CU(launch_colsum(g, out, rows, n, alpha, (cudaStream_t)stream));
+  CU(launch_colsum(g, out, rows, n, alpha, (cudaStream_t)stream, accumulate != 0));
   return CGG_OK;
 }
 

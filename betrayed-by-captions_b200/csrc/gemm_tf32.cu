@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
               for (int c4 = 0; c4 < 8; ++c4) {
                 bv[c4] = (bias && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 rv[c4] = (rrow && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.accumulate && c4 < nq) {             // C += ...: the old values ride in the residual registers
+                  const float4 ov = dst[c4];
+                  rv[c4].x += ov.x; rv[c4].y += ov.y; rv[c4].z += ov.z; rv[c4].w += ov.w;
+                }
               }
               const bool relu = n0 + j >= p.relu_from;             // relu_from is a multiple of 32 here (0 or "never")
 #pragma unroll
@@ -325,8 +329,10 @@ int operand_major(const float* base, long sb, long sb2, long sr, long sk, int ro
 
 struct Tf32Ctx {
   EncodeTiledFn encode = nullptr;
-  float* partial = nullptr;
-  size_t partial_bytes = 0;
+  // split-K partial sums: one buffer per workspace slot (GemmF32::slot) -- products issued on two streams at once (the
+  // weight-gradient products run on a side stream) must not share one
+  float* partial[2] = {nullptr, nullptr};
+  size_t partial_bytes[2] = {0, 0};
   int sm_count = 148;
   bool attr_set = false;
   std::string err;
@@ -349,7 +355,7 @@ Tf32Ctx* tf32_create() {
 }
 void tf32_destroy(Tf32Ctx* t) {
   if (!t) return;
-  if (t->partial) cudaFree(t->partial);
+  for (int i = 0; i < 2; ++i) if (t->partial[i]) cudaFree(t->partial[i]);
   delete t;
 }
 const char* tf32_last_error(const Tf32Ctx* t) { return t ? t->err.c_str() : ""; }
@@ -420,15 +426,16 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   p.accumulate = g.accumulate ? 1 : 0;
   if (p.splits > 1) {
     const size_t need = (size_t)p.splits * g.batch * g.M * g.N * sizeof(float);
-    if (need > t->partial_bytes) {
+    const int slot = g.slot ? 1 : 0;
+    if (need > t->partial_bytes[slot]) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(s, &cs);
       if (cs != cudaStreamCaptureStatusNone) { t->err = "split-K buffer must be sized by an eager step before graph capture"; return -1; }
-      if (t->partial) { cudaDeviceSynchronize(); cudaFree(t->partial); t->partial = nullptr; t->partial_bytes = 0; }
-      if (cudaMalloc(&t->partial, need) != cudaSuccess) { t->err = "cudaMalloc(split-K partials) failed"; return -1; }
-      t->partial_bytes = need;
+      if (t->partial[slot]) { cudaDeviceSynchronize(); cudaFree(t->partial[slot]); t->partial[slot] = nullptr; t->partial_bytes[slot] = 0; }
+      if (cudaMalloc(&t->partial[slot], need) != cudaSuccess) { t->err = "cudaMalloc(split-K partials) failed"; return -1; }
+      t->partial_bytes[slot] = need;
     }
-    p.partial = t->partial;
+    p.partial = t->partial[slot];
   }
   CUtensorMap mA, mB;
   if (make_map(t, &mA, g.A, a_major, g.sAb, g.sAb2, g.sAm, g.sAk, g.M, g.K, g.batch, p.batch_inner, BM)) return -1;
@@ -436,7 +443,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.partial) p.epi_mode = (g.N % 4 == 0) ? 1 : 0;
-  else if (!g.accumulate && g.sCn == 1 && g.sCm % 4 == 0 && g.sCb % 4 == 0 && g.sCb2 % 4 == 0 && g.N % 4 == 0 && al16(g.C) && (!g.bias || al16(g.bias)) &&
+  else if (g.sCn == 1 && g.sCm % 4 == 0 && g.sCb % 4 == 0 && g.sCb2 % 4 == 0 && g.N % 4 == 0 && al16(g.C) && (!g.bias || al16(g.bias)) &&
            (!g.R || (g.sRn == 1 && g.sRm % 4 == 0 && g.sRb % 4 == 0 && al16(g.R) && g.r_ncols >= g.N)) &&
            (g.relu_from % 32 == 0))
     p.epi_mode = 1;

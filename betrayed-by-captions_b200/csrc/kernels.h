@@ -28,6 +28,7 @@ struct GemmF32 {
   // two-level batch: z in [0, batch) -> (z / batch_inner) * sXb + (z % batch_inner) * sXb2 for A, W and C (R: z * sRb)
   int batch_inner = 1; long sAb2 = 0, sWb2 = 0, sCb2 = 0;
   bool accumulate = false;   // C = epi(...) + C  (gradient accumulation in place)
+  int slot = 0;              // workspace slot of the split-K partial sums (one per concurrently used stream)
   int relu_from = 1 << 30;   // relu applied to columns n >= relu_from
   float alpha = 1.f;
   bool a_mmajor = false, c_mmajor = false;
@@ -83,7 +84,7 @@ cudaError_t launch_sum_batch(const float* g, float* out, int batch, long per, cu
 cudaError_t launch_mem_prep(const float* mem, const float* level, const float* pos_level, float* key_in, float* val_in,
                             int B, int C, int K, cudaStream_t s);
 cudaError_t launch_mem_prep_bwd(const float* dkey, const float* dval, float* dmem, int B, int C, int K, cudaStream_t s);
-cudaError_t launch_colsum(const float* g, float* out, long rows, int n, float alpha, cudaStream_t s);
+cudaError_t launch_colsum(const float* g, float* out, long rows, int n, float alpha, cudaStream_t s, bool accumulate = false);
 // lse, dsum: (B, heads, Q) scratch each
 cudaError_t launch_attention_bwd(const float* q, const float* k, const float* v, long kv_stride, long kv_bstride,
                                  const uint32_t* bitmap, const uint8_t* all_masked, const float* o, const float* dout,

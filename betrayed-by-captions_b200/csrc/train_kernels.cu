@@ -525,9 +525,9 @@ cudaError_t launch_mem_prep_bwd(const float* dkey, const float* dval, float* dme
   return cudaGetLastError();
 }
 
-cudaError_t launch_colsum(const float* g, float* out, long rows, int n, float alpha, cudaStream_t s) {
+cudaError_t launch_colsum(const float* g, float* out, long rows, int n, float alpha, cudaStream_t s, bool accumulate) {
   if (n <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), s);
+  cudaError_t e = accumulate ? cudaSuccess : cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), s);
   if (e != cudaSuccess || rows <= 0) return e;
   colsum_kernel<<<dim3((n + 31) / 32, (unsigned)((rows + 255) / 256)), 256, 0, s>>>(g, out, rows, n, alpha);
   count_launch();

@@ -117,6 +117,10 @@ class Mask2FormerHeadOpenB200(nn.Module):
         self.train_precision = kwargs.get('train_precision', 'tf32' if precision == 'bf16' else 'fp32')
         if self.train_precision not in ('fp32', 'tf32'):
             raise ValueError("train_precision must be 'fp32' or 'tf32'")
+        # weight / bias gradients of the linear layers accumulated straight into the .grad tensors on a side stream
+        # (train._WgradSide): True = for parameters managed by a train.GradReducer, 'always' = whenever .grad exists at
+        # forward time, False = never (everything through autograd)
+        self.fused_wgrad = kwargs.get('fused_wgrad', True)
         self.text_emb_norm = kwargs.get('text_emb_norm', True)
         self.pixel_decoder = pixel_decoder if isinstance(pixel_decoder, nn.Module) else None
         # ---- parameters under the reference's names

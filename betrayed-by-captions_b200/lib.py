@@ -54,7 +54,7 @@ class GemmDesc(C.Structure):
                 ('C', C.c_void_p), ('sCb', C.c_long), ('sCm', C.c_long), ('sCn', C.c_long),
                 ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch', C.c_int),
                 ('relu', C.c_int), ('alpha', C.c_float), ('a_mmajor', C.c_int), ('c_mmajor', C.c_int), ('tf32', C.c_int),
-                ('batch_inner', C.c_int), ('sAb2', C.c_long), ('sWb2', C.c_long), ('sCb2', C.c_long), ('accumulate', C.c_int)]
+                ('batch_inner', C.c_int), ('sAb2', C.c_long), ('sWb2', C.c_long), ('sCb2', C.c_long), ('accumulate', C.c_int), ('slot', C.c_int)]
 
 
 class CggError(RuntimeError):
@@ -113,7 +113,7 @@ def load():
     lib.cgg_axpy.argtypes = [vp, vp, vp, lg, f32, vp]
     lib.cgg_add_rows.argtypes = [vp, vp, vp, vp, i, lg, vp]
     lib.cgg_sum_batch.argtypes = [vp, vp, vp, i, lg, vp]
-    lib.cgg_colsum.argtypes = [vp, vp, vp, lg, i, f32, vp]
+    lib.cgg_colsum.argtypes = [vp, vp, vp, lg, i, f32, i, vp]
     lib.cgg_mem_prep.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cgg_mem_prep_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp]
     lib.cgg_sine_pos.argtypes = [vp, vp, i, i, i, vp]

@@ -30,6 +30,8 @@ class _K:
     def __init__(self, rt, tf32=False):
         self.rt, self.lib, self.h, self.dev = rt, rt.lib, rt.handle, rt.device
         self.tf32 = int(bool(tf32))      # contractions on tcgen05 kind::tf32 MMAs instead of fp32 FMAs
+        self.slot = 0
+        self.wgrad = None                # _WgradSide of the step being recorded (fused weight gradients), or None
 
     def s(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -62,21 +64,97 @@ class _K:
         d.tf32 = self.tf32
         d.batch_inner, (d.sAb2, d.sWb2, d.sCb2) = batch_inner, s2     # (image, head) batches: inner strides of A, W, C
         d.accumulate = int(accumulate)                                # C += result (in-place gradient accumulation)
+        d.slot = self.slot                                            # split-K workspace (1 on the weight-gradient side stream)
         self.chk(self.lib.cgg_gemm_f32(self.h, C.byref(d), self.s()), 'cgg_gemm_f32')
 
 
 # ------------------------------------------------------------------------------------------- autograd nodes
+class _WgradSide:
+    """Weight / bias gradients of the linear layers written straight into the parameters' `.grad` (the GradReducer's
+    bucket views, or any pre-allocated .grad) by the GEMM epilogue (`accumulate`), on a SIDE stream: they are leaves of the
+    backward, so the dX chain on the main stream never waits for them, and autograd's own accumulation kernels
+    (`p.grad += dW`, the slice scatter of the fused in-projections) disappear.  Autograd gets None for these gradients;
+    the reducer (if any) is told directly when a parameter's gradient is complete.  The side stream joins the main stream
+    in an engine callback at the end of the backward."""
+
+    _side = {}
+
+    def __init__(self, dev):
+        if dev not in _WgradSide._side:
+            _WgradSide._side[dev] = torch.cuda.Stream(dev)
+        self.dev, self.stream = dev, _WgradSide._side[dev]
+        self.parts = {}          # parameter -> number of fused products that write into its .grad
+        self.done = {}
+        self.queued = False
+        self.keep = []           # operands of the side-stream products: alive until the join (no allocator reuse under them)
+
+    def target(self, param, view):
+        """Registers `view` (param.grad or a slice of it) as the destination of one fused product; None if not possible."""
+        if view is None:
+            return None
+        self.parts[param] = self.parts.get(param, 0) + 1
+        return (param, view)
+
+    def launch(self, k, fn, keep):
+        """Runs fn() (kernel launches) on the side stream after everything issued so far on the current stream.  Outside
+        a graph capture the products are issued in line instead: the fork / join events would cost the host more than the
+        overlap gives a launch-bound eager step (the in-place accumulation is what matters there)."""
+        if not torch.cuda.is_current_stream_capturing():
+            self.inline = True
+            slot, k.slot = k.slot, 1       # (the side stream's split-K workspace: sized here, before any capture)
+            try:
+                fn()
+            finally:
+                k.slot = slot
+            return
+        self.inline = False
+        main = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        slot = k.slot
+        with torch.cuda.stream(self.stream):
+            k.slot = 1
+            try:
+                fn()
+            finally:
+                k.slot = slot
+        self.keep.extend(keep)
+        if not self.queued:
+            self.queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.join)
+
+    def written(self, param):
+        self.done[param] = self.done.get(param, 0) + 1
+        if self.done[param] == self.parts.get(param, 1):
+            red = _FUSED_REDUCERS.get(param)
+            if red is not None:
+                red.param_done(param, None if getattr(self, 'inline', False) else self.stream)
+
+    def join(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        self.queued = False
+        self.done = {}
+        self.keep = []
+
+
+_FUSED_REDUCERS = {}        # parameter -> GradReducer that must hear about gradients written outside autograd
+
+
 class _Linear(torch.autograd.Function):
-    """y = relu?((x W^T + b) * alpha + res).  x (rows, K) contiguous, W (N, K), res (rows, N) or None."""
+    """y = relu?((x W^T + b) * alpha + res).  x (rows, K) contiguous, W (N, K), res (rows, N) or None.
+    wdst / bdst: optional (parameter, grad view) pairs from _WgradSide.target: the weight / bias gradient is then
+    accumulated into that view on the side stream and None is returned for it."""
 
     @staticmethod
-    def forward(ctx, k, x, W, b, res, alpha, relu):
+    def forward(ctx, k, x, W, b, res, alpha, relu, wdst=None, bdst=None):
         rows, Kd = x.shape
         N = W.shape[0]
         y = k.new(rows, N)
         k.gemm(x, (0, Kd, 1), W, (0, Kd, 1), y, (0, N, 1), rows, N, Kd, bias=b, R=res, sR=(0, N, 1), r_mod=rows,
                alpha=alpha, relu=relu)
         ctx.k, ctx.alpha, ctx.relu, ctx.has_res, ctx.has_b = k, alpha, relu, res is not None, b is not None
+        ctx.wdst, ctx.bdst, ctx.wgrad = wdst, bdst, k.wgrad
         ctx.save_for_backward(x, W, y if relu else None)
         return y
 
@@ -92,17 +170,36 @@ class _Linear(torch.autograd.Function):
             g = k.new(rows, N)
             k.chk(k.lib.cgg_relu_backward(k.h, _p(y), _p(dy), _p(g), rows * N, 1.0, k.s()), 'cgg_relu_backward')
         dx = dW = db = None
+        side = ctx.wgrad
+        fuse_w = side is not None and ctx.wdst is not None and ctx.needs_input_grad[2]
+        fuse_b = side is not None and ctx.bdst is not None and ctx.has_b and ctx.needs_input_grad[3]
+        if fuse_w or fuse_b:
+            def leaves():
+                if fuse_w:                                # W.grad[n,kk] += alpha * sum_m g[m,n] x[m,kk]
+                    k.gemm(g, (0, 1, N), x, (0, 1, Kd), ctx.wdst[1], (0, Kd, 1), N, Kd, rows, alpha=ctx.alpha, a_mmajor=True,
+                           accumulate=True)
+                if fuse_b:
+                    k.chk(k.lib.cgg_colsum(k.h, _p(g), _p(ctx.bdst[1]), rows, N, ctx.alpha, 1, k.s()), 'cgg_colsum')
+            side.launch(k, leaves, (g, x))
+            if fuse_w:
+                side.written(ctx.wdst[0])
+            if fuse_b:
+                side.written(ctx.bdst[0])
         if ctx.needs_input_grad[1]:                       # dx[m,kk] = alpha * sum_n g[m,n] W[n,kk]
             dx = k.new(rows, Kd)
             k.gemm(g, (0, N, 1), W, (0, 1, Kd), dx, (0, Kd, 1), rows, Kd, N, alpha=ctx.alpha)
-        if ctx.needs_input_grad[2]:                       # dW[n,kk] = alpha * sum_m g[m,n] x[m,kk]
+        if ctx.needs_input_grad[2] and not fuse_w:        # dW[n,kk] = alpha * sum_m g[m,n] x[m,kk]
             dW = k.new(N, Kd)
             k.gemm(g, (0, 1, N), x, (0, 1, Kd), dW, (0, Kd, 1), N, Kd, rows, alpha=ctx.alpha, a_mmajor=True)
-        if ctx.has_b and ctx.needs_input_grad[3]:
+        if ctx.has_b and ctx.needs_input_grad[3] and not fuse_b:
             db = k.new(N)
-            k.chk(k.lib.cgg_colsum(k.h, _p(g), _p(db), rows, N, ctx.alpha, k.s()), 'cgg_colsum')
+            k.chk(k.lib.cgg_colsum(k.h, _p(g), _p(db), rows, N, ctx.alpha, 0, k.s()), 'cgg_colsum')
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
-        return None, dx, dW, db, dres, None, None
+        if dres is not None and (fuse_w or fuse_b) and not getattr(side, 'inline', True):
+            # autograd may add the residual stream's other gradients INTO the tensor it is handed, on the main stream,
+            # while the side stream still reads dy: it gets its own copy
+            dres = dy.clone()
+        return None, dx, dW, db, dres, None, None, None, None
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -178,8 +275,8 @@ class _MemPrep(torch.autograd.Function):
             k.chk(k.lib.cgg_mem_prep_backward(k.h, _p(dkey), _p(dval), _p(dmem), B, Cc, K, k.s()), 'cgg_mem_prep_backward')
         if ctx.needs_input_grad[2]:
             a, b2 = k.new(Cc), k.new(Cc)
-            k.chk(k.lib.cgg_colsum(k.h, _p(dkey), _p(a), B * K, Cc, 1.0, k.s()), 'cgg_colsum')
-            k.chk(k.lib.cgg_colsum(k.h, _p(dval), _p(b2), B * K, Cc, 1.0, k.s()), 'cgg_colsum')
+            k.chk(k.lib.cgg_colsum(k.h, _p(dkey), _p(a), B * K, Cc, 1.0, 0, k.s()), 'cgg_colsum')
+            k.chk(k.lib.cgg_colsum(k.h, _p(dval), _p(b2), B * K, Cc, 1.0, 0, k.s()), 'cgg_colsum')
             k.chk(k.lib.cgg_axpy(k.h, _p(b2), _p(a), Cc, 1.0, k.s()), 'cgg_axpy')
             dlevel = a
         return None, dmem, dlevel, None
@@ -379,9 +476,28 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
         pos = [rt.sine_pos(h, w) for (h, w) in sizes]                          # (K_l, C) constants
     prep = [_MemPrep.apply(k, mems[l], head.level_embed.weight[l], pos[l]) for l in range(3)]
 
+    # fused weight gradients: when the parameters already carry a .grad at forward time (GradReducer.zero(), or zeroed by
+    # the caller), the linear layers write dW / db into it on a side stream (see _WgradSide)
+    side = _WgradSide(mask_features.device) if (head.fused_wgrad and torch.is_grad_enabled()) else None
+    k.wgrad = side
+
+    def dst(param, sl=None):
+        # (only for parameters whose gradient bookkeeping is ours -- a GradReducer -- or on request: anything that relies on
+        # autograd's accumulation hooks for these parameters, e.g. torch's DDP, would never see the gradient arrive)
+        if side is None or param.grad is None or not param.requires_grad:
+            return None
+        if param not in _FUSED_REDUCERS and head.fused_wgrad != 'always':
+            return None
+        return side.target(param, param.grad if sl is None else param.grad[sl])
+
     def lin(x, m, res=None, alpha=1.0, relu=False, rows=None):
-        W, b = (m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m
-        return _Linear.apply(k, x, W, b, res, alpha, relu)
+        return _Linear.apply(k, x, m.weight, m.bias, res, alpha, relu, dst(m.weight), dst(m.bias))
+
+    def lin_in(x, attn, part, alpha=1.0):
+        """One third (0 = q, 1 = k, 2 = v) of a fused nn.MultiheadAttention in-projection."""
+        sl = slice(part * Cc, (part + 1) * Cc)
+        return _Linear.apply(k, x, attn.in_proj_weight[sl], attn.in_proj_bias[sl], None, alpha, False,
+                             dst(attn.in_proj_weight, sl), dst(attn.in_proj_bias, sl))
 
     def ln(x, m):
         return _LayerNorm.apply(k, x, m.weight, m.bias, 1e-5)
@@ -416,19 +532,19 @@ def decoder_forward_train(head, mask_features, multi_scale_memorys, forced_attn_
         x2d = x.view(B * Q, Cc)
         # ---- masked cross-attention (mmcv MultiheadAttention wrapper: identity + attn, value gets no pos)
         xq = _AddRows.apply(k, x, qe, B).view(B * Q, Cc)
-        q = _Linear.apply(k, xq, ca.in_proj_weight[:Cc], ca.in_proj_bias[:Cc], None, scale, False)
-        kk = _Linear.apply(k, key_in.view(B * K, Cc), ca.in_proj_weight[Cc:2 * Cc], ca.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
-        vv = _Linear.apply(k, val_in.view(B * K, Cc), ca.in_proj_weight[2 * Cc:], ca.in_proj_bias[2 * Cc:], None, 1.0, False)
+        q = lin_in(xq, ca, 0, scale)
+        kk = lin_in(key_in.view(B * K, Cc), ca, 1)
+        vv = lin_in(val_in.view(B * K, Cc), ca, 2)
         o = attention.apply(k, q.view(B, Q, Cc), kk.view(B, K, Cc), vv.view(B, K, Cc), bm, am)
-        t = _Linear.apply(k, o.view(B * Q, Cc), ca.out_proj.weight, ca.out_proj.bias, x2d, 1.0, False)
+        t = lin(o.view(B * Q, Cc), ca.out_proj, res=x2d)
         x1 = ln(t, layer.norms[0])
         # ---- self-attention: q = k-input = x1 + query_embed, v-input = x1
         x1q = _AddRows.apply(k, x1.view(B, Q, Cc), qe, B).view(B * Q, Cc)
-        q2 = _Linear.apply(k, x1q, sa.in_proj_weight[:Cc], sa.in_proj_bias[:Cc], None, scale, False)
-        k2 = _Linear.apply(k, x1q, sa.in_proj_weight[Cc:2 * Cc], sa.in_proj_bias[Cc:2 * Cc], None, 1.0, False)
-        v2 = _Linear.apply(k, x1, sa.in_proj_weight[2 * Cc:], sa.in_proj_bias[2 * Cc:], None, 1.0, False)
+        q2 = lin_in(x1q, sa, 0, scale)
+        k2 = lin_in(x1q, sa, 1)
+        v2 = lin_in(x1, sa, 2)
         o2 = attention.apply(k, q2.view(B, Q, Cc), k2.view(B, Q, Cc), v2.view(B, Q, Cc), None, None)
-        t2 = _Linear.apply(k, o2.view(B * Q, Cc), sa.out_proj.weight, sa.out_proj.bias, x1, 1.0, False)
+        t2 = lin(o2.view(B * Q, Cc), sa.out_proj, res=x1)
         x2 = ln(t2, layer.norms[1])
         # ---- FFN
         f = lin(x2, layer.ffns[0].layers[0][0], relu=True)
@@ -476,6 +592,8 @@ class GradReducer:
                 self.index[p] = (bi, off)
                 p.grad = bk['flat'][off:off + p.numel()].view_as(p)
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        for p in self.params:
+            _FUSED_REDUCERS[p] = self          # gradients written outside autograd (_WgradSide) report here
         self.t_bwd_end = self.t_comm_end = None
         self.timing = True
         self.reset()
@@ -487,6 +605,7 @@ class GradReducer:
         for bk in self.buckets:
             bk['pending'] = len(bk['params'])
             bk['work'] = None
+            bk['producers'] = set()
 
     def zero(self):
         """Start of a step: clear the buckets (the backward accumulates into them) and re-attach any .grad that was
@@ -498,16 +617,24 @@ class GradReducer:
                 if p.grad is None or p.grad.data_ptr() != view.data_ptr():
                     p.grad = view
 
-    def _hook(self, p):
+    def param_done(self, p, stream):
+        """A gradient written straight into the bucket by kernels on `stream` (fused weight gradients) is complete."""
+        self._hook(p, producer=stream)
+
+    def _hook(self, p, producer=None):
         bi, off = self.index[p]
         bk = self.buckets[bi]
         if p.grad.data_ptr() != bk['flat'].data_ptr() + 4 * off:       # the caller replaced .grad: fold it back in
             bk['flat'][off:off + p.numel()].copy_(p.grad.reshape(-1))
             p.grad = bk['flat'][off:off + p.numel()].view_as(p)
+        if producer is not None:
+            bk.setdefault('producers', set()).add(producer)
         bk['pending'] -= 1
         if bk['pending'] == 0 and self.world > 1:
             if self.cuda:
                 self.stream.wait_stream(torch.cuda.current_stream())
+                for st in bk.get('producers', ()):
+                    self.stream.wait_stream(st)
                 with torch.cuda.stream(self.stream):
                     bk['work'] = dist.all_reduce(bk['flat'], group=self.group, async_op=True)
             else:
@@ -544,6 +671,9 @@ class GradReducer:
     def remove(self):
         for h in self.handles:
             h.remove()
+        for p in self.params:
+            if _FUSED_REDUCERS.get(p) is self:
+                del _FUSED_REDUCERS[p]
 
 
 class GraphedStep:

@@ -251,6 +251,8 @@ typedef struct {
                                * (z % batch_inner) * sXb2 -- (image, head) batches of the attention products */
   long sAb2, sWb2, sCb2;
   int accumulate;             /* 1: C = (the above) + C, in place (a gradient that several products contribute to) */
+  int slot;                   /* 0 / 1: which split-K workspace to use -- calls issued concurrently on two streams (the
+                               * weight-gradient products of the training step run on a side stream) pass different slots */
 } cgg_gemm_desc;
 int cgg_gemm_f32(cgg_handle *h, const cgg_gemm_desc *d, void *stream);
 
@@ -268,8 +270,8 @@ int cgg_axpy(cgg_handle *h, const float *in, float *out, long n, float alpha, vo
 int cgg_add_rows(cgg_handle *h, const float *x, const float *add, float *out, int batch, long per, void *stream);
 /* out[i] = sum_b g[b,i]   (its backward) */
 int cgg_sum_batch(cgg_handle *h, const float *g, float *out, int batch, long per, void *stream);
-/* out[n] = alpha * sum_rows g[row,n]   (bias gradients) */
-int cgg_colsum(cgg_handle *h, const float *g, float *out, long rows, int n, float alpha, void *stream);
+/* out[n] (+)= alpha * sum_rows g[row,n]   (bias gradients; accumulate = 1 adds to out in place) */
+int cgg_colsum(cgg_handle *h, const float *g, float *out, long rows, int n, float alpha, int accumulate, void *stream);
 /* head.py:792-804: key_in[b,key,:] = mem[b,:,key] + level + pos[key,:], val_in = mem[b,:,key] + level, and the backward
  * dmem[b,c,key] = dkey_in[b,key,c] + dval_in[b,key,c].  pos_level (K,C) = pos + level. */
 int cgg_mem_prep(cgg_handle *h, const float *mem, const float *level, const float *pos_level, float *key_in,

@@ -195,3 +195,31 @@ def test_graphed_step_replays_the_eager_gradients():
             p.grad = None
         del loss_e, gs        # (an autograd graph built on the default stream must not outlive into the next capture:
         #                        its AccumulateGrad nodes are bound to that stream)
+
+
+@pytest.mark.parametrize('train_precision', ['fp32', 'tf32'])
+def test_fused_weight_gradients_equal_the_autograd_path(train_precision):
+    """fused_wgrad: dW / db of the linear layers accumulated into pre-existing .grad tensors by the GEMM epilogue on a side
+    stream (train._WgradSide) -- same gradients as the autograd path, and they ADD to what .grad already holds."""
+    from cgg_b200.train import decoder_forward_train
+    Q, B, ncls1 = 24, 2, 49
+    sd, mf, mems, probes, cap, cap_mask = _setup(Q, B, 128, 160, ncls1)
+    probes_d = {k: [t.to(DEV) for t in v] for k, v in probes.items()}
+
+    def run(fused):
+        head = build_head_from_state_dict(sd, Q, ncls1, 'fp32', DEV, train_precision=train_precision,
+                                          fused_wgrad='always' if fused else False).train()
+        if fused:
+            for p in head.parameters():
+                p.grad = torch.full_like(p, 0.25)          # pre-existing content must be kept (accumulation)
+        cls, emb, mask = decoder_forward_train(head, mf.to(DEV), [m.to(DEV) for m in mems])
+        loss = _loss_from_outputs(cls, emb, mask, probes_d, cap.to(DEV), cap_mask.to(DEV),
+                                  lambda e, c, m: grounding_loss(e, c, m, 10.0, 2.0))
+        loss.backward()
+        torch.cuda.synchronize()
+        return {k: (p.grad - 0.25 if fused else p.grad).clone() for k, p in head.named_parameters()}
+
+    a, b_ = run(False), run(True)
+    for k in a:
+        scale = float(a[k].abs().max()) + 1e-12
+        assert float((a[k] - b_[k]).abs().max()) <= 2e-5 * scale + 1e-6, (k, float((a[k] - b_[k]).abs().max()), scale)
