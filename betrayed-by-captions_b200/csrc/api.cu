@@ -748,6 +748,11 @@ extern "C" int cgg_gemm_f32(cgg_handle* h, const cgg_gemm_desc* d, void* stream)
   }
   p.accumulate = d->accumulate != 0;
   p.slot = d->slot;
+  if (d->conv_cin > 0) {
+    if (d->K != 9 * d->conv_cin || d->A2 || d->batch_inner < 1) return fail(h, CGG_ERR_BAD_SHAPE, "conv_cin: K must be 9 * conv_cin, batch_inner = image height");
+    p.conv_cin = d->conv_cin;
+    p.batch_inner = d->batch_inner; p.sAb2 = d->sAb2; p.sWb2 = d->sWb2; p.sCb2 = d->sCb2;
+  }
   if (d->tf32) {
     if (!h->tf32 && !(h->tf32 = tf32_create())) return fail(h, CGG_ERR_CUDA, "tf32_create failed");
     const int r = launch_gemm_tf32(h->tf32, p, (cudaStream_t)stream);
@@ -967,5 +972,95 @@ extern "C" int cgg_softmax_rows(cgg_handle* h, float* x, int rows, int n, void* 
   if (!h || !x) return CGG_ERR_NULL;
   if (rows < 0 || n < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
   CU(launch_softmax_rows(x, rows, n, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+// ====================================================================== the pixel decoder before the path (row f3)
+extern "C" int cgg_ms_deform_attn(cgg_handle* h, const float* value, const float* offsets, const float* weight_logits, float* out,
+                                  int batch, int tokens, int heads, int levels, int points, const int* level_h, const int* level_w,
+                                  void* stream) {
+  if (!h || !value || !offsets || !weight_logits || !out || !level_h || !level_w) return CGG_ERR_NULL;
+  if (batch < 0 || tokens < 1 || heads < 1 || heads > 8 || levels < 1 || levels > 4 || points < 1 || levels * points > 16)
+    return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: heads <= 8 (x 32 channels), levels <= 4, levels * points <= 16");
+  long tot = 0;
+  for (int l = 0; l < levels; ++l) tot += (long)level_h[l] * level_w[l];
+  if (tot != tokens) return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: level sizes do not add up to the token count");
+  CU(launch_ms_deform_attn(value, offsets, weight_logits, out, batch, tokens, heads, levels, points, level_h, level_w, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_ms_deform_attn_backward(cgg_handle* h, const float* value, const float* offsets, const float* weight_logits,
+                                           const float* dout, float* dvalue, float* doffsets, float* dweight_logits, int batch,
+                                           int tokens, int heads, int levels, int points, const int* level_h, const int* level_w,
+                                           void* stream) {
+  if (!h || !value || !offsets || !weight_logits || !dout || !dvalue || !doffsets || !dweight_logits || !level_h || !level_w) return CGG_ERR_NULL;
+  if (batch < 0 || tokens < 1 || heads < 1 || heads > 8 || levels < 1 || levels > 4 || points < 1 || levels * points > 16)
+    return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: heads <= 8 (x 32 channels), levels <= 4, levels * points <= 16");
+  long tot = 0;
+  for (int l = 0; l < levels; ++l) tot += (long)level_h[l] * level_w[l];
+  if (tot != tokens) return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: level sizes do not add up to the token count");
+  CU(launch_ms_deform_attn_bwd(value, offsets, weight_logits, dout, dvalue, doffsets, dweight_logits, batch, tokens, heads, levels, points,
+                               level_h, level_w, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+static bool gn_shape_ok(int batch, int pixels, int channels, int groups) {
+  return batch >= 0 && pixels >= 1 && channels >= 4 && groups >= 1 && channels % groups == 0 && (channels / groups) % 4 == 0 &&
+         (long)batch <= 65535;
+}
+
+extern "C" size_t cgg_group_norm_scratch_bytes(int batch, int pixels, int channels, int groups) {
+  return gn_shape_ok(batch, pixels, channels, groups) ? group_norm_scratch_floats(batch, pixels, channels, groups) * sizeof(float) : 0;
+}
+
+extern "C" int cgg_group_norm_tokens(cgg_handle* h, const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+                                     void* scratch, size_t scratch_bytes, int batch, int pixels, int channels, int groups, float eps,
+                                     int relu, void* stream) {
+  if (!h || !x || !gamma || !beta || !y || !mean_rstd || !scratch) return CGG_ERR_NULL;
+  if (!gn_shape_ok(batch, pixels, channels, groups)) return fail(h, CGG_ERR_BAD_SHAPE, "group_norm: channels / groups must be a multiple of 4");
+  if (scratch_bytes < cgg_group_norm_scratch_bytes(batch, pixels, channels, groups)) return fail(h, CGG_ERR_WORKSPACE, "group_norm scratch too small");
+  CU(launch_group_norm(x, gamma, beta, y, mean_rstd, (float*)scratch, batch, pixels, channels, groups, eps, relu != 0, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_group_norm_tokens_backward(cgg_handle* h, const float* x, const float* dy, const float* mean_rstd, const float* gamma,
+                                              float* dx, float* dgamma, float* dbeta, void* scratch, size_t scratch_bytes, int batch,
+                                              int pixels, int channels, int groups, void* stream) {
+  if (!h || !x || !dy || !mean_rstd || !gamma || !dx || !dgamma || !dbeta || !scratch) return CGG_ERR_NULL;
+  if (!gn_shape_ok(batch, pixels, channels, groups)) return fail(h, CGG_ERR_BAD_SHAPE, "group_norm: channels / groups must be a multiple of 4");
+  if (scratch_bytes < cgg_group_norm_scratch_bytes(batch, pixels, channels, groups)) return fail(h, CGG_ERR_WORKSPACE, "group_norm scratch too small");
+  CU(launch_group_norm_bwd(x, dy, mean_rstd, gamma, dx, dgamma, dbeta, (float*)scratch, batch, pixels, channels, groups, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_upsample_add_tokens(cgg_handle* h, const float* lateral, const float* coarse, long coarse_batch_stride, float* out,
+                                       int batch, int H, int W, int ch, int cw, int channels, void* stream) {
+  if (!h || !lateral || !coarse || !out) return CGG_ERR_NULL;
+  if (batch < 0 || H < 1 || W < 1 || ch < 1 || cw < 1 || channels < 4 || channels % 4) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_upsample_add(lateral, coarse, coarse_batch_stride, out, batch, H, W, ch, cw, channels, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_upsample_add_tokens_backward(cgg_handle* h, const float* dout, float* dcoarse, int batch, int H, int W, int ch, int cw,
+                                                int channels, void* stream) {
+  if (!h || !dout || !dcoarse) return CGG_ERR_NULL;
+  if (batch < 0 || H < 1 || W < 1 || ch < 1 || cw < 1 || channels < 4 || channels % 4) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_upsample_add_bwd(dout, dcoarse, batch, H, W, ch, cw, channels, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_tokens_to_nchw(cgg_handle* h, const float* tokens, long token_batch_stride, void* out, int out_bf16, int batch,
+                                  int pixels, int channels, void* stream) {
+  if (!h || !tokens || !out) return CGG_ERR_NULL;
+  if (batch < 0 || batch > 65535 || pixels < 1 || channels < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_tokens_to_nchw(tokens, token_batch_stride, out, out_bf16 != 0, batch, pixels, channels, (cudaStream_t)stream));
+  return CGG_OK;
+}
+
+extern "C" int cgg_nchw_to_tokens(cgg_handle* h, const float* in, float* tokens, long token_batch_stride, int batch, int pixels,
+                                  int channels, int accumulate, void* stream) {
+  if (!h || !in || !tokens) return CGG_ERR_NULL;
+  if (batch < 0 || batch > 65535 || pixels < 1 || channels < 1) return fail(h, CGG_ERR_BAD_SHAPE, "bad shape");
+  CU(launch_nchw_to_tokens(in, tokens, token_batch_stride, batch, pixels, channels, accumulate != 0, (cudaStream_t)stream));
   return CGG_OK;
 }

@@ -45,6 +45,7 @@ struct Tf32P {
   float* partial;              // != nullptr: raw accumulators to partial[((split*batch + b)*M + m)*N + n]
   int epi_mode;                // 1: float4 rows, 2: m-contiguous C, 0: scalar
   int accumulate;              // C += result
+  int conv_cpt;                // > 0: implicit 3x3 convolution, 32-channel chunks per tap (GemmF32::conv_cin / 32)
 };
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -126,7 +127,10 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
           uint8_t* sB = sA + A_STAGE_BYTES;
           ptx::mbar_expect_tx(&full[st], tx);
           const int bi = b % p.batch_inner, bo = b / p.batch_inner;
-          if (!p.a_mn) ptx::tma_load_4d(sA, &mA, &full[st], c * BK, m0, bi, bo);                       // (32 k, 128 rows)
+          if (p.conv_cpt > 0) {        // tap (dy, dx) of the 3x3 window: the TMA unit zero-fills rows / columns outside the image
+            const int tap = c / p.conv_cpt;
+            ptx::tma_load_4d(sA, &mA, &full[st], (c - tap * p.conv_cpt) * BK, m0 + tap % 3 - 1, bi + tap / 3 - 1, bo);
+          } else if (!p.a_mn) ptx::tma_load_4d(sA, &mA, &full[st], c * BK, m0, bi, bo);                // (32 k, 128 rows)
           else
             for (int g = 0; g < 4; ++g) ptx::tma_load_4d(sA + g * 4096, &mA, &full[st], m0 + g * 32, c * BK, bi, bo);   // (32 m, 32 k)
           if (!p.b_mn) ptx::tma_load_4d(sB, &mB, &full[st], c * BK, n0, bi, bo);
@@ -396,7 +400,9 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   const int b_major = operand_major(g.W, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, g.batch_inner);
   if (a_major < 0 || b_major < 0) return 1;
   if (g.batch_inner > 1 && g.R) return 1;
+  if (g.conv_cin > 0 && (a_major != 0 || g.conv_cin % BK != 0 || g.K != 9 * g.conv_cin)) return 1;
   Tf32P p = {};
+  p.conv_cpt = g.conv_cin > 0 ? g.conv_cin / BK : 0;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.a_mn = a_major; p.b_mn = b_major;
   p.n_tile = g.N <= 256 ? round_up(g.N, 16) : 128;
@@ -438,7 +444,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
     p.partial = t->partial[slot];
   }
   CUtensorMap mA, mB;
-  if (make_map(t, &mA, g.A, a_major, g.sAb, g.sAb2, g.sAm, g.sAk, g.M, g.K, g.batch, p.batch_inner, BM)) return -1;
+  if (make_map(t, &mA, g.A, a_major, g.sAb, g.sAb2, g.sAm, g.sAk, g.M, g.conv_cin > 0 ? g.conv_cin : g.K, g.batch, p.batch_inner, BM)) return -1;
   if (make_map(t, &mB, g.W, b_major, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, p.batch_inner, p.n_tile)) return -1;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

@@ -29,6 +29,10 @@ struct GemmF32 {
   int batch_inner = 1; long sAb2 = 0, sWb2 = 0, sCb2 = 0;
   bool accumulate = false;   // C = epi(...) + C  (gradient accumulation in place)
   int slot = 0;              // workspace slot of the split-K partial sums (one per concurrently used stream)
+  // conv_cin > 0: 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM over token-major images.  The batch is
+  // (image, row y) = (z / batch_inner, z % batch_inner) with batch_inner = H, m = column x (M = W), k = tap * conv_cin + c
+  // (K = 9 * conv_cin, tap = 3 * (dy + 1) + (dx + 1)):  A[z, m, k] = X[image, y + dy, x + dx, c], zero outside the image.
+  int conv_cin = 0;
   int relu_from = 1 << 30;   // relu applied to columns n >= relu_from
   float alpha = 1.f;
   bool a_mmajor = false, c_mmajor = false;
@@ -116,6 +120,23 @@ cudaError_t launch_weighted_ce(const float* logits, const int64_t* labels, const
                                float* row_w, float* lse, cudaStream_t s);
 cudaError_t launch_weighted_ce_bwd(const float* logits, const int64_t* labels, const float* cw, const float* lse, int R, int C1,
                                    const float* grow, float* dlogits, cudaStream_t s);
+
+// ---- the pixel decoder before the path (pixdec_kernels.cu), token-major fp32 activations
+cudaError_t launch_ms_deform_attn(const float* value, const float* off, const float* logits, float* out, int B, int S, int heads,
+                                  int levels, int points, const int* hs, const int* ws, cudaStream_t s);
+cudaError_t launch_ms_deform_attn_bwd(const float* value, const float* off, const float* logits, const float* dout, float* dvalue,
+                                      float* doff, float* dlogits, int B, int S, int heads, int levels, int points, const int* hs,
+                                      const int* ws, cudaStream_t s);
+size_t group_norm_scratch_floats(int B, int P, int C, int G);
+cudaError_t launch_group_norm(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd, float* scratch, int B,
+                              int P, int C, int G, float eps, bool relu, cudaStream_t s);
+cudaError_t launch_group_norm_bwd(const float* x, const float* dy, const float* mean_rstd, const float* gamma, float* dx, float* dgamma,
+                                  float* dbeta, float* scratch, int B, int P, int C, int G, cudaStream_t s);
+cudaError_t launch_upsample_add(const float* lat, const float* prev, long prev_bstride, float* out, int B, int H, int W, int h, int w,
+                                int C, cudaStream_t s);
+cudaError_t launch_upsample_add_bwd(const float* dout, float* dprev, int B, int H, int W, int h, int w, int C, cudaStream_t s);
+cudaError_t launch_tokens_to_nchw(const float* in, long in_bstride, void* out, bool out_bf16, int B, int P, int C, cudaStream_t s);
+cudaError_t launch_nchw_to_tokens(const float* in, float* out, long out_bstride, int B, int P, int C, bool accumulate, cudaStream_t s);
 
 // ---- test-time step after the path (post_kernels.cu)
 cudaError_t launch_upsample_masks(const void* logits, bool bf16, float* out, int planes, int h4, int w4, int up_h, int up_w,

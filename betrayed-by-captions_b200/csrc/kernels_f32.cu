@@ -51,8 +51,15 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
       if (gm < p.M && gk < p.K) {
-        v = A[(long)gm * p.sAm + (long)gk * p.sAk];
-        if (p.A2) v += p.A2[(long)(gm % p.a2_mod) * p.sA2m + (long)gk * p.sA2k];
+        if (p.conv_cin > 0) {          // implicit 3x3 convolution: k = (tap, channel), taps outside the image are zero
+          const int tap = gk / p.conv_cin, cc = gk - tap * p.conv_cin;
+          const int yy = (int)bi + tap / 3 - 1, xx = gm + tap % 3 - 1;
+          if (yy >= 0 && yy < p.batch_inner && xx >= 0 && xx < p.M)
+            v = p.A[bo * p.sAb + (long)yy * p.sAb2 + (long)xx * p.sAm + (long)cc * p.sAk];
+        } else {
+          v = A[(long)gm * p.sAm + (long)gk * p.sAk];
+          if (p.A2) v += p.A2[(long)(gm % p.a2_mod) * p.sA2m + (long)gk * p.sA2k];
+        }
       }
       As[k][m] = v;
       const int kb = idx & 15, n = idx >> 4;

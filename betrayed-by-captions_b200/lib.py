@@ -22,7 +22,11 @@ EXPORTS = ['cgg_create', 'cgg_destroy', 'cgg_last_error', 'cgg_version', 'cgg_la
            'cgg_attention_f32', 'cgg_attention_backward', 'cgg_attn_softmax_rows', 'cgg_attn_dscore', 'cgg_point_sample', 'cgg_point_sample_backward',
            'cgg_matching_cost', 'cgg_point_losses', 'cgg_point_losses_backward', 'cgg_weighted_ce', 'cgg_weighted_ce_backward',
            # test-time step after the path
-           'cgg_upsample_masks', 'cgg_instance_mask_stats', 'cgg_softmax_rows']
+           'cgg_upsample_masks', 'cgg_instance_mask_stats', 'cgg_softmax_rows',
+           # the pixel decoder before the path
+           'cgg_ms_deform_attn', 'cgg_ms_deform_attn_backward', 'cgg_group_norm_scratch_bytes', 'cgg_group_norm_tokens',
+           'cgg_group_norm_tokens_backward', 'cgg_upsample_add_tokens', 'cgg_upsample_add_tokens_backward',
+           'cgg_tokens_to_nchw', 'cgg_nchw_to_tokens']
 
 
 class Config(C.Structure):
@@ -54,7 +58,7 @@ class GemmDesc(C.Structure):
                 ('C', C.c_void_p), ('sCb', C.c_long), ('sCm', C.c_long), ('sCn', C.c_long),
                 ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('batch', C.c_int),
                 ('relu', C.c_int), ('alpha', C.c_float), ('a_mmajor', C.c_int), ('c_mmajor', C.c_int), ('tf32', C.c_int),
-                ('batch_inner', C.c_int), ('sAb2', C.c_long), ('sWb2', C.c_long), ('sCb2', C.c_long), ('accumulate', C.c_int), ('slot', C.c_int)]
+                ('batch_inner', C.c_int), ('sAb2', C.c_long), ('sWb2', C.c_long), ('sCb2', C.c_long), ('accumulate', C.c_int), ('slot', C.c_int), ('conv_cin', C.c_int)]
 
 
 class CggError(RuntimeError):
@@ -132,6 +136,17 @@ def load():
     lib.cgg_upsample_masks.argtypes = [vp, vp, i, vp, i, i, i, i, i, vp]
     lib.cgg_instance_mask_stats.argtypes = [vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     lib.cgg_softmax_rows.argtypes = [vp, vp, i, i, vp]
+    ip = C.POINTER(C.c_int)
+    lib.cgg_ms_deform_attn.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, ip, ip, vp]
+    lib.cgg_ms_deform_attn_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, ip, ip, vp]
+    lib.cgg_group_norm_scratch_bytes.argtypes = [i, i, i, i]
+    lib.cgg_group_norm_scratch_bytes.restype = sz
+    lib.cgg_group_norm_tokens.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, f32, i, vp]
+    lib.cgg_group_norm_tokens_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, i, vp]
+    lib.cgg_upsample_add_tokens.argtypes = [vp, vp, vp, lg, vp, i, i, i, i, i, i, vp]
+    lib.cgg_upsample_add_tokens_backward.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.cgg_tokens_to_nchw.argtypes = [vp, vp, lg, vp, i, i, i, i, vp]
+    lib.cgg_nchw_to_tokens.argtypes = [vp, vp, vp, lg, i, i, i, i, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('cgg_destroy',):

@@ -148,3 +148,54 @@ def make_caption_params(seed=0, cfg=None, vocab=None, scale=2.0, eos_bias=2.0):
     sd['bert_embeddings.LayerNorm.weight'] = 1.0 + 0.1 * torch.randn((768,), generator=g)
     sd['bert_embeddings.LayerNorm.bias'] = 0.05 * torch.randn((768,), generator=g)
     return sd
+
+
+def make_pixel_decoder_params(seed=0, in_channels=(256, 512, 1024, 2048), feat=256, out_channels=256, ffn=1024,
+                              num_layers=6, heads=8, levels=3, points=4):
+    """Seeded weights of mmdet's MSDeformAttnPixelDecoder (configs/instance/coco_b48n17.py:38-70) under mmdet's state_dict
+    keys (the reference head holds them under `pixel_decoder.`).  Every tensor is random -- including the sampling-offset
+    and attention-weight projections, which mmcv initialises to a fixed grid / zero -- so that no term of the arithmetic
+    is hidden by a zero; the offsets come out a few pixels wide, like a trained model's."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    sd = {}
+    n_in = len(in_channels)
+    for i in range(levels):
+        cin = in_channels[n_in - 1 - i]
+        sd['input_convs.%d.conv.weight' % i] = _xavier_normal(g, (feat, cin)).view(feat, cin, 1, 1).contiguous()
+        sd['input_convs.%d.conv.bias' % i] = 0.05 * torch.randn(feat, generator=g)
+        sd['input_convs.%d.gn.weight' % i] = 1 + 0.1 * torch.randn(feat, generator=g)
+        sd['input_convs.%d.gn.bias' % i] = 0.05 * torch.randn(feat, generator=g)
+    for l in range(num_layers):
+        p = 'encoder.layers.%d.' % l
+        a = p + 'attentions.0.'
+        sd[a + 'sampling_offsets.weight'] = 0.02 * torch.randn((heads * levels * points * 2, feat), generator=g)
+        sd[a + 'sampling_offsets.bias'] = 1.5 * torch.randn(heads * levels * points * 2, generator=g)
+        sd[a + 'attention_weights.weight'] = 0.05 * torch.randn((heads * levels * points, feat), generator=g)
+        sd[a + 'attention_weights.bias'] = 0.3 * torch.randn(heads * levels * points, generator=g)
+        for n in ('value_proj', 'output_proj'):
+            sd[a + n + '.weight'] = _xavier_normal(g, (feat, feat))
+            sd[a + n + '.bias'] = 0.05 * torch.randn(feat, generator=g)
+        sd[p + 'ffns.0.layers.0.0.weight'] = _xavier_normal(g, (ffn, feat))
+        sd[p + 'ffns.0.layers.0.0.bias'] = _uniform(g, (ffn,), 1.0 / math.sqrt(feat))
+        sd[p + 'ffns.0.layers.1.weight'] = _xavier_normal(g, (feat, ffn))
+        sd[p + 'ffns.0.layers.1.bias'] = _uniform(g, (feat,), 1.0 / math.sqrt(ffn))
+        for n in (0, 1):
+            sd[p + 'norms.%d.weight' % n] = 1 + 0.1 * torch.randn(feat, generator=g)
+            sd[p + 'norms.%d.bias' % n] = 0.05 * torch.randn(feat, generator=g)
+    sd['level_encoding.weight'] = torch.randn((levels, feat), generator=g)
+    for i in range(n_in - levels):
+        sd['lateral_convs.%d.conv.weight' % i] = _xavier_normal(g, (feat, in_channels[i])).view(feat, in_channels[i], 1, 1).contiguous()
+        sd['output_convs.%d.conv.weight' % i] = (torch.randn((feat, feat, 3, 3), generator=g) * math.sqrt(2.0 / (9 * feat)))
+        for n in ('lateral_convs', 'output_convs'):
+            sd['%s.%d.gn.weight' % (n, i)] = 1 + 0.1 * torch.randn(feat, generator=g)
+            sd['%s.%d.gn.bias' % (n, i)] = 0.05 * torch.randn(feat, generator=g)
+    sd['mask_feature.weight'] = _xavier_normal(g, (out_channels, feat)).view(out_channels, feat, 1, 1).contiguous()
+    sd['mask_feature.bias'] = 0.05 * torch.randn(out_channels, generator=g)
+    return sd
+
+
+def make_backbone_feats(seed, batch, height, width, in_channels=(256, 512, 1024, 2048), dtype=torch.float32):
+    """Synthetic backbone maps at strides 4, 8, 16, 32 (highest resolution first), post-ReLU-like (non-negative)."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    return [torch.randn((batch, c, height // s, width // s), generator=g).clamp_(min=0).to(dtype)
+            for c, s in zip(in_channels, (4, 8, 16, 32))]

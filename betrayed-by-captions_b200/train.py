@@ -43,7 +43,7 @@ class _K:
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
     def gemm(self, A, sA, W, sW, Cc, sC, M, N, K, batch=1, bias=None, R=None, sR=(0, 0, 0), r_mod=None, alpha=1.0,
-             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0), accumulate=False):
+             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0), accumulate=False, conv_cin=0):
         """C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); element strides
         sA = (b, m, k), sW = (b, n, k), sC = (b, m, n), sR = (b, m, n)."""
         d = _lib.GemmDesc()
@@ -65,6 +65,7 @@ class _K:
         d.batch_inner, (d.sAb2, d.sWb2, d.sCb2) = batch_inner, s2     # (image, head) batches: inner strides of A, W, C
         d.accumulate = int(accumulate)                                # C += result (in-place gradient accumulation)
         d.slot = self.slot                                            # split-K workspace (1 on the weight-gradient side stream)
+        d.conv_cin = conv_cin                                         # 3x3 convolution as an implicit GEMM (pixel decoder)
         self.chk(self.lib.cgg_gemm_f32(self.h, C.byref(d), self.s()), 'cgg_gemm_f32')
 
 

@@ -253,6 +253,11 @@ typedef struct {
   int accumulate;             /* 1: C = (the above) + C, in place (a gradient that several products contribute to) */
   int slot;                   /* 0 / 1: which split-K workspace to use -- calls issued concurrently on two streams (the
                                * weight-gradient products of the training step run on a side stream) pass different slots */
+  int conv_cin;               /* > 0: 3x3 convolution (stride 1, zero padding 1: the pixel decoder's output_convs) as an
+                               * implicit GEMM over a token-major image batch X (images, H, W, conv_cin): batch = images * H
+                               * with batch_inner = H (sAb / sAb2 = image / row strides of X), M = W, sAm = pixel stride,
+                               * K = 9 * conv_cin, W[n, tap * conv_cin + c] with tap = 3 * ky + kx.  The tf32 form fetches
+                               * each tap with TMA, whose out-of-bounds zero fill is the padding. */
 } cgg_gemm_desc;
 int cgg_gemm_f32(cgg_handle *h, const cgg_gemm_desc *d, void *stream);
 
@@ -356,6 +361,52 @@ int cgg_instance_mask_stats(cgg_handle *h, const void *logits, int is_bf16, cons
                             int w4, int up_h, int up_w, int max_out_h, int max_out_w, uint32_t *bits, int *count,
                             float *sig_sum, int *bbox, void *stream);
 int cgg_softmax_rows(cgg_handle *h, float *x, int rows, int n, void *stream);
+
+/* ---- the step before the path: mmdet MSDeformAttnPixelDecoder ------------------------------
+ * `mask_features, multi_scale_memorys = self.pixel_decoder(feats)` (mask2former_head.py:787; configured at
+ * configs/instance/coco_b48n17.py:38-70).  mmdet 2.28.2 / mmcv-full 1.7.1 are un-vendored dependencies of the reference;
+ * each entry point names the third-party function it stands for.  Activations are TOKEN-MAJOR fp32: (images, pixels,
+ * channels), the levels of the encoder concatenated along the pixel axis, lowest resolution first.  The contractions (1x1
+ * convs, the 3x3 conv via cgg_gemm_desc.conv_cin, all linear layers) are cgg_gemm_f32 calls; LayerNorm is cgg_layernorm.
+ *
+ * cgg_ms_deform_attn: mmcv MultiScaleDeformableAttention core (ops/multi_scale_deform_attn.py, CUDA op
+ *   ms_deform_attn_forward): value (B, S, heads*32) = value_proj(x); offsets (B, S, heads*levels*points*2) = the
+ *   sampling_offsets projection of (x + pos), (x, y) in pixels of the sampled level; weight_logits (B, S, heads*levels*
+ *   points) = the attention_weights projection BEFORE its softmax (done here, over levels*points).  Reference point of
+ *   token s = its own pixel centre ((x+.5)/w, (y+.5)/h) in every level (all-valid padding mask, as the reference runs it);
+ *   bilinear taps, zero outside, align_corners=False.  out (B, S, heads*32).  level_h / level_w: HOST arrays.
+ *   The backward returns dvalue (zeroed here, then scattered with atomics), doffsets and dweight_logits (through the
+ *   softmax). */
+int cgg_ms_deform_attn(cgg_handle *h, const float *value, const float *offsets, const float *weight_logits, float *out,
+                       int batch, int tokens, int heads, int levels, int points, const int *level_h, const int *level_w,
+                       void *stream);
+int cgg_ms_deform_attn_backward(cgg_handle *h, const float *value, const float *offsets, const float *weight_logits,
+                                const float *dout, float *dvalue, float *doffsets, float *dweight_logits, int batch,
+                                int tokens, int heads, int levels, int points, const int *level_h, const int *level_w,
+                                void *stream);
+/* GroupNorm of mmcv's ConvModule (norm_cfg GN, num_groups 32; eps 1e-5) + optional ReLU over token-major x (B, pixels,
+ * channels): statistics per (image, group of channels/groups consecutive channels).  mean_rstd (B, groups, 2) is kept
+ * for the backward; dy of the backward must already carry the ReLU mask (cgg_relu_backward).  Deterministic. */
+size_t cgg_group_norm_scratch_bytes(int batch, int pixels, int channels, int groups);
+int cgg_group_norm_tokens(cgg_handle *h, const float *x, const float *gamma, const float *beta, float *y, float *mean_rstd,
+                          void *scratch, size_t scratch_bytes, int batch, int pixels, int channels, int groups, float eps,
+                          int relu, void *stream);
+int cgg_group_norm_tokens_backward(cgg_handle *h, const float *x, const float *dy, const float *mean_rstd,
+                                   const float *gamma, float *dx, float *dgamma, float *dbeta, void *scratch,
+                                   size_t scratch_bytes, int batch, int pixels, int channels, int groups, void *stream);
+/* FPN top-down step of MSDeformAttnPixelDecoder.forward: out = lateral + F.interpolate(coarse, size=(H, W), bilinear,
+ * align_corners=False); lateral / out (B, H*W, C), coarse (B, ch*cw, C) with its own batch stride (a level's slice of the
+ * encoder's token buffer).  Backward: dlateral = dout; dcoarse (B, ch*cw, C) contiguous, zeroed here, then scattered. */
+int cgg_upsample_add_tokens(cgg_handle *h, const float *lateral, const float *coarse, long coarse_batch_stride, float *out,
+                            int batch, int H, int W, int ch, int cw, int channels, void *stream);
+int cgg_upsample_add_tokens_backward(cgg_handle *h, const float *dout, float *dcoarse, int batch, int H, int W, int ch,
+                                     int cw, int channels, void *stream);
+/* Layout change at the boundary: tokens (B, pixels, C) with a batch stride -> NCHW (B, C, pixels) fp32 or bf16 (what
+ * cgg_decoder_forward consumes), and back (optionally accumulating: a gradient joining the token buffer). */
+int cgg_tokens_to_nchw(cgg_handle *h, const float *tokens, long token_batch_stride, void *out, int out_bf16, int batch,
+                       int pixels, int channels, void *stream);
+int cgg_nchw_to_tokens(cgg_handle *h, const float *in, float *tokens, long token_batch_stride, int batch, int pixels,
+                       int channels, int accumulate, void *stream);
 
 #ifdef __cplusplus
 }
