@@ -46,6 +46,7 @@ struct Tf32P {
   int epi_mode;                // 1: float4 rows, 2: m-contiguous C, 0: scalar
   int accumulate;              // C += result
   int conv_cpt;                // > 0: implicit 3x3 convolution, 32-channel chunks per tap (GemmF32::conv_cin / 32)
+  int w_shared;                // the W operand has no batch stride (one weight matrix for every batch entry)
 };
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   const int stage_bytes = A_STAGE_BYTES + ((b_stage_bytes + 1023) & ~1023);
   __shared__ uint64_t full[4], empty[4], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[4][256];     // per epilogue warp: the bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = p.tmem_cols >> 1;                 // two accumulators: the epilogue of tile i overlaps tile i + 1
@@ -103,11 +105,12 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  // persistent tile loop (all three roles walk the same sequence): tile -> (m tile fastest, n tile, batch, K split)
+  // persistent tile loop (all three roles walk the same sequence): tile -> (n tile fastest, m tile, batch, K split): the
+  // CTAs that run side by side share one A tile (fetched from HBM once, re-read through L2) and the weights stay in L2
   const long tiles = (long)p.mt * p.nt * p.batch * p.splits;
   auto decode = [&](long t, int& m0, int& n0, int& b, int& split) {
-    m0 = (int)(t % p.mt) * BM; t /= p.mt;
     n0 = (int)(t % p.nt) * p.n_tile; t /= p.nt;
+    m0 = (int)(t % p.mt) * BM; t /= p.mt;
     split = (int)(t % p.splits);
     b = (int)(t / p.splits);
   };
@@ -133,9 +136,10 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
           } else if (!p.a_mn) ptx::tma_load_4d(sA, &mA, &full[st], c * BK, m0, bi, bo);                // (32 k, 128 rows)
           else
             for (int g = 0; g < 4; ++g) ptx::tma_load_4d(sA + g * 4096, &mA, &full[st], m0 + g * 32, c * BK, bi, bo);   // (32 m, 32 k)
-          if (!p.b_mn) ptx::tma_load_4d(sB, &mB, &full[st], c * BK, n0, bi, bo);
+          const int wbi = p.w_shared ? 0 : bi, wbo = p.w_shared ? 0 : bo;
+          if (!p.b_mn) ptx::tma_load_4d(sB, &mB, &full[st], c * BK, n0, wbi, wbo);
           else
-            for (int g = 0; g < p.b_groups; ++g) ptx::tma_load_4d(sB + g * 4096, &mB, &full[st], n0 + g * 32, c * BK, bi, bo);
+            for (int g = 0; g < p.b_groups; ++g) ptx::tma_load_4d(sB + g * 4096, &mB, &full[st], n0 + g * 32, c * BK, wbi, wbo);
         }
       }
     }
@@ -187,13 +191,42 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       int m0, n0, b, split;
       decode(t, m0, n0, b, split);
       const uint32_t buf = lt & 1u;
-      ptx::mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
-      ptx::tc_fence_after();
       const int gm = m0 + quarter * 32 + lane;
       const bool rowok = gm < p.M;
       float* crow = p.partial ? p.partial + (((long)split * p.batch + b) * p.M + gm) * p.N
                               : p.C + (long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2 + (long)gm * p.sCm;
       const float* rrow = (R && !p.partial) ? R + (long)b * p.sRb + (long)(p.r_mod >= p.M ? gm : gm % p.r_mod) * p.sRm : nullptr;
+      // Everything the epilogue reads from memory is requested BEFORE the accumulator is waited for: the tile's bias goes to
+      // the warp's shared-memory row, the residual / old-C values of a 32-column chunk ride in registers one chunk ahead
+      // (they were a serial load -> add -> store chain per chunk: the FADDs waiting on them were the top stall of the kernel).
+      const bool rich = p.epi_mode == 1 && !p.partial && !plain;
+      auto prefetch = [&](float4* rv, int j) {
+        const int nq = min(8, (p.N - (n0 + j)) >> 2);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          rv[c4] = (rrow && rowok && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.accumulate && rowok && c4 < nq) {          // C += ...: the old values ride in the residual registers
+            const float4 ov = reinterpret_cast<const float4*>(crow + n0 + j)[c4];
+            rv[c4].x += ov.x; rv[c4].y += ov.y; rv[c4].z += ov.z; rv[c4].w += ov.w;
+          }
+        }
+      };
+      float4 va[8], vb[8];
+      if (rich) {
+        if (bias) {
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int c = lane * 4 + 128 * t;
+            *reinterpret_cast<float4*>(&bias_s[quarter][c]) =
+                (c < p.n_tile && n0 + c < p.N) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+        }
+        prefetch(va, 0);
+      }
+      ptx::mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
+      ptx::tc_fence_after();
       // The accumulator is read 32 columns at a time; the tcgen05.ld of the next chunk is in flight while the current
       // chunk's stores are issued (two register sets, loop unrolled by two so that both stay in registers).
       const uint32_t tbase = tmem + buf * (uint32_t)acc_cols + ((uint32_t)(quarter * 32) << 16);
@@ -205,7 +238,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
           for (int i = 16; i < 32; ++i) r[i] = 0u;
       };
       auto waitr = [&](uint32_t* r) { ptx::tmem_ld_wait16(r); ptx::tmem_ld_wait16(r + 16); };
-      auto process = [&](const uint32_t* r, int j) {
+      auto process = [&](const uint32_t* r, const float4* rv, int j) {
         if (!rowok) return;
         float v[32];
 #pragma unroll
@@ -218,17 +251,10 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
               for (int c4 = 0; c4 < 8; ++c4)
                 if (c4 < nq) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
             } else {
-              // all loads of the chunk are issued before the first store (the stores could alias them for all the compiler knows)
-              float4 bv[8], rv[8];
+              float4 bv[8];
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                bv[c4] = (bias && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                rv[c4] = (rrow && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.accumulate && c4 < nq) {             // C += ...: the old values ride in the residual registers
-                  const float4 ov = dst[c4];
-                  rv[c4].x += ov.x; rv[c4].y += ov.y; rv[c4].z += ov.z; rv[c4].w += ov.w;
-                }
-              }
+              for (int c4 = 0; c4 < 8; ++c4)
+                bv[c4] = bias ? *reinterpret_cast<const float4*>(&bias_s[quarter][j + 4 * c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
               const bool relu = n0 + j >= p.relu_from;             // relu_from is a multiple of 32 here (0 or "never")
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
@@ -276,14 +302,14 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       waitr(ra);
       while (true) {
         bool more = more_after(j);
-        if (more) issue(rb, j + 32);
-        process(ra, j);
+        if (more) { issue(rb, j + 32); if (rich) prefetch(vb, j + 32); }
+        process(ra, va, j);
         if (!more) break;
         waitr(rb);
         j += 32;
         more = more_after(j);
-        if (more) issue(ra, j + 32);
-        process(rb, j);
+        if (more) { issue(ra, j + 32); if (rich) prefetch(va, j + 32); }
+        process(rb, vb, j);
         if (!more) break;
         waitr(ra);
         j += 32;
@@ -397,7 +423,9 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   if (g.A2 || g.K <= 0) return 1;
   if ((reinterpret_cast<uintptr_t>(g.C) & 3)) return 1;
   const int a_major = operand_major(g.A, g.sAb, g.sAb2, g.sAm, g.sAk, g.M, g.K, g.batch, g.batch_inner);
-  const int b_major = operand_major(g.W, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, g.batch_inner);
+  const bool w_shared = g.batch > 1 && g.sWb == 0 && g.sWb2 == 0;
+  const int b_major = w_shared ? operand_major(g.W, 0, 0, g.sWn, g.sWk, g.N, g.K, 1, 1)
+                               : operand_major(g.W, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, g.batch_inner);
   if (a_major < 0 || b_major < 0) return 1;
   if (g.batch_inner > 1 && g.R) return 1;
   if (g.conv_cin > 0 && (a_major != 0 || g.conv_cin % BK != 0 || g.K != 9 * g.conv_cin)) return 1;
@@ -405,7 +433,8 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   p.conv_cpt = g.conv_cin > 0 ? g.conv_cin / BK : 0;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.a_mn = a_major; p.b_mn = b_major;
-  p.n_tile = g.N <= 256 ? round_up(g.N, 16) : 128;
+  p.w_shared = w_shared ? 1 : 0;
+  p.n_tile = g.N <= 256 ? round_up(g.N, 16) : (g.N % 256 == 0 ? 256 : 128);
   p.b_groups = (p.n_tile + 31) / 32;
   const int b_stage = ((p.b_mn ? p.b_groups * 32 : p.n_tile) * BK * 4 + 1023) & ~1023;
   const int stage_bytes = A_STAGE_BYTES + b_stage;
@@ -445,7 +474,8 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   }
   CUtensorMap mA, mB;
   if (make_map(t, &mA, g.A, a_major, g.sAb, g.sAb2, g.sAm, g.sAk, g.M, g.conv_cin > 0 ? g.conv_cin : g.K, g.batch, p.batch_inner, BM)) return -1;
-  if (make_map(t, &mB, g.W, b_major, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, p.batch_inner, p.n_tile)) return -1;
+  if (w_shared ? make_map(t, &mB, g.W, b_major, 0, 0, g.sWn, g.sWk, g.N, g.K, 1, 1, p.n_tile)
+               : make_map(t, &mB, g.W, b_major, g.sWb, g.sWb2, g.sWn, g.sWk, g.N, g.K, g.batch, p.batch_inner, p.n_tile)) return -1;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.partial) p.epi_mode = (g.N % 4 == 0) ? 1 : 0;
@@ -456,7 +486,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   else if (g.sCm == 1) p.epi_mode = 2;
   else p.epi_mode = 0;
   if (!t->attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192) != cudaSuccess) {
       t->err = "cudaFuncSetAttribute(gemm_tf32_kernel) failed";
       return -1;
     }

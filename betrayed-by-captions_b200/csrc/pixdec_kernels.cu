@@ -24,6 +24,7 @@ constexpr int MAX_LEVELS = 4;
 struct MsdaP {
   int B, S, heads, levels, points;     // head_dim fixed at 32 (8 lanes x float4)
   int h[MAX_LEVELS], w[MAX_LEVELS], start[MAX_LEVELS];
+  int pw[MAX_LEVELS], pstart[MAX_LEVELS + 1];   // 8x8-query patches per level row / first patch of the level
 };
 
 __device__ __forceinline__ float group8_sum(float v) {
@@ -38,28 +39,37 @@ __device__ __forceinline__ float4 fma4(float s, const float4& a, const float4& c
   return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
 }
 
-// One thread = (image, query, head, 4 channels); 8 consecutive lanes share a head, 64 threads a query.
+// One thread = (image, query, head, 4 channels); 8 consecutive lanes share a (query, head).  A CTA is an 8x8 patch of
+// queries of one level x ONE head: its 64 x levels x points x 4 taps fall into a window of a few pixels around the patch in
+// each level, so most of them hit L1 (the query-major mapping of mmcv's op re-fetches every tap from L2: 17 GB per layer
+// at 16 x 1024^2).
 // value (B, S, heads*32); off (B, S, heads*levels*points*2) as (x, y) pixel offsets; logits (B, S, heads*levels*points).
 // Reference point of query s at level-local (y, x): ((x + 0.5) / w, (y + 0.5) / h) -- the same for every level
 // (valid ratios are one).  Sampling location in level l: ref + off / (w_l, h_l); pixel = loc * size - 0.5.
 template <bool BWD>
-__global__ void __launch_bounds__(256) ms_deform_attn_kernel(const MsdaP p, const float* __restrict__ value,
+__global__ void __launch_bounds__(512) ms_deform_attn_kernel(const MsdaP p, const float* __restrict__ value,
                                                              const float* __restrict__ off, const float* __restrict__ logits,
                                                              float* __restrict__ out, const float* __restrict__ dout,
                                                              float* __restrict__ dvalue, float* __restrict__ doff,
                                                              float* __restrict__ dlogits) {
   const int C = p.heads * 32;
-  const long tq = (long)blockIdx.x * 4 + (threadIdx.x >> 6);       // (image, query)
-  if (tq >= (long)p.B * p.S) return;
-  const int b = (int)(tq / p.S), s = (int)(tq % p.S);
-  const int head = (threadIdx.x & 63) >> 3, c4 = (threadIdx.x & 7) * 4;
+  const int head = (int)(blockIdx.x % p.heads);
+  long r = blockIdx.x / p.heads;
+  const int total_patches = p.pstart[p.levels];
+  int pl = (int)(r % total_patches);
+  const int b = (int)(r / total_patches);
   int ql = 0;
 #pragma unroll
   for (int l = 1; l < MAX_LEVELS; ++l)
-    if (l < p.levels && s >= p.start[l]) ql = l;
-  const int sl = s - p.start[ql];
-  const float ref_x = ((float)(sl % p.w[ql]) + 0.5f) / (float)p.w[ql];
-  const float ref_y = ((float)(sl / p.w[ql]) + 0.5f) / (float)p.h[ql];
+    if (l < p.levels && pl >= p.pstart[l]) ql = l;
+  pl -= p.pstart[ql];
+  const int qi = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+  const int qy = (pl / p.pw[ql]) * 8 + (qi >> 3), qx = (pl % p.pw[ql]) * 8 + (qi & 7);
+  const bool valid = qy < p.h[ql] && qx < p.w[ql];
+  const int s = p.start[ql] + (valid ? qy * p.w[ql] + qx : 0);
+  const long tq = (long)b * p.S + s;
+  const float ref_x = ((float)qx + 0.5f) / (float)p.w[ql];
+  const float ref_y = ((float)qy + 0.5f) / (float)p.h[ql];
   const int LP = p.levels * p.points;                                // <= 16
   const float* lg = logits + ((long)tq * p.heads + head) * LP;
   const float* of = off + ((long)tq * p.heads + head) * LP * 2;
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(256) ms_deform_attn_kernel(const MsdaP p, cons
   const float inv = 1.0f / sum;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (BWD) g = *reinterpret_cast<const float4*>(dout + (long)tq * C + head * 32 + c4);
+  if (BWD && valid) g = *reinterpret_cast<const float4*>(dout + (long)tq * C + head * 32 + c4);
   float daw[16];
   float dot_aw = 0.f;
 #pragma unroll
@@ -87,7 +97,7 @@ __global__ void __launch_bounds__(256) ms_deform_attn_kernel(const MsdaP p, cons
     const float loc_x = ref_x + of[2 * i] / (float)W, loc_y = ref_y + of[2 * i + 1] / (float)H;
     const float wim = loc_x * (float)W - 0.5f, him = loc_y * (float)H - 0.5f;
     float dwx = 0.f, dwy = 0.f, dsample = 0.f;
-    if (him > -1.f && wim > -1.f && him < (float)H && wim < (float)W) {
+    if (valid && him > -1.f && wim > -1.f && him < (float)H && wim < (float)W) {
       const int hl = (int)floorf(him), wl = (int)floorf(wim);
       const float lh = him - (float)hl, lw = wim - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
       const float* vb = value + ((long)b * p.S + p.start[l]) * C + head * 32 + c4;
@@ -120,20 +130,112 @@ __global__ void __launch_bounds__(256) ms_deform_attn_kernel(const MsdaP p, cons
       dwx = group8_sum(dwx); dwy = group8_sum(dwy); dsample = group8_sum(dsample);
       daw[i] = dsample;
       dot_aw += a * dsample;
-      if ((threadIdx.x & 7) == 0) {
+      if (valid && (threadIdx.x & 7) == 0) {
         float* dof = doff + ((long)tq * p.heads + head) * LP * 2;
         dof[2 * i] = dwx; dof[2 * i + 1] = dwy;
       }
     }
   }
   if (!BWD) {
-    *reinterpret_cast<float4*>(out + (long)tq * C + head * 32 + c4) = acc;
-  } else if ((threadIdx.x & 7) == 0) {
+    if (valid) *reinterpret_cast<float4*>(out + (long)tq * C + head * 32 + c4) = acc;
+  } else if (valid && (threadIdx.x & 7) == 0) {
     float* dl = dlogits + ((long)tq * p.heads + head) * LP;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (i < LP) dl[i] = aw[i] * inv * (daw[i] - dot_aw);
   }
+}
+
+// Forward, inference form.  Same CTA = (8x8 query patch of one level) x (one head), 512 threads, but in two phases:
+//  1. lane j of a (query, head) group prepares points j and j + 8: softmax weight, the four tap offsets (elements from the
+//     head's value base) and the four tap weights a * bilinear (0 for taps outside the level) -> shared memory, 8 words per
+//     point.  The coordinate arithmetic is done once per point instead of once per lane.
+//  2. every lane walks the group's levels*points*4 (offset, weight) pairs -- branch-free: one LDS.64, one LDG.128, four FMAs
+//     per tap, so the compiler keeps many independent loads in flight (the one-phase form was latency-bound: 16 warps per
+//     SM each waiting on a load -> coordinates -> four loads chain per point).
+__global__ void __launch_bounds__(512, 2) ms_deform_attn_fwd_kernel(const MsdaP p, const float* __restrict__ value,
+                                                                    const float* __restrict__ off, const float* __restrict__ logits,
+                                                                    float* __restrict__ out) {
+  __shared__ int2 taps[64][16 * 4 + 1];          // (element offset, weight bits) per (query, point, tap); rows padded: the 4 groups of a warp read different banks
+  // (level geometry is picked with static selects: a kernel parameter indexed by a run-time level is an indexed
+  // constant load, and those -- the ADU pipe -- were the busiest unit of the first version)
+  auto geom = [&](int l, int& H, int& W, int& start) {
+    H = p.h[0]; W = p.w[0]; start = p.start[0];
+#pragma unroll
+    for (int q = 1; q < MAX_LEVELS; ++q)
+      if (l == q) { H = p.h[q]; W = p.w[q]; start = p.start[q]; }
+  };
+  const int C = p.heads * 32;
+  const int head = blockIdx.x, b = blockIdx.z;
+  int pl = blockIdx.y, ql = 0, pfirst = 0, pwq = p.pw[0];
+#pragma unroll
+  for (int l = 1; l < MAX_LEVELS; ++l)
+    if (l < p.levels && pl >= p.pstart[l]) { ql = l; pfirst = p.pstart[l]; pwq = p.pw[l]; }
+  pl -= pfirst;
+  int Hq, Wq, startq;
+  geom(ql, Hq, Wq, startq);
+  const int qi = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const int qy = (pl / pwq) * 8 + (qi >> 3), qx = (pl % pwq) * 8 + (qi & 7);
+  const bool valid = qy < Hq && qx < Wq;
+  const int s = startq + (valid ? qy * Wq + qx : 0);
+  const long tq = (long)b * p.S + s;
+  const float ref_x = ((float)qx + 0.5f) / (float)Wq;
+  const float ref_y = ((float)qy + 0.5f) / (float)Hq;
+  const int LP = p.levels * p.points;                                // <= 16
+  const float* lg = logits + ((long)tq * p.heads + head) * LP;
+  const float2* of = reinterpret_cast<const float2*>(off + ((long)tq * p.heads + head) * LP * 2);
+  // ---- phase 1: this lane's points j and j + 8
+  float e[2];
+  float2 o[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = j + 8 * t;
+    e[t] = i < LP ? lg[i] : -INFINITY;
+    o[t] = i < LP ? of[i] : make_float2(0.f, 0.f);
+    mx = fmaxf(mx, e[t]);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) { e[t] = (j + 8 * t) < LP ? expf(e[t] - mx) : 0.f; sum += e[t]; }
+  sum = group8_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = j + 8 * t;
+    if (i >= LP) continue;
+    const int l = (i >= p.points) + (i >= 2 * p.points) + (i >= 3 * p.points);
+    const float a = e[t] * inv;
+    int H, W, startl;
+    geom(l, H, W, startl);
+    const float loc_x = ref_x + o[t].x / (float)W, loc_y = ref_y + o[t].y / (float)H;
+    const float wim = loc_x * (float)W - 0.5f, him = loc_y * (float)H - 0.5f;
+    const bool inside = valid && him > -1.f && wim > -1.f && him < (float)H && wim < (float)W;
+    const int hl = (int)floorf(him), wl = (int)floorf(wim);
+    const float lh = him - (float)hl, lw = wim - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
+    const bool t0 = inside && hl >= 0, t1 = inside && hl + 1 <= H - 1, l0 = wl >= 0, l1 = wl + 1 <= W - 1;
+    const int base = (startl + hl * W + wl) * C;                    // (< 2^31 elements per image: checked by the launcher)
+    int2* dst = &taps[qi][i * 4];
+    dst[0] = make_int2((t0 && l0) ? base : 0, __float_as_int((t0 && l0) ? a * hh * hw : 0.f));
+    dst[1] = make_int2((t0 && l1) ? base + C : 0, __float_as_int((t0 && l1) ? a * hh * lw : 0.f));
+    dst[2] = make_int2((t1 && l0) ? base + W * C : 0, __float_as_int((t1 && l0) ? a * lh * hw : 0.f));
+    dst[3] = make_int2((t1 && l1) ? base + W * C + C : 0, __float_as_int((t1 && l1) ? a * lh * lw : 0.f));
+  }
+  __syncwarp();
+  // ---- phase 2
+  const float* vb = value + (long)b * p.S * C + head * 32 + j * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n = LP * 4;
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) {
+    const int2 tw = taps[qi][i];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(vb + tw.x));
+    acc = fma4(__int_as_float(tw.y), v, acc);
+  }
+  if (valid) *reinterpret_cast<float4*>(out + (long)tq * C + head * 32 + j * 4) = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
@@ -395,11 +497,17 @@ cudaError_t launch_ms_deform_attn(const float* value, const float* off, const fl
                                   int levels, int points, const int* hs, const int* ws, cudaStream_t s) {
   MsdaP p = {};
   p.B = B; p.S = S; p.heads = heads; p.levels = levels; p.points = points;
-  int st = 0;
-  for (int l = 0; l < levels; ++l) { p.h[l] = hs[l]; p.w[l] = ws[l]; p.start[l] = st; st += hs[l] * ws[l]; }
+  int st = 0, ps = 0;
+  for (int l = 0; l < levels; ++l) {
+    p.h[l] = hs[l]; p.w[l] = ws[l]; p.start[l] = st; st += hs[l] * ws[l];
+    p.pw[l] = (ws[l] + 7) / 8; p.pstart[l] = ps; ps += p.pw[l] * ((hs[l] + 7) / 8);
+  }
+  p.pstart[levels] = ps;
   const long tq = (long)B * S;
   if (tq <= 0) return cudaSuccess;
-  ms_deform_attn_kernel<false><<<(unsigned)((tq + 3) / 4), 256, 0, s>>>(p, value, off, logits, out, nullptr, nullptr, nullptr, nullptr);
+  if ((long)S * heads * 32 > 0x7fffffffL) return cudaErrorInvalidValue;
+  if (ps > 65535 || B > 65535) return cudaErrorInvalidValue;
+  ms_deform_attn_fwd_kernel<<<dim3(heads, ps, B), 512, 0, s>>>(p, value, off, logits, out);
   count_launch();
   return cudaGetLastError();
 }
@@ -409,13 +517,17 @@ cudaError_t launch_ms_deform_attn_bwd(const float* value, const float* off, cons
                                       const int* ws, cudaStream_t s) {
   MsdaP p = {};
   p.B = B; p.S = S; p.heads = heads; p.levels = levels; p.points = points;
-  int st = 0;
-  for (int l = 0; l < levels; ++l) { p.h[l] = hs[l]; p.w[l] = ws[l]; p.start[l] = st; st += hs[l] * ws[l]; }
+  int st = 0, ps = 0;
+  for (int l = 0; l < levels; ++l) {
+    p.h[l] = hs[l]; p.w[l] = ws[l]; p.start[l] = st; st += hs[l] * ws[l];
+    p.pw[l] = (ws[l] + 7) / 8; p.pstart[l] = ps; ps += p.pw[l] * ((hs[l] + 7) / 8);
+  }
+  p.pstart[levels] = ps;
   const long tq = (long)B * S;
   if (tq <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(dvalue, 0, (size_t)tq * heads * 32 * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  ms_deform_attn_kernel<true><<<(unsigned)((tq + 3) / 4), 256, 0, s>>>(p, value, off, logits, nullptr, dout, dvalue, doff, dlogits);
+  ms_deform_attn_kernel<true><<<(unsigned)((long)B * ps * heads), 512, 0, s>>>(p, value, off, logits, nullptr, dout, dvalue, doff, dlogits);
   count_launch();
   return cudaGetLastError();
 }

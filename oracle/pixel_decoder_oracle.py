@@ -78,7 +78,7 @@ def ms_deform_attn(sd, pre, x, pos, ref, shapes):
     off = O.linear(q, sd[pre + 'sampling_offsets.weight'], sd[pre + 'sampling_offsets.bias']).view(B, S, HEADS, LEVELS, POINTS, 2)
     aw = O.linear(q, sd[pre + 'attention_weights.weight'], sd[pre + 'attention_weights.bias']).view(B, S, HEADS, LEVELS * POINTS)
     aw = aw.softmax(-1).view(B, S, HEADS, LEVELS, POINTS)
-    norm = torch.tensor([[w, h] for (h, w) in shapes], dtype=torch.float32)           # offset_normalizer: (w, h) per level
+    norm = torch.tensor([[w, h] for (h, w) in shapes], dtype=torch.float32, device=x.device)   # offset_normalizer: (w, h) per level
     loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
     out = ms_deform_attn_core(value, shapes, loc, aw)
     return O.linear(out, sd[pre + 'output_proj.weight'], sd[pre + 'output_proj.bias']) + x
@@ -107,10 +107,10 @@ def pixel_decoder_forward(sd, feats, num_layers=6, return_debug=False):
         h, w = f.shape[-2:]
         shapes.append((h, w))
         tokens.append(p.flatten(2).transpose(1, 2))                                   # (B, hw, C)
-        pos.append(O.sine_pos_enc(h, w) + sd['level_encoding.weight'][i][None])     # level_embed + pos_embed
+        pos.append(O.sine_pos_enc(h, w).to(f.device) + sd['level_encoding.weight'][i][None])     # level_embed + pos_embed
     x = torch.cat(tokens, 1)
     pos = torch.cat(pos, 0)[None]
-    ref = reference_points(shapes)
+    ref = reference_points(shapes).to(x.device)
     dbg = {'tokens_in': x}
     for l in range(num_layers):
         x = encoder_layer(sd, l, x, pos, ref, shapes)
