@@ -328,6 +328,65 @@ def grounding_leg(dev, Bg=16, Q=100, T=35, D=768):
                 note='cgg_grounding_loss + cgg_grounding_loss_backward, one head call, fp32')
 
 
+def pixel_decoder_leg(dev, B, head=None, precision='tf32', steps=5):
+    """Row f3 alone, then chained: mmdet's MSDeformAttnPixelDecoder (the step before the path, head.py:787) at the configs[1]
+    shapes -- B images of 1024^2, R50 channel widths (256/512/1024/2048 at strides 4..32), 6 encoder layers -- through
+    cgg_b200.pixel_decoder (every contraction on tcgen05 kind::tf32), and the same step as plain torch CUDA ops (the oracle on
+    the GPU: cuDNN convs, ATen GroupNorm / grid_sample -- mmcv's pure-torch deformable attention).  Algorithmic FLOPs: the
+    contractions only."""
+    from cgg_b200 import synth
+    from cgg_b200.pixel_decoder import build_pixel_decoder_from_state_dict
+    from oracle import pixel_decoder_oracle as PO
+    chs = (256, 512, 1024, 2048)
+    sd = synth.make_pixel_decoder_params(0, in_channels=chs)
+    feats = [f.to(dev) for f in synth.make_backbone_feats(0, B, H, W, chs)]
+    m = build_pixel_decoder_from_state_dict(sd, chs, dev, precision=precision).eval()
+
+    def timed(fn, n, w=2):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    S = sum((H // s) * (W // s) for s in (32, 16, 8))
+    P4 = (H // 4) * (W // 4)
+    fl = 2.0 * 256 * sum(c * (H // s) * (W // s) for c, s in zip(chs[1:], (8, 16, 32)))          # input convs
+    fl += 6 * 2.0 * S * (256 * (256 + 192 + 96 + 256) + 2 * 256 * 1024)                         # encoder linears
+    fl += 2.0 * P4 * 256 * (chs[0] + 9 * 256 + 256)                                             # lateral, 3x3 output conv, mask conv
+    out = dict(batch=B, precision=precision, tokens_per_image=S, gflop_per_image=fl / 1e9)
+    with torch.no_grad():
+        ms = timed(lambda: m(feats), steps)
+        out.update(ms=ms, images_per_s=B / ms * 1e3, tflops=fl * B / (ms * 1e-3) / 1e12)
+        if head is not None:                     # pixel decoder -> decoder head in one call (Mask2FormerHeadOpenB200.forward)
+            m.out_dtype = torch.bfloat16 if head.precision == 'bf16' else torch.float32
+            head.pixel_decoder = m
+            metas = [dict()] * B
+            ms2 = timed(lambda: head(feats, metas), steps)
+            head.pixel_decoder = None
+            out['with_decoder_head'] = dict(ms=ms2, images_per_s=B / ms2 * 1e3,
+                                            note='Mask2FormerHeadOpenB200.forward(feats, img_metas): pixel decoder + the '
+                                                 '10-head-call decoder path, eager launches, one batch in flight')
+        sd_d = {k: v.to(dev) for k, v in sd.items()}
+        base = {}
+        for name, tf32 in (('fp32', False), ('tf32', True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            base[name + '_ms'] = timed(lambda: PO.pixel_decoder_forward(sd_d, feats), 3, 1)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = True
+        out['torch_gpu_baseline'] = base
+        out['speedup_vs_faster'] = min(base.values()) / ms
+    out['note'] = ('cgg_b200.pixel_decoder.MSDeformAttnPixelDecoderB200 forward, token-major fp32 activations, contractions on '
+                   'tcgen05 kind::tf32; inputs resident in HBM (%.0f MB per step)' % (sum(f.numel() for f in feats) * 4 / 1e6))
+    return out
+
+
 def matching_leg(dev, B=2, Q=200, ncls1=118, G=20, h=256, w=256, P=12544):
     """Row f2 alone: the matching-based terms of loss_single for ONE head call at the configs[3] shapes (B images, Q
     queries, G ground-truth masks per image, 12 544 points): point sampling, cost matrix, Hungarian solve (host),
@@ -815,11 +874,16 @@ def run_b200_arm(args):
                                     sustained_frac=flops_per_image(Q) * sustained['value'] / world / 1e12 / peaks['tflops']))
 
     # ---- stage / config legs
-    grounding = train = matching_rec = None
+    grounding = train = matching_rec = pixdec = None
     if not args.no_train:
         try:
             grounding = grounding_leg(dev) if rank == 0 else None
             matching_rec = matching_leg(dev) if rank == 0 else None
+            if rank == 0 and world == 1 and not args.no_pixel_decoder:
+                try:
+                    pixdec = pixel_decoder_leg(dev, B, heads[0])
+                except Exception as e:      # noqa: BLE001
+                    pixdec = dict(error=repr(e)[:300])
             del heads, fly_in
             torch.cuda.empty_cache()
             train = train_leg(args, rank, world, dev)
@@ -858,6 +922,8 @@ def run_b200_arm(args):
             line['grounding'] = grounding
         if matching_rec is not None:
             line['matching_losses'] = matching_rec
+        if pixdec is not None:
+            line['pixel_decoder'] = pixdec
         if tgb is not None:
             line['torch_gpu_baseline'] = tgb
         if cpu is not None:
@@ -879,6 +945,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-torch-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the configs[3] training-step leg and the K7 stage leg')
+    ap.add_argument('--no-pixel-decoder', action='store_true', help='skip the row-f3 pixel-decoder leg')
     ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling leg')
     ap.add_argument('--train-batch', type=int, default=2, help='images per GPU in the training-step leg')
     ap.add_argument('--train-steps', type=int, default=5)

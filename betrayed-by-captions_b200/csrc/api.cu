@@ -976,16 +976,20 @@ extern "C" int cgg_softmax_rows(cgg_handle* h, float* x, int rows, int n, void* 
 }
 
 // ====================================================================== the pixel decoder before the path (row f3)
-extern "C" int cgg_ms_deform_attn(cgg_handle* h, const float* value, const float* offsets, const float* weight_logits, float* out,
-                                  int batch, int tokens, int heads, int levels, int points, const int* level_h, const int* level_w,
-                                  void* stream) {
+extern "C" int cgg_ms_deform_attn(cgg_handle* h, const float* value, long value_stride, const float* offsets, long offset_stride,
+                                  const float* weight_logits, long logit_stride, float* out, int batch, int tokens, int heads,
+                                  int levels, int points, const int* level_h, const int* level_w, void* stream) {
   if (!h || !value || !offsets || !weight_logits || !out || !level_h || !level_w) return CGG_ERR_NULL;
+  if (value_stride < heads * 32 || value_stride % 4 || offset_stride < heads * levels * points * 2 || offset_stride % 2 ||
+      logit_stride < heads * levels * points || (reinterpret_cast<uintptr_t>(value) & 15) || (reinterpret_cast<uintptr_t>(offsets) & 7))
+    return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: token strides / alignment (value rows 16-byte, offset rows 8-byte aligned)");
   if (batch < 0 || tokens < 1 || heads < 1 || heads > 8 || levels < 1 || levels > 4 || points < 1 || levels * points > 16)
     return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: heads <= 8 (x 32 channels), levels <= 4, levels * points <= 16");
   long tot = 0;
   for (int l = 0; l < levels; ++l) tot += (long)level_h[l] * level_w[l];
   if (tot != tokens) return fail(h, CGG_ERR_BAD_SHAPE, "ms_deform_attn: level sizes do not add up to the token count");
-  CU(launch_ms_deform_attn(value, offsets, weight_logits, out, batch, tokens, heads, levels, points, level_h, level_w, (cudaStream_t)stream));
+  CU(launch_ms_deform_attn(value, value_stride, offsets, offset_stride, weight_logits, logit_stride, out, batch, tokens, heads, levels, points,
+                           level_h, level_w, (cudaStream_t)stream));
   return CGG_OK;
 }
 

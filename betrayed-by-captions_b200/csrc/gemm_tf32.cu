@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   __shared__ uint64_t full[4], empty[4], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[4][256];     // per epilogue warp: the bias of the current tile's columns
+  __shared__ __align__(16) float stage_s[4][1024];   // per epilogue warp: a 32 x 32 chunk on its way from row-per-thread to coalesced rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = p.tmem_cols >> 1;                 // two accumulators: the epilogue of tile i overlaps tile i + 1
@@ -195,16 +196,29 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       const bool rowok = gm < p.M;
       float* crow = p.partial ? p.partial + (((long)split * p.batch + b) * p.M + gm) * p.N
                               : p.C + (long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2 + (long)gm * p.sCm;
+      // Row-major C (mode 1).  Everything the epilogue reads from memory is requested BEFORE the accumulator is waited for:
+      // the tile's bias goes to the warp's shared-memory row, the residual / old-C values of a 32-column chunk ride in
+      // registers one chunk ahead (a serial load -> add -> store chain per chunk was the top stall of the first version).
+      // A thread owns an accumulator ROW, so stores straight from the registers touch 32 different lines per instruction,
+      // 16 bytes each.  Products WITHOUT a residual therefore send each 32 x 32 chunk through the warp's shared-memory tile
+      // (float4 index XOR row: conflict-free both ways) and store whole 128-byte lines, 4 rows per instruction (measured on
+      // the 344 k x 1024 x 256 FFN product: 0.68 -> 0.57 ms); with a residual the row-per-thread form is the faster one
+      // (0.38 vs 0.43 ms on 344 k x 256 x 256 + residual) and is kept.
+      const bool add = R || p.accumulate;
+      const bool rich = p.epi_mode == 1 && !p.partial;
+      const bool staged = rich && !add;
+      const bool rich2 = p.epi_mode == 2 && !p.partial && !plain && !R && !p.accumulate;   // m-contiguous C with bias / alpha / relu
+      const int rsub = lane >> 3, cq = lane & 7;
+      const int gm0 = m0 + quarter * 32;                     // first row of this warp
+      float* cbase = p.C + (long)(b / p.batch_inner) * p.sCb + (long)(b % p.batch_inner) * p.sCb2;
       const float* rrow = (R && !p.partial) ? R + (long)b * p.sRb + (long)(p.r_mod >= p.M ? gm : gm % p.r_mod) * p.sRm : nullptr;
-      // Everything the epilogue reads from memory is requested BEFORE the accumulator is waited for: the tile's bias goes to
-      // the warp's shared-memory row, the residual / old-C values of a 32-column chunk ride in registers one chunk ahead
-      // (they were a serial load -> add -> store chain per chunk: the FADDs waiting on them were the top stall of the kernel).
-      const bool rich = p.epi_mode == 1 && !p.partial && !plain;
+      const int col_end = min(p.N, n0 + p.n_tile);
       auto prefetch = [&](float4* rv, int j) {
-        const int nq = min(8, (p.N - (n0 + j)) >> 2);
+        const int nq = min(8, (col_end - (n0 + j)) >> 2);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          rv[c4] = (rrow && rowok && c4 < nq) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[c4] = (rrow && rowok && c4 < nq && n0 + j < p.r_ncols) ? __ldg(reinterpret_cast<const float4*>(rrow + n0 + j) + c4)
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.accumulate && rowok && c4 < nq) {          // C += ...: the old values ride in the residual registers
             const float4 ov = reinterpret_cast<const float4*>(crow + n0 + j)[c4];
             rv[c4].x += ov.x; rv[c4].y += ov.y; rv[c4].z += ov.z; rv[c4].w += ov.w;
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
         }
       };
       float4 va[8], vb[8];
-      if (rich) {
+      if (rich || rich2) {
         if (bias) {
           __syncwarp();
 #pragma unroll
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
           }
           __syncwarp();
         }
-        prefetch(va, 0);
+        if (rich && add) prefetch(va, 0);
       }
       ptx::mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
       ptx::tc_fence_after();
@@ -239,23 +253,40 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       };
       auto waitr = [&](uint32_t* r) { ptx::tmem_ld_wait16(r); ptx::tmem_ld_wait16(r + 16); };
       auto process = [&](const uint32_t* r, const float4* rv, int j) {
-        if (!rowok) return;
+        if (!rowok && !staged) return;                   // (the staged path is warp-collective)
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.epi_mode == 1) {
-            const int nq = min(8, (p.N - (n0 + j)) >> 2);          // float4 groups of this chunk inside N
-            float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
-            if (p.partial || plain) {
+          if (staged) {
+            float* stg = stage_s[quarter];
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4)
-                if (c4 < nq) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-            } else {
+            for (int c4 = 0; c4 < 8; ++c4)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            __syncwarp();
+            const int col = n0 + j + cq * 4;
+            const bool colok = col < col_end;
+            const float4 bv = bias ? *reinterpret_cast<const float4*>(&bias_s[quarter][j + cq * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool relu = n0 + j >= p.relu_from;               // relu_from is a multiple of 32 here (0 or "never")
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              const float4 a = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cq ^ (rr & 7)) << 2));
+              float4 o;
+              o.x = (a.x + bv.x) * p.alpha; o.y = (a.y + bv.y) * p.alpha; o.z = (a.z + bv.z) * p.alpha; o.w = (a.w + bv.w) * p.alpha;
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (colok && gm0 + rr < p.M) *reinterpret_cast<float4*>(cbase + (long)(gm0 + rr) * p.sCm + col) = o;
+            }
+            __syncwarp();
+          } else if (rich) {                                 // with a residual / C +=: row per thread
+            if (rowok) {
+              const int nq = min(8, (col_end - (n0 + j)) >> 2);
+              float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
               float4 bv[8];
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4)
                 bv[c4] = bias ? *reinterpret_cast<const float4*>(&bias_s[quarter][j + 4 * c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const bool relu = n0 + j >= p.relu_from;             // relu_from is a multiple of 32 here (0 or "never")
+              const bool relu = n0 + j >= p.relu_from;
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
                 float4 o;
@@ -267,17 +298,34 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
                 if (c4 < nq) dst[c4] = o;
               }
             }
+          } else if (p.epi_mode == 1) {                    // split-K partial sums: raw accumulator rows
+            const int nq = min(8, min(p.N - (n0 + j), p.n_tile - j) >> 2);
+            float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              if (c4 < nq) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
           } else if (p.epi_mode == 2 && plain) {
             float* cp = crow + (long)(n0 + j) * p.sCn;
-            const int nc = min(32, p.N - (n0 + j));
+            const int nc = min(32, min(p.N - (n0 + j), p.n_tile - j));
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (i < nc) *cp = v[i];
               cp += p.sCn;
             }
+          } else if (rich2) {                              // one 128-byte line per column; the column's bias is warp-uniform
+            float* cp = crow + (long)(n0 + j) * p.sCn;
+            const int nc = min(32, min(p.N - (n0 + j), p.n_tile - j));
+            const bool relu = n0 + j >= p.relu_from;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float o = (v[i] + (bias ? bias_s[quarter][j + i] : 0.f)) * p.alpha;
+              if (relu) o = fmaxf(o, 0.f);
+              if (i < nc) *cp = o;
+              cp += p.sCn;
+            }
           } else if (p.epi_mode == 2 && plain_acc) {       // C += acc: the chunk's 32 old values are read before any store
             float* cp = crow + (long)(n0 + j) * p.sCn;
-            const int nc = min(32, p.N - (n0 + j));
+            const int nc = min(32, min(p.N - (n0 + j), p.n_tile - j));
             float old[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) old[i] = (i < nc) ? cp[(long)i * p.sCn] : 0.f;
@@ -302,13 +350,13 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       waitr(ra);
       while (true) {
         bool more = more_after(j);
-        if (more) { issue(rb, j + 32); if (rich) prefetch(vb, j + 32); }
+        if (more) { issue(rb, j + 32); if (rich && add) prefetch(vb, j + 32); }
         process(ra, va, j);
         if (!more) break;
         waitr(rb);
         j += 32;
         more = more_after(j);
-        if (more) { issue(ra, j + 32); if (rich) prefetch(va, j + 32); }
+        if (more) { issue(ra, j + 32); if (rich && add) prefetch(va, j + 32); }
         process(rb, vb, j);
         if (!more) break;
         waitr(ra);
@@ -434,7 +482,9 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.a_mn = a_major; p.b_mn = b_major;
   p.w_shared = w_shared ? 1 : 0;
-  p.n_tile = g.N <= 256 ? round_up(g.N, 16) : (g.N % 256 == 0 ? 256 : 128);
+  // N <= 256: one tile of the whole width; wider: the fewest tiles of <= 256 columns, evenly sized (544 -> 3 x 192, 288 -> 2 x 144)
+  // (several column tiles: multiples of 32, the epilogue's chunk width, so that no chunk straddles two tiles)
+  { const int nt0 = (g.N + 255) / 256; p.n_tile = round_up((g.N + nt0 - 1) / nt0, nt0 > 1 ? 32 : 16); }
   p.b_groups = (p.n_tile + 31) / 32;
   const int b_stage = ((p.b_mn ? p.b_groups * 32 : p.n_tile) * BK * 4 + 1023) & ~1023;
   const int stage_bytes = A_STAGE_BYTES + b_stage;
@@ -480,13 +530,13 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.partial) p.epi_mode = (g.N % 4 == 0) ? 1 : 0;
   else if (g.sCn == 1 && g.sCm % 4 == 0 && g.sCb % 4 == 0 && g.sCb2 % 4 == 0 && g.N % 4 == 0 && al16(g.C) && (!g.bias || al16(g.bias)) &&
-           (!g.R || (g.sRn == 1 && g.sRm % 4 == 0 && g.sRb % 4 == 0 && al16(g.R) && g.r_ncols >= g.N)) &&
+           (!g.R || (g.sRn == 1 && g.sRm % 4 == 0 && g.sRb % 4 == 0 && al16(g.R) && (g.r_ncols >= g.N || g.r_ncols % 32 == 0))) &&
            (g.relu_from % 32 == 0))
     p.epi_mode = 1;
-  else if (g.sCm == 1) p.epi_mode = 2;
+  else if (g.sCm == 1 && (g.relu_from % 32 == 0 || g.relu_from >= g.N) && (!g.bias || al16(g.bias)) && (!g.bias || g.N % 4 == 0)) p.epi_mode = 2;
   else p.epi_mode = 0;
   if (!t->attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 24 * 1024) != cudaSuccess) {
       t->err = "cudaFuncSetAttribute(gemm_tf32_kernel) failed";
       return -1;
     }

@@ -122,8 +122,9 @@ cudaError_t launch_weighted_ce_bwd(const float* logits, const int64_t* labels, c
                                    const float* grow, float* dlogits, cudaStream_t s);
 
 // ---- the pixel decoder before the path (pixdec_kernels.cu), token-major fp32 activations
-cudaError_t launch_ms_deform_attn(const float* value, const float* off, const float* logits, float* out, int B, int S, int heads,
-                                  int levels, int points, const int* hs, const int* ws, cudaStream_t s);
+cudaError_t launch_ms_deform_attn(const float* value, long value_stride, const float* off, long off_stride, const float* logits,
+                                  long logit_stride, float* out, int B, int S, int heads, int levels, int points, const int* hs,
+                                  const int* ws, cudaStream_t s);
 cudaError_t launch_ms_deform_attn_bwd(const float* value, const float* off, const float* logits, const float* dout, float* dvalue,
                                       float* doff, float* dlogits, int B, int S, int heads, int levels, int points, const int* hs,
                                       const int* ws, cudaStream_t s);

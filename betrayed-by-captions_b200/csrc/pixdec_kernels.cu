@@ -25,6 +25,7 @@ struct MsdaP {
   int B, S, heads, levels, points;     // head_dim fixed at 32 (8 lanes x float4)
   int h[MAX_LEVELS], w[MAX_LEVELS], start[MAX_LEVELS];
   int pw[MAX_LEVELS], pstart[MAX_LEVELS + 1];   // 8x8-query patches per level row / first patch of the level
+  int vs, os, ls;                      // forward: elements between consecutive tokens of value / offsets / logits
 };
 
 __device__ __forceinline__ float group8_sum(float v) {
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(512, 2) ms_deform_attn_fwd_kernel(const MsdaP 
   const float ref_x = ((float)qx + 0.5f) / (float)Wq;
   const float ref_y = ((float)qy + 0.5f) / (float)Hq;
   const int LP = p.levels * p.points;                                // <= 16
-  const float* lg = logits + ((long)tq * p.heads + head) * LP;
-  const float2* of = reinterpret_cast<const float2*>(off + ((long)tq * p.heads + head) * LP * 2);
+  const float* lg = logits + (long)tq * p.ls + head * LP;
+  const float2* of = reinterpret_cast<const float2*>(off + (long)tq * p.os + head * LP * 2);
   // ---- phase 1: this lane's points j and j + 8
   float e[2];
   float2 o[2];
@@ -217,16 +218,16 @@ __global__ void __launch_bounds__(512, 2) ms_deform_attn_fwd_kernel(const MsdaP 
     const int hl = (int)floorf(him), wl = (int)floorf(wim);
     const float lh = him - (float)hl, lw = wim - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
     const bool t0 = inside && hl >= 0, t1 = inside && hl + 1 <= H - 1, l0 = wl >= 0, l1 = wl + 1 <= W - 1;
-    const int base = (startl + hl * W + wl) * C;                    // (< 2^31 elements per image: checked by the launcher)
+    const int base = (startl + hl * W + wl) * p.vs;                 // (< 2^31 elements per image: checked by the launcher)
     int2* dst = &taps[qi][i * 4];
     dst[0] = make_int2((t0 && l0) ? base : 0, __float_as_int((t0 && l0) ? a * hh * hw : 0.f));
-    dst[1] = make_int2((t0 && l1) ? base + C : 0, __float_as_int((t0 && l1) ? a * hh * lw : 0.f));
-    dst[2] = make_int2((t1 && l0) ? base + W * C : 0, __float_as_int((t1 && l0) ? a * lh * hw : 0.f));
-    dst[3] = make_int2((t1 && l1) ? base + W * C + C : 0, __float_as_int((t1 && l1) ? a * lh * lw : 0.f));
+    dst[1] = make_int2((t0 && l1) ? base + p.vs : 0, __float_as_int((t0 && l1) ? a * hh * lw : 0.f));
+    dst[2] = make_int2((t1 && l0) ? base + W * p.vs : 0, __float_as_int((t1 && l0) ? a * lh * hw : 0.f));
+    dst[3] = make_int2((t1 && l1) ? base + W * p.vs + p.vs : 0, __float_as_int((t1 && l1) ? a * lh * lw : 0.f));
   }
   __syncwarp();
   // ---- phase 2
-  const float* vb = value + (long)b * p.S * C + head * 32 + j * 4;
+  const float* vb = value + (long)b * p.S * p.vs + head * 32 + j * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int n = LP * 4;
 #pragma unroll 8
@@ -291,23 +292,32 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
   }
 }
 
-// mean / rstd per (image, group) from the stage-1 channel sums
+// mean / rstd per (image, group) from the stage-1 channel sums: one warp per group, lanes stride over the row chunks,
+// fixed-order tree over the lanes (deterministic), double accumulation
 __global__ void gn_finish_kernel(const float* __restrict__ partial, float* __restrict__ mean_rstd, int P, int C, int G, int chunks,
                                  float eps) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
+  const int b = blockIdx.x, lane = threadIdx.x & 31;
   const int cpg = C / G;
-  double s1 = 0.0, s2 = 0.0;
-  for (int ch = 0; ch < chunks; ++ch)
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const float* o = partial + (((long)b * chunks + ch) * C + c) * 2;
-      s1 += (double)o[0]; s2 += (double)o[1];
+  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int ch = lane; ch < chunks; ch += 32)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        const float* o = partial + (((long)b * chunks + ch) * C + c) * 2;
+        s1 += (double)o[0]; s2 += (double)o[1];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-  const double n = (double)P * cpg, mu = s1 / n;
-  double var = s2 / n - mu * mu;
-  if (var < 0.0) var = 0.0;
-  mean_rstd[((long)b * G + g) * 2] = (float)mu;
-  mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (lane == 0) {
+      const double n = (double)P * cpg, mu = s1 / n;
+      double var = s2 / n - mu * mu;
+      if (var < 0.0) var = 0.0;
+      mean_rstd[((long)b * G + g) * 2] = (float)mu;
+      mean_rstd[((long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
@@ -493,9 +503,11 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __rest
 
 }  // namespace
 
-cudaError_t launch_ms_deform_attn(const float* value, const float* off, const float* logits, float* out, int B, int S, int heads,
-                                  int levels, int points, const int* hs, const int* ws, cudaStream_t s) {
+cudaError_t launch_ms_deform_attn(const float* value, long value_stride, const float* off, long off_stride, const float* logits,
+                                  long logit_stride, float* out, int B, int S, int heads, int levels, int points, const int* hs,
+                                  const int* ws, cudaStream_t s) {
   MsdaP p = {};
+  p.vs = (int)value_stride; p.os = (int)off_stride; p.ls = (int)logit_stride;
   p.B = B; p.S = S; p.heads = heads; p.levels = levels; p.points = points;
   int st = 0, ps = 0;
   for (int l = 0; l < levels; ++l) {
@@ -505,7 +517,7 @@ cudaError_t launch_ms_deform_attn(const float* value, const float* off, const fl
   p.pstart[levels] = ps;
   const long tq = (long)B * S;
   if (tq <= 0) return cudaSuccess;
-  if ((long)S * heads * 32 > 0x7fffffffL) return cudaErrorInvalidValue;
+  if ((long)S * value_stride > 0x7fffffffL) return cudaErrorInvalidValue;
   if (ps > 65535 || B > 65535) return cudaErrorInvalidValue;
   ms_deform_attn_fwd_kernel<<<dim3(heads, ps, B), 512, 0, s>>>(p, value, off, logits, out);
   count_launch();
@@ -542,7 +554,7 @@ cudaError_t launch_group_norm(const float* x, const float* gamma, const float* b
   if (B <= 0 || P <= 0) return cudaSuccess;
   const int chunks = (P + GN_ROWS - 1) / GN_ROWS;
   gn_partial_kernel<<<dim3(chunks, B), 256, 0, s>>>(x, nullptr, 0, nullptr, G, scratch, P, C, chunks);
-  gn_finish_kernel<<<B, ((G + 31) / 32) * 32, 0, s>>>(scratch, mean_rstd, P, C, G, chunks, eps);
+  gn_finish_kernel<<<B, 32 * (G < 32 ? G : 32), 0, s>>>(scratch, mean_rstd, P, C, G, chunks, eps);
   const long total4 = (long)B * P * (C / 4);
   gn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(x, mean_rstd, gamma, beta, y, total4, P, C, G, relu ? 1 : 0);
   count_launch(3);

@@ -137,7 +137,7 @@ def load():
     lib.cgg_instance_mask_stats.argtypes = [vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     lib.cgg_softmax_rows.argtypes = [vp, vp, i, i, vp]
     ip = C.POINTER(C.c_int)
-    lib.cgg_ms_deform_attn.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, ip, ip, vp]
+    lib.cgg_ms_deform_attn.argtypes = [vp, vp, lg, vp, lg, vp, lg, vp, i, i, i, i, i, ip, ip, vp]
     lib.cgg_ms_deform_attn_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, ip, ip, vp]
     lib.cgg_group_norm_scratch_bytes.argtypes = [i, i, i, i]
     lib.cgg_group_norm_scratch_bytes.restype = sz

@@ -185,8 +185,8 @@ class _MSDeformCore(torch.autograd.Function):
         hs = (C.c_int * L)(*[s[0] for s in shapes])
         ws = (C.c_int * L)(*[s[1] for s in shapes])
         out = k.new(B, S, Cc)
-        k.chk(k.lib.cgg_ms_deform_attn(k.h, _p(value), _p(off), _p(logits), _p(out), B, S, heads, L, points, hs, ws, k.s()),
-              'cgg_ms_deform_attn')
+        k.chk(k.lib.cgg_ms_deform_attn(k.h, _p(value), Cc, _p(off), off.shape[-1], _p(logits), logits.shape[-1], _p(out), B, S,
+                                       heads, L, points, hs, ws, k.s()), 'cgg_ms_deform_attn')
         ctx.k, ctx.geom = k, (hs, ws, heads, L, points)
         ctx.save_for_backward(value, off, logits)
         return out
@@ -397,14 +397,36 @@ class MSDeformAttnPixelDecoderB200(nn.Module):
             starts.append(starts[-1] + h * w)
         # ---- encoder: (self_attn, norm, ffn, norm) x num_layers
         x = x.view(B * S, Cc)
+        fused = not torch.is_grad_enabled()
+        hs = (C.c_int * self.levels)(*[s_[0] for s_ in shapes])
+        ws = (C.c_int * self.levels)(*[s_[1] for s_ in shapes])
         for layer in self.encoder.layers:
             a = layer.attentions[0]
-            q = _AddRows.apply(k, x.view(B, S, Cc), pos, B).view(B * S, Cc)
-            value = _Linear.apply(k, x, a.value_proj.weight, a.value_proj.bias, None, 1.0, False)
-            off = _Linear.apply(k, q, a.sampling_offsets.weight, a.sampling_offsets.bias, None, 1.0, False)
-            lg = _Linear.apply(k, q, a.attention_weights.weight, a.attention_weights.bias, None, 1.0, False)
-            core = _MSDeformCore.apply(k, value.view(B, S, Cc), off.view(B, S, -1), lg.view(B, S, -1), shapes, self.heads,
-                                       self.points)
+            if fused:
+                # inference: ONE projection [offsets | logits | value] of the token buffer.  (x + pos) W^T = x W^T + pos W^T: the
+                # positional part is a (S, 288) table per layer, added by the epilogue as a row-periodic residual -- x + pos is
+                # never materialised and x is read once instead of three times.
+                n_off, n_lg = a.sampling_offsets.weight.shape[0], a.attention_weights.weight.shape[0]
+                Wq = torch.cat([a.sampling_offsets.weight, a.attention_weights.weight], 0)
+                Wcat = torch.cat([Wq, a.value_proj.weight], 0)
+                bcat = torch.cat([a.sampling_offsets.bias, a.attention_weights.bias, a.value_proj.bias], 0)
+                ptab = k.new(S, n_off + n_lg)
+                k.gemm(pos, (0, Cc, 1), Wq, (0, Cc, 1), ptab, (0, n_off + n_lg, 1), S, n_off + n_lg, Cc)
+                N = Wcat.shape[0]
+                proj = k.new(B * S, N)
+                k.gemm(x, (0, Cc, 1), Wcat, (0, Cc, 1), proj, (0, N, 1), B * S, N, Cc, bias=bcat, R=ptab,
+                       sR=(0, n_off + n_lg, 1), r_mod=S, r_ncols=n_off + n_lg)
+                core = k.new(B, S, Cc)
+                k.chk(k.lib.cgg_ms_deform_attn(k.h, C.c_void_p(proj.data_ptr() + 4 * (n_off + n_lg)), N, _p(proj), N,
+                                               C.c_void_p(proj.data_ptr() + 4 * n_off), N, _p(core), B, S, self.heads,
+                                               self.levels, self.points, hs, ws, k.s()), 'cgg_ms_deform_attn')
+            else:
+                q = _AddRows.apply(k, x.view(B, S, Cc), pos, B).view(B * S, Cc)
+                value = _Linear.apply(k, x, a.value_proj.weight, a.value_proj.bias, None, 1.0, False)
+                off = _Linear.apply(k, q, a.sampling_offsets.weight, a.sampling_offsets.bias, None, 1.0, False)
+                lg = _Linear.apply(k, q, a.attention_weights.weight, a.attention_weights.bias, None, 1.0, False)
+                core = _MSDeformCore.apply(k, value.view(B, S, Cc), off.view(B, S, -1), lg.view(B, S, -1), shapes, self.heads,
+                                           self.points)
             t = _Linear.apply(k, core.view(B * S, Cc), a.output_proj.weight, a.output_proj.bias, x, 1.0, False)
             x1 = _LayerNorm.apply(k, t, layer.norms[0].weight, layer.norms[0].bias, 1e-5)
             fc1, fc2 = layer.ffns[0].layers[0][0], layer.ffns[0].layers[1]

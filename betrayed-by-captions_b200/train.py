@@ -43,7 +43,7 @@ class _K:
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
 
     def gemm(self, A, sA, W, sW, Cc, sC, M, N, K, batch=1, bias=None, R=None, sR=(0, 0, 0), r_mod=None, alpha=1.0,
-             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0), accumulate=False, conv_cin=0):
+             relu=False, a_mmajor=False, c_mmajor=False, batch_inner=1, s2=(0, 0, 0), accumulate=False, conv_cin=0, r_ncols=1 << 30):
         """C[b,m,n] = relu?((sum_k A[b,m,k] W[b,n,k] + bias[n]) * alpha + R[b, m % r_mod, n]); element strides
         sA = (b, m, k), sW = (b, n, k), sC = (b, m, n), sR = (b, m, n)."""
         d = _lib.GemmDesc()
@@ -56,7 +56,7 @@ class _K:
             d.r_mod = r_mod if r_mod is not None else M
         else:
             d.R, d.r_mod = None, 1
-        d.r_ncols = 1 << 30
+        d.r_ncols = r_ncols                                           # the residual applies to columns n < r_ncols
         d.C, (d.sCb, d.sCm, d.sCn) = Cc.data_ptr(), sC
         d.M, d.N, d.K, d.batch = M, N, K, batch
         d.relu, d.alpha = int(relu), float(alpha)

@@ -375,11 +375,13 @@ int cgg_softmax_rows(cgg_handle *h, float *x, int rows, int n, void *stream);
  *   points) = the attention_weights projection BEFORE its softmax (done here, over levels*points).  Reference point of
  *   token s = its own pixel centre ((x+.5)/w, (y+.5)/h) in every level (all-valid padding mask, as the reference runs it);
  *   bilinear taps, zero outside, align_corners=False.  out (B, S, heads*32).  level_h / level_w: HOST arrays.
+ *   The three inputs of the forward carry their own token stride (elements between consecutive tokens), so that they can
+ *   be column blocks of ONE fused projection [offsets | logits | value] of the token buffer.
  *   The backward returns dvalue (zeroed here, then scattered with atomics), doffsets and dweight_logits (through the
  *   softmax). */
-int cgg_ms_deform_attn(cgg_handle *h, const float *value, const float *offsets, const float *weight_logits, float *out,
-                       int batch, int tokens, int heads, int levels, int points, const int *level_h, const int *level_w,
-                       void *stream);
+int cgg_ms_deform_attn(cgg_handle *h, const float *value, long value_stride, const float *offsets, long offset_stride,
+                       const float *weight_logits, long logit_stride, float *out, int batch, int tokens, int heads,
+                       int levels, int points, const int *level_h, const int *level_w, void *stream);
 int cgg_ms_deform_attn_backward(cgg_handle *h, const float *value, const float *offsets, const float *weight_logits,
                                 const float *dout, float *dvalue, float *doffsets, float *dweight_logits, int batch,
                                 int tokens, int heads, int levels, int points, const int *level_h, const int *level_w,
