@@ -382,6 +382,34 @@ def pixel_decoder_leg(dev, B, head=None, precision='tf32', steps=5):
         torch.backends.cudnn.allow_tf32 = True
         out['torch_gpu_baseline'] = base
         out['speedup_vs_faster'] = min(base.values()) / ms
+    # ---- training form: forward + backward at the configs[3] batch (2 images per GPU), gradients to every parameter and to
+    # the backbone maps, against the same step as plain torch CUDA ops + autograd
+    try:
+        Bt = 2
+        ft = [f[:Bt].clone().requires_grad_(True) for f in feats]
+        m.out_dtype = torch.float32
+        m.train()
+
+        def ours():
+            for p_ in m.parameters():
+                p_.grad = None
+            mf, mems = m(ft)
+            (mf.square().mean() + sum(t.square().mean() for t in mems)).backward()
+
+        sd_g = {k: v.to(dev).requires_grad_(True) for k, v in sd.items()}
+
+        def plain():
+            for v in sd_g.values():
+                v.grad = None
+            mf, mems = PO.pixel_decoder_forward(sd_g, ft)
+            (mf.square().mean() + sum(t.square().mean() for t in mems)).backward()
+
+        torch.backends.cuda.matmul.allow_tf32 = True
+        out['train_step'] = dict(batch=Bt, ms_fwd_bwd=timed(ours, 3, 2), torch_tf32_ms_fwd_bwd=timed(plain, 3, 1))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        m.eval()
+    except Exception as e:      # noqa: BLE001
+        out['train_step'] = dict(error=repr(e)[:300])
     out['note'] = ('cgg_b200.pixel_decoder.MSDeformAttnPixelDecoderB200 forward, token-major fp32 activations, contractions on '
                    'tcgen05 kind::tf32; inputs resident in HBM (%.0f MB per step)' % (sum(f.numel() for f in feats) * 4 / 1e6))
     return out

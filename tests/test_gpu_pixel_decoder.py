@@ -230,3 +230,46 @@ def test_pixel_decoder_feeds_the_decoder_head():
     for j in (0, 9):
         assert _rel(mask[j].float().cpu(), ref['mask'][j]) < 2e-3
         assert _rel(cls[j].float().cpu(), ref['cls'][j]) < 2e-3
+
+
+def test_training_chain_backbone_maps_to_head_losses():
+    """The whole trained module of the reference's head: backbone maps -> pixel decoder -> decoder head -> a loss over all
+    ten head calls -> gradients of the pixel decoder's parameters, the head's parameters and the backbone maps, against the
+    oracle chain's autograd (fp32 FMA mode; attention masks forced to the oracle's, they are detached constants of the graph)."""
+    from cgg_b200.head import build_head_from_state_dict
+    from cgg_b200.train import decoder_forward_train
+    from oracle import cgg_oracle as O
+    chs = (32, 64, 96, 160)
+    B, H, W, Q = 1, 96, 128, 12
+    sd_p = synth.make_pixel_decoder_params(9, in_channels=chs)
+    sd_h = synth.make_params(seed=9, num_queries=Q, perturb=True)
+    feats = synth.make_backbone_feats(9, B, H, W, chs)
+    g = torch.Generator().manual_seed(9)
+    sd_po = {k: v.clone().requires_grad_(True) for k, v in sd_p.items()}
+    sd_ho = {k: v.clone().requires_grad_(k != 'class_embs') for k, v in sd_h.items()}
+    feats_o = [f.clone().requires_grad_(True) for f in feats]
+    mf_o, mems_o = P.pixel_decoder_forward(sd_po, feats_o)
+    ref = O.decoder_forward(sd_ho, mf_o, mems_o)
+    probes = [torch.randn(ref['mask'][j].shape, generator=g) for j in range(10)]
+    eprobes = [torch.randn(ref['emb'][j].shape, generator=g) for j in range(10)]
+    sum((ref['mask'][j] * probes[j]).sum() * 0.01 + (ref['emb'][j] * eprobes[j]).sum() * 0.1 for j in range(10)).backward()
+    pd = build_pixel_decoder_from_state_dict(sd_p, chs, DEV, precision='fp32').train()
+    head = build_head_from_state_dict(sd_h, Q, 49, 'fp32', DEV, train_precision='fp32').train()
+    fs = [f.to(DEV).requires_grad_(True) for f in feats]
+    mf, mems = pd(fs)
+    assert mf.requires_grad and mems[0].requires_grad
+    forced = [(O.pack_mask_bits(ref['masked'][j].detach()).to(DEV), ref['masked'][j].detach().all(-1).to(torch.uint8).to(DEV))
+              for j in range(9)]
+    cls, emb, mask = decoder_forward_train(head, mf, mems, forced_attn_masks=forced)
+    sum((mask[j] * probes[j].to(DEV)).sum() * 0.01 + (emb[j] * eprobes[j].to(DEV)).sum() * 0.1 for j in range(10)).backward()
+    torch.cuda.synchronize()
+    assert _rel(mask[9].detach().cpu(), ref['mask'][9].detach()) < 2e-3
+    bad = [(n, _rel(p.grad.cpu(), sd_po[n].grad)) for n, p in pd.named_parameters() if _rel(p.grad.cpu(), sd_po[n].grad) > 5e-3]
+    bad += [('feats[%d]' % i, _rel(f.grad.cpu(), fo.grad)) for i, (f, fo) in enumerate(zip(fs, feats_o))
+            if _rel(f.grad.cpu(), fo.grad) > 5e-3]
+    for n, p in head.named_parameters():
+        if sd_ho[n].grad is None or float(sd_ho[n].grad.abs().max()) == 0.0:      # (the class logits are not in this loss)
+            continue
+        if _rel(p.grad.cpu(), sd_ho[n].grad) > 5e-3:
+            bad.append((n, _rel(p.grad.cpu(), sd_ho[n].grad)))
+    assert not bad, bad
