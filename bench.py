@@ -117,6 +117,12 @@ class ClockSampler:
                     reasons=sorted(n for m, n in self.REASONS if bits & m))
 
 
+def trace(msg):
+    if os.environ.get('CGG_BENCH_TRACE'):
+        sys.stderr.write('[bench %s rank %s] %s\n' % (time.strftime('%H:%M:%S'), os.environ.get('RANK', '0'), msg))
+        sys.stderr.flush()
+
+
 def reduce_max(value, world, device):
     """MAX over ranks of a per-rank scalar (the timing rule: slowest rank defines the step)."""
     import torch.distributed as dist
@@ -548,12 +554,17 @@ def train_leg(args, rank, world, dev):
         reducer.finish()
 
     n = args.train_steps
+    trace('train: setup done')
     for _ in range(2):
         full_loss_step()
+    trace('train: full-loss warm-up done')
     full_ms, _ = timed(full_loss_step, n)
+    trace('train: full-loss timed')
     for _ in range(2):
         eager_step()
+    trace('train: eager warm-up done')
     eager_ms, exposed = timed(eager_step, n, after=reducer.exposed)
+    trace('train: eager timed')
     exposed = reduce_max(exposed, world, dev)
     out = dict(batch_per_gpu=B, queries=Q, classes_p1=ncls1, precision=args.train_precision,
                grad_bytes=4 * sum(p.numel() for p in head.parameters()),
@@ -567,8 +578,10 @@ def train_leg(args, rank, world, dev):
     if not args.no_train_graph:
         reducer.timing = False
         gs = GraphedStep(loss_fn, head.parameters(), reducer=reducer)
+        trace('train: graph captured')
         for _ in range(2):
             gs.replay()
+        trace('train: graph replayed')
         ms, _ = timed(gs.replay, max(n, 10))
         out['cuda_graph'] = True
     out.update(ms_per_step=ms, images_per_s=world * B / (ms * 1e-3),
@@ -729,6 +742,7 @@ def run_b200_arm(args):
         sampler2.start()
     ms_sus = reduce_max(timed(n_sus), world, dev)
     sus_clocks = sampler2.stop() if rank == 0 else None
+    trace('sustained leg done')
     sustained = dict(value=whole_job_value(world, B, n_sus, ms_sus), unit=UNIT, steps=n_sus, seconds=ms_sus * 1e-3,
                      ms_per_step=ms_sus / n_sus, clocks=sus_clocks)
 
@@ -786,6 +800,7 @@ def run_b200_arm(args):
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
     barrier()
+    trace('e2e leg done')
     e2e_val = whole_job_value(world, B, e2e_steps, 1e3 * reduce_max(time.perf_counter() - t0, world, dev))
     d2h = sum(x.numel() * x.element_size() for x in res_h)
     del in_bufs
@@ -883,6 +898,7 @@ def run_b200_arm(args):
     if os.path.exists(wpath):
         write_only = json.load(open(wpath))
     per_gpu_value = value / world
+    trace('strong + roofline legs done')
     roofline = dict(bound='hbm' if hbm_bound else 'tensor',
                     achieved=ach_gbs if hbm_bound else ach_tf, peak=peaks['hbm_gbs'] if hbm_bound else peaks['tflops'],
                     unit='GB/s' if hbm_bound else 'TFLOP/s', frac=frac_h if hbm_bound else frac_t,
@@ -905,8 +921,10 @@ def run_b200_arm(args):
     grounding = train = matching_rec = pixdec = None
     if not args.no_train:
         try:
-            grounding = grounding_leg(dev) if rank == 0 else None
-            matching_rec = matching_leg(dev) if rank == 0 else None
+            # single-process stage legs: N = 1 only (the matching losses average their positives over the ranks -- a
+            # collective -- so running them on rank 0 alone under torchrun would leave the other ranks out of step)
+            grounding = grounding_leg(dev) if (rank == 0 and world == 1) else None
+            matching_rec = matching_leg(dev) if (rank == 0 and world == 1) else None
             if rank == 0 and world == 1 and not args.no_pixel_decoder:
                 try:
                     pixdec = pixel_decoder_leg(dev, B, heads[0])
@@ -914,7 +932,9 @@ def run_b200_arm(args):
                     pixdec = dict(error=repr(e)[:300])
             del heads, fly_in
             torch.cuda.empty_cache()
+            trace('stage legs done, train leg starts')
             train = train_leg(args, rank, world, dev)
+            trace('train leg done')
         except Exception as e:      # noqa: BLE001
             train = dict(error=repr(e)[:300])
     tgb = None

@@ -27,6 +27,13 @@ namespace {
 
 constexpr int BM = 128, BK = 32;                       // BK fp32 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;             // 16 KB
+// epilogue warps: 4 = one per TMEM lane quarter; 8 = two per quarter taking alternate 32-column chunks of a tile.  Measured
+// with 8 (344 k-row products of the pixel decoder): residual products 0.41 -> 0.34 ms, but the FFN1 product 0.54 -> 0.75 ms
+// (three TMA stages instead of four: the staging tiles take the shared memory; 168 registers with spills) and the
+// training step 17.5 -> 18.9 ms -- so 4 it stays.
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_STEP = 32 * (EPI_WARPS / 4);
 
 struct Tf32P {
   int M, N, K, batch;
@@ -79,7 +86,7 @@ __device__ __forceinline__ float epi_value(const Tf32P& p, float acc, int b, int
   return v;
 }
 
-__global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ CUtensorMap mA,
+__global__ void __launch_bounds__(THREADS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap mA,
                                                         const __grid_constant__ CUtensorMap mB, const Tf32P p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -87,15 +94,15 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   const int stage_bytes = A_STAGE_BYTES + ((b_stage_bytes + 1023) & ~1023);
   __shared__ uint64_t full[4], empty[4], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float bias_s[4][256];     // per epilogue warp: the bias of the current tile's columns
-  __shared__ __align__(16) float stage_s[4][1024];   // per epilogue warp: a 32 x 32 chunk on its way from row-per-thread to coalesced rows
+  __shared__ __align__(16) float bias_s[EPI_WARPS][256];     // per epilogue warp: the bias of the current tile's columns
+  __shared__ __align__(16) float stage_s[EPI_WARPS][1024];   // per epilogue warp: a 32 x 32 chunk on its way from row-per-thread to coalesced rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = p.tmem_cols >> 1;                 // two accumulators: the epilogue of tile i overlaps tile i + 1
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], EPI_WARPS); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&mA);
     ptx::prefetch_tmap(&mB);
@@ -182,7 +189,8 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
     // A single warp per lane quarter walks the whole tile, so the instruction count per element is what bounds it:
     // mode 1 (row-major C, 16-byte aligned rows) writes float4s straight from the registers, mode 2 (m-contiguous C:
     // the mask einsum and d mask_features) writes one 128-byte line per column; mode 0 is the scalar catch-all.
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, ew = warp - 2;
+    const int j0 = (ew >> 2) * 32;                         // this warp's first chunk of a tile
     const float* __restrict__ bias = p.bias;
     const float* __restrict__ R = p.R;
     const bool plain = !p.partial && !bias && !R && p.alpha == 1.0f && p.relu_from >= p.N && !p.accumulate;
@@ -232,12 +240,12 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int c = lane * 4 + 128 * t;
-            *reinterpret_cast<float4*>(&bias_s[quarter][c]) =
+            *reinterpret_cast<float4*>(&bias_s[ew][c]) =
                 (c < p.n_tile && n0 + c < p.N) ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp();
         }
-        if (rich && add) prefetch(va, 0);
+        if (rich && add && j0 < p.n_tile) prefetch(va, j0);
       }
       ptx::mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
       ptx::tc_fence_after();
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (staged) {
-            float* stg = stage_s[quarter];
+            float* stg = stage_s[ew];
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4)
               *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
             __syncwarp();
             const int col = n0 + j + cq * 4;
             const bool colok = col < col_end;
-            const float4 bv = bias ? *reinterpret_cast<const float4*>(&bias_s[quarter][j + cq * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bv = bias ? *reinterpret_cast<const float4*>(&bias_s[ew][j + cq * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
             const bool relu = n0 + j >= p.relu_from;               // relu_from is a multiple of 32 here (0 or "never")
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
               float4 bv[8];
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4)
-                bv[c4] = bias ? *reinterpret_cast<const float4*>(&bias_s[quarter][j + 4 * c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bv[c4] = bias ? *reinterpret_cast<const float4*>(&bias_s[ew][j + 4 * c4]) : make_float4(0.f, 0.f, 0.f, 0.f);
               const bool relu = n0 + j >= p.relu_from;
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
             const bool relu = n0 + j >= p.relu_from;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float o = (v[i] + (bias ? bias_s[quarter][j + i] : 0.f)) * p.alpha;
+              float o = (v[i] + (bias ? bias_s[ew][j + i] : 0.f)) * p.alpha;
               if (relu) o = fmaxf(o, 0.f);
               if (i < nc) *cp = o;
               cp += p.sCn;
@@ -343,24 +351,26 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
             }
           }
       };
-      auto more_after = [&](int j) { return j + 32 < p.n_tile && n0 + j + 32 < p.N; };
+      auto more_after = [&](int j) { return j + EPI_STEP < p.n_tile && n0 + j + EPI_STEP < p.N; };
       uint32_t ra[32], rb[32];
-      int j = 0;
-      issue(ra, 0);
-      waitr(ra);
-      while (true) {
-        bool more = more_after(j);
-        if (more) { issue(rb, j + 32); if (rich && add) prefetch(vb, j + 32); }
-        process(ra, va, j);
-        if (!more) break;
-        waitr(rb);
-        j += 32;
-        more = more_after(j);
-        if (more) { issue(ra, j + 32); if (rich && add) prefetch(va, j + 32); }
-        process(rb, vb, j);
-        if (!more) break;
+      int j = j0;
+      if (j < p.n_tile && n0 + j < p.N) {
+        issue(ra, j);
         waitr(ra);
-        j += 32;
+        while (true) {
+          bool more = more_after(j);
+          if (more) { issue(rb, j + EPI_STEP); if (rich && add) prefetch(vb, j + EPI_STEP); }
+          process(ra, va, j);
+          if (!more) break;
+          waitr(rb);
+          j += EPI_STEP;
+          more = more_after(j);
+          if (more) { issue(ra, j + EPI_STEP); if (rich && add) prefetch(va, j + EPI_STEP); }
+          process(rb, vb, j);
+          if (!more) break;
+          waitr(ra);
+          j += EPI_STEP;
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -488,7 +498,7 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   p.b_groups = (p.n_tile + 31) / 32;
   const int b_stage = ((p.b_mn ? p.b_groups * 32 : p.n_tile) * BK * 4 + 1023) & ~1023;
   const int stage_bytes = A_STAGE_BYTES + b_stage;
-  p.stages = 4;
+  p.stages = (EPI_WARPS > 4 && stage_bytes > 32 * 1024) ? 3 : 4;   // (with 8 epilogue warps 40 KB of static shared memory go to the staging tiles)
   p.tmem_cols = 2 * (p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256);
   p.chunks = (g.K + BK - 1) / BK;
   const long mt = (g.M + BM - 1) / BM, nt = (g.N + p.n_tile - 1) / p.n_tile;
@@ -536,14 +546,14 @@ int launch_gemm_tf32(Tf32Ctx* t, const GemmF32& g, cudaStream_t s) {
   else if (g.sCm == 1 && (g.relu_from % 32 == 0 || g.relu_from >= g.N) && (!g.bias || al16(g.bias)) && (!g.bias || g.N % 4 == 0)) p.epi_mode = 2;
   else p.epi_mode = 0;
   if (!t->attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 24 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (EPI_WARPS > 4 ? 44 : 24) * 1024) != cudaSuccess) {
       t->err = "cudaFuncSetAttribute(gemm_tf32_kernel) failed";
       return -1;
     }
     t->attr_set = true;
   }
   const long total = mt * nt * g.batch * p.splits;
-  gemm_tf32_kernel<<<(unsigned)(total < t->sm_count ? total : t->sm_count), 192, smem, s>>>(mA, mB, p);
+  gemm_tf32_kernel<<<(unsigned)(total < t->sm_count ? total : t->sm_count), THREADS, smem, s>>>(mA, mB, p);
   count_launch();
   if (p.splits > 1) {
     const long per = (long)g.batch * g.M * g.N;

@@ -607,6 +607,7 @@ class GradReducer:
             bk['pending'] = len(bk['params'])
             bk['work'] = None
             bk['producers'] = set()
+            bk['reported'] = set()
 
     def zero(self):
         """Start of a step: clear the buckets (the backward accumulates into them) and re-attach any .grad that was
@@ -625,6 +626,14 @@ class GradReducer:
     def _hook(self, p, producer=None):
         bi, off = self.index[p]
         bk = self.buckets[bi]
+        # A parameter reports ONCE per step.  One whose gradient was written by the fused path (param_done) is reported a
+        # second time by autograd: the engine still runs the parameter's accumulation node -- after every node that feeds
+        # it, hence after the last fused product was enqueued -- and its post-accumulate hook fires although the gradient
+        # it was handed is undefined.  Counting that report would launch the bucket's all-reduce before other gradients
+        # of the bucket are complete (seen as wrong averages on 2 GPUs; harmless on one, where nothing is reduced).
+        if id(p) in bk['reported']:
+            return
+        bk['reported'].add(id(p))
         if p.grad.data_ptr() != bk['flat'].data_ptr() + 4 * off:       # the caller replaced .grad: fold it back in
             bk['flat'][off:off + p.numel()].copy_(p.grad.reshape(-1))
             p.grad = bk['flat'][off:off + p.numel()].view_as(p)
