@@ -273,3 +273,22 @@ def test_training_chain_backbone_maps_to_head_losses():
         if _rel(p.grad.cpu(), sd_ho[n].grad) > 5e-3:
             bad.append((n, _rel(p.grad.cpu(), sd_ho[n].grad)))
     assert not bad, bad
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('tf32', 1e-2)])
+def test_pixel_decoder_matches_the_committed_golden_vectors(precision, tol):
+    """The CUDA path against tests/golden/pixel_decoder.npz: outputs of an independent implementation (HF's pixel decoder)."""
+    import os
+    import numpy as np
+    import make_pixel_decoder_golden as G
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(G.__file__)), 'pixel_decoder.npz'))
+    c = G.CASE
+    sd = synth.make_pixel_decoder_params(c['seed'], in_channels=c['in_channels'])
+    feats = synth.make_backbone_feats(c['seed'], c['batch'], c['height'], c['width'], c['in_channels'])
+    m = build_pixel_decoder_from_state_dict(sd, c['in_channels'], DEV, precision=precision).eval()
+    with torch.no_grad():
+        mf, mems = m([f.to(DEV) for f in feats])
+    torch.cuda.synchronize()
+    assert _rel(mf.cpu(), torch.from_numpy(z['mask_features'])) < tol
+    for i, t in enumerate(mems):
+        assert _rel(t.cpu(), torch.from_numpy(z['memory%d' % i])) < tol
