@@ -53,24 +53,29 @@ __global__ void __launch_bounds__(512) ms_deform_attn_kernel(const MsdaP p, cons
                                                              float* __restrict__ out, const float* __restrict__ dout,
                                                              float* __restrict__ dvalue, float* __restrict__ doff,
                                                              float* __restrict__ dlogits) {
+  // (level geometry through static selects, blockIdx as (head, patch, image): see the forward kernel below)
+  auto geom = [&](int l, int& H, int& W, int& start) {
+    H = p.h[0]; W = p.w[0]; start = p.start[0];
+#pragma unroll
+    for (int q = 1; q < MAX_LEVELS; ++q)
+      if (l == q) { H = p.h[q]; W = p.w[q]; start = p.start[q]; }
+  };
   const int C = p.heads * 32;
-  const int head = (int)(blockIdx.x % p.heads);
-  long r = blockIdx.x / p.heads;
-  const int total_patches = p.pstart[p.levels];
-  int pl = (int)(r % total_patches);
-  const int b = (int)(r / total_patches);
-  int ql = 0;
+  const int head = blockIdx.x, b = blockIdx.z;
+  int pl = blockIdx.y, ql = 0, pfirst = 0, pwq = p.pw[0];
 #pragma unroll
   for (int l = 1; l < MAX_LEVELS; ++l)
-    if (l < p.levels && pl >= p.pstart[l]) ql = l;
-  pl -= p.pstart[ql];
+    if (l < p.levels && pl >= p.pstart[l]) { ql = l; pfirst = p.pstart[l]; pwq = p.pw[l]; }
+  pl -= pfirst;
+  int Hq, Wq, startq;
+  geom(ql, Hq, Wq, startq);
   const int qi = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-  const int qy = (pl / p.pw[ql]) * 8 + (qi >> 3), qx = (pl % p.pw[ql]) * 8 + (qi & 7);
-  const bool valid = qy < p.h[ql] && qx < p.w[ql];
-  const int s = p.start[ql] + (valid ? qy * p.w[ql] + qx : 0);
+  const int qy = (pl / pwq) * 8 + (qi >> 3), qx = (pl % pwq) * 8 + (qi & 7);
+  const bool valid = qy < Hq && qx < Wq;
+  const int s = startq + (valid ? qy * Wq + qx : 0);
   const long tq = (long)b * p.S + s;
-  const float ref_x = ((float)qx + 0.5f) / (float)p.w[ql];
-  const float ref_y = ((float)qy + 0.5f) / (float)p.h[ql];
+  const float ref_x = ((float)qx + 0.5f) / (float)Wq;
+  const float ref_y = ((float)qy + 0.5f) / (float)Hq;
   const int LP = p.levels * p.points;                                // <= 16
   const float* lg = logits + ((long)tq * p.heads + head) * LP;
   const float* of = off + ((long)tq * p.heads + head) * LP * 2;
@@ -92,17 +97,18 @@ __global__ void __launch_bounds__(512) ms_deform_attn_kernel(const MsdaP p, cons
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     if (i >= LP) continue;
-    const int l = i / p.points;
+    const int l = (i >= p.points) + (i >= 2 * p.points) + (i >= 3 * p.points);
     const float a = aw[i] * inv;
-    const int H = p.h[l], W = p.w[l];
+    int H, W, startl;
+    geom(l, H, W, startl);
     const float loc_x = ref_x + of[2 * i] / (float)W, loc_y = ref_y + of[2 * i + 1] / (float)H;
     const float wim = loc_x * (float)W - 0.5f, him = loc_y * (float)H - 0.5f;
     float dwx = 0.f, dwy = 0.f, dsample = 0.f;
     if (valid && him > -1.f && wim > -1.f && him < (float)H && wim < (float)W) {
       const int hl = (int)floorf(him), wl = (int)floorf(wim);
       const float lh = him - (float)hl, lw = wim - (float)wl, hh = 1.f - lh, hw = 1.f - lw;
-      const float* vb = value + ((long)b * p.S + p.start[l]) * C + head * 32 + c4;
-      float* gb = BWD ? dvalue + ((long)b * p.S + p.start[l]) * C + head * 32 + c4 : nullptr;
+      const float* vb = value + ((long)b * p.S + startl) * C + head * 32 + c4;
+      float* gb = BWD ? dvalue + ((long)b * p.S + startl) * C + head * 32 + c4 : nullptr;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool t0 = hl >= 0, t1 = hl + 1 <= H - 1, l0 = wl >= 0, l1 = wl + 1 <= W - 1;
       const long o1 = ((long)hl * W + wl) * C, o2 = o1 + C, o3 = o1 + (long)W * C, o4 = o3 + C;
@@ -539,7 +545,8 @@ cudaError_t launch_ms_deform_attn_bwd(const float* value, const float* off, cons
   if (tq <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(dvalue, 0, (size_t)tq * heads * 32 * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  ms_deform_attn_kernel<true><<<(unsigned)((long)B * ps * heads), 512, 0, s>>>(p, value, off, logits, nullptr, dout, dvalue, doff, dlogits);
+  if (ps > 65535 || B > 65535) return cudaErrorInvalidValue;
+  ms_deform_attn_kernel<true><<<dim3(heads, ps, B), 512, 0, s>>>(p, value, off, logits, nullptr, dout, dvalue, doff, dlogits);
   count_launch();
   return cudaGetLastError();
 }

@@ -498,7 +498,7 @@ class _Runtime:
                     self._forward_eager(mf, mems, False)          # warm-up outside capture
                     side.synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=side):
+                    with _lib.no_gc_during_capture(), torch.cuda.graph(g, stream=side):
                         outs = self._forward_eager(mf, mems, False)
                 cur.wait_stream(side)
                 entry = dict(graph=g, outs=outs, mf=mf, mems=mems, owned=own,

@@ -165,3 +165,25 @@ def check(status, handle=None, what=''):
         if handle:
             msg = load().cgg_last_error(handle).decode()
         raise CggError('%s failed: %s %s' % (what, STATUS.get(status, status), msg))
+
+
+class no_gc_during_capture:
+    """Context for a CUDA-graph capture: collects garbage first and keeps the cyclic collector off while the stream is
+    capturing.  A head and its runtime reference each other, so a dropped head is freed by the CYCLIC collector, at an
+    arbitrary later allocation -- and its `cgg_destroy` (cudaFree, cudaStreamDestroy) in the middle of a global-mode capture
+    invalidates the capture (cudaErrorStreamCaptureInvalidated at the next launch).  torch.cuda.graph no longer collects on
+    entry by itself."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+        return False
+

@@ -245,7 +245,13 @@ class _AddRows(torch.autograd.Function):
         dadd = None
         if ctx.needs_input_grad[2]:
             dadd = k.new(*g.shape[1:])
-            k.chk(k.lib.cgg_sum_batch(k.h, _p(g), _p(dadd), ctx.batch, dadd.numel(), k.s()), 'cgg_sum_batch')
+            per = dadd.numel()
+            if ctx.batch > per and (ctx.batch + 255) // 256 <= 65535:
+                # many short rows (a level embedding added to every pixel's position row): a column sum over `batch` rows --
+                # cgg_sum_batch would walk the whole batch with `per` threads
+                k.chk(k.lib.cgg_colsum(k.h, _p(g), _p(dadd), ctx.batch, per, 1.0, 0, k.s()), 'cgg_colsum')
+            else:
+                k.chk(k.lib.cgg_sum_batch(k.h, _p(g), _p(dadd), ctx.batch, per, k.s()), 'cgg_sum_batch')
         return None, (g if ctx.has_x else None), dadd, None
 
 
@@ -713,7 +719,7 @@ class GraphedStep:
             for p in self.params:
                 p.grad = None                     # the captured backward allocates .grad from the graph's pool
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with _lib.no_gc_during_capture(), torch.cuda.graph(self.graph):
             self.loss = self._one()
 
     def _one(self):
