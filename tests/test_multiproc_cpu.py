@@ -148,6 +148,76 @@ def test_bucketed_grad_reducer_two_ranks_gloo():
             torch.testing.assert_close(g, p.grad, rtol=1e-5, atol=1e-7)
 
 
+class _FusedLinear(torch.autograd.Function):
+    """A stand-in for the fused weight-gradient path of cgg_b200.train._Linear: dW is accumulated straight into the
+    parameter's .grad (the reducer's bucket view), the reducer is told so, and autograd gets None for it."""
+
+    @staticmethod
+    def forward(ctx, x, W, red):
+        ctx.save_for_backward(x, W)
+        ctx.red = red
+        return x @ W.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        W.grad.add_(dy.t() @ x)
+        ctx.red.param_done(W, None)
+        ctx.red._hook(W)          # ... and the second report autograd's post-accumulate hook adds on the GPU path (seen with
+        #                           an empty Python stack right after param_done: the engine still runs the accumulation node)
+        for bk in ctx.red.buckets:                  # (a collective launched too early is made to finish now, so that the
+            if bk['work'] is not None:              #  outcome does not depend on a race with the rest of the backward)
+                bk['work'].wait()
+        return dy @ W, None, None
+
+
+def _fused_reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from cgg_b200.train import GradReducer
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    W1, W2 = torch.nn.Parameter(torch.randn(64, 16)), torch.nn.Parameter(torch.randn(8, 64))
+    b2 = torch.nn.Parameter(torch.randn(8))
+    red = GradReducer([W1, W2, b2], bucket_mb=1.0)              # one bucket: b2 (autograd hook) is produced FIRST in the backward
+    x = torch.randn((8, 16), generator=torch.Generator().manual_seed(10 + rank))
+    for _ in range(2):
+        red.zero()
+        h = torch.relu(_FusedLinear.apply(x, W1, red))
+        (_FusedLinear.apply(h, W2, red) + b2).pow(2).mean().backward()
+        red.finish()
+    q.put((rank, [p.grad.clone() for p in (W1, W2, b2)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_counts_a_fused_parameter_once():
+    """Regression test of a 2-GPU failure: a parameter whose gradient is written outside autograd reports through
+    `param_done`, and autograd's post-accumulate hook may fire for it as well -- the bucket's all-reduce must still wait for
+    EVERY parameter of the bucket (here W1, produced last) and the result must be the mean over the ranks."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 36500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_fused_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    W1, W2 = torch.nn.Parameter(torch.randn(64, 16)), torch.nn.Parameter(torch.randn(8, 64))
+    b2 = torch.nn.Parameter(torch.randn(8))
+    total = 0.0
+    for rank in range(2):
+        x = torch.randn((8, 16), generator=torch.Generator().manual_seed(10 + rank))
+        total = total + (torch.relu(x @ W1.t()) @ W2.t() + b2).pow(2).mean()
+    (total / 2).backward()
+    for rank, grads in res:
+        for g, p in zip(grads, (W1, W2, b2)):
+            torch.testing.assert_close(g, p.grad, rtol=1e-5, atol=1e-7)
+
+
 def test_reference_arm_runs_on_rank0_only():
     env = dict(os.environ, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
