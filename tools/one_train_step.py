@@ -1,6 +1,7 @@
 """Two eager training steps of bench.py's train leg (BASELINE configs[3]: Q=200, 118 class rows, B=2, 1024x1024) --
 the `ncu` target for the training step's launch list and for the tf32 GEMM captures.
-  python tools/one_train_step.py [fp32|tf32] [steps]"""
+  python tools/one_train_step.py [fp32|tf32] [steps] [reducer]     (reducer: gradients go to a GradReducer's buckets, which
+  turns on the fused weight-gradient path -- the form the bench's train leg runs)"""
 import sys
 import torch
 sys.path.insert(0, '.')
@@ -22,9 +23,16 @@ cap_mask = cap_mask.to(dev)
 g = torch.Generator().manual_seed(0)
 labels = torch.randint(0, ncls1, (B, Q), generator=g).to(dev)
 targets = (torch.rand((B, Q, H // 4, W // 4), generator=g) > 0.5).to(dev).float()
+red = None
+if len(sys.argv) > 3 and sys.argv[3] == 'reducer':
+    from cgg_b200.train import GradReducer
+    red = GradReducer(head.parameters())
 for _ in range(steps):
-    for p in head.parameters():
-        p.grad = None
+    if red is not None:
+        red.zero()
+    else:
+        for p in head.parameters():
+            p.grad = None
     cls, emb, mask = head.decoder_forward_auto(mf, mems)
     loss = 0.0
     for j in range(len(cls)):
@@ -32,5 +40,7 @@ for _ in range(steps):
         loss = loss + torch.nn.functional.cross_entropy(similarity(emb[j].reshape(B * Q, -1), head.class_embs, 0.1), labels.reshape(-1))
         loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(mask[j], targets)
     loss.backward()
+    if red is not None:
+        red.finish()
 torch.cuda.synchronize()
 print('loss', float(loss))
