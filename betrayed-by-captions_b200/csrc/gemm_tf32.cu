@@ -11,11 +11,19 @@
 // TMA side, layout type 1 in the matrix descriptor.)  Shapes whose strides TMA cannot describe (row pitch not a multiple
 // of 16 bytes: the 118-class rows) are reported as ineligible and run on the SIMT kernel.
 //
-// Persistent CTAs (one per SM) walk the (128 x n_tile) output tiles: warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2-5 = epilogue (one TMEM lane quarter each); two TMEM accumulators, so the epilogue of one tile overlaps the
-// main loop of the next.  Products with few output tiles and a long contraction (dW of the K/V projections, d mask_embed
-// of the mask einsum: K = 65 536) are split over K into a dense fp32 partial buffer and summed, in a fixed order, by
-// splitk_reduce_kernel, which also applies the epilogue.
+// Persistent CTAs (one per SM) walk the (128 x n_tile) output tiles, n fastest (CTAs running side by side share an A tile
+// through L2): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane quarter each); two TMEM
+// accumulators, so the epilogue of one tile overlaps the main loop of the next.  Products with few output tiles and a long
+// contraction (dW of the K/V projections, d mask_embed of the mask einsum: K = 65 536) are split over K into a dense fp32
+// partial buffer and summed, in a fixed order, by splitk_reduce_kernel, which also applies the epilogue.
+//
+// Epilogue forms (chosen per launch): row-major C without a residual goes through a per-warp XOR-swizzled shared-memory
+// tile and leaves as whole 128-byte lines; with a residual / C += the thread keeps its accumulator row and the residual of
+// the next 32-column chunk is requested one chunk ahead (the first before the accumulator barrier); m-contiguous C (NCHW
+// outputs, the mask einsum) writes one line per column, with an optional bias; the tile's bias lives in a per-warp
+// shared-memory row.  conv_cin turns the A loads into the nine taps of a 3x3 convolution over a token-major image (the TMA
+// unit's out-of-bounds zero fill is the padding); a weight matrix shared by every batch entry is a tensor map without
+// batch dimensions.
 #include "tc_ptx.cuh"
 #include "kernels.h"
 #include "gemm_tf32.h"

@@ -101,3 +101,21 @@ def test_synth_is_deterministic():
     y, _ = synth.make_inputs(1, 1, 64, 96)
     assert torch.equal(x, y) and x.shape == (1, 256, 16, 24)
     assert synth.level_sizes(1024, 1024) == ((256, 256), [(32, 32), (64, 64), (128, 128)])
+
+
+def test_no_gc_during_capture_context():
+    """CUDA-graph captures run with the cyclic collector off (a dropped head's cgg_destroy in the middle of a capture
+    invalidates it) and the collector's state is restored afterwards."""
+    import gc
+    was = gc.isenabled()
+    with clib.no_gc_during_capture():
+        assert not gc.isenabled()
+    assert gc.isenabled() == was
+    gc.disable()
+    try:
+        with clib.no_gc_during_capture():
+            assert not gc.isenabled()
+        assert not gc.isenabled()          # it was off before: stays off
+    finally:
+        if was:
+            gc.enable()
